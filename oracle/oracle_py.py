@@ -1,0 +1,119 @@
+"""ctypes binding of the CPU oracle (oracle/pgo_oracle.c). TEST INFRASTRUCTURE ONLY:
+importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libpgo_oracle.so")
+
+LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
+
+
+class Options(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int), ("jacobi_scaling", C.c_int),
+                ("loss_type", C.c_int), ("loss_a", C.c_double), ("ordering", C.c_int)]
+
+
+class Iteration(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("step_is_valid", C.c_int), ("step_is_successful", C.c_int),
+                ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double),
+                ("gradient_norm", C.c_double), ("step_norm", C.c_double),
+                ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("num_successful_steps", C.c_int), ("num_unsuccessful_steps", C.c_int),
+                ("num_iterations", C.c_int), ("termination_type", C.c_int), ("message", C.c_char * 160),
+                ("time_total_s", C.c_double), ("time_residual_s", C.c_double),
+                ("time_jacobian_s", C.c_double), ("time_linear_solver_s", C.c_double),
+                ("factor_nnz_blocks", C.c_longlong), ("num_jacobian_evals", C.c_int),
+                ("num_residual_evals", C.c_int)]
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "pgo_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+        _lib.oracle_default_options.argtypes = [C.POINTER(Options)]
+        _lib.oracle_evaluate.restype = C.c_int
+        _lib.oracle_solve.restype = C.c_int
+        _lib.oracle_normal_solve.restype = C.c_int
+    return _lib
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def default_options() -> Options:
+    o = Options()
+    lib().oracle_default_options(C.byref(o))
+    return o
+
+
+def evaluate(g, poses=None, loss_type=LOSS_HUBER, loss_a=1.0, want_jac=True):
+    poses = np.ascontiguousarray(g.poses if poses is None else poses, np.float64)
+    n, e = g.n_poses, g.n_edges
+    cost = C.c_double()
+    res = np.zeros(6 * e)
+    grad = np.zeros(6 * n)
+    jac = np.zeros((e, 2, 36)) if want_jac else None
+    ids = np.ascontiguousarray(g.edge_ids, np.int32)
+    rc = lib().oracle_evaluate(C.c_int(n), _p(poses), _p(np.ascontiguousarray(g.pose_const, np.uint8), C.c_ubyte),
+                               C.c_int(e), _p(ids, C.c_int), _p(np.ascontiguousarray(g.edge_meas)),
+                               _p(np.ascontiguousarray(g.edge_sqrt_info)), C.c_int(loss_type), C.c_double(loss_a),
+                               C.byref(cost), _p(res), _p(grad), _p(jac))
+    assert rc == 0
+    return cost.value, res.reshape(e, 6), grad.reshape(n, 6), jac
+
+
+def plus(poses, delta):
+    poses = np.ascontiguousarray(poses, np.float64)
+    delta = np.ascontiguousarray(delta, np.float64)
+    out = np.empty_like(poses)
+    lib().oracle_plus(C.c_int(poses.shape[0]), _p(poses), _p(delta), _p(out))
+    return out
+
+
+def solve(g, options: Options | None = None, max_log=2048):
+    o = options or default_options()
+    poses = np.ascontiguousarray(g.poses, np.float64).copy()
+    s = Summary()
+    log = (Iteration * max_log)()
+    ids = np.ascontiguousarray(g.edge_ids, np.int32)
+    rc = lib().oracle_solve(C.c_int(g.n_poses), _p(poses), _p(np.ascontiguousarray(g.pose_const, np.uint8), C.c_ubyte),
+                            C.c_int(g.n_edges), _p(ids, C.c_int), _p(np.ascontiguousarray(g.edge_meas)),
+                            _p(np.ascontiguousarray(g.edge_sqrt_info)), C.byref(o), C.byref(s), log, C.c_int(max_log))
+    assert rc == 0
+    its = [log[i] for i in range(min(s.num_iterations, max_log))]
+    return poses, s, its
+
+
+def normal_solve(g, jac, d, rhs, ordering=1):
+    y = np.zeros(6 * g.n_poses)
+    ids = np.ascontiguousarray(g.edge_ids, np.int32)
+    rc = lib().oracle_normal_solve(C.c_int(g.n_poses), _p(np.ascontiguousarray(g.pose_const, np.uint8), C.c_ubyte),
+                                   C.c_int(g.n_edges), _p(ids, C.c_int), _p(np.ascontiguousarray(jac, np.float64)),
+                                   _p(np.ascontiguousarray(d, np.float64)), _p(np.ascontiguousarray(rhs, np.float64)),
+                                   _p(y), C.c_int(ordering))
+    return rc, y.reshape(-1, 6)
