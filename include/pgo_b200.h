@@ -1,0 +1,197 @@
+/*
+ * pgo_b200.h -- C-ABI of the B200-native pose-graph Levenberg-Marquardt solver.
+ *
+ * Drop-in boundary for the ONE hot path of TurtleZhong/PoseGraph-Ceres
+ * (REF = /root/reference/src/POSE_GRAPH_CERES_PLUS):
+ *
+ *   BuildOptimizationProblem()   REF/test/pose_graph_ceres_plus_finial.cpp:461-497
+ *       ceres::Problem::AddResidualBlock(PoseGraph3dErrorTerm, HuberLoss(1.0), p_a, q_a, p_b, q_b)
+ *       ceres::Problem::SetParameterization(q, EigenQuaternionParameterization)
+ *       ceres::Problem::SetParameterBlockConstant(first pose)
+ *   SolveOptimizationProblem()   REF/test/pose_graph_ceres_plus_finial.cpp:500-514
+ *       ceres::Solve(options{max_num_iterations = 1000, SPARSE_NORMAL_CHOLESKY}, problem, &summary)
+ *   PoseGraph3dErrorTerm         REF/include/PoseGraph3dError.h:21-54   (the residual)
+ *
+ * Plain pointers and sizes only; all arrays are HOST memory unless a name ends in _dev.
+ * Every function returns 0 on success, a negative pgo_status otherwise; pgo_last_error()
+ * returns a message.  There is NO CPU fallback: without a CUDA device the calls fail.
+ *
+ * Array conventions (double precision):
+ *   poses          [n_poses][7]  x y z qx qy qz qw   (Pose3d, REF/include/types.h:16-21; Eigen coeffs order)
+ *   edge_ids       [n_edges][2]  id_begin, id_end    (Edge3d, REF/include/types.h:30-45)
+ *   edge_meas      [n_edges][7]  t_be = T_begin^-1 * T_end, same layout as a pose
+ *   edge_sqrt_info [n_edges][36] ROW-major 6x6 sqrt_information (residual = S * r); NULL = identity
+ *   pose_const     [n_poses]     1 = SetParameterBlockConstant(p) and (q)
+ *   tangent vectors (gradient, steps) are [n_poses][6]: (dx dy dz, d_rot[3]) in the local
+ *   coordinates of EigenQuaternionParameterization: p+ = p + dp, q+ = Quat(cos|d|, sin|d|/|d| d) * q.
+ */
+#ifndef PGO_B200_H_
+#define PGO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGO_B200_ABI_VERSION 1
+
+typedef enum {
+  PGO_OK = 0,
+  PGO_ERR_INVALID_ARGUMENT = -1,
+  PGO_ERR_CUDA = -2,
+  PGO_ERR_NO_DEVICE = -3,
+  PGO_ERR_NCCL = -4,
+  PGO_ERR_NUMERICAL = -5
+} pgo_status;
+
+/* ceres::LossFunction the reference can pass to AddResidualBlock (NULL / HuberLoss / CauchyLoss). */
+typedef enum { PGO_LOSS_TRIVIAL = 0, PGO_LOSS_HUBER = 1, PGO_LOSS_CAUCHY = 2 } pgo_loss_type;
+
+/* ceres::TerminationType */
+typedef enum { PGO_CONVERGENCE = 0, PGO_NO_CONVERGENCE = 1, PGO_FAILURE = 2 } pgo_termination_type;
+
+/* Linear solver for the damped normal equations (replaces options.linear_solver_type =
+ * SPARSE_NORMAL_CHOLESKY, REF/test/pose_graph_ceres_plus_finial.cpp:505). */
+typedef enum {
+  PGO_LINEAR_PCG_BLOCK_JACOBI = 0,   /* 6x6 block-Jacobi preconditioned CG (block-SpMV kernel)        */
+  PGO_LINEAR_PCG_LEVEL_CHOLESKY = 1, /* PCG preconditioned by a level-scheduled block Cholesky factor */
+  PGO_LINEAR_AUTO = 2                /* LEVEL_CHOLESKY when the symbolic fill is small, else BLOCK_JACOBI */
+} pgo_linear_solver_type;
+
+/* Mirrors the ceres::Solver::Options fields that matter on this path; defaults = Ceres defaults
+ * except max_num_iterations, which the reference sets to 1000. */
+typedef struct {
+  int max_num_iterations;
+  double function_tolerance;
+  double gradient_tolerance;
+  double parameter_tolerance;
+  double initial_trust_region_radius;
+  double max_trust_region_radius;
+  double min_trust_region_radius;
+  double min_relative_decrease;
+  double min_lm_diagonal;
+  double max_lm_diagonal;
+  int max_num_consecutive_invalid_steps;
+  int jacobi_scaling;
+  int loss_type;                 /* pgo_loss_type */
+  double loss_a;
+  int linear_solver_type;        /* pgo_linear_solver_type */
+  int pcg_max_iterations;        /* per LM step */
+  double pcg_tolerance;          /* stop when sqrt(r^T M^-1 r) <= tol * sqrt(b^T M^-1 b) */
+  int pcg_num_ctas;              /* 0 = auto (persistent grid size of the PCG kernel) */
+  int verbose;
+} pgo_solver_options;
+
+/* One row per minimizer iteration (ceres::IterationSummary). */
+typedef struct {
+  int iteration;
+  int step_is_valid;
+  int step_is_successful;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  int linear_solver_iterations;
+  double pcg_relative_residual;
+} pgo_iteration_summary;
+
+/* ceres::Solver::Summary subset + device timings. */
+typedef struct {
+  double initial_cost;
+  double final_cost;
+  int num_successful_steps;
+  int num_unsuccessful_steps;
+  int num_iterations;            /* rows produced for the iteration log (incl. iteration 0) */
+  int termination_type;          /* pgo_termination_type */
+  char message[160];
+  int num_linearizations;        /* residual + Jacobian + Hessian kernel launches */
+  int num_cost_evaluations;      /* residual-only kernel launches */
+  long long total_pcg_iterations;
+  long long kernel_launches;     /* kernels of this library launched by the call */
+  double time_total_s;           /* host wall clock of the call */
+  double time_setup_s;           /* structure analysis + uploads */
+  double time_linearize_ms;      /* CUDA-event time in the linearize kernel(s) */
+  double time_linear_solver_ms;  /* CUDA-event time in the linear solver */
+  int linear_solver_used;        /* pgo_linear_solver_type actually used */
+  long long hessian_blocks;      /* 6x6 blocks in the block-CSR Hessian (diag + off-diag) */
+  long long factor_blocks;       /* 6x6 blocks in the level-Cholesky factor (0 if unused) */
+  int factor_levels;
+} pgo_solver_summary;
+
+typedef struct pgo_graph pgo_graph;   /* opaque: a pose graph resident in HBM */
+
+const char* pgo_last_error(void);
+int pgo_abi_version(void);
+int pgo_device_count(void);
+void pgo_default_options(pgo_solver_options* options);
+
+/* Upload a pose graph (the content of ceres::Problem after BuildOptimizationProblem) to
+ * device `device` and analyse its block structure (block-CSR Hessian pattern, edge->block map). */
+int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
+                     const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
+                     const unsigned char* pose_const);
+void pgo_graph_destroy(pgo_graph* g);
+
+int pgo_graph_num_poses(const pgo_graph* g);
+int pgo_graph_num_edges(const pgo_graph* g);
+int pgo_graph_set_poses(pgo_graph* g, const double* poses);   /* host -> device */
+int pgo_graph_get_poses(pgo_graph* g, double* poses);         /* device -> host */
+/* keep / restore a device-side copy of the initial poses (bench: inputs already in HBM) */
+int pgo_graph_snapshot_poses(pgo_graph* g);
+int pgo_graph_restore_poses(pgo_graph* g);
+
+/* Multi-GPU: this rank holds an edge shard and a replica of all poses; J^T r, the Hessian
+ * diagonal and every PCG SpMV product are all-reduced over NCCL.  unique_id is the 128-byte
+ * ncclUniqueId produced by rank 0 (pgo_nccl_unique_id) and distributed by the caller. */
+int pgo_nccl_unique_id(unsigned char unique_id[128]);
+int pgo_graph_init_comm(pgo_graph* g, const unsigned char unique_id[128], int rank, int world_size);
+
+/* ceres::Problem::Evaluate on the device: cost, robustified residuals [n_edges][6], gradient
+ * [n_poses][6] (unscaled, zero for constant poses), per-edge local Jacobians [n_edges][2][36]
+ * (row-major 6x6; block 0 = d r / d pose_begin, block 1 = d r / d pose_end). Outputs may be NULL. */
+int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, double* cost, double* residuals,
+                       double* gradient, double* jacobians);
+
+/* One launch of the fused residual + Jacobian + J^T J / J^T r kernel at the current poses with
+ * column scaling `scale` ([n_poses][6], NULL = ones). Leaves H and g in device memory.
+ * Returns the cost; elapsed_ms (may be NULL) is the CUDA-event time of the kernel alone. */
+int pgo_graph_linearize(pgo_graph* g, int loss_type, double loss_a, const double* scale,
+                        double* cost, float* elapsed_ms);
+
+/* Copy the assembled block-CSR Hessian to the host (tests): row_ptr [n_poses+1], col_idx [nnzb],
+ * values [nnzb][36] ROW-major 6x6, diagonal block included (first in each row). Pass NULLs to
+ * query nnzb. gradient [n_poses][6] = J^T r (scaled as H). */
+int pgo_graph_get_hessian(pgo_graph* g, long long* nnzb, int* row_ptr, int* col_idx, double* values,
+                          double* gradient);
+
+/* y = (H + diag(d)) x with the block-SpMV kernel (tests / bench). x, y, d: [n_poses][6]; d may be NULL. */
+int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, double* y, int repeats,
+                   float* elapsed_ms);
+
+/* Solve (H + diag(d)) y = b for the currently assembled H with the selected linear solver. */
+int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* options, const double* d,
+                           const double* b, double* y, int* iterations, double* relative_residual,
+                           float* elapsed_ms);
+
+/* ceres::Solve: Levenberg-Marquardt on the device-resident graph; poses are updated in HBM
+ * (read them back with pgo_graph_get_poses). iteration_log may be NULL. */
+int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* options, pgo_solver_summary* summary,
+                    pgo_iteration_summary* iteration_log, int iteration_log_capacity);
+
+/* Convenience = what ceres::Solve(options, &problem, &summary) does for the reference: upload,
+ * solve, write the optimised poses back into `poses` (in/out, host). */
+int pgo_solve_pose_graph(int device, int n_poses, double* poses, int n_edges, const int* edge_ids,
+                         const double* edge_meas, const double* edge_sqrt_info,
+                         const unsigned char* pose_const, const pgo_solver_options* options,
+                         pgo_solver_summary* summary, pgo_iteration_summary* iteration_log,
+                         int iteration_log_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGO_B200_H_ */

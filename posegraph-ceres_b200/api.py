@@ -1,0 +1,241 @@
+"""ctypes binding of libpgo_b200.so (include/pgo_b200.h) -- the C-ABI drop-in for the reference's
+ceres::Problem / ceres::Solve pose-graph path.  Used by tests/ and bench.py; the C++ host-side
+mirror of the Ceres surface is include/ceres_b200/ceres.h.
+
+There is no CPU fallback: loading fails loudly when the CUDA library has not been built, and every
+compute entry point returns PGO_ERR_NO_DEVICE without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(_CSRC, "libpgo_b200.so")
+
+LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
+LINEAR_PCG_BLOCK_JACOBI, LINEAR_PCG_LEVEL_CHOLESKY, LINEAR_AUTO = 0, 1, 2
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+
+EXPORTED_SYMBOLS = [
+    "pgo_last_error", "pgo_abi_version", "pgo_device_count", "pgo_default_options", "pgo_graph_create",
+    "pgo_graph_destroy", "pgo_graph_num_poses", "pgo_graph_num_edges", "pgo_graph_set_poses",
+    "pgo_graph_get_poses", "pgo_graph_snapshot_poses", "pgo_graph_restore_poses", "pgo_nccl_unique_id",
+    "pgo_graph_init_comm", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
+    "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
+]
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int), ("jacobi_scaling", C.c_int),
+                ("loss_type", C.c_int), ("loss_a", C.c_double), ("linear_solver_type", C.c_int),
+                ("pcg_max_iterations", C.c_int), ("pcg_tolerance", C.c_double), ("pcg_num_ctas", C.c_int),
+                ("verbose", C.c_int)]
+
+
+class IterationSummary(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("step_is_valid", C.c_int), ("step_is_successful", C.c_int),
+                ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double),
+                ("gradient_norm", C.c_double), ("step_norm", C.c_double), ("relative_decrease", C.c_double),
+                ("trust_region_radius", C.c_double), ("linear_solver_iterations", C.c_int),
+                ("pcg_relative_residual", C.c_double)]
+
+
+class SolverSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("num_successful_steps", C.c_int),
+                ("num_unsuccessful_steps", C.c_int), ("num_iterations", C.c_int), ("termination_type", C.c_int),
+                ("message", C.c_char * 160), ("num_linearizations", C.c_int), ("num_cost_evaluations", C.c_int),
+                ("total_pcg_iterations", C.c_longlong), ("kernel_launches", C.c_longlong),
+                ("time_total_s", C.c_double), ("time_setup_s", C.c_double), ("time_linearize_ms", C.c_double),
+                ("time_linear_solver_ms", C.c_double), ("linear_solver_used", C.c_int),
+                ("hessian_blocks", C.c_longlong), ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int)]
+
+
+class PgoError(RuntimeError):
+    pass
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (csrc/build.sh); cross-compiles without a GPU."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_CSRC), "..", "include", "pgo_b200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["bash", os.path.join(_CSRC, "build.sh")])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgoError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                           "(posegraph-ceres_b200/csrc/build.sh). There is no CPU fallback.")
+        try:                      # torch ships the libnccl.so.2 this library is linked against
+            import torch  # noqa: F401
+        except Exception:
+            pass
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib.pgo_last_error.restype = C.c_char_p
+        _lib.pgo_graph_destroy.restype = None
+        _lib.pgo_default_options.restype = None
+        for name in EXPORTED_SYMBOLS:
+            getattr(_lib, name)
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PgoError(f"pgo_b200 error {rc}: {lib().pgo_last_error().decode()}")
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def default_options() -> SolverOptions:
+    o = SolverOptions()
+    lib().pgo_default_options(C.byref(o))
+    return o
+
+
+def device_count() -> int:
+    return int(lib().pgo_device_count())
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    _check(lib().pgo_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class Graph:
+    """A pose graph resident in HBM (pgo_graph)."""
+
+    def __init__(self, poses, edge_ids, edge_meas, edge_sqrt_info=None, pose_const=None, device: int = 0):
+        self._h = C.c_void_p()
+        poses = np.ascontiguousarray(poses, np.float64)
+        edge_ids = np.ascontiguousarray(edge_ids, np.int32)
+        edge_meas = np.ascontiguousarray(edge_meas, np.float64)
+        self.n_poses, self.n_edges = int(poses.shape[0]), int(edge_ids.shape[0])
+        si = None if edge_sqrt_info is None else np.ascontiguousarray(edge_sqrt_info, np.float64)
+        pc = None if pose_const is None else np.ascontiguousarray(pose_const, np.uint8)
+        _check(lib().pgo_graph_create(C.byref(self._h), C.c_int(device), C.c_int(self.n_poses), C.c_int(self.n_edges),
+                                      _dp(poses), edge_ids.ctypes.data_as(C.POINTER(C.c_int)), _dp(edge_meas), _dp(si),
+                                      pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None))
+
+    @classmethod
+    def from_dataset(cls, g, device: int = 0):
+        return cls(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, device)
+
+    def close(self):
+        if self._h:
+            lib().pgo_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_poses(self, poses):
+        _check(lib().pgo_graph_set_poses(self._h, _dp(np.ascontiguousarray(poses, np.float64))))
+
+    def get_poses(self):
+        out = np.empty((self.n_poses, 7))
+        _check(lib().pgo_graph_get_poses(self._h, _dp(out)))
+        return out
+
+    def snapshot_poses(self):
+        _check(lib().pgo_graph_snapshot_poses(self._h))
+
+    def restore_poses(self):
+        _check(lib().pgo_graph_restore_poses(self._h))
+
+    def init_comm(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _check(lib().pgo_graph_init_comm(self._h, buf, C.c_int(rank), C.c_int(world)))
+
+    def evaluate(self, loss_type=LOSS_HUBER, loss_a=1.0, want_jacobians=True):
+        cost = C.c_double()
+        res = np.zeros((self.n_edges, 6))
+        grad = np.zeros((self.n_poses, 6))
+        jac = np.zeros((self.n_edges, 2, 36)) if want_jacobians else None
+        _check(lib().pgo_graph_evaluate(self._h, C.c_int(loss_type), C.c_double(loss_a), C.byref(cost), _dp(res),
+                                        _dp(grad), _dp(jac)))
+        return cost.value, res, grad, jac
+
+    def linearize(self, loss_type=LOSS_HUBER, loss_a=1.0, scale=None):
+        cost = C.c_double()
+        ms = C.c_float()
+        sc = None if scale is None else np.ascontiguousarray(scale, np.float64)
+        _check(lib().pgo_graph_linearize(self._h, C.c_int(loss_type), C.c_double(loss_a), _dp(sc), C.byref(cost), C.byref(ms)))
+        return cost.value, ms.value
+
+    def hessian(self):
+        """(row_ptr, col_idx, values[nnzb,6,6], gradient[N,6]) of the last linearisation."""
+        nnzb = C.c_longlong()
+        _check(lib().pgo_graph_get_hessian(self._h, C.byref(nnzb), None, None, None, None))
+        rp = np.zeros(self.n_poses + 1, np.int32)
+        ci = np.zeros(nnzb.value, np.int32)
+        vals = np.zeros((nnzb.value, 36))
+        grad = np.zeros((self.n_poses, 6))
+        _check(lib().pgo_graph_get_hessian(self._h, C.byref(nnzb), rp.ctypes.data_as(C.POINTER(C.c_int)),
+                                           ci.ctypes.data_as(C.POINTER(C.c_int)), _dp(vals), _dp(grad)))
+        return rp, ci, vals.reshape(-1, 6, 6), grad
+
+    def spmv(self, x, d=None, repeats: int = 1):
+        x = np.ascontiguousarray(x, np.float64)
+        dd = None if d is None else np.ascontiguousarray(d, np.float64)
+        y = np.zeros((self.n_poses, 6))
+        ms = C.c_float()
+        _check(lib().pgo_graph_spmv(self._h, _dp(x), _dp(dd), _dp(y), C.c_int(repeats), C.byref(ms)))
+        return y, ms.value
+
+    def linear_solve(self, d, b, options: SolverOptions | None = None):
+        o = options or default_options()
+        y = np.zeros((self.n_poses, 6))
+        it = C.c_int()
+        rel = C.c_double()
+        ms = C.c_float()
+        _check(lib().pgo_graph_linear_solve(self._h, C.byref(o), _dp(np.ascontiguousarray(d, np.float64)),
+                                            _dp(np.ascontiguousarray(b, np.float64)), _dp(y), C.byref(it), C.byref(rel),
+                                            C.byref(ms)))
+        return y, it.value, rel.value, ms.value
+
+    def solve(self, options: SolverOptions | None = None, max_log: int = 2048):
+        o = options or default_options()
+        s = SolverSummary()
+        log = (IterationSummary * max_log)()
+        _check(lib().pgo_graph_solve(self._h, C.byref(o), C.byref(s), log, C.c_int(max_log)))
+        return s, [log[i] for i in range(min(s.num_iterations, max_log))]
+
+
+def solve_pose_graph(poses, edge_ids, edge_meas, edge_sqrt_info=None, pose_const=None,
+                     options: SolverOptions | None = None, device: int = 0, max_log: int = 2048):
+    """ceres::Solve for the reference's pose graph, host buffers in and out (pgo_solve_pose_graph)."""
+    o = options or default_options()
+    poses = np.ascontiguousarray(poses, np.float64).copy()
+    edge_ids = np.ascontiguousarray(edge_ids, np.int32)
+    edge_meas = np.ascontiguousarray(edge_meas, np.float64)
+    si = None if edge_sqrt_info is None else np.ascontiguousarray(edge_sqrt_info, np.float64)
+    pc = None if pose_const is None else np.ascontiguousarray(pose_const, np.uint8)
+    s = SolverSummary()
+    log = (IterationSummary * max_log)()
+    _check(lib().pgo_solve_pose_graph(C.c_int(device), C.c_int(poses.shape[0]), _dp(poses), C.c_int(edge_ids.shape[0]),
+                                      edge_ids.ctypes.data_as(C.POINTER(C.c_int)), _dp(edge_meas), _dp(si),
+                                      pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None,
+                                      C.byref(o), C.byref(s), log, C.c_int(max_log)))
+    return poses, s, [log[i] for i in range(min(s.num_iterations, max_log))]

@@ -1,0 +1,811 @@
+// pgo_b200.cu -- host side of libpgo_b200.so: graph upload + block structure analysis, the
+// Levenberg-Marquardt driver (a restatement of ceres::internal::TrustRegionMinimizer +
+// LevenbergMarquardtStrategy as the reference configures them,
+// REF/test/pose_graph_ceres_plus_finial.cpp:500-514) and the C-ABI of include/pgo_b200.h.
+// All numerical work happens in the kernels of pgo_kernels.cuh; there is no CPU fallback.
+#include "../../include/pgo_b200.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pgo_kernels.cuh"
+
+using namespace pgo;
+
+static thread_local std::string g_last_error;
+static int set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return set_error(PGO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                                            cudaGetErrorString(_e), __FILE__, __LINE__);         \
+  } while (0)
+#define NCCL_TRY(expr)                                                                           \
+  do {                                                                                           \
+    ncclResult_t _e = (expr);                                                                    \
+    if (_e != ncclSuccess) return set_error(PGO_ERR_NCCL, "%s failed: %s (%s:%d)", #expr,        \
+                                            ncclGetErrorString(_e), __FILE__, __LINE__);         \
+  } while (0)
+#define PGO_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != PGO_OK) return _rc; \
+  } while (0)
+
+#include "pgo_level_chol.cuh"
+
+static double wall_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct pgo_graph {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int N = 0, E = 0, T = 0;
+  bool identity_info = true;
+  bool has_dup_blocks = false;
+  long long nnz_off = 0;
+  int num_sms = 0;
+  int pcg_max_ctas = 0;
+  std::vector<unsigned char> active_h;
+  std::vector<int> row_ptr_h, col_idx_h;
+  // device
+  double *poses = nullptr, *poses_cand = nullptr, *poses_snap = nullptr;
+  double *scale = nullptr, *scale_eval = nullptr;
+  EdgeCoreTile* core = nullptr;
+  EdgeInfoTile* info = nullptr;
+  double *Hdiag = nullptr, *Hoff = nullptr;
+  int *row_ptr = nullptr, *col_idx = nullptr;
+  double *grad = nullptr, *grad_unscaled = nullptr;
+  double *diagonal = nullptr, *dlm = nullptr, *Minv = nullptr;
+  double *vx = nullptr, *vr = nullptr, *vu = nullptr, *vw = nullptr, *vp = nullptr, *vs = nullptr, *vb = nullptr;
+  unsigned char* active = nullptr;
+  DeviceScalars* scalars = nullptr;
+  DeviceScalars* scalars_h = nullptr;  // pinned
+  double* partials = nullptr;
+  unsigned int* barrier = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // level-scheduled Cholesky preconditioner (optional)
+  LevelChol* chol = nullptr;
+  long long launches = 0;
+  double setup_s = 0.0;
+};
+
+extern "C" const char* pgo_last_error(void) { return g_last_error.c_str(); }
+extern "C" int pgo_abi_version(void) { return PGO_B200_ABI_VERSION; }
+extern "C" int pgo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" void pgo_default_options(pgo_solver_options* o) {
+  o->max_num_iterations = 1000;  // REF/test/pose_graph_ceres_plus_finial.cpp:504
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->loss_type = PGO_LOSS_HUBER;  // :463
+  o->loss_a = 1.0;
+  o->linear_solver_type = PGO_LINEAR_AUTO;
+  o->pcg_max_iterations = 20000;
+  o->pcg_tolerance = 1e-10;
+  o->pcg_num_ctas = 0;
+  o->verbose = 0;
+}
+
+template <typename Tp>
+static int dev_alloc(Tp** p, size_t count) {
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(Tp)));
+  return PGO_OK;
+}
+
+extern "C" void pgo_graph_destroy(pgo_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->comm) ncclCommDestroy(g->comm);
+  if (g->chol) level_chol_destroy(g->chol);
+  void* ptrs[] = {g->poses, g->poses_cand, g->poses_snap, g->scale, g->scale_eval, g->core, g->info, g->Hdiag,
+                  g->Hoff, g->row_ptr, g->col_idx, g->grad, g->grad_unscaled, g->diagonal, g->dlm, g->Minv,
+                  g->vx, g->vr, g->vu, g->vw, g->vp, g->vs, g->vb, g->active, g->scalars, g->partials, g->barrier};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (g->scalars_h) cudaFreeHost(g->scalars_h);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
+                                const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
+                                const unsigned char* pose_const) {
+  if (!out || n_poses <= 0 || n_edges < 0 || !poses || (n_edges > 0 && (!edge_ids || !edge_meas)))
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_create: null or empty input");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(PGO_ERR_NO_DEVICE, "pgo_graph_create: no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  for (int e = 0; e < n_edges; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    if (a < 0 || a >= n_poses || b < 0 || b >= n_poses || a == b)
+      return set_error(PGO_ERR_INVALID_ARGUMENT, "edge %d has invalid endpoints (%d, %d)", e, a, b);
+  }
+  const double t0 = wall_s();
+  CUDA_TRY(cudaSetDevice(device));
+  pgo_graph* g = new pgo_graph();
+  g->device = device;
+  g->N = n_poses; g->E = n_edges; g->T = (n_edges + kTile - 1) / kTile;
+  const int N = g->N, E = g->E, T = g->T;
+  auto fail = [&](int rc) { pgo_graph_destroy(g); return rc; };
+#define G_TRY(expr) do { int _rc = (expr); if (_rc != PGO_OK) return fail(_rc); } while (0)
+#define GC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(set_error(PGO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); } while (0)
+  GC_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  GC_TRY(cudaEventCreate(&g->ev0));
+  GC_TRY(cudaEventCreate(&g->ev1));
+  cudaDeviceProp prop;
+  GC_TRY(cudaGetDeviceProperties(&prop, device));
+  g->num_sms = prop.multiProcessorCount;
+
+  // ---- which poses are variables: used by an edge and not constant ----
+  g->active_h.assign(N, 0);
+  for (int e = 0; e < E; ++e) { g->active_h[edge_ids[2 * e]] = 1; g->active_h[edge_ids[2 * e + 1]] = 1; }
+  if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) g->active_h[i] = 0;
+
+  // ---- identity information? ----
+  g->identity_info = true;
+  if (edge_sqrt_info) {
+    for (size_t k = 0; k < (size_t)E * 36 && g->identity_info; ++k) {
+      const int rc = (int)(k % 36);
+      if (edge_sqrt_info[k] != ((rc / 6 == rc % 6) ? 1.0 : 0.0)) g->identity_info = false;
+    }
+  }
+
+  // ---- block-CSR pattern of the off-diagonal part ----
+  std::vector<unsigned long long> keys;
+  keys.reserve(2 * (size_t)E);
+  for (int e = 0; e < E; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    if (g->active_h[a] && g->active_h[b]) {
+      keys.push_back(((unsigned long long)a << 32) | (unsigned)b);
+      keys.push_back(((unsigned long long)b << 32) | (unsigned)a);
+    }
+  }
+  std::vector<unsigned long long> sorted = keys;
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<unsigned long long> uniq;
+  std::vector<int> mult;
+  uniq.reserve(sorted.size());
+  for (size_t k = 0; k < sorted.size(); ++k) {
+    if (k == 0 || sorted[k] != sorted[k - 1]) { uniq.push_back(sorted[k]); mult.push_back(1); }
+    else mult.back()++;
+  }
+  g->nnz_off = (long long)uniq.size();
+  g->row_ptr_h.assign(N + 1, 0);
+  g->col_idx_h.resize(uniq.size());
+  for (size_t k = 0; k < uniq.size(); ++k) {
+    g->row_ptr_h[(int)(uniq[k] >> 32) + 1]++;
+    g->col_idx_h[k] = (int)(uniq[k] & 0xffffffffu);
+    if (mult[k] > 1) g->has_dup_blocks = true;
+  }
+  for (int i = 0; i < N; ++i) g->row_ptr_h[i + 1] += g->row_ptr_h[i];
+  auto slot_of = [&](int r, int c) -> int {
+    const unsigned long long key = ((unsigned long long)r << 32) | (unsigned)c;
+    const size_t pos = std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin();
+    return mult[pos] > 1 ? -(int)pos - 2 : (int)pos;
+  };
+
+  // ---- edge tiles (field-major, one warp per tile) ----
+  std::vector<EdgeCoreTile> core_h(std::max(T, 1));
+  std::memset(core_h.data(), 0, core_h.size() * sizeof(EdgeCoreTile));
+  std::vector<EdgeInfoTile> info_h;
+  if (!g->identity_info) { info_h.resize(std::max(T, 1)); std::memset(info_h.data(), 0, info_h.size() * sizeof(EdgeInfoTile)); }
+  for (int e = 0; e < E; ++e) {
+    EdgeCoreTile& t = core_h[e / kTile];
+    const int l = e % kTile;
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    t.a[l] = a; t.b[l] = b;
+    if (g->active_h[a] && g->active_h[b]) { t.slot_ab[l] = slot_of(a, b); t.slot_ba[l] = slot_of(b, a); }
+    else { t.slot_ab[l] = -1; t.slot_ba[l] = -1; }
+    for (int k = 0; k < 7; ++k) t.meas[k][l] = edge_meas[7 * (size_t)e + k];
+    if (!g->identity_info) for (int k = 0; k < 36; ++k) info_h[e / kTile].S[k][l] = edge_sqrt_info[36 * (size_t)e + k];
+  }
+  for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
+
+  // ---- device allocations + uploads ----
+  G_TRY(dev_alloc(&g->poses, (size_t)N * 8));
+  G_TRY(dev_alloc(&g->poses_cand, (size_t)N * 8));
+  G_TRY(dev_alloc(&g->poses_snap, (size_t)N * 8));
+  G_TRY(dev_alloc(&g->scale, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->scale_eval, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->core, (size_t)std::max(T, 1)));
+  if (!g->identity_info) G_TRY(dev_alloc(&g->info, (size_t)std::max(T, 1)));
+  G_TRY(dev_alloc(&g->Hdiag, (size_t)N * 36));
+  G_TRY(dev_alloc(&g->Hoff, (size_t)g->nnz_off * 36));
+  G_TRY(dev_alloc(&g->row_ptr, (size_t)N + 1));
+  G_TRY(dev_alloc(&g->col_idx, (size_t)g->nnz_off));
+  G_TRY(dev_alloc(&g->grad, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->grad_unscaled, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->diagonal, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->dlm, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->Minv, (size_t)N * 36));
+  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb}) G_TRY(dev_alloc(v, (size_t)N * 6));
+  G_TRY(dev_alloc(&g->active, (size_t)N));
+  G_TRY(dev_alloc(&g->scalars, 1));
+  GC_TRY(cudaMallocHost(reinterpret_cast<void**>(&g->scalars_h), sizeof(DeviceScalars)));
+  G_TRY(dev_alloc(&g->barrier, 4));
+
+  GC_TRY(cudaMemcpyAsync(g->core, core_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
+  if (!g->identity_info) GC_TRY(cudaMemcpyAsync(g->info, info_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
+  GC_TRY(cudaMemcpyAsync(g->row_ptr, g->row_ptr_h.data(), ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+  if (g->nnz_off) GC_TRY(cudaMemcpyAsync(g->col_idx, g->col_idx_h.data(), (size_t)g->nnz_off * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+  GC_TRY(cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)N, cudaMemcpyHostToDevice, g->stream));
+  {
+    std::vector<double> se((size_t)N * 6);
+    for (int i = 0; i < N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
+    GC_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    GC_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    GC_TRY(cudaStreamSynchronize(g->stream));
+  }
+  GC_TRY(cudaMemsetAsync(g->Hoff, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
+  GC_TRY(cudaStreamSynchronize(g->stream));
+
+  // persistent PCG grid: all CTAs must be co-resident (cooperative launch)
+  int per_sm = 0;
+  GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kPcgThreads, 0));
+  g->pcg_max_ctas = std::max(1, std::min(per_sm, 4) * g->num_sms);
+  G_TRY(dev_alloc(&g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
+
+  *out = g;
+  int rc = pgo_graph_set_poses(g, poses);
+  if (rc != PGO_OK) { *out = nullptr; return fail(rc); }
+  g->setup_s = wall_s() - t0;
+  return PGO_OK;
+#undef G_TRY
+#undef GC_TRY
+}
+
+extern "C" int pgo_graph_num_poses(const pgo_graph* g) { return g ? g->N : 0; }
+extern "C" int pgo_graph_num_edges(const pgo_graph* g) { return g ? g->E : 0; }
+
+extern "C" int pgo_graph_set_poses(pgo_graph* g, const double* poses) {
+  if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_set_poses: null argument");
+  CUDA_TRY(cudaSetDevice(g->device));
+  // [N][7] host -> [N][8] device (pitched copy), pad column zeroed once
+  CUDA_TRY(cudaMemsetAsync(g->poses, 0, (size_t)g->N * 8 * sizeof(double), g->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(g->poses, 8 * sizeof(double), poses, 7 * sizeof(double), 7 * sizeof(double), g->N,
+                             cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_get_poses(pgo_graph* g, double* poses) {
+  if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_get_poses: null argument");
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaMemcpy2DAsync(poses, 7 * sizeof(double), g->poses, 8 * sizeof(double), 7 * sizeof(double), g->N,
+                             cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_snapshot_poses(pgo_graph* g) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaMemcpyAsync(g->poses_snap, g->poses, (size_t)g->N * 8 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PGO_OK;
+}
+extern "C" int pgo_graph_restore_poses(pgo_graph* g) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaMemcpyAsync(g->poses, g->poses_snap, (size_t)g->N * 8 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PGO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL plumbing: edges sharded across ranks, poses replicated.
+// ------------------------------------------------------------------------------------------------
+extern "C" int pgo_nccl_unique_id(unsigned char unique_id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  std::memcpy(unique_id, &id, 128);
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_init_comm(pgo_graph* g, const unsigned char unique_id[128], int rank, int world_size) {
+  if (!g || !unique_id || world_size < 1 || rank < 0 || rank >= world_size)
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_init_comm: bad arguments");
+  CUDA_TRY(cudaSetDevice(g->device));
+  if (world_size == 1) { g->rank = 0; g->world = 1; return PGO_OK; }
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, 128);
+  NCCL_TRY(ncclCommInitRank(&g->comm, world_size, id, rank));
+  g->rank = rank; g->world = world_size;
+  return PGO_OK;
+}
+
+static int allreduce_sum(pgo_graph* g, double* buf, size_t count) {
+  if (g->world <= 1) return PGO_OK;
+  NCCL_TRY(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, g->comm, g->stream));
+  return PGO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch helpers
+// ------------------------------------------------------------------------------------------------
+template <bool kIdent, int kMode>
+static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
+  constexpr int stage = kCoreTileBytes + (kIdent ? 0 : kInfoTileBytes);
+  constexpr int smem = kLinWarps * 2 * stage + kLinWarps * 2 * 8;
+  auto kern = linearize_kernel<kIdent, kMode, true>;
+  static bool attr_set = false;
+  if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+  const int ctas = std::max(1, std::min((g->T + kLinWarps - 1) / kLinWarps, 2 * g->num_sms));
+  kern<<<ctas, kLinWarps * 32, smem, g->stream>>>(p);
+  g->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return PGO_OK;
+}
+
+static int launch_linearize(pgo_graph* g, int mode, const double* poses, const double* scale, int loss_type,
+                            double loss_a, double* res_out = nullptr, double* jac_out = nullptr) {
+  LinParams p;
+  p.n_edges = g->E; p.n_tiles = g->T; p.core = g->core; p.info = g->info; p.poses = poses; p.scale = scale;
+  p.Hdiag = g->Hdiag; p.Hoff = g->Hoff; p.grad = g->grad; p.scalars = g->scalars;
+  p.loss_type = loss_type; p.loss_a = loss_a; p.res_out = res_out; p.jac_out = jac_out;
+  if (g->E == 0) return PGO_OK;
+  if (g->identity_info) {
+    if (mode == kLinFull) return launch_linearize_t<true, kLinFull>(g, p);
+    if (mode == kLinCost) return launch_linearize_t<true, kLinCost>(g, p);
+    return launch_linearize_t<true, kLinEval>(g, p);
+  }
+  if (mode == kLinFull) return launch_linearize_t<false, kLinFull>(g, p);
+  if (mode == kLinCost) return launch_linearize_t<false, kLinCost>(g, p);
+  return launch_linearize_t<false, kLinEval>(g, p);
+}
+
+static int zero_system(pgo_graph* g, bool hessian) {
+  if (hessian) {
+    CUDA_TRY(cudaMemsetAsync(g->Hdiag, 0, (size_t)g->N * 36 * sizeof(double), g->stream));
+    if (g->has_dup_blocks && g->nnz_off) CUDA_TRY(cudaMemsetAsync(g->Hoff, 0, (size_t)g->nnz_off * 36 * sizeof(double), g->stream));
+  }
+  CUDA_TRY(cudaMemsetAsync(g->grad, 0, (size_t)g->N * 6 * sizeof(double), g->stream));
+  return PGO_OK;
+}
+
+static int zero_scalars(pgo_graph* g) {
+  CUDA_TRY(cudaMemsetAsync(g->scalars, 0, sizeof(DeviceScalars), g->stream));
+  return PGO_OK;
+}
+static int fetch_scalars(pgo_graph* g) {
+  CUDA_TRY(cudaMemcpyAsync(g->scalars_h, g->scalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PGO_OK;
+}
+
+// full linearization at `poses` with column scaling `scale`: H, g (all-reduced across ranks)
+static int linearize_full(pgo_graph* g, const double* poses, const double* scale, int loss_type, double loss_a) {
+  PGO_TRY(zero_system(g, true));
+  PGO_TRY(launch_linearize(g, kLinFull, poses, scale, loss_type, loss_a));
+  if (g->world > 1) {
+    PGO_TRY(allreduce_sum(g, g->Hdiag, (size_t)g->N * 36));
+    PGO_TRY(allreduce_sum(g, g->grad, (size_t)g->N * 6));
+    PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
+  }
+  return PGO_OK;
+}
+
+static int cost_only(pgo_graph* g, const double* poses, int loss_type, double loss_a) {
+  PGO_TRY(launch_linearize(g, kLinCost, poses, g->scale, loss_type, loss_a));
+  if (g->world > 1) PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
+  return PGO_OK;
+}
+
+static BsrView bsr_view(const pgo_graph* g) {
+  BsrView A;
+  A.n = g->N; A.Hdiag = g->Hdiag; A.Hoff = g->Hoff; A.row_ptr = g->row_ptr; A.col_idx = g->col_idx;
+  return A;
+}
+
+static int pcg_grid(const pgo_graph* g, const pgo_solver_options* o) {
+  int want = (g->N + (kPcgThreads / 32) * kRowsPerWarp - 1) / ((kPcgThreads / 32) * kRowsPerWarp);
+  if (o && o->pcg_num_ctas > 0) want = o->pcg_num_ctas;
+  return std::max(1, std::min(want, g->pcg_max_ctas));
+}
+
+// Single-GPU persistent PCG: (H + diag(dlm)) x = b, x in g->vx. Results land in g->scalars.
+static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b) {
+  PcgParams P;
+  P.A = bsr_view(g);
+  P.d = g->dlm; P.Minv = g->Minv; P.b = b;
+  P.x = g->vx; P.r = g->vr; P.u = g->vu; P.w = g->vw; P.p = g->vp; P.s = g->vs;
+  P.partials = g->partials; P.barrier = g->barrier; P.scalars = g->scalars;
+  P.max_iterations = o->pcg_max_iterations; P.tolerance = o->pcg_tolerance;
+  CUDA_TRY(cudaMemsetAsync(g->barrier, 0, 4 * sizeof(unsigned int), g->stream));
+  void* args[] = {&P};
+  const int grid = pcg_grid(g, o);
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(kPcgThreads), args, 0, g->stream));
+  g->launches++;
+  return PGO_OK;
+}
+
+#include "pgo_pcg_multi.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: evaluate / linearize / hessian / spmv / linear solve
+// ------------------------------------------------------------------------------------------------
+extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, double* cost, double* residuals,
+                                  double* gradient, double* jacobians) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  double *res_d = nullptr, *jac_d = nullptr;
+  PGO_TRY(dev_alloc(&res_d, (size_t)g->E * 6));
+  PGO_TRY(dev_alloc(&jac_d, (size_t)g->E * 72));
+  int rc = PGO_OK;
+  do {
+    if ((rc = zero_system(g, false)) != PGO_OK) break;
+    if ((rc = zero_scalars(g)) != PGO_OK) break;
+    if ((rc = launch_linearize(g, kLinEval, g->poses, g->scale_eval, loss_type, loss_a, res_d, jac_d)) != PGO_OK) break;
+    if (g->world > 1) {
+      if ((rc = allreduce_sum(g, g->grad, (size_t)g->N * 6)) != PGO_OK) break;
+      if ((rc = allreduce_sum(g, &g->scalars->cost, 1)) != PGO_OK) break;
+    }
+    if ((rc = fetch_scalars(g)) != PGO_OK) break;
+    if (cost) *cost = g->scalars_h->cost;
+    cudaError_t ce = cudaSuccess;
+    if (residuals && g->E) ce = cudaMemcpy(residuals, res_d, (size_t)g->E * 6 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && jacobians && g->E) ce = cudaMemcpy(jacobians, jac_d, (size_t)g->E * 72 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess && gradient) ce = cudaMemcpy(gradient, g->grad, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) rc = set_error(PGO_ERR_CUDA, "evaluate copy-back failed: %s", cudaGetErrorString(ce));
+  } while (0);
+  cudaFree(res_d); cudaFree(jac_d);
+  return rc;
+}
+
+extern "C" int pgo_graph_linearize(pgo_graph* g, int loss_type, double loss_a, const double* scale, double* cost,
+                                   float* elapsed_ms) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  if (scale) CUDA_TRY(cudaMemcpyAsync(g->scale, scale, (size_t)g->N * 6 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  else CUDA_TRY(cudaMemcpyAsync(g->scale, g->scale_eval, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+  PGO_TRY(zero_system(g, true));
+  PGO_TRY(zero_scalars(g));
+  CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+  PGO_TRY(launch_linearize(g, kLinFull, g->poses, g->scale, loss_type, loss_a));
+  CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+  if (g->world > 1) {
+    PGO_TRY(allreduce_sum(g, g->Hdiag, (size_t)g->N * 36));
+    PGO_TRY(allreduce_sum(g, g->grad, (size_t)g->N * 6));
+    PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
+  }
+  PGO_TRY(fetch_scalars(g));
+  if (cost) *cost = g->scalars_h->cost;
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_get_hessian(pgo_graph* g, long long* nnzb, int* row_ptr, int* col_idx, double* values,
+                                     double* gradient) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  const long long total = g->nnz_off + g->N;
+  if (nnzb) *nnzb = total;
+  if (gradient) CUDA_TRY(cudaMemcpy(gradient, g->grad, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!row_ptr || !col_idx || !values) return PGO_OK;
+  std::vector<double> hd((size_t)g->N * 36), ho((size_t)std::max<long long>(g->nnz_off, 1) * 36);
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpy(hd.data(), g->Hdiag, hd.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (g->nnz_off) CUDA_TRY(cudaMemcpy(ho.data(), g->Hoff, (size_t)g->nnz_off * 36 * sizeof(double), cudaMemcpyDeviceToHost));
+  long long k = 0;
+  for (int i = 0; i < g->N; ++i) {
+    row_ptr[i] = (int)k;
+    col_idx[k] = i;
+    for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) values[36 * k + r * 6 + c] = hd[36 * (size_t)i + pidx(r, c)];
+    ++k;
+    for (int p = g->row_ptr_h[i]; p < g->row_ptr_h[i + 1]; ++p) {
+      col_idx[k] = g->col_idx_h[p];
+      for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) values[36 * k + r * 6 + c] = ho[36 * (size_t)p + pidx(r, c)];
+      ++k;
+    }
+  }
+  row_ptr[g->N] = (int)k;
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, double* y, int repeats, float* elapsed_ms) {
+  if (!g || !x || !y) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_spmv: null argument");
+  CUDA_TRY(cudaSetDevice(g->device));
+  const size_t nv = (size_t)g->N * 6 * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(g->vu, x, nv, cudaMemcpyHostToDevice, g->stream));
+  if (d) CUDA_TRY(cudaMemcpyAsync(g->dlm, d, nv, cudaMemcpyHostToDevice, g->stream));
+  const int warps = (g->N + kRowsPerWarp - 1) / kRowsPerWarp;
+  const int ctas = std::max(1, std::min((warps + 7) / 8, 8 * g->num_sms));
+  CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+  for (int k = 0; k < std::max(repeats, 1); ++k) {
+    spmv_kernel<<<ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, d ? g->dlm : nullptr, g->vw, g->rank == 0);
+    g->launches++;
+  }
+  CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (g->world > 1) PGO_TRY(allreduce_sum(g, g->vw, (size_t)g->N * 6));
+  CUDA_TRY(cudaMemcpyAsync(y, g->vw, nv, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
+  return PGO_OK;
+}
+
+static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
+  int t = o->linear_solver_type;
+  if (g->world > 1) return PGO_LINEAR_PCG_BLOCK_JACOBI;  // the factor is not distributed
+  if (t == PGO_LINEAR_AUTO || t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
+    if (!g->chol) {
+      LevelChol* c = nullptr;
+      const int rc = level_chol_analyze(&c, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(),
+                                        t == PGO_LINEAR_AUTO ? 8.0 : 1e30, g->stream);
+      if (rc == PGO_OK) g->chol = c;
+      else if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return rc;
+    }
+    if (g->chol && g->chol->usable) return PGO_LINEAR_PCG_LEVEL_CHOLESKY;
+    if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return set_error(PGO_ERR_NUMERICAL, "level Cholesky analysis failed");
+    return PGO_LINEAR_PCG_BLOCK_JACOBI;
+  }
+  return PGO_LINEAR_PCG_BLOCK_JACOBI;
+}
+
+// Solve (H + diag(dlm)) x = b with the chosen solver; x -> g->vx, stats -> g->scalars (after fetch).
+static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b) {
+  if (g->world > 1) return pcg_multi(g, o, b);
+  if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
+    PGO_TRY(level_chol_factor(g->chol, bsr_view(g), g->dlm, g->stream, &g->launches));
+    return level_chol_pcg(g->chol, bsr_view(g), g->dlm, b, g->vx, g->vr, g->vu, g->vw, g->vp, o->pcg_max_iterations,
+                          o->pcg_tolerance, g->scalars, g->stream, &g->launches);
+  }
+  return launch_pcg(g, o, b);
+}
+
+extern "C" int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* options, const double* d,
+                                      const double* b, double* y, int* iterations, double* relative_residual,
+                                      float* elapsed_ms) {
+  if (!g || !options || !d || !b || !y) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_linear_solve: null argument");
+  CUDA_TRY(cudaSetDevice(g->device));
+  const size_t nv = (size_t)g->N * 6 * sizeof(double);
+  const int solver = resolve_linear_solver(g, options);
+  if (solver < 0) return solver;
+  CUDA_TRY(cudaMemcpyAsync(g->dlm, d, nv, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->vb, b, nv, cudaMemcpyHostToDevice, g->stream));
+  const int tpb = 128;
+  lm_prepare_kernel<<<(g->N + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->N, g->Hdiag, g->active, 2, 0.0, 0.0, 1.0,
+                                                                   g->diagonal, g->dlm, g->Minv);
+  g->launches++;
+  PGO_TRY(zero_scalars(g));
+  CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+  PGO_TRY(linear_solve_device(g, options, solver, g->vb));
+  CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+  PGO_TRY(fetch_scalars(g));
+  CUDA_TRY(cudaMemcpy(y, g->vx, nv, cudaMemcpyDeviceToHost));
+  if (iterations) *iterations = g->scalars_h->pcg_iterations;
+  if (relative_residual) *relative_residual = g->scalars_h->pcg_gamma0 > 0 ? std::sqrt(g->scalars_h->pcg_gamma / g->scalars_h->pcg_gamma0) : 0.0;
+  if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
+  return PGO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ceres::Solve: TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy (ceres 1.13 flow),
+// the same sequence of decisions as oracle/pgo_oracle.c:oracle_solve, driven from the host with
+// two stream synchronisations per iteration.
+// ------------------------------------------------------------------------------------------------
+extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_solver_summary* summary,
+                               pgo_iteration_summary* log, int log_cap) {
+  if (!g || !opt || !summary) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_solve: null argument");
+  CUDA_TRY(cudaSetDevice(g->device));
+  const double t_begin = wall_s();
+  std::memset(summary, 0, sizeof *summary);
+  const long long launches0 = g->launches;
+  const int N = g->N;
+  const int tpb = 128, nblk = (N + tpb - 1) / tpb;
+  float ms = 0.f;
+  auto push_log = [&](const pgo_iteration_summary& it) {
+    if (log && summary->num_iterations < log_cap) log[summary->num_iterations] = it;
+    summary->num_iterations++;
+  };
+  const int solver = resolve_linear_solver(g, opt);
+  if (solver < 0) return solver;
+  summary->linear_solver_used = solver;
+  summary->hessian_blocks = g->nnz_off + g->N;
+  if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) { summary->factor_blocks = g->chol->factor_blocks; summary->factor_levels = g->chol->num_levels; }
+  summary->time_setup_s = g->setup_s;
+
+  // ---- IterationZero: evaluate, Jacobi scaling from the unscaled diagonal, re-linearize scaled ----
+  CUDA_TRY(cudaMemcpyAsync(g->scale, g->scale_eval, (size_t)N * 6 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+  PGO_TRY(zero_scalars(g));
+  CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+  PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
+  summary->num_linearizations++;
+  if (opt->jacobi_scaling) {
+    jacobi_scale_kernel<<<nblk, tpb, 0, g->stream>>>(N, g->Hdiag, g->active, 1, g->scale);
+    g->launches++;
+    PGO_TRY(zero_scalars(g));
+    PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
+    summary->num_linearizations++;
+  }
+  CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+  xnorm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->active, g->scalars);
+  gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
+  g->launches += 2;
+  PGO_TRY(fetch_scalars(g));
+  CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+  summary->time_linearize_ms += ms;
+
+  double x_cost = g->scalars_h->cost;
+  double x_norm = std::sqrt(g->scalars_h->x_norm2);
+  double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int num_consecutive_invalid = 0, iter = 0;
+  pgo_iteration_summary it;
+  std::memset(&it, 0, sizeof it);
+  it.cost = x_cost; it.trust_region_radius = radius;
+  { long long bits = (long long)g->scalars_h->gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
+  it.gradient_norm = std::sqrt(g->scalars_h->gnorm2);
+  summary->initial_cost = x_cost;
+  push_log(it);
+  if (!std::isfinite(x_cost)) {
+    summary->termination_type = PGO_FAILURE;
+    snprintf(summary->message, sizeof summary->message, "Initial cost is not finite.");
+    summary->final_cost = x_cost;
+    summary->time_total_s = wall_s() - t_begin;
+    return PGO_OK;
+  }
+
+  for (;;) {
+    if (iter >= opt->max_num_iterations) { summary->termination_type = PGO_NO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Maximum number of iterations reached. Number of iterations: %d.", iter); break; }
+    if (it.gradient_max_norm <= opt->gradient_tolerance) { summary->termination_type = PGO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt->gradient_tolerance); break; }
+    if (radius < opt->min_trust_region_radius) { summary->termination_type = PGO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Minimum trust region radius reached."); break; }
+    ++iter;
+    { const double gm = it.gradient_max_norm, gn = it.gradient_norm; std::memset(&it, 0, sizeof it); it.iteration = iter; it.gradient_max_norm = gm; it.gradient_norm = gn; }
+
+    // ---- LevenbergMarquardtStrategy::ComputeStep: D = diag / radius, solve (H + D) y = g, step = -y ----
+    lm_prepare_kernel<<<nblk, tpb, 0, g->stream>>>(N, g->Hdiag, g->active, reuse_diagonal ? 1 : 0, opt->min_lm_diagonal,
+                                                   opt->max_lm_diagonal, radius, g->diagonal, g->dlm, g->Minv);
+    g->launches++;
+    PGO_TRY(zero_scalars(g));
+    CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+    PGO_TRY(linear_solve_device(g, opt, solver, g->grad));
+    CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+    reuse_diagonal = true;
+    // ---- speculatively: candidate = Plus(x, -y .* scale), its cost, |step|, |x_cand| ----
+    plus_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
+    g->launches++;
+    PGO_TRY(cost_only(g, g->poses_cand, opt->loss_type, opt->loss_a));
+    summary->num_cost_evaluations++;
+    PGO_TRY(fetch_scalars(g));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+    summary->time_linear_solver_ms += ms;
+    const DeviceScalars sc = *g->scalars_h;
+    summary->total_pcg_iterations += sc.pcg_iterations;
+    it.linear_solver_iterations = sc.pcg_iterations;
+    it.pcg_relative_residual = sc.pcg_gamma0 > 0 ? std::sqrt(std::fabs(sc.pcg_gamma) / sc.pcg_gamma0) : 0.0;
+    it.trust_region_radius = radius;
+
+    // model_cost_change = -(J step)^T (r + J step / 2) = y^T g - y^T H y / 2
+    const double model_cost_change = sc.xtb - 0.5 * (sc.xtAx - sc.xtDx);
+    bool step_valid = sc.pcg_flag != 2 && std::isfinite(model_cost_change) && model_cost_change > 0.0;
+    if (opt->verbose)
+      fprintf(stderr, "[pgo] it %d radius %.3e pcg %d (flag %d, rel %.2e) model %.6e\n", iter, radius, sc.pcg_iterations,
+              sc.pcg_flag, it.pcg_relative_residual, model_cost_change);
+    if (!step_valid) {
+      it.step_is_valid = 0; it.cost = x_cost;
+      if (++num_consecutive_invalid >= opt->max_num_consecutive_invalid_steps) {
+        summary->termination_type = PGO_FAILURE;
+        snprintf(summary->message, sizeof summary->message, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", opt->max_num_consecutive_invalid_steps);
+        push_log(it);
+        break;
+      }
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      summary->num_unsuccessful_steps++;
+      push_log(it);
+      continue;
+    }
+    num_consecutive_invalid = 0;
+    it.step_is_valid = 1;
+    double cand_cost = sc.cost;
+    if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+    const double step_norm = std::sqrt(sc.step_norm2);
+    it.step_norm = step_norm;
+    if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
+      summary->termination_type = PGO_CONVERGENCE;
+      snprintf(summary->message, sizeof summary->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", step_norm / (x_norm + opt->parameter_tolerance), opt->parameter_tolerance);
+      it.cost = x_cost; push_log(it);
+      break;
+    }
+    const double cost_change = x_cost - cand_cost;
+    it.cost_change = cost_change;
+    if (std::fabs(cost_change) <= opt->function_tolerance * x_cost) {
+      summary->termination_type = PGO_CONVERGENCE;
+      snprintf(summary->message, sizeof summary->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(cost_change) / x_cost, opt->function_tolerance);
+      it.cost = x_cost; push_log(it);
+      break;
+    }
+    const double relative_decrease = cost_change / model_cost_change;
+    it.relative_decrease = relative_decrease;
+    if (relative_decrease > opt->min_relative_decrease) {
+      // HandleSuccessfulStep: x = candidate, re-linearize there
+      std::swap(g->poses, g->poses_cand);
+      x_norm = std::sqrt(sc.x_norm2);
+      PGO_TRY(zero_scalars(g));
+      CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
+      PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
+      CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+      summary->num_linearizations++;
+      gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
+      g->launches++;
+      PGO_TRY(fetch_scalars(g));
+      CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+      summary->time_linearize_ms += ms;
+      x_cost = g->scalars_h->cost;
+      { long long bits = (long long)g->scalars_h->gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
+      it.gradient_norm = std::sqrt(g->scalars_h->gnorm2);
+      it.step_is_successful = 1; it.cost = x_cost;
+      summary->num_successful_steps++;
+      double t = 2.0 * relative_decrease - 1.0;
+      t = 1.0 - t * t * t;
+      if (t < 1.0 / 3.0) t = 1.0 / 3.0;
+      radius = std::min(radius / t, opt->max_trust_region_radius);
+      decrease_factor = 2.0; reuse_diagonal = false;
+    } else {
+      it.step_is_successful = 0; it.cost = x_cost;
+      summary->num_unsuccessful_steps++;
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+    }
+    push_log(it);
+  }
+  summary->final_cost = x_cost;
+  summary->kernel_launches = g->launches - launches0;
+  summary->time_total_s = wall_s() - t_begin;
+  return PGO_OK;
+}
+
+extern "C" int pgo_solve_pose_graph(int device, int n_poses, double* poses, int n_edges, const int* edge_ids,
+                                    const double* edge_meas, const double* edge_sqrt_info,
+                                    const unsigned char* pose_const, const pgo_solver_options* options,
+                                    pgo_solver_summary* summary, pgo_iteration_summary* iteration_log,
+                                    int iteration_log_capacity) {
+  pgo_graph* g = nullptr;
+  PGO_TRY(pgo_graph_create(&g, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const));
+  pgo_solver_options defaults;
+  if (!options) { pgo_default_options(&defaults); options = &defaults; }
+  int rc = pgo_graph_solve(g, options, summary, iteration_log, iteration_log_capacity);
+  if (rc == PGO_OK) rc = pgo_graph_get_poses(g, poses);
+  pgo_graph_destroy(g);
+  return rc;
+}

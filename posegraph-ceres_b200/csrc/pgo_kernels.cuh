@@ -1,0 +1,684 @@
+// pgo_kernels.cuh -- the sm_100a kernels of the pose-graph LM solver.
+//
+//  linearize_kernel   : per edge residual + both 6x6 Jacobians + J^T J blocks + J^T r, fused.
+//                       Edge tiles are staged global->shared by 1-D bulk TMA (cp.async.bulk +
+//                       mbarrier, double buffered per warp); poses are gathered with 128-bit loads;
+//                       diagonal blocks shared by neighbouring lanes are merged with warp shuffles
+//                       before fp64 RED atomics into the block-CSR Hessian.
+//  pcg_kernel         : persistent block-Jacobi PCG (Chronopoulos-Gear form, 2 grid barriers per
+//                       iteration); its SpMV is bsr6_row() -- 6 lanes per 6x6 block row.
+//  spmv_kernel        : the same bsr6_row() as a stand-alone launch (tests, bench, multi-GPU path).
+#pragma once
+
+#include "pgo_common.cuh"
+#include "pgo_edge_math.cuh"
+
+namespace pgo {
+
+enum LinMode { kLinFull = 0, kLinCost = 1, kLinEval = 2 };
+
+struct LinParams {
+  int n_edges;
+  int n_tiles;
+  const EdgeCoreTile* core;
+  const EdgeInfoTile* info;     // nullptr when identity
+  const double* poses;          // [N][8]
+  const double* scale;          // [N][6]
+  double* Hdiag;                // [N][36] panel
+  double* Hoff;                 // [nnz][36] panel
+  double* grad;                 // [N][6]
+  DeviceScalars* scalars;
+  int loss_type;
+  double loss_a;
+  // kLinEval outputs
+  double* res_out;              // [E][6]
+  double* jac_out;              // [E][2][36] row-major
+};
+
+__device__ __forceinline__ void load_pose(const double* poses, int i, double* p) {
+  const double2* q = reinterpret_cast<const double2*>(poses + 8 * (size_t)i);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y; p[4] = c.x; p[5] = c.y; p[6] = d.x;
+}
+__device__ __forceinline__ void load_vec6(const double* v, int i, double* s) {
+  const double2* q = reinterpret_cast<const double2*>(v + 6 * (size_t)i);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y; s[4] = c.x; s[5] = c.y;
+}
+
+// 3x3 = X^T Y over the 6 rows of two 6x3 panels
+__device__ __forceinline__ void xty(const double (&X)[6][3], const double (&Y)[6][3], double (&P)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fma(X[k][i], Y[k][j], s);
+      P[i][j] = s;
+    }
+}
+
+template <bool kIdentityInfo, int kMode, bool kMerge>
+__global__ void __launch_bounds__(kLinWarps * 32, 2) linearize_kernel(const LinParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kStageBytes = kCoreTileBytes + (kIdentityInfo ? 0 : kInfoTileBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wbase = smem_raw + (size_t)warp * 2 * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kLinWarps * 2 * kStageBytes) + warp * 2;
+
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int gw = blockIdx.x * kLinWarps + warp;
+  const int nw = gridDim.x * kLinWarps;
+  auto issue = [&](int tile, int stage) {
+    unsigned char* dst = wbase + (size_t)stage * kStageBytes;
+    mbar_expect_tx(&bars[stage], kStageBytes);
+    tma_load_1d(dst, p.core + tile, kCoreTileBytes, &bars[stage]);
+    if (!kIdentityInfo) tma_load_1d(dst + kCoreTileBytes, p.info + tile, kInfoTileBytes, &bars[stage]);
+  };
+
+  int stage = 0;
+  uint32_t phase0 = 0, phase1 = 0;
+  double cost_acc = 0.0;
+  if (gw < p.n_tiles && lane == 0) issue(gw, 0);
+
+  for (int tile = gw; tile < p.n_tiles; tile += nw) {
+    const int next = tile + nw;
+    if (next < p.n_tiles && lane == 0) issue(next, stage ^ 1);
+    if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+    else            { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+
+    const EdgeCoreTile* ct = reinterpret_cast<const EdgeCoreTile*>(wbase + (size_t)stage * kStageBytes);
+    const EdgeInfoTile* it = reinterpret_cast<const EdgeInfoTile*>(wbase + (size_t)stage * kStageBytes + kCoreTileBytes);
+    const int e = tile * kTile + lane;
+    const bool valid = e < p.n_edges;
+    const int a = valid ? ct->a[lane] : 0;
+    const int b = valid ? ct->b[lane] : 0;
+
+    double pa[7], pb[7], m[7];
+    load_pose(p.poses, a, pa);
+    load_pose(p.poses, b, pb);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) m[k] = ct->meas[k][lane];
+    auto S = [&](int i, int k) -> double { return it->S[i * 6 + k][lane]; };
+
+    if (kMode == kLinCost) {
+      double r[6];
+      edge_residual_only<kIdentityInfo>(pa, pb, m, S, r);
+      double sq = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sq = fma(r[i], r[i], sq);
+      double rho1;
+      const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
+      if (valid) cost_acc += 0.5 * rho;
+      __syncwarp();
+      stage ^= 1;
+      continue;
+    }
+
+    EdgePanels L;
+    edge_linearize<kIdentityInfo>(pa, pb, m, S, L);
+    double sq = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sq = fma(L.r[i], L.r[i], sq);
+    double rho1;
+    const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
+    if (valid) cost_acc += 0.5 * rho;
+    if (!valid) rho1 = 0.0;   // padded lanes contribute exact zeros
+
+    double sa[6], sb[6];
+    load_vec6(p.scale, a, sa);
+    load_vec6(p.scale, b, sb);
+
+    if (kMode == kLinEval) {
+      // Problem::Evaluate parity outputs: corrected residual and Jacobians (row-major 6x6).
+      const double sr = sqrt(rho1);
+      if (valid) {
+        double* ro = p.res_out + 6 * (size_t)e;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ro[i] = sr * L.r[i];
+        double* ja = p.jac_out + 72 * (size_t)e;
+        double* jb = ja + 36;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            ja[i * 6 + k] = -sr * L.B1[i][k] * sa[k];
+            ja[i * 6 + 3 + k] = sr * L.C[i][k] * sa[3 + k];
+            jb[i * 6 + k] = sr * L.B1[i][k] * sb[k];
+            jb[i * 6 + 3 + k] = -sr * L.B2[i][k] * sb[3 + k];
+          }
+      }
+    }
+
+    // ---- gradient J^T r (robustified: rho' J^T r), column-scaled ----
+    {
+      double g1[3], g2[3], gc[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double s1 = 0.0, s2 = 0.0, sc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s1 = fma(L.B1[i][k], L.r[i], s1); s2 = fma(L.B2[i][k], L.r[i], s2); sc = fma(L.C[i][k], L.r[i], sc); }
+        g1[k] = rho1 * s1; g2[k] = rho1 * s2; gc[k] = rho1 * sc;
+      }
+      // g_a = sa .* [-g1; gc], g_b = sb .* [g1; -g2]. Merge lane+1's g_b into g_a when it hits the same pose.
+      const int b_next = __shfl_down_sync(0xffffffffu, b, 1);
+      const bool take = kMerge && lane < 31 && b_next == a;          // I absorb lane+1's b contribution
+      const int a_prev = __shfl_up_sync(0xffffffffu, a, 1);
+      const bool given = kMerge && lane > 0 && a_prev == b;          // lane-1 absorbed mine
+      double* ga = p.grad + 6 * (size_t)a;
+      double* gb = p.grad + 6 * (size_t)b;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double vb0 = sb[k] * g1[k], vb1 = -sb[3 + k] * g2[k];
+        double va0 = -sa[k] * g1[k], va1 = sa[3 + k] * gc[k];
+        if (kMerge) {
+          const double n0 = __shfl_down_sync(0xffffffffu, vb0, 1), n1 = __shfl_down_sync(0xffffffffu, vb1, 1);
+          if (take) { va0 += n0; va1 += n1; }
+        }
+        if (valid) {
+          atomicAdd(ga + k, va0); atomicAdd(ga + 3 + k, va1);
+          if (!given) { atomicAdd(gb + k, vb0); atomicAdd(gb + 3 + k, vb1); }
+        }
+      }
+
+      if (kMode == kLinFull) {
+        // ---- 3x3 products of the panels ----
+        double P11[3][3], P12[3][3], P22[3][3], P1C[3][3], PCC[3][3], PC2[3][3];
+        xty(L.B1, L.B1, P11); xty(L.B1, L.B2, P12); xty(L.B2, L.B2, P22);
+        xty(L.B1, L.C, P1C);  xty(L.C, L.C, PCC);   xty(L.C, L.B2, PC2);
+        // element accessors of the unscaled J^T J blocks (rho' applied below)
+        auto Haa = [&](int r, int c) -> double {
+          return (r < 3) ? ((c < 3) ? P11[r][c] : -P1C[r][c - 3]) : ((c < 3) ? -P1C[c][r - 3] : PCC[r - 3][c - 3]);
+        };
+        auto Hbb = [&](int r, int c) -> double {
+          return (r < 3) ? ((c < 3) ? P11[r][c] : -P12[r][c - 3]) : ((c < 3) ? -P12[c][r - 3] : P22[r - 3][c - 3]);
+        };
+        // H_ab = Ja^T Jb = [[-P11, P12], [C^T B1, -C^T B2]] ; C^T B1 = P1C^T
+        auto Hab = [&](int r, int c) -> double {
+          return (r < 3) ? ((c < 3) ? -P11[r][c] : P12[r][c - 3]) : ((c < 3) ? P1C[c][r - 3] : -PC2[r - 3][c - 3]);
+        };
+        double* da = p.Hdiag + 36 * (size_t)a;
+        double* db = p.Hdiag + 36 * (size_t)b;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const double hb = rho1 * sb[r] * sb[c] * Hbb(r, c);
+            double ha = rho1 * sa[r] * sa[c] * Haa(r, c);
+            if (kMerge) {
+              const double nb = __shfl_down_sync(0xffffffffu, hb, 1);
+              if (take) ha += nb;
+            }
+            if (valid) {
+              atomicAdd(da + pidx(r, c), ha);
+              if (!given) atomicAdd(db + pidx(r, c), hb);
+            }
+          }
+        // off-diagonal blocks: (a,b) = H_ab, (b,a) = H_ab^T
+        const int s_ab = valid ? ct->slot_ab[lane] : -1;
+        const int s_ba = valid ? ct->slot_ba[lane] : -1;
+        if (s_ab >= 0) {
+          double2* o = reinterpret_cast<double2*>(p.Hoff + 36 * (size_t)s_ab);
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp)
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+              o[cp * 6 + r] = make_double2(rho1 * sa[r] * sb[2 * cp] * Hab(r, 2 * cp), rho1 * sa[r] * sb[2 * cp + 1] * Hab(r, 2 * cp + 1));
+        } else if (s_ab <= -2) {
+          double* o = p.Hoff + 36 * (size_t)(-s_ab - 2);
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) atomicAdd(o + pidx(r, c), rho1 * sa[r] * sb[c] * Hab(r, c));
+        }
+        if (s_ba >= 0) {
+          double2* o = reinterpret_cast<double2*>(p.Hoff + 36 * (size_t)s_ba);
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp)
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+              o[cp * 6 + r] = make_double2(rho1 * sb[r] * sa[2 * cp] * Hab(2 * cp, r), rho1 * sb[r] * sa[2 * cp + 1] * Hab(2 * cp + 1, r));
+        } else if (s_ba <= -2) {
+          double* o = p.Hoff + 36 * (size_t)(-s_ba - 2);
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) atomicAdd(o + pidx(r, c), rho1 * sb[r] * sa[c] * Hab(c, r));
+        }
+      }
+    }
+    __syncwarp();
+    stage ^= 1;
+  }
+  cost_acc = warp_sum(cost_acc);
+  if (lane == 0 && cost_acc != 0.0) atomicAdd(&p.scalars->cost, cost_acc);
+}
+
+// --------------------------------------------------------------------------------------------
+// Block-CSR 6x6 SpMV row: lane `r` (0..5) of a 6-lane group returns row r of
+//   y_i = (Hdiag_i + diag(d_i)) x_i + sum_j Hoff_ij x_j .
+// Panel layout => the 6 lanes of a group read 96 contiguous bytes per 128-bit load.
+// kCoherent: gather x with ld.global.cg (x was written by other CTAs of the same launch).
+// --------------------------------------------------------------------------------------------
+template <bool kCoherent>
+__device__ __forceinline__ double bsr6_row(const double* __restrict__ Hdiag, const double* __restrict__ Hoff,
+                                           const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                           const double* x, const double* __restrict__ d, int i, int r, bool with_diag = true) {
+  auto ldx = [&](const double* q) -> double2 {
+    return kCoherent ? __ldcg(reinterpret_cast<const double2*>(q)) : __ldg(reinterpret_cast<const double2*>(q));
+  };
+  const double2* hd = reinterpret_cast<const double2*>(Hdiag + 36 * (size_t)i) + r;
+  const double2 h0 = __ldg(hd), h1 = __ldg(hd + 6), h2 = __ldg(hd + 12);
+  const double* xi = x + 6 * (size_t)i;
+  const double2 x0 = ldx(xi), x1 = ldx(xi + 2), x2 = ldx(xi + 4);
+  double acc = h0.x * x0.x;
+  acc = fma(h0.y, x0.y, acc); acc = fma(h1.x, x1.x, acc); acc = fma(h1.y, x1.y, acc);
+  acc = fma(h2.x, x2.x, acc); acc = fma(h2.y, x2.y, acc);
+  if (!with_diag) acc = 0.0;   // multi-GPU: the all-reduced diagonal is applied by rank 0 only
+  if (d != nullptr && with_diag) {
+    const double xr = (r == 0) ? x0.x : (r == 1) ? x0.y : (r == 2) ? x1.x : (r == 3) ? x1.y : (r == 4) ? x2.x : x2.y;
+    acc = fma(__ldg(d + 6 * (size_t)i + r), xr, acc);
+  }
+  const int p0 = __ldg(row_ptr + i), p1 = __ldg(row_ptr + i + 1);
+  double acc2 = 0.0;
+  int p = p0;
+  for (; p + 1 < p1; p += 2) {
+    const int j0 = __ldg(col_idx + p), j1 = __ldg(col_idx + p + 1);
+    const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
+    const double2* hb = ha + 18;
+    const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
+    const double2 b0 = __ldg(hb), b1 = __ldg(hb + 6), b2 = __ldg(hb + 12);
+    const double* xa = x + 6 * (size_t)j0;
+    const double* xb = x + 6 * (size_t)j1;
+    const double2 u0 = ldx(xa), u1 = ldx(xa + 2), u2 = ldx(xa + 4);
+    const double2 v0 = ldx(xb), v1 = ldx(xb + 2), v2 = ldx(xb + 4);
+    acc = fma(a0.x, u0.x, acc); acc = fma(a0.y, u0.y, acc); acc = fma(a1.x, u1.x, acc);
+    acc = fma(a1.y, u1.y, acc); acc = fma(a2.x, u2.x, acc); acc = fma(a2.y, u2.y, acc);
+    acc2 = fma(b0.x, v0.x, acc2); acc2 = fma(b0.y, v0.y, acc2); acc2 = fma(b1.x, v1.x, acc2);
+    acc2 = fma(b1.y, v1.y, acc2); acc2 = fma(b2.x, v2.x, acc2); acc2 = fma(b2.y, v2.y, acc2);
+  }
+  if (p < p1) {
+    const int j0 = __ldg(col_idx + p);
+    const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
+    const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
+    const double* xa = x + 6 * (size_t)j0;
+    const double2 u0 = ldx(xa), u1 = ldx(xa + 2), u2 = ldx(xa + 4);
+    acc = fma(a0.x, u0.x, acc); acc = fma(a0.y, u0.y, acc); acc = fma(a1.x, u1.x, acc);
+    acc = fma(a1.y, u1.y, acc); acc = fma(a2.x, u2.x, acc); acc = fma(a2.y, u2.y, acc);
+  }
+  return acc + acc2;
+}
+
+struct BsrView {
+  int n;                       // block rows
+  const double* Hdiag;
+  const double* Hoff;
+  const int* row_ptr;
+  const int* col_idx;
+};
+
+// y = (H + diag(d)) x ; grid-stride over groups of 5 rows per warp.
+__global__ void __launch_bounds__(256) spmv_kernel(const BsrView A, const double* __restrict__ x,
+                                                   const double* __restrict__ d, double* __restrict__ y,
+                                                   bool with_diag) {
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / 6, r = lane - grp * 6;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const int nw = gridDim.x * warps_per_cta;
+  for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
+    const int i = base + grp;
+    if (grp < kRowsPerWarp && i < A.n) {
+      const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, r, with_diag);
+      y[6 * (size_t)i + r] = v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Grid barrier for the persistent PCG kernel (cooperative launch => all CTAs co-resident).
+// Monotonic arrival counter; thread 0 of each CTA arrives and spins.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - epoch) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct PcgParams {
+  BsrView A;
+  const double* d;        // [N][6] LM diagonal (added to H)
+  const double* Minv;     // [N][36] row-major inverse of (Hdiag + diag(d)) blocks
+  const double* b;        // [N][6]
+  double* x; double* r; double* u; double* w; double* p; double* s;
+  double* partials;       // [2 parities][3 slots][gridDim.x]
+  unsigned int* barrier;
+  DeviceScalars* scalars;
+  int max_iterations;
+  double tolerance;
+};
+
+__device__ __forceinline__ double cta_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nwarp = blockDim.x >> 5;
+  for (int k = 0; k < nwarp; ++k) t += red[k];
+  return t;
+}
+
+// every thread sums the per-CTA partials in the same fixed order -> bitwise identical everywhere
+__device__ __forceinline__ double sum_partials(const double* part, int n) {
+  double t = 0.0;
+  for (int k = 0; k < n; ++k) t += __ldcg(part + k);
+  return t;
+}
+
+__global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
+  __shared__ double red[kPcgThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / 6, r = lane - grp * 6;
+  const bool lane_on = grp < kRowsPerWarp;
+  const int warps_per_cta = kPcgThreads / 32;
+  const int gw = blockIdx.x * warps_per_cta + warp;
+  const int nw = gridDim.x * warps_per_cta;
+  const int n = P.A.n;
+  const int G = gridDim.x;
+  unsigned int epoch = 0;
+  const unsigned gmask = 0xffffffffu;
+
+  // u_i = Minv_i r_i for the row this lane group owns; rnew is this lane's component of r_i
+  auto precond = [&](int i, double rnew) -> double {
+    const double2* mi = reinterpret_cast<const double2*>(P.Minv + 36 * (size_t)i + 6 * r);
+    const double2 m0 = __ldg(mi), m1 = __ldg(mi + 1), m2 = __ldg(mi + 2);
+    const int g0 = grp * 6;
+    const double r0 = __shfl_sync(gmask, rnew, g0), r1 = __shfl_sync(gmask, rnew, g0 + 1), r2 = __shfl_sync(gmask, rnew, g0 + 2);
+    const double r3 = __shfl_sync(gmask, rnew, g0 + 3), r4 = __shfl_sync(gmask, rnew, g0 + 4), r5 = __shfl_sync(gmask, rnew, g0 + 5);
+    return m0.x * r0 + m0.y * r1 + m1.x * r2 + m1.y * r3 + m2.x * r4 + m2.y * r5;
+  };
+
+  // ---- init: x = 0, r = b, u = Minv r, p = s = 0 ; gamma = r.u ----
+  double acc = 0.0;
+  for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
+    const int i = base + grp;
+    const bool on = lane_on && i < n;
+    const size_t k = 6 * (size_t)(on ? i : 0) + r;
+    const double rv = on ? P.b[k] : 0.0;
+    const double uv = precond(on ? i : 0, rv);
+    if (on) { P.x[k] = 0.0; P.r[k] = rv; P.u[k] = uv; P.p[k] = 0.0; P.s[k] = 0.0; acc += rv * uv; }
+  }
+  acc = cta_sum(acc, red);
+  if (threadIdx.x == 0) P.partials[0 * 3 * G + 0 * G + blockIdx.x] = acc;
+  grid_barrier(P.barrier, epoch);
+  const double gamma0 = sum_partials(P.partials + 0, G);
+  double gamma = gamma0, gamma_old = 0.0, alpha = 0.0, beta = 0.0;
+  int iter = 0;
+  int flag = 0;
+  const double stop = P.tolerance * P.tolerance * gamma0;
+
+  if (gamma0 > 0.0) {
+    for (;;) {
+      const int par = iter & 1;
+      double* part = P.partials + (size_t)par * 3 * G;
+      // ---- phase B: w = A u, delta = w.u ----
+      acc = 0.0;
+      for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
+        const int i = base + grp;
+        if (lane_on && i < n) {
+          const double wv = bsr6_row<true>(P.A.Hdiag, P.A.Hoff, P.A.row_ptr, P.A.col_idx, P.u, P.d, i, r);
+          const size_t k = 6 * (size_t)i + r;
+          P.w[k] = wv;
+          acc += wv * P.u[k];
+        }
+      }
+      acc = cta_sum(acc, red);
+      if (threadIdx.x == 0) part[1 * G + blockIdx.x] = acc;
+      grid_barrier(P.barrier, epoch);
+      const double delta = sum_partials(part + 1 * G, G);
+      // ---- scalars (identical on every thread) ----
+      if (iter == 0) { beta = 0.0; alpha = gamma / delta; }
+      else { beta = gamma / gamma_old; alpha = gamma / (delta - beta * gamma / alpha); }
+      if (!(alpha > 0.0) || !isfinite(alpha)) { flag = 2; break; }
+      ++iter;
+      // ---- phase A: p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = Minv r, gamma' = r.u ----
+      acc = 0.0;
+      for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
+        const int i = base + grp;
+        const bool on = lane_on && i < n;
+        const size_t k = 6 * (size_t)(on ? i : 0) + r;
+        double rv = 0.0;
+        if (on) {
+          const double pv = P.u[k] + beta * P.p[k];
+          const double sv = P.w[k] + beta * P.s[k];
+          P.p[k] = pv; P.s[k] = sv;
+          P.x[k] += alpha * pv;
+          rv = P.r[k] - alpha * sv;
+          P.r[k] = rv;
+        }
+        const double uv = precond(on ? i : 0, rv);
+        if (on) { P.u[k] = uv; acc += rv * uv; }
+      }
+      acc = cta_sum(acc, red);
+      double* partn = P.partials + (size_t)(iter & 1) * 3 * G;
+      if (threadIdx.x == 0) partn[0 * G + blockIdx.x] = acc;
+      grid_barrier(P.barrier, epoch);
+      gamma_old = gamma;
+      gamma = sum_partials(partn + 0 * G, G);
+      if (gamma <= stop) { flag = 0; break; }
+      if (iter >= P.max_iterations) { flag = 1; break; }
+    }
+  }
+
+  // ---- epilogue: x^T b, x^T (H + D) x, x^T D x for the model cost change ----
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
+    const int i = base + grp;
+    if (lane_on && i < n) {
+      const double ax = bsr6_row<true>(P.A.Hdiag, P.A.Hoff, P.A.row_ptr, P.A.col_idx, P.x, P.d, i, r);
+      const size_t k = 6 * (size_t)i + r;
+      const double xv = P.x[k];
+      a0 += xv * P.b[k]; a1 += xv * ax; a2 += xv * xv * P.d[k];
+    }
+  }
+  a0 = cta_sum(a0, red); a1 = cta_sum(a1, red); a2 = cta_sum(a2, red);
+  double* parte = P.partials + (size_t)((iter + 1) & 1) * 3 * G;
+  if (threadIdx.x == 0) { parte[0 * G + blockIdx.x] = a0; parte[1 * G + blockIdx.x] = a1; parte[2 * G + blockIdx.x] = a2; }
+  grid_barrier(P.barrier, epoch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    P.scalars->xtb = sum_partials(parte + 0 * G, G);
+    P.scalars->xtAx = sum_partials(parte + 1 * G, G);
+    P.scalars->xtDx = sum_partials(parte + 2 * G, G);
+    P.scalars->pcg_gamma0 = gamma0;
+    P.scalars->pcg_gamma = gamma;
+    P.scalars->pcg_iterations = iter;
+    P.scalars->pcg_flag = flag;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Per-pose helpers
+// --------------------------------------------------------------------------------------------
+// Jacobi scaling (trust_region_minimizer.cc: 1 / (1 + sqrt(column norm^2))) from the diagonal of the
+// unscaled Hessian; 0 for constant / unused poses so that their columns vanish from the problem.
+__global__ void jacobi_scale_kernel(int n, const double* __restrict__ Hdiag, const unsigned char* __restrict__ active,
+                                    int use_scaling, double* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double s = 0.0;
+    if (active[i]) s = use_scaling ? 1.0 / (1.0 + sqrt(Hdiag[36 * (size_t)i + pidx(c, c)])) : 1.0;
+    scale[6 * (size_t)i + c] = s;
+  }
+}
+
+// LevenbergMarquardtStrategy::ComputeStep prologue: diagonal (unless reused), D = diagonal / radius,
+// and the block-Jacobi preconditioner Minv = (Hdiag + D)^-1 by Cholesky.
+__global__ void lm_prepare_kernel(int n, const double* __restrict__ Hdiag, const unsigned char* __restrict__ active,
+                                  int mode /*0: new diagonal, 1: reuse diagonal, 2: dlm given*/, double min_diag,
+                                  double max_diag, double radius, double* __restrict__ diagonal,
+                                  double* __restrict__ dlm, double* __restrict__ Minv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double A[6][6];
+  double dd[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[r][c] = Hdiag[36 * (size_t)i + pidx(r, c)];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    if (mode == 2) {
+      dd[c] = dlm[6 * (size_t)i + c];
+    } else {
+      double v;
+      if (mode == 1) v = diagonal[6 * (size_t)i + c];
+      else { v = fmin(fmax(A[c][c], min_diag), max_diag); diagonal[6 * (size_t)i + c] = v; }
+      dd[c] = v / radius;
+      dlm[6 * (size_t)i + c] = dd[c];
+    }
+    A[c][c] += dd[c];
+  }
+  double* out = Minv + 36 * (size_t)i;
+  if (!active[i]) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) out[k] = 0.0;
+    return;
+  }
+  // Cholesky A = L L^T (in place, lower), then Minv = L^-T L^-1
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < j) s -= A[j][k] * A[j][k];
+    if (!(s > 0.0)) { ok = false; s = 1.0; }
+    const double l = sqrt(s);
+    A[j][j] = l;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > j) {
+      double t = A[r][j];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k < j) t -= A[r][k] * A[j][k];
+      A[r][j] = t / l;
+    }
+  }
+  // Linv (lower)
+  double Li[6][6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r < c) { Li[r][c] = 0.0; continue; }
+      double t = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k >= c && k < r) t -= A[r][k] * Li[k][c];
+      Li[r][c] = t / A[r][r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k >= r && k >= c) t += Li[k][r] * Li[k][c];
+      out[r * 6 + c] = ok ? t : ((r == c) ? 1.0 / (dd[r] > 0 ? dd[r] : 1.0) : 0.0);
+    }
+}
+
+// x_cand = Plus(x, sign * y .* scale) for active poses; accumulates |x - x_cand|^2 and |x_cand|^2.
+__global__ void __launch_bounds__(256) plus_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                                   const double* __restrict__ scale, const unsigned char* __restrict__ active,
+                                                   double sign, double* __restrict__ out, DeviceScalars* scalars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double sn = 0.0, xn = 0.0;
+  if (i < n) {
+    double xi[7], d[6], o[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) xi[k] = x[8 * (size_t)i + k];
+    if (active[i]) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d[k] = sign * y[6 * (size_t)i + k] * scale[6 * (size_t)i + k];
+      pose_plus(xi, d, o);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const double t = xi[k] - o[k]; sn += t * t; xn += o[k] * o[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) o[k] = xi[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) out[8 * (size_t)i + k] = o[k];
+    out[8 * (size_t)i + 7] = 0.0;
+  }
+  sn = warp_sum(sn); xn = warp_sum(xn);
+  if ((threadIdx.x & 31) == 0 && (sn != 0.0 || xn != 0.0)) { atomicAdd(&scalars->step_norm2, sn); atomicAdd(&scalars->x_norm2, xn); }
+}
+
+// gradient norms as Ceres reports them: |x - Plus(x, -g)| with g = unscaled gradient = g_s / scale.
+__global__ void __launch_bounds__(256) gradient_norm_kernel(int n, const double* __restrict__ x, const double* __restrict__ gs,
+                                                            const double* __restrict__ scale, const unsigned char* __restrict__ active,
+                                                            double* __restrict__ g_unscaled, DeviceScalars* scalars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double mx = 0.0, l2 = 0.0;
+  if (i < n) {
+    double g[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double s = scale[6 * (size_t)i + k];
+      g[k] = (active[i] && s > 0.0) ? gs[6 * (size_t)i + k] / s : 0.0;
+      if (g_unscaled) g_unscaled[6 * (size_t)i + k] = g[k];
+    }
+    if (active[i]) {
+      double xi[7], d[6], o[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) xi[k] = x[8 * (size_t)i + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d[k] = -g[k];
+      pose_plus(xi, d, o);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { const double t = fabs(xi[k] - o[k]); mx = fmax(mx, t); l2 += t * t; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  l2 = warp_sum(l2);
+  if ((threadIdx.x & 31) == 0 && (mx != 0.0 || l2 != 0.0)) {
+    atomicMax(&scalars->gmax_bits, (unsigned long long)__double_as_longlong(mx));
+    atomicAdd(&scalars->gnorm2, l2);
+  }
+}
+
+// x_norm^2 over active poses (iteration zero)
+__global__ void __launch_bounds__(256) xnorm_kernel(int n, const double* __restrict__ x, const unsigned char* __restrict__ active,
+                                                    DeviceScalars* scalars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double xn = 0.0;
+  if (i < n && active[i]) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { const double t = x[8 * (size_t)i + k]; xn += t * t; }
+  }
+  xn = warp_sum(xn);
+  if ((threadIdx.x & 31) == 0 && xn != 0.0) atomicAdd(&scalars->x_norm2, xn);
+}
+
+}  // namespace pgo

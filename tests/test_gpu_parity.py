@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of include/pgo_b200.h) against the CPU oracle
+on the same seeded inputs.  Tolerances are written next to each assertion; BASELINE.json's
+north_star tolerance for converged poses is 1e-4 m / 1e-4 rad."""
+import numpy as np
+import pytest
+
+from helpers import bsr_to_dict, hessian_from_jac, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+
+
+def _graphs(P):
+    D = P.datasets
+    return {
+        "manhattan": D.manhattan_loop(),                       # configs[0]
+        "kitti00": D.kitti00(),                                # configs[1]
+        "sphere": D.sphere(10, 20, None),                      # small sphere, correlated information
+        "grid": D.manhattan_grid(12, 15, 20),
+        "torus": D.torus(400, winds=10),
+    }
+
+
+@pytest.fixture(scope="module")
+def graphs(pgo):
+    return _graphs(pgo)
+
+
+@pytest.mark.parametrize("name", ["manhattan", "kitti00", "sphere", "grid", "torus"])
+@pytest.mark.parametrize("loss", [0, 1, 2])
+def test_evaluate_matches_oracle(pgo, oracle, graphs, name, loss):
+    """residual + both 6x6 Jacobians + gradient: analytic CUDA kernel vs the oracle's jets."""
+    g = graphs[name]
+    G = pgo.Graph.from_dataset(g)
+    cost, res, grad, jac = G.evaluate(loss_type=loss, loss_a=1.0)
+    ocost, ores, ograd, ojac = oracle.evaluate(g, loss_type=loss, loss_a=1.0)
+    jscale = max(1.0, np.abs(ojac).max())
+    assert abs(cost - ocost) <= 1e-12 * max(1.0, abs(ocost))
+    assert np.abs(res - ores).max() <= 1e-12 * max(1.0, np.abs(ores).max())
+    assert np.abs(jac - ojac).max() <= 1e-12 * jscale          # fp64, relative to the largest entry
+    assert np.abs(grad - ograd).max() <= 1e-11 * max(1.0, np.abs(ograd).max())
+    G.close()
+
+
+@pytest.mark.parametrize("name", ["manhattan", "sphere", "torus"])
+def test_hessian_matches_oracle(pgo, oracle, graphs, name):
+    """block-CSR J^T J assembled by the fused kernel (atomics + shuffles) vs numpy from oracle Jacobians,
+    with a non-trivial column scaling."""
+    g = graphs[name]
+    G = pgo.Graph.from_dataset(g)
+    rng = np.random.default_rng(0)
+    scale = rng.uniform(0.2, 1.0, (g.n_poses, 6))
+    scale[g.pose_const.astype(bool)] = 0.0
+    cost, _ = G.linearize(loss_type=1, loss_a=1.0, scale=scale)
+    rp, ci, vals, grad = G.hessian()
+    ocost, ores, ograd, ojac = oracle.evaluate(g, loss_type=1, loss_a=1.0)
+    ref = hessian_from_jac(g, ojac, scale)
+    got = bsr_to_dict(rp, ci, vals)
+    hmax = max(np.abs(v).max() for v in ref.values())
+    for key, blk in ref.items():
+        if np.abs(blk).max() == 0.0 and key not in got:
+            continue  # blocks touching constant poses are not stored
+        assert key in got, key
+        assert np.abs(got[key] - blk).max() <= 1e-11 * hmax, key
+    assert np.abs(grad - ograd * scale).max() <= 1e-11 * max(1.0, np.abs(ograd).max())
+    assert abs(cost - ocost) <= 1e-12 * max(1.0, ocost)
+    G.close()
+
+
+def test_hessian_duplicate_edges(pgo, oracle):
+    """two measurements between the same pair of poses land in one block (atomic path)."""
+    D = pgo.datasets
+    g = D.manhattan_loop(40, 50)
+    ids = np.concatenate([g.edge_ids, g.edge_ids[5:8], g.edge_ids[5:6, ::-1]], 0)
+    meas = np.concatenate([g.edge_meas, g.edge_meas[5:8], D.relative_pose(g.truth[g.edge_ids[5:6, 1]], g.truth[g.edge_ids[5:6, 0]])], 0)
+    si = np.concatenate([g.edge_sqrt_info, g.edge_sqrt_info[5:8], g.edge_sqrt_info[5:6]], 0)
+    g2 = D.PoseGraph("dup", g.poses, ids, meas, si, g.pose_const)
+    G = pgo.Graph.from_dataset(g2)
+    G.linearize(loss_type=1, loss_a=1.0)
+    rp, ci, vals, grad = G.hessian()
+    _, _, ograd, ojac = oracle.evaluate(g2, loss_type=1, loss_a=1.0)
+    ref = hessian_from_jac(g2, ojac)
+    got = bsr_to_dict(rp, ci, vals)
+    hmax = max(np.abs(v).max() for v in ref.values())
+    for key, blk in ref.items():
+        if key in got:
+            assert np.abs(got[key] - blk).max() <= 1e-11 * hmax, key
+        else:
+            assert np.abs(blk).max() == 0.0
+    G.close()
+
+
+@pytest.mark.parametrize("name", ["manhattan", "sphere", "grid"])
+def test_spmv_matches_numpy(pgo, graphs, name):
+    g = graphs[name]
+    G = pgo.Graph.from_dataset(g)
+    G.linearize(loss_type=1, loss_a=1.0)
+    rp, ci, vals, _ = G.hessian()
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(g.n_poses, 6))
+    d = rng.uniform(0.0, 1.0, (g.n_poses, 6))
+    y, _ = G.spmv(x, d)
+    ref = d * x
+    for i in range(g.n_poses):
+        for p in range(rp[i], rp[i + 1]):
+            ref[i] += vals[p] @ x[ci[p]]
+    assert np.abs(y - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    y2, _ = G.spmv(x, None)
+    assert np.abs(y2 - (ref - d * x)).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    G.close()
+
+
+@pytest.mark.parametrize("name", ["manhattan", "sphere", "grid", "torus"])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_linear_solve_matches_oracle_cholesky(pgo, oracle, graphs, name, solver):
+    """(J^T J + D) y = J^T r: PCG (block-Jacobi / level-Cholesky preconditioned) vs the oracle's sparse Cholesky."""
+    g = graphs[name]
+    G = pgo.Graph.from_dataset(g)
+    G.linearize(loss_type=1, loss_a=1.0)
+    _, _, _, grad = G.hessian()
+    _, _, ograd, ojac = oracle.evaluate(g, loss_type=1, loss_a=1.0)
+    rng = np.random.default_rng(2)
+    d = rng.uniform(1e-3, 1e-2, (g.n_poses, 6))
+    rc, yref = oracle.normal_solve(g, ojac, d.ravel(), ograd.ravel())
+    assert rc == 0
+    o = pgo.default_options()
+    o.linear_solver_type = solver
+    o.pcg_tolerance = 1e-12
+    o.pcg_max_iterations = 20000
+    y, iters, rel, ms = G.linear_solve(d, grad, o)
+    assert rel <= 1e-10
+    assert np.abs(y - yref).max() <= 1e-8 * max(1.0, np.abs(yref).max())
+    G.close()
+
+
+def _compare_solves(pgo, oracle, g, solver, pos_tol=1e-4, rot_tol=1e-4, **opts):
+    oo = oracle.default_options()
+    o = pgo.default_options()
+    o.linear_solver_type = solver
+    o.pcg_tolerance = 1e-12
+    o.pcg_max_iterations = 100000
+    for k, v in opts.items():
+        setattr(oo, k, v)
+        setattr(o, k, v)
+    ref_poses, rs, rits = oracle.solve(g, oo)
+    G = pgo.Graph.from_dataset(g)
+    s, its = G.solve(o)
+    poses = G.get_poses()
+    G.close()
+    assert s.termination_type == rs.termination_type
+    assert len(its) == len(rits), (len(its), len(rits), s.message, rs.message)
+    for a, b in zip(its, rits):
+        assert a.step_is_successful == b.step_is_successful
+        assert abs(a.cost - b.cost) <= 1e-7 * max(1.0, abs(b.cost))
+    dp = np.abs(poses[:, :3] - ref_poses[:, :3]).max()
+    dr = rot_angle_between(poses[:, 3:], ref_poses[:, 3:]).max()
+    assert dp <= pos_tol, dp      # north_star: <= 1e-4 m
+    assert dr <= rot_tol, dr      # north_star: <= 1e-4 rad
+    return s, its
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("name", ["manhattan", "sphere", "grid", "torus"])
+def test_solve_matches_oracle_small(pgo, oracle, graphs, name, solver):
+    """ceres::Solve parity: same accept/reject sequence, costs and converged poses as the oracle."""
+    _compare_solves(pgo, oracle, graphs[name], solver)
+
+
+def test_solve_trivial_loss_and_no_scaling(pgo, oracle, graphs):
+    _compare_solves(pgo, oracle, graphs["sphere"], 0, loss_type=0, jacobi_scaling=0)
+
+
+def test_solve_kitti00_matches_oracle(pgo, oracle, graphs):
+    """configs[1]: KITTI-00, 4541 poses / 5179 edges, reference settings (Huber(1.0), 1000 iterations)."""
+    s, its = _compare_solves(pgo, oracle, graphs["kitti00"], 2)
+    assert s.termination_type == 0
+
+
+def test_e2e_host_buffers(pgo, oracle, graphs):
+    """pgo_solve_pose_graph: host buffers in, optimised poses out."""
+    g = graphs["manhattan"]
+    poses, s, its = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
+    ref, rs, _ = oracle.solve(g)
+    assert np.abs(poses[:, :3] - ref[:, :3]).max() <= 1e-4
+    assert abs(s.final_cost - rs.final_cost) <= 1e-7 * max(1.0, rs.final_cost)
+
+
+def test_empty_and_degenerate_inputs(pgo):
+    D = pgo.datasets
+    g = D.manhattan_loop(10, 12)
+    # no edges: solve terminates immediately (gradient tolerance), poses untouched
+    G = pgo.Graph(g.poses, np.zeros((0, 2), np.int32), np.zeros((0, 7)), None, g.pose_const)
+    s, its = G.solve()
+    assert s.termination_type == 0 and np.array_equal(G.get_poses(), g.poses)
+    G.close()
+    with pytest.raises(pgo.PgoError):
+        pgo.Graph(g.poses, np.array([[0, 0]], np.int32), g.edge_meas[:1])      # self loop
+    with pytest.raises(pgo.PgoError):
+        pgo.Graph(g.poses, np.array([[0, 99]], np.int32), g.edge_meas[:1])     # out of range
+    # ragged: edge count not a multiple of the 32-edge tile, all poses constant
+    const = np.ones(g.n_poses, np.uint8)
+    G = pgo.Graph(g.poses, g.edge_ids[:7], g.edge_meas[:7], g.edge_sqrt_info[:7], const)
+    s, its = G.solve()
+    assert s.termination_type == 0 and np.array_equal(G.get_poses(), g.poses)
+    G.close()
