@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""bench.py -- LM iterations/s on the KITTI-00 pose graph (BASELINE.json configs[1]).
+
+A step = one complete Levenberg-Marquardt solve of the KITTI-00 graph (4541 poses, 4540 odometry +
+639 loop edges) from the reference's initial trajectory with the reference's settings
+(HuberLoss(1.0), EigenQuaternionParameterization, first pose constant, max 1000 iterations).
+
+  value      LM iterations / s, inputs resident in HBM (poses restored from a device snapshot)
+  e2e        same metric through pgo_solve_pose_graph: HOST buffers in, structure analysis,
+             H2D upload, solve, D2H of the poses, all inside the timed region
+  roofline   dominant kernel of the step vs the measured HBM copy bandwidth
+  kernels    HBM roofline of the two hot kernels (linearize, block-SpMV) on the 1M-pose grid
+  cpu_baseline / --impl reference: the CPU oracle (a port of the reference's Ceres path) on the host
+
+N > 1 (torchrun): every rank solves its own KITTI-00 replica (independent objects, no data-path
+collective) -> weak scaling; `--shard-edges` instead shards the edges of one large grid graph
+across ranks with NCCL all-reduces of J^T r and of every PCG SpMV product.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def lm_iterations(summary):
+    return summary.num_iterations - 1   # rows of the log minus iteration 0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path (oracle port, 1 thread as Ceres' default
+    num_threads) on the same workload; each step = one full KITTI-00 solve."""
+    if rank != 0:
+        return
+    import oracle_py as O
+    import posegraph_ceres_b200.datasets as D  # host-only module
+    O.build()
+    g = D.kitti00()
+    for _ in range(max(args.warmup, 0)):
+        O.solve(g)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(args.steps):
+        _, s, _ = O.solve(g)
+        iters += s.num_iterations - 1
+    dt = time.perf_counter() - t0
+    v = iters / dt
+    line = {"impl": "reference", "metric": "lm_iterations_per_sec_kitti00", "value": v, "unit": "LM iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (fixture from the reference's own "
+                                   "trajectory_origin/edges_for_loop files; loop measurements synthesised), "
+                                   "Huber(1.0), LM to Ceres' default tolerances"},
+            "cpu_baseline": {"value": v, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+                             "sample": f"{args.steps} full KITTI-00 solves with oracle/pgo_oracle.c"},
+            "e2e": {"value": v, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shard-edges", action="store_true", help="N>1: shard one large grid graph's edges over NCCL")
+    ap.add_argument("--no-large", action="store_true", help="skip the 1M-pose kernel roofline section")
+    ap.add_argument("--grid", type=int, default=1000, help="side of the large Manhattan grid (poses = side^2)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import posegraph_ceres_b200 as P
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_kind = load_peaks()
+    args.warmup = max(args.warmup, 3)
+
+    g = P.datasets.kitti00()
+    G = P.Graph.from_dataset(g, device=local_rank)
+    stream = torch.cuda.current_stream()
+    G.set_stream(stream.cuda_stream)
+    G.snapshot_poses()
+    opts = P.default_options()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident steps ----------------
+    for _ in range(args.warmup):
+        G.restore_poses()
+        G.solve(opts)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    total_ms = 0.0
+    iters = launches = lin = 0
+    lin_ms = solver_ms = 0.0
+    last = None
+    for _ in range(args.steps):
+        G.restore_poses()
+        flush.fill_(1)                       # L2 flush between timed iterations (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        s, _ = G.solve(opts)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        iters += lm_iterations(s)
+        launches += s.kernel_launches
+        lin += s.num_linearizations
+        lin_ms += s.time_linearize_ms
+        solver_ms += s.time_linear_solver_ms
+        last = s
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(iters), float(lin * g.n_edges), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    max_ms = float(t.item())
+    value = float(cnt[0].item()) / (max_ms * 1e-3)
+    edge_jac_per_s = float(cnt[1].item()) / (max_ms * 1e-3)
+
+    # ---------------- end to end through the C-ABI with host buffers ----------------
+    poses_h = np.ascontiguousarray(g.poses)
+    h2d = poses_h.nbytes + g.edge_ids.nbytes + g.edge_meas.nbytes + g.edge_sqrt_info.nbytes + g.pose_const.nbytes
+    d2h = poses_h.nbytes
+    for _ in range(2):
+        P.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, opts, device=local_rank)
+    barrier()
+    e2e_s = 0.0
+    e2e_iters = 0
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, s2, _ = P.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, opts, device=local_rank)
+        e2e_s += time.perf_counter() - t0
+        e2e_iters += lm_iterations(s2)
+    barrier()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ce = torch.tensor([float(e2e_iters)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    e2e_value = float(ce.item()) / float(te.item())
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # ---------------- roofline of the dominant kernel of the step ----------------
+    # KITTI-00 is launch/latency bound: the persistent linear-solver kernel dominates. Its algorithmic
+    # bytes per launch: scatter of H (read H, write F), factor (read+write F), per PCG iteration one SpMV
+    # (read H) and one forward+backward sweep (read F twice); 288 B per 6x6 fp64 block.
+    n_solves = max(1, iters)
+    pcg_per_solve = last.total_pcg_iterations / max(1, lm_iterations(last))
+    Hb, Fb = last.hessian_blocks, max(last.factor_blocks, 0)
+    if last.linear_solver_used == P.LINEAR_PCG_LEVEL_CHOLESKY:
+        bytes_per_launch = 288.0 * (Hb + 3 * Fb + (pcg_per_solve + 1) * (Hb + 2 * Fb))
+        kname = "level_chol_pcg_kernel"
+    else:
+        bytes_per_launch = 288.0 * Hb * (pcg_per_solve + 1)
+        kname = "pcg_kernel"
+    k_ms = solver_ms / n_solves
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                "ms_per_launch": k_ms, "share_of_step": solver_ms / max(total_ms, 1e-9),
+                "note": "4541-pose graph: latency/barrier bound, working set (4 MB) lives in L2"}
+
+    line = None
+    if rank == 0:
+        import oracle_py as O
+        O.build()
+        # CPU baseline: the oracle port on this host, bounded sample
+        t0 = time.perf_counter()
+        c_iters = 0
+        n_cpu = 0
+        while time.perf_counter() - t0 < 10.0 and n_cpu < 50:
+            _, cs, _ = O.solve(g)
+            c_iters += cs.num_iterations - 1
+            n_cpu += 1
+        c_dt = time.perf_counter() - t0
+        cpu = {"value": c_iters / c_dt, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} full KITTI-00 solves (oracle/pgo_oracle.c, sparse block Cholesky, 1 thread like Ceres' default)",
+               "ms_per_solve": 1e3 * c_dt / n_cpu}
+        line = {"metric": "lm_iterations_per_sec_kitti00", "value": value, "unit": "LM iterations/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (fixture from the reference's own "
+                                       "trajectory_origin/edges_for_loop files; loop measurements synthesised), "
+                                       "Huber(1.0), LM to Ceres' default tolerances, one full solve per step",
+                           "lm_iterations_per_solve": lm_iterations(last), "linear_solver": kname,
+                           "pcg_iterations_per_solve": int(last.total_pcg_iterations),
+                           "l2": "flushed (256 MB write) between timed steps",
+                           "multi_gpu": "one KITTI-00 replica per rank, no collective" if world > 1 else "n/a"},
+                "edge_jacobians_per_sec": edge_jac_per_s,
+                "e2e": {"value": e2e_value, "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+                        "includes": "structure analysis, cudaMalloc, H2D, solve, D2H"},
+                "gpu_launches": int(cnt[2].item()),
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "time_split_ms_per_step": {"linearize": lin_ms / args.steps, "linear_solver": solver_ms / args.steps}}
+    G.close()
+    del flush
+
+    # ---------------- the two hot kernels on the 1M-pose / 2M-edge grid (HBM roofline) ----------------
+    if not args.no_large and (world == 1 or args.shard_edges):
+        try:
+            big = P.datasets.manhattan_grid(args.grid, args.grid, 50 * args.grid)
+            if world > 1:
+                big = P.datasets.shard_edges(big, rank, world)
+            GB = P.Graph.from_dataset(big, device=local_rank)
+            if world > 1:
+                uid = [P.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                GB.init_comm(uid[0], rank, world)
+            E, N = big.n_edges, big.n_poses
+            lin_best = min(GB.linearize()[1] for _ in range(5))
+            rp_blocks = GB.solve  # noqa: F841 (keep handle alive)
+            x = np.random.default_rng(0).normal(size=(N, 6))
+            reps = 20
+            _, sp_ms = GB.spmv(x, None, reps)
+            _, sp_ms = GB.spmv(x, None, reps)
+            nnzb = GB.hessian_blocks()
+            # algorithmic bytes: per edge = ids 8 + meas 56 + sqrt_info 288 + slots 8 + 2 poses 128 + 2 scales 96
+            #   + diag RED 2*288 + off-diag stores 2*288 + gradient RED 96 ; SpMV = 288/block + x,y vectors + indices
+            lin_bytes = E * (8 + 56 + 288 + 8 + 128 + 96 + 576 + 576 + 96)
+            sp_bytes = nnzb * 288 + N * (48 * 2) + (nnzb - N) * 4 + (N + 1) * 4
+            kern = {"graph": f"{N} poses / {E} edges per rank", "linearize_ms": lin_best,
+                    "linearize_GBps": lin_bytes / (lin_best * 1e-3) / 1e9, "linearize_frac": lin_bytes / (lin_best * 1e-3) / 1e9 / hbm_peak,
+                    "edge_jacobians_per_sec": E / (lin_best * 1e-3),
+                    "spmv_ms": sp_ms / reps, "spmv_GBps": sp_bytes / (sp_ms / reps * 1e-3) / 1e9,
+                    "spmv_frac": sp_bytes / (sp_ms / reps * 1e-3) / 1e9 / hbm_peak, "peak": hbm_peak, "peak_source": peak_kind}
+            if line is not None:
+                line["kernels_large_graph"] = kern
+            GB.close()
+        except Exception as ex:  # the headline line must still be printed
+            if line is not None:
+                line["kernels_large_graph"] = {"error": str(ex)[:200]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,10 @@ int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, cons
                      const unsigned char* pose_const);
 void pgo_graph_destroy(pgo_graph* g);
 
+/* Run all subsequent work of this graph on the caller's CUDA stream (a cudaStream_t passed as
+ * void*, e.g. torch.cuda.current_stream().cuda_stream); NULL restores the graph's own stream. */
+int pgo_graph_set_stream(pgo_graph* g, void* cuda_stream);
+
 int pgo_graph_num_poses(const pgo_graph* g);
 int pgo_graph_num_edges(const pgo_graph* g);
 int pgo_graph_set_poses(pgo_graph* g, const double* poses);   /* host -> device */

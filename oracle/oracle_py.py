@@ -65,6 +65,10 @@ def _p(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
+def set_num_threads(n: int):
+    lib().oracle_set_num_threads(C.c_int(n))
+
+
 def default_options() -> Options:
     o = Options()
     lib().oracle_default_options(C.byref(o))

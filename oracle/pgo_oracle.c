@@ -263,6 +263,12 @@ static double edge_evaluate(const double* pa, const double* pb, const double* me
 }
 
 /* ceres::Problem::Evaluate / ProgramEvaluator::Evaluate over all residual blocks. */
+static int g_oracle_threads = 1;
+/* Threads for the per-edge evaluation loop (Ceres' Solver::Options::num_threads; the reference
+ * leaves it at its default of 1). The sparse Cholesky stays serial, as in Ceres. */
+void oracle_set_num_threads(int n) { g_oracle_threads = n > 0 ? n : 1; }
+int oracle_get_num_threads(void) { return g_oracle_threads; }
+
 int oracle_evaluate(int n_poses, const double* poses, const unsigned char* pose_const,
                     int n_edges, const int* edge_ids, const double* edge_meas,
                     const double* edge_sqrt_info, int loss_type, double loss_a,
@@ -270,20 +276,33 @@ int oracle_evaluate(int n_poses, const double* poses, const unsigned char* pose_
   double total = 0.0;
   int e, r, c;
   const int need_j = (gradient != NULL) || (jac != NULL);
+  double* jbuf = jac;
+  double* rbuf = residuals;
   if (gradient) memset(gradient, 0, sizeof(double) * 6 * (size_t)n_poses);
   for (e = 0; e < n_edges; ++e) {
     const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-    double res[6], Ja[36], Jb[36];
     if (a < 0 || a >= n_poses || b < 0 || b >= n_poses) return -1;
+  }
+  if (need_j && !jbuf) jbuf = (double*)malloc(sizeof(double) * 72 * (size_t)(n_edges + 1));
+  if (gradient && !rbuf) rbuf = (double*)malloc(sizeof(double) * 6 * (size_t)(n_edges + 1));
+#pragma omp parallel for schedule(static) reduction(+ : total) num_threads(g_oracle_threads) if (g_oracle_threads > 1)
+  for (e = 0; e < n_edges; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    double res[6];
+    double* Ja = need_j ? jbuf + 72 * (size_t)e : NULL;
+    double* Jb = need_j ? Ja + 36 : NULL;
     total += edge_evaluate(poses + 7 * a, poses + 7 * b, edge_meas + 7 * e, edge_sqrt_info + 36 * e,
-                           loss_type, loss_a, res, need_j ? Ja : NULL, need_j ? Jb : NULL);
+                           loss_type, loss_a, res, Ja, Jb);
     if (need_j) {
-      if (pose_const && pose_const[a]) memset(Ja, 0, sizeof Ja);
-      if (pose_const && pose_const[b]) memset(Jb, 0, sizeof Jb);
+      if (pose_const && pose_const[a]) memset(Ja, 0, 36 * sizeof(double));
+      if (pose_const && pose_const[b]) memset(Jb, 0, 36 * sizeof(double));
     }
-    if (residuals) memcpy(residuals + 6 * e, res, sizeof res);
-    if (jac) { memcpy(jac + 72 * (size_t)e, Ja, sizeof Ja); memcpy(jac + 72 * (size_t)e + 36, Jb, sizeof Jb); }
-    if (gradient) {
+    if (rbuf) memcpy(rbuf + 6 * (size_t)e, res, sizeof res);
+  }
+  if (gradient) {
+    for (e = 0; e < n_edges; ++e) {
+      const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+      const double* Ja = jbuf + 72 * (size_t)e; const double* Jb = Ja + 36; const double* res = rbuf + 6 * (size_t)e;
       for (c = 0; c < 6; ++c) {
         double ga = 0.0, gb = 0.0;
         for (r = 0; r < 6; ++r) { ga += Ja[r * 6 + c] * res[r]; gb += Jb[r * 6 + c] * res[r]; }
@@ -291,6 +310,8 @@ int oracle_evaluate(int n_poses, const double* poses, const unsigned char* pose_
       }
     }
   }
+  if (jbuf != jac) free(jbuf);
+  if (rbuf != residuals) free(rbuf);
   if (cost) *cost = total;
   return 0;
 }

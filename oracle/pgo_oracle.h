@@ -92,6 +92,10 @@ typedef struct {
 
 void oracle_default_options(oracle_options* o);
 
+/* threads of the per-edge evaluation loop (default 1 = Ceres' default num_threads) */
+void oracle_set_num_threads(int n);
+int oracle_get_num_threads(void);
+
 /* Problem::Evaluate: cost, robustified residuals [6E], gradient [6N] (local/tangent coordinates,
  * zero for constant poses) and the per-edge local Jacobian blocks jac[E][2][36] (row-major 6x6,
  * block 0 w.r.t. pose a, block 1 w.r.t. pose b; zero for constant poses). Any output may be NULL. */

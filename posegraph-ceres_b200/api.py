@@ -22,7 +22,7 @@ CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "pgo_last_error", "pgo_abi_version", "pgo_device_count", "pgo_default_options", "pgo_graph_create",
-    "pgo_graph_destroy", "pgo_graph_num_poses", "pgo_graph_num_edges", "pgo_graph_set_poses",
+    "pgo_graph_destroy", "pgo_graph_set_stream", "pgo_graph_num_poses", "pgo_graph_num_edges", "pgo_graph_set_poses",
     "pgo_graph_get_poses", "pgo_graph_snapshot_poses", "pgo_graph_restore_poses", "pgo_nccl_unique_id",
     "pgo_graph_init_comm", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
@@ -150,6 +150,9 @@ class Graph:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream: int | None):
+        _check(lib().pgo_graph_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
     def set_poses(self, poses):
         _check(lib().pgo_graph_set_poses(self._h, _dp(np.ascontiguousarray(poses, np.float64))))
 
@@ -195,6 +198,11 @@ class Graph:
         _check(lib().pgo_graph_get_hessian(self._h, C.byref(nnzb), rp.ctypes.data_as(C.POINTER(C.c_int)),
                                            ci.ctypes.data_as(C.POINTER(C.c_int)), _dp(vals), _dp(grad)))
         return rp, ci, vals.reshape(-1, 6, 6), grad
+
+    def hessian_blocks(self) -> int:
+        nnzb = C.c_longlong()
+        _check(lib().pgo_graph_get_hessian(self._h, C.byref(nnzb), None, None, None, None))
+        return int(nnzb.value)
 
     def spmv(self, x, d=None, repeats: int = 1):
         x = np.ascontiguousarray(x, np.float64)

@@ -58,6 +58,7 @@ static double wall_s() {
 struct pgo_graph {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   int N = 0, E = 0, T = 0;
   bool identity_info = true;
   bool has_dup_blocks = false;
@@ -140,7 +141,7 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->scalars_h) cudaFreeHost(g->scalars_h);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
-  if (g->stream) cudaStreamDestroy(g->stream);
+  if (g->own_stream) cudaStreamDestroy(g->own_stream);
   delete g;
 }
 
@@ -169,7 +170,8 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   auto fail = [&](int rc) { pgo_graph_destroy(g); return rc; };
 #define G_TRY(expr) do { int _rc = (expr); if (_rc != PGO_OK) return fail(_rc); } while (0)
 #define GC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(set_error(PGO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); } while (0)
-  GC_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  GC_TRY(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
+  g->stream = g->own_stream;
   GC_TRY(cudaEventCreate(&g->ev0));
   GC_TRY(cudaEventCreate(&g->ev1));
   cudaDeviceProp prop;
@@ -292,6 +294,14 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   return PGO_OK;
 #undef G_TRY
 #undef GC_TRY
+}
+
+extern "C" int pgo_graph_set_stream(pgo_graph* g, void* cuda_stream) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  g->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g->own_stream;
+  return PGO_OK;
 }
 
 extern "C" int pgo_graph_num_poses(const pgo_graph* g) { return g ? g->N : 0; }
@@ -587,9 +597,9 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
 static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b) {
   if (g->world > 1) return pcg_multi(g, o, b);
   if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
-    PGO_TRY(level_chol_factor(g->chol, bsr_view(g), g->dlm, g->stream, &g->launches));
-    return level_chol_pcg(g->chol, bsr_view(g), g->dlm, b, g->vx, g->vr, g->vu, g->vw, g->vp, o->pcg_max_iterations,
-                          o->pcg_tolerance, g->scalars, g->stream, &g->launches);
+    return level_chol_solve(g->chol, bsr_view(g), g->dlm, b, g->vx, g->vr, g->vu, g->vw, g->vp,
+                            std::min(o->pcg_max_iterations, 200), o->pcg_tolerance, o->pcg_num_ctas, g->scalars,
+                            g->stream, &g->launches);
   }
   return launch_pcg(g, o, b);
 }

@@ -386,15 +386,24 @@ __device__ __forceinline__ double cta_sum(double v, double* red) {
   return t;
 }
 
-// every thread sums the per-CTA partials in the same fixed order -> bitwise identical everywhere
-__device__ __forceinline__ double sum_partials(const double* part, int n) {
-  double t = 0.0;
-  for (int k = 0; k < n; ++k) t += __ldcg(part + k);
-  return t;
+__device__ __forceinline__ double reduce_partials(const double* part, int n, double* bcast) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    double t = 0.0;
+    for (int k = lane; k < n; k += 32) t += __ldcg(part + k);
+    t = warp_sum(t);
+    if (lane == 0) *bcast = t;
+  }
+  __syncthreads();
+  const double v = *bcast;
+  __syncthreads();
+  return v;
 }
+
 
 __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   __shared__ double red[kPcgThreads / 32];
+  __shared__ double bcast;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / 6, r = lane - grp * 6;
   const bool lane_on = grp < kRowsPerWarp;
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   acc = cta_sum(acc, red);
   if (threadIdx.x == 0) P.partials[0 * 3 * G + 0 * G + blockIdx.x] = acc;
   grid_barrier(P.barrier, epoch);
-  const double gamma0 = sum_partials(P.partials + 0, G);
+  const double gamma0 = reduce_partials(P.partials + 0, G, &bcast);
   double gamma = gamma0, gamma_old = 0.0, alpha = 0.0, beta = 0.0;
   int iter = 0;
   int flag = 0;
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
       acc = cta_sum(acc, red);
       if (threadIdx.x == 0) part[1 * G + blockIdx.x] = acc;
       grid_barrier(P.barrier, epoch);
-      const double delta = sum_partials(part + 1 * G, G);
+      const double delta = reduce_partials(part + 1 * G, G, &bcast);
       // ---- scalars (identical on every thread) ----
       if (iter == 0) { beta = 0.0; alpha = gamma / delta; }
       else { beta = gamma / gamma_old; alpha = gamma / (delta - beta * gamma / alpha); }
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
       if (threadIdx.x == 0) partn[0 * G + blockIdx.x] = acc;
       grid_barrier(P.barrier, epoch);
       gamma_old = gamma;
-      gamma = sum_partials(partn + 0 * G, G);
+      gamma = reduce_partials(partn + 0 * G, G, &bcast);
       if (gamma <= stop) { flag = 0; break; }
       if (iter >= P.max_iterations) { flag = 1; break; }
     }
@@ -503,10 +512,13 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   double* parte = P.partials + (size_t)((iter + 1) & 1) * 3 * G;
   if (threadIdx.x == 0) { parte[0 * G + blockIdx.x] = a0; parte[1 * G + blockIdx.x] = a1; parte[2 * G + blockIdx.x] = a2; }
   grid_barrier(P.barrier, epoch);
+  const double e0 = reduce_partials(parte + 0 * G, G, &bcast);
+  const double e1 = reduce_partials(parte + 1 * G, G, &bcast);
+  const double e2 = reduce_partials(parte + 2 * G, G, &bcast);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    P.scalars->xtb = sum_partials(parte + 0 * G, G);
-    P.scalars->xtAx = sum_partials(parte + 1 * G, G);
-    P.scalars->xtDx = sum_partials(parte + 2 * G, G);
+    P.scalars->xtb = e0;
+    P.scalars->xtAx = e1;
+    P.scalars->xtDx = e2;
     P.scalars->pcg_gamma0 = gamma0;
     P.scalars->pcg_gamma = gamma;
     P.scalars->pcg_iterations = iter;

@@ -1,0 +1,239 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's golden files and independent numerics,
+host-side logic, and the C-ABI library (load + exported symbols; no compute without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import hessian_from_jac
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def D():
+    import posegraph_ceres_b200.datasets as d
+    return d
+
+
+@pytest.fixture(scope="module")
+def fixture():
+    return np.load(os.path.join(ROOT, "tests", "golden", "kitti00_fixture.npz"))
+
+
+# ------------------------------------------------------------------ golden files of the reference
+def test_fixture_matches_reference_files(fixture):
+    """shapes / topology facts of the reference's own result files (see make_kitti00_fixture.py)."""
+    assert fixture["poses_before"].shape == (4541, 7) and fixture["poses_after"].shape == (4541, 7)
+    loops = fixture["loop_edges"]
+    assert loops.shape == (639, 2)
+    assert (loops[:, 0] - loops[:, 1] > 100).all()          # only pairs > 100 frames apart are logged (:250)
+    cur, ptr, idx = fixture["cand_cur"], fixture["cand_ptr"], fixture["cand_idx"]
+    assert (cur == np.arange(1, 4541)).all()
+    cand = {int(c): set(idx[ptr[k]:ptr[k + 1]].tolist()) for k, c in enumerate(cur)}
+    assert all(int(b) in cand[int(a)] for a, b in loops)      # every accepted loop edge was a candidate
+    assert all((c - 1) in cand[c] for c in cand)              # the odometry neighbour is always a candidate
+
+
+def test_kitti00_graph_is_built_like_the_reference(D, oracle):
+    g = D.kitti00()
+    assert g.n_poses == 4541 and g.n_edges == 4540 + 639 and g.pose_const[0] == 1 and g.pose_const.sum() == 1
+    odo = (g.edge_ids[:, 0] - g.edge_ids[:, 1]) == 1
+    assert odo.sum() == 4540
+    # odometry measurements are Tcw_i * Twc_{i-1} of the initial poses => zero cost before loops are added
+    go = D.PoseGraph("odo", g.poses, g.edge_ids[odo], g.edge_meas[odo], g.edge_sqrt_info[odo], g.pose_const)
+    cost, res, _, _ = oracle.evaluate(go)
+    assert cost <= 1e-20 and np.abs(res).max() <= 1e-10
+    # reversing the edge direction convention (begin <-> end) is NOT consistent with the data
+    gr = D.PoseGraph("rev", g.poses, go.edge_ids[:, ::-1].copy(), go.edge_meas, go.edge_sqrt_info, g.pose_const)
+    assert oracle.evaluate(gr)[0] > 1000.0
+
+
+def test_reference_ceres_output_is_stationary_for_the_oracle(D, oracle, fixture):
+    """Partial pin against a REAL Ceres run: at the reference's optimised trajectory the oracle's
+    gradient must vanish on every pose that carries no loop edge (their cost terms -- two odometry
+    edges -- are fully known), up to the 6-significant-digit rounding of the text files.  On poses
+    with loop edges the (unknown) loop terms are missing, so the same gradient is much larger."""
+    g = D.kitti00()
+    after, loops = fixture["poses_after"], fixture["loop_edges"]
+    odo = (g.edge_ids[:, 0] - g.edge_ids[:, 1]) == 1
+    go = D.PoseGraph("odo", g.poses, g.edge_ids[odo], g.edge_meas[odo], g.edge_sqrt_info[odo], g.pose_const)
+    _, _, grad, _ = oracle.evaluate(go, poses=after)
+    gn = np.linalg.norm(grad, axis=1)
+    has_loop = np.zeros(g.n_poses, bool)
+    has_loop[loops.ravel()] = True
+    free = ~has_loop
+    free[0] = False
+    assert gn[free].max() <= 5e-3                       # file precision: positions ~1e-3 m at |p| ~ 100 m
+    assert np.median(gn[has_loop]) >= 20 * np.median(gn[free])
+
+
+def test_oracle_solve_moves_towards_reference_output(D, oracle, fixture):
+    g = D.kitti00()
+    poses, s, its = oracle.solve(g)
+    assert s.termination_type == 0 and s.final_cost < 0.05 * s.initial_cost
+    err_after = np.linalg.norm(poses[:, :3] - fixture["poses_after"][:, :3], axis=1)
+    err_before = np.linalg.norm(g.poses[:, :3] - fixture["poses_after"][:, :3], axis=1)
+    assert err_after.mean() < 0.35 * err_before.mean()
+    costs = [it.cost for it in its if it.step_is_successful]
+    assert all(b <= a for a, b in zip(costs, costs[1:]))
+
+
+# ------------------------------------------------------------------ known answers / independent numerics
+def test_residual_known_answers(D, oracle):
+    I = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    half = np.sqrt(0.5)
+    pa = np.array([1.0, 2.0, 3.0, 0, 0, half, half])          # yaw +90 deg
+    pb = np.array([1.0, 4.0, 3.0, 0, 0, 1.0, 0.0])            # yaw 180 deg
+    # b seen from a: translation R_a^T (0,2,0) = (2,0,0), rotation +90 deg about z
+    meas = np.array([2.0, 0, 0, 0, 0, half, half])
+    g = D.PoseGraph("t", np.stack([pa, pb]), np.array([[0, 1]], np.int32), meas[None], np.eye(6).reshape(1, 36), np.zeros(2, np.uint8))
+    cost, res, _, _ = oracle.evaluate(g, loss_type=0)
+    assert np.abs(res).max() < 1e-15 and cost < 1e-30
+    # 1 m translation error along a's x axis and a 0.2 rad rotation error about z
+    meas2 = np.array([1.0, 0, 0, 0, 0, np.sin(np.pi / 4 + 0.1), np.cos(np.pi / 4 + 0.1)])
+    g2 = D.PoseGraph("t", np.stack([pa, pb]), g.edge_ids, meas2[None], g.edge_sqrt_info, g.pose_const)
+    cost2, res2, _, _ = oracle.evaluate(g2, loss_type=0)
+    assert np.allclose(res2[0, :3], [1.0, 0, 0], atol=1e-15)
+    assert np.allclose(res2[0, 3:], [0, 0, 2 * np.sin(0.1)], atol=1e-15)      # 2 * vec(delta_q)
+    assert abs(cost2 - 0.5 * (1 + 4 * np.sin(0.1) ** 2)) < 1e-15
+    # Huber(1): rho(s) = 2 sqrt(s) - 1 for s > 1
+    s = 1 + 4 * np.sin(0.1) ** 2
+    assert abs(oracle.evaluate(g2, loss_type=1, loss_a=1.0)[0] - 0.5 * (2 * np.sqrt(s) - 1)) < 1e-15
+    # sqrt_information scales the residual
+    g3 = D.PoseGraph("t", g2.poses, g.edge_ids, meas2[None], (np.diag([2.0, 1, 1, 1, 1, 3])).reshape(1, 36), g.pose_const)
+    assert np.allclose(oracle.evaluate(g3, loss_type=0)[1][0], [2.0, 0, 0, 0, 0, 6 * np.sin(0.1)], atol=1e-15)
+    del I
+
+
+@pytest.mark.parametrize("loss", [0, 1, 2])
+def test_jacobians_match_central_differences(D, oracle, loss):
+    """jets (autodiff) + local parameterization + corrector vs finite differences through Plus."""
+    g = D.sphere(4, 8, None, init_sigma_t=0.8, init_sigma_r=0.3)
+    g.poses[:, 3:] *= (1 + 1e-3 * np.random.default_rng(0).normal(size=(g.n_poses, 1)))   # slightly non-unit q
+    cost, res, grad, jac = oracle.evaluate(g, loss_type=loss, loss_a=0.7)
+    h = 1e-6
+    rng = np.random.default_rng(1)
+    for e in rng.choice(g.n_edges, 6, replace=False):
+        for blk in (0, 1):
+            node = g.edge_ids[e, blk]
+            if g.pose_const[node]:
+                continue
+            for k in range(6):
+                d = np.zeros((g.n_poses, 6))
+                d[node, k] = h
+                rp = oracle.evaluate(g, poses=oracle.plus(g.poses, d), loss_type=0)[1][e]
+                rm = oracle.evaluate(g, poses=oracle.plus(g.poses, -d), loss_type=0)[1][e]
+                fd = (rp - rm) / (2 * h)
+                # un-robustified Jacobian column from the corrected one: for these losses J_c = sqrt(rho') J
+                r0 = oracle.evaluate(g, loss_type=0)[1][e]
+                s = r0 @ r0
+                if loss == 0:
+                    rho1 = 1.0
+                elif loss == 1:
+                    rho1 = 1.0 if s <= 0.49 else 0.7 / np.sqrt(s)
+                else:
+                    rho1 = 1.0 / (1.0 + s / 0.49)
+                col = jac[e, blk].reshape(6, 6)[:, k] / np.sqrt(rho1)
+                assert np.abs(col - fd).max() <= 2e-7 * max(1.0, np.abs(fd).max())
+    # the gradient is the derivative of the robustified cost
+    for node in rng.choice(np.arange(1, g.n_poses), 4, replace=False):
+        for k in range(6):
+            d = np.zeros((g.n_poses, 6))
+            d[node, k] = h
+            cp = oracle.evaluate(g, poses=oracle.plus(g.poses, d), loss_type=loss, loss_a=0.7)[0]
+            cm = oracle.evaluate(g, poses=oracle.plus(g.poses, -d), loss_type=loss, loss_a=0.7)[0]
+            assert abs((cp - cm) / (2 * h) - grad[node, k]) <= 1e-5 * max(1.0, abs(grad[node, k]))
+
+
+def test_normal_solve_matches_scipy(D, oracle):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    g = D.sphere(6, 10, None)
+    _, _, grad, jac = oracle.evaluate(g)
+    blocks = hessian_from_jac(g, jac)
+    n = g.n_poses
+    rows, cols, vals = [], [], []
+    for (i, j), b in blocks.items():
+        for r in range(6):
+            for c in range(6):
+                rows.append(6 * i + r); cols.append(6 * j + c); vals.append(b[r, c])
+    d = np.random.default_rng(3).uniform(0.01, 0.1, 6 * n)
+    H = sp.coo_matrix((vals, (rows, cols)), shape=(6 * n, 6 * n)).tocsc() + sp.diags(d)
+    free = np.repeat(~g.pose_const.astype(bool), 6)
+    ref = np.zeros(6 * n)
+    ref[free] = spl.spsolve(H[free][:, free], grad.ravel()[free])
+    for ordering in (0, 1):
+        rc, y = oracle.normal_solve(g, jac, d, grad.ravel(), ordering)
+        assert rc == 0 and np.abs(y.ravel() - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_lm_bookkeeping_and_orderings(D, oracle):
+    g = D.manhattan_loop()
+    o = oracle.default_options()
+    p1, s1, its1 = oracle.solve(g, o)
+    o.ordering = 0
+    p0, s0, its0 = oracle.solve(g, o)
+    assert s1.num_iterations == s0.num_iterations and np.abs(p1 - p0).max() < 1e-9
+    assert s1.num_successful_steps + s1.num_unsuccessful_steps <= s1.num_iterations
+    assert its1[0].iteration == 0 and its1[0].trust_region_radius == 1e4
+    for a, b in zip(its1, its1[1:]):
+        if b.step_is_successful:
+            assert b.cost < a.cost
+    # the first pose is constant
+    assert np.array_equal(p1[0], g.poses[0])
+    # threads do not change the result beyond rounding
+    oracle.set_num_threads(4)
+    p4, _, _ = oracle.solve(g)
+    oracle.set_num_threads(1)
+    assert np.abs(p4 - p1).max() < 1e-9
+
+
+# ------------------------------------------------------------------ datasets (BASELINE.json configs)
+def test_dataset_shapes(D):
+    m = D.manhattan_loop()
+    assert (m.n_poses, m.n_edges) == (100, 120)
+    s = D.sphere()
+    assert (s.n_poses, s.n_edges) == (2500, 9799)
+    gr = D.manhattan_grid(20, 30, 40)
+    assert gr.n_poses == 600 and gr.n_edges >= 599 + 19 * 30 - 19 and (gr.edge_ids[:, 0] != gr.edge_ids[:, 1]).all()
+    t = D.torus(2000, winds=20)
+    assert t.n_poses == 2000 and t.n_edges > 2000 * 2
+    for g in (m, s, gr, t):
+        assert np.allclose(np.linalg.norm(g.edge_meas[:, 3:], axis=1), 1.0, atol=1e-12)
+        assert g.edge_ids.min() >= 0 and g.edge_ids.max() < g.n_poses
+    shards = [D.shard_edges(gr, r, 3) for r in range(3)]
+    assert sum(x.n_edges for x in shards) == gr.n_edges
+    assert np.array_equal(np.concatenate([x.edge_ids for x in shards]), gr.edge_ids)
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def test_cabi_exports_every_declared_symbol(pgo):
+    hdr = open(os.path.join(ROOT, "include", "pgo_b200.h")).read()
+    declared = set(re.findall(r"\b(pgo_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"pgo_status"}
+    lib = pgo.lib()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(pgo.EXPORTED_SYMBOLS) == declared
+    assert lib.pgo_abi_version() == 1
+
+
+def test_cabi_defaults_mirror_ceres_and_reference(pgo):
+    o = pgo.default_options()
+    assert o.max_num_iterations == 1000            # REF test/pose_graph_ceres_plus_finial.cpp:504
+    assert (o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (1e-6, 1e-10, 1e-8)
+    assert (o.initial_trust_region_radius, o.min_relative_decrease) == (1e4, 1e-3)
+    assert o.loss_type == pgo.LOSS_HUBER and o.loss_a == 1.0 and o.jacobi_scaling == 1
+
+
+def test_no_cpu_fallback(pgo):
+    """Without a GPU every compute entry point must fail loudly (never route through the oracle)."""
+    if pgo.device_count() > 0:
+        pytest.skip("GPU present")
+    g = pgo.datasets.manhattan_loop()
+    with pytest.raises(pgo.PgoError, match="no CUDA device"):
+        pgo.Graph.from_dataset(g)
+    with pytest.raises(pgo.PgoError, match="no CUDA device"):
+        pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
