@@ -12,6 +12,19 @@ Sources (all under /root/reference/src/POSE_GRAPH_CERES_PLUS):
   config/Edge_Candidates_index.txt                     candidate topology read by
         getEdegsCandidateIndex() (include/ReadEdges.h:9-48)
 
+Quaternion columns.  The files are used AS PRINTED: columns 5-8 are what OutputPoses() streams
+as q.x() q.y() q.z() q.w(), i.e. the values ceres::Solve saw in the Eigen coeffs() slots x,y,z,w.
+Physically those four numbers are (w, x, y, z) of the camera rotation -- row 0 reads "1 0 0 0" and
+only that reading gives a body-frame step R_i^T (p_{i+1} - p_i) = (0.00, -0.01, +0.82) m, a car
+driving along the camera's +z axis -- because the revision of the reference that produced the
+committed result files filled Eigen::Quaterniond through its coefficient-pointer constructor with a
+{w,x,y,z} array (the same slip is still visible in src/GroundTruth.cc:62-63, loadPoses1).  For
+solver parity only the numbers Ceres optimised matter, and tests/test_oracle_cpu.py::
+test_reference_ceres_output_is_stationary_for_the_oracle confirms the as-printed reading: with it
+the oracle's gradient at the reference's optimised trajectory vanishes (<= 5e-3, file rounding) on
+every pose without a loop edge, while the physically "corrected" w-first reading leaves a median
+gradient of 5.7e-2 and a maximum of 0.45 on the same poses.
+
 What is NOT in the reference tree: the PnP-estimated loop measurements (they were computed
 from KITTI images at run time, test/pose_graph_ceres_plus_finial.cpp:203-255, and never
 written out).  The fixture therefore stores topology + before/after poses only; loop
