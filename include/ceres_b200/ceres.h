@@ -28,12 +28,14 @@
 #define CERES_B200_CERES_H_
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -147,7 +149,8 @@ class PoseGraph3dCostFunction : public CostFunction {
 class PoseGraph3dErrorTerm {
  public:
   // Matrix6 is anything indexable as m(i, j) -- e.g. the Eigen::Matrix<double, 6, 6> the reference passes.
-  template <typename PoseT, typename Matrix6>
+  template <typename PoseT, typename Matrix6,
+            typename = typename std::enable_if<std::is_class<PoseT>::value && std::is_class<Matrix6>::value>::type>
   static CostFunction* Create(const PoseT& t_ab_measured, const Matrix6& sqrt_information) {
     double t[7], s[36];
     pose_to_array(t_ab_measured, t);

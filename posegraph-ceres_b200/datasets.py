@@ -276,6 +276,57 @@ def torus(n_poses: int = 100000, loop_fraction: float = 0.10, seed: int = 4, R: 
                      _sqrt_info_from_sigmas(len(ids), sigma_t, sigma_r), const, truth=truth)
 
 
+# ---------------------------------------------------------------- g2o files (VERTEX_SE3:QUAT / EDGE_SE3:QUAT)
+def write_g2o(g: PoseGraph, path: str) -> None:
+    """Write the graph as a g2o file.  g2o stores the INFORMATION matrix (upper triangle, row-major);
+    the reference turns it into sqrt_information = information.llt().matrixL() (REF/test/
+    pose_graph_ceres_plus_finial.cpp:508), so information = S S^T is written for a lower-triangular S."""
+    with open(path, "w") as f:
+        for i in range(g.n_poses):
+            f.write("VERTEX_SE3:QUAT %d %s\n" % (i, " ".join(repr(float(v)) for v in g.poses[i])))
+        for e in range(g.n_edges):
+            S = g.edge_sqrt_info[e].reshape(6, 6)
+            if np.abs(np.triu(S, 1)).max() != 0.0:
+                raise ValueError("write_g2o: sqrt_information must be lower triangular (an llt().matrixL())")
+            info = S @ S.T
+            up = [repr(float(info[r, c])) for r in range(6) for c in range(r, 6)]
+            f.write("EDGE_SE3:QUAT %d %d %s %s\n" % (g.edge_ids[e, 0], g.edge_ids[e, 1],
+                                                     " ".join(repr(float(v)) for v in g.edge_meas[e]), " ".join(up)))
+
+
+def read_g2o(path: str, name: str | None = None) -> PoseGraph:
+    """Read VERTEX_SE3:QUAT / EDGE_SE3:QUAT records; vertex ids are compacted in ascending order (the
+    reference keeps poses in a std::map<int, Pose3d>) and the first vertex is held constant."""
+    vid, vpose, eids, emeas, einfo = [], [], [], [], []
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "VERTEX_SE3:QUAT":
+                vid.append(int(t[1]))
+                vpose.append([float(x) for x in t[2:9]])
+            elif t[0] == "EDGE_SE3:QUAT":
+                eids.append((int(t[1]), int(t[2])))
+                emeas.append([float(x) for x in t[3:10]])
+                up = [float(x) for x in t[10:31]]
+                info = np.zeros((6, 6))
+                k = 0
+                for r in range(6):
+                    for c in range(r, 6):
+                        info[r, c] = info[c, r] = up[k]
+                        k += 1
+                einfo.append(np.linalg.cholesky(info).reshape(36))
+    order = np.argsort(np.asarray(vid, np.int64), kind="stable")
+    remap = {int(vid[k]): i for i, k in enumerate(order)}
+    poses = np.asarray(vpose, np.float64)[order]
+    ids = np.asarray([(remap[a], remap[b]) for a, b in eids], np.int32).reshape(-1, 2)
+    const = np.zeros(len(vid), np.uint8)
+    const[0] = 1
+    return PoseGraph(name or os.path.basename(path), poses, ids, np.asarray(emeas, np.float64).reshape(-1, 7),
+                     np.asarray(einfo, np.float64).reshape(-1, 36), const)
+
+
 def shard_edges(g: PoseGraph, rank: int, world: int) -> PoseGraph:
     """Contiguous edge shard for rank `rank` of `world` (poses are replicated)."""
     e = g.n_edges
