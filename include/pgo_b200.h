@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PGO_B200_ABI_VERSION 1
+#define PGO_B200_ABI_VERSION 2
 
 typedef enum {
   PGO_OK = 0,
@@ -123,12 +123,34 @@ typedef struct {
   int factor_levels;
 } pgo_solver_summary;
 
+/* Result of the host-side structure analysis (no GPU needed). */
+typedef struct {
+  int variable_poses;            /* poses that are used by an edge and not constant */
+  long long hessian_blocks;      /* 6x6 blocks of the block-CSR Hessian (diag + off-diag) */
+  int factor_usable;             /* 1 when the level-scheduled Cholesky fits max_fill_ratio */
+  long long factor_blocks;       /* 6x6 blocks of L (diag + off-diag) */
+  int factor_levels;             /* elimination levels = grid/cluster barriers per sweep */
+  int factor_max_degree;
+  long long factor_tasks;        /* 6x6 Schur update products per factorisation */
+  double analysis_seconds;
+} pgo_structure_info;
+
 typedef struct pgo_graph pgo_graph;   /* opaque: a pose graph resident in HBM */
 
 const char* pgo_last_error(void);
 int pgo_abi_version(void);
 int pgo_device_count(void);
 void pgo_default_options(pgo_solver_options* options);
+
+/* Host-only: variable poses, block-CSR Hessian pattern and the level-scheduled elimination order that
+ * pgo_graph_create / pgo_graph_solve would use for this topology (what Ceres' program preprocessing and
+ * symbolic factorisation do inside ceres::Solve).  max_fill_ratio <= 0: no fill limit. */
+int pgo_analyze_structure(int n_poses, int n_edges, const int* edge_ids, const unsigned char* pose_const,
+                          double max_fill_ratio, pgo_structure_info* info);
+
+/* Device memory, streams, events and pinned buffers of destroyed graphs are cached per device and reused
+ * by the next pgo_graph_create / pgo_solve_pose_graph; this returns them to the driver (device < 0: all). */
+void pgo_release_cached_memory(int device);
 
 /* Upload a pose graph (the content of ceres::Problem after BuildOptimizationProblem) to
  * device `device` and analyse its block structure (block-CSR Hessian pattern, edge->block map). */

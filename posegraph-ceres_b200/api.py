@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "pgo_graph_get_poses", "pgo_graph_snapshot_poses", "pgo_graph_restore_poses", "pgo_nccl_unique_id",
     "pgo_graph_init_comm", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
+    "pgo_analyze_structure", "pgo_release_cached_memory",
 ]
 
 
@@ -59,6 +60,12 @@ class SolverSummary(C.Structure):
                 ("hessian_blocks", C.c_longlong), ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int)]
 
 
+class StructureInfo(C.Structure):
+    _fields_ = [("variable_poses", C.c_int), ("hessian_blocks", C.c_longlong), ("factor_usable", C.c_int),
+                ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int), ("factor_max_degree", C.c_int),
+                ("factor_tasks", C.c_longlong), ("analysis_seconds", C.c_double)]
+
+
 class PgoError(RuntimeError):
     pass
 
@@ -90,6 +97,7 @@ def lib() -> C.CDLL:
         _lib.pgo_last_error.restype = C.c_char_p
         _lib.pgo_graph_destroy.restype = None
         _lib.pgo_default_options.restype = None
+        _lib.pgo_release_cached_memory.restype = None
         for name in EXPORTED_SYMBOLS:
             getattr(_lib, name)
     return _lib
@@ -112,6 +120,21 @@ def default_options() -> SolverOptions:
 
 def device_count() -> int:
     return int(lib().pgo_device_count())
+
+
+def analyze_structure(n_poses, edge_ids, pose_const=None, max_fill_ratio: float = 0.0) -> StructureInfo:
+    """Host-only structure analysis (pgo_analyze_structure); works without a GPU."""
+    edge_ids = np.ascontiguousarray(edge_ids, np.int32)
+    pc = None if pose_const is None else np.ascontiguousarray(pose_const, np.uint8)
+    info = StructureInfo()
+    _check(lib().pgo_analyze_structure(C.c_int(n_poses), C.c_int(edge_ids.shape[0]), edge_ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                       pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None,
+                                       C.c_double(max_fill_ratio), C.byref(info)))
+    return info
+
+
+def release_cached_memory(device: int = -1):
+    lib().pgo_release_cached_memory(C.c_int(device))
 
 
 def nccl_unique_id() -> bytes:

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "pgo_kernels.cuh"
+#include "pgo_pool.cuh"
 
 using namespace pgo;
 
@@ -90,7 +91,88 @@ struct pgo_graph {
   LevelChol* chol = nullptr;
   long long launches = 0;
   double setup_s = 0.0;
+  std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
 };
+
+// Host-only structure analysis shared by pgo_graph_create and pgo_analyze_structure: variable poses (used by an
+// edge and not constant) and the block-CSR pattern of the off-diagonal part of J^T J.
+struct HostPattern {
+  std::vector<unsigned char> active;
+  std::vector<int> row_ptr, col_idx, mult;
+  std::vector<unsigned long long> uniq;   // (row << 32 | col), sorted
+  bool has_dup = false;
+};
+static void build_pattern(int N, int E, const int* edge_ids, const unsigned char* pose_const, HostPattern* out) {
+  out->active.assign(N, 0);
+  for (int e = 0; e < E; ++e) { out->active[edge_ids[2 * e]] = 1; out->active[edge_ids[2 * e + 1]] = 1; }
+  if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) out->active[i] = 0;
+  std::vector<unsigned long long> sorted;
+  sorted.reserve(2 * (size_t)E);
+  for (int e = 0; e < E; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    if (out->active[a] && out->active[b]) {
+      sorted.push_back(((unsigned long long)a << 32) | (unsigned)b);
+      sorted.push_back(((unsigned long long)b << 32) | (unsigned)a);
+    }
+  }
+  std::sort(sorted.begin(), sorted.end());
+  out->uniq.reserve(sorted.size());
+  for (size_t k = 0; k < sorted.size(); ++k) {
+    if (k == 0 || sorted[k] != sorted[k - 1]) { out->uniq.push_back(sorted[k]); out->mult.push_back(1); }
+    else { out->mult.back()++; out->has_dup = true; }
+  }
+  out->row_ptr.assign(N + 1, 0);
+  out->col_idx.resize(out->uniq.size());
+  for (size_t k = 0; k < out->uniq.size(); ++k) {
+    out->row_ptr[(int)(out->uniq[k] >> 32) + 1]++;
+    out->col_idx[k] = (int)(out->uniq[k] & 0xffffffffu);
+  }
+  for (int i = 0; i < N; ++i) out->row_ptr[i + 1] += out->row_ptr[i];
+}
+
+static int check_edges(int n_poses, int n_edges, const int* edge_ids) {
+  for (int e = 0; e < n_edges; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    if (a < 0 || a >= n_poses || b < 0 || b >= n_poses || a == b)
+      return set_error(PGO_ERR_INVALID_ARGUMENT, "edge %d has invalid endpoints (%d, %d)", e, a, b);
+  }
+  return PGO_OK;
+}
+
+extern "C" int pgo_analyze_structure(int n_poses, int n_edges, const int* edge_ids, const unsigned char* pose_const,
+                                     double max_fill_ratio, pgo_structure_info* info) {
+  if (!info || n_poses <= 0 || n_edges < 0 || (n_edges > 0 && !edge_ids))
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_analyze_structure: null or empty input");
+  PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
+  const double t0 = wall_s();
+  std::memset(info, 0, sizeof *info);
+  HostPattern pat;
+  build_pattern(n_poses, n_edges, edge_ids, pose_const, &pat);
+  for (unsigned char a : pat.active) info->variable_poses += a;
+  info->hessian_blocks = (long long)pat.col_idx.size() + n_poses;
+  LevelCholSymbolic S;
+  PGO_TRY(level_chol_symbolic(&S, n_poses, pat.active.data(), pat.row_ptr.data(), pat.col_idx.data(),
+                              max_fill_ratio > 0.0 ? max_fill_ratio : 1e30));
+  info->factor_usable = S.usable ? 1 : 0;
+  if (S.usable) {
+    info->factor_blocks = S.n_slots + S.n_nodes;
+    info->factor_levels = S.num_levels;
+    info->factor_max_degree = S.max_degree;
+    info->factor_tasks = (long long)S.tasks.size();
+    // invariants of the schedule (checked here so that CPU tests cover the host logic):
+    // nodes of one level are pairwise non-adjacent in the filled graph, every slot row is eliminated later
+    std::vector<int> pos(n_poses, -1), lvl(n_poses, -1);
+    for (int l = 0; l < S.num_levels; ++l)
+      for (int k = S.level_ptr[l]; k < S.level_ptr[l + 1]; ++k) { pos[S.nodes[k].x] = k; lvl[S.nodes[k].x] = l; }
+    for (int k = 0; k < S.n_nodes; ++k)
+      for (int p = S.nodes[k].y; p < S.nodes[k].z; ++p) {
+        const int u = S.col_row[p];
+        if (pos[u] <= k || lvl[u] <= lvl[S.nodes[k].x]) return set_error(PGO_ERR_NUMERICAL, "level schedule violates elimination order");
+      }
+  }
+  info->analysis_seconds = wall_s() - t0;
+  return PGO_OK;
+}
 
 extern "C" const char* pgo_last_error(void) { return g_last_error.c_str(); }
 extern "C" int pgo_abi_version(void) { return PGO_B200_ABI_VERSION; }
@@ -123,8 +205,10 @@ extern "C" void pgo_default_options(pgo_solver_options* o) {
 }
 
 template <typename Tp>
-static int dev_alloc(Tp** p, size_t count) {
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(Tp)));
+static int dev_alloc(pgo_graph* g, Tp** p, size_t count) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+  CUDA_TRY(pool_alloc(g->device, reinterpret_cast<void**>(p), bytes));
+  g->blocks.emplace_back(static_cast<void*>(*p), bytes);
   return PGO_OK;
 }
 
@@ -132,18 +216,18 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->own_stream && g->own_stream != g->stream) cudaStreamSynchronize(g->own_stream);
   if (g->comm) ncclCommDestroy(g->comm);
-  if (g->chol) level_chol_destroy(g->chol);
-  void* ptrs[] = {g->poses, g->poses_cand, g->poses_snap, g->scale, g->scale_eval, g->core, g->info, g->Hdiag,
-                  g->Hoff, g->row_ptr, g->col_idx, g->grad, g->grad_unscaled, g->diagonal, g->dlm, g->Minv,
-                  g->vx, g->vr, g->vu, g->vw, g->vp, g->vs, g->vb, g->active, g->scalars, g->partials, g->barrier};
-  for (void* p : ptrs) if (p) cudaFree(p);
-  if (g->scalars_h) cudaFreeHost(g->scalars_h);
-  if (g->ev0) cudaEventDestroy(g->ev0);
-  if (g->ev1) cudaEventDestroy(g->ev1);
-  if (g->own_stream) cudaStreamDestroy(g->own_stream);
+  if (g->chol) level_chol_destroy(g->chol, g->device);
+  for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
+  pool_pinned_release(g->device, g->scalars_h);
+  pool_event_release(g->device, g->ev0);
+  pool_event_release(g->device, g->ev1);
+  pool_stream_release(g->device, g->own_stream);
   delete g;
 }
+
+extern "C" void pgo_release_cached_memory(int device) { pool_release(device); }
 
 extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
                                 const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
@@ -156,11 +240,7 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
     return set_error(PGO_ERR_NO_DEVICE, "pgo_graph_create: no CUDA device available (this library has no CPU path)");
   }
   if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
-  for (int e = 0; e < n_edges; ++e) {
-    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-    if (a < 0 || a >= n_poses || b < 0 || b >= n_poses || a == b)
-      return set_error(PGO_ERR_INVALID_ARGUMENT, "edge %d has invalid endpoints (%d, %d)", e, a, b);
-  }
+  PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
   const double t0 = wall_s();
   CUDA_TRY(cudaSetDevice(device));
   pgo_graph* g = new pgo_graph();
@@ -170,20 +250,13 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   auto fail = [&](int rc) { pgo_graph_destroy(g); return rc; };
 #define G_TRY(expr) do { int _rc = (expr); if (_rc != PGO_OK) return fail(_rc); } while (0)
 #define GC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(set_error(PGO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); } while (0)
-  GC_TRY(cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking));
+  GC_TRY(pool_stream(device, &g->own_stream));
   g->stream = g->own_stream;
-  GC_TRY(cudaEventCreate(&g->ev0));
-  GC_TRY(cudaEventCreate(&g->ev1));
-  cudaDeviceProp prop;
-  GC_TRY(cudaGetDeviceProperties(&prop, device));
-  g->num_sms = prop.multiProcessorCount;
+  GC_TRY(pool_event(device, &g->ev0));
+  GC_TRY(pool_event(device, &g->ev1));
+  g->num_sms = pool_num_sms(device);
 
-  // ---- which poses are variables: used by an edge and not constant ----
-  g->active_h.assign(N, 0);
-  for (int e = 0; e < E; ++e) { g->active_h[edge_ids[2 * e]] = 1; g->active_h[edge_ids[2 * e + 1]] = 1; }
-  if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) g->active_h[i] = 0;
-
-  // ---- identity information? ----
+  // ---- which poses are variables, identity information?, block-CSR pattern of the off-diagonal part ----
   g->identity_info = true;
   if (edge_sqrt_info) {
     for (size_t k = 0; k < (size_t)E * 36 && g->identity_info; ++k) {
@@ -191,35 +264,15 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
       if (edge_sqrt_info[k] != ((rc / 6 == rc % 6) ? 1.0 : 0.0)) g->identity_info = false;
     }
   }
-
-  // ---- block-CSR pattern of the off-diagonal part ----
-  std::vector<unsigned long long> keys;
-  keys.reserve(2 * (size_t)E);
-  for (int e = 0; e < E; ++e) {
-    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-    if (g->active_h[a] && g->active_h[b]) {
-      keys.push_back(((unsigned long long)a << 32) | (unsigned)b);
-      keys.push_back(((unsigned long long)b << 32) | (unsigned)a);
-    }
-  }
-  std::vector<unsigned long long> sorted = keys;
-  std::sort(sorted.begin(), sorted.end());
-  std::vector<unsigned long long> uniq;
-  std::vector<int> mult;
-  uniq.reserve(sorted.size());
-  for (size_t k = 0; k < sorted.size(); ++k) {
-    if (k == 0 || sorted[k] != sorted[k - 1]) { uniq.push_back(sorted[k]); mult.push_back(1); }
-    else mult.back()++;
-  }
-  g->nnz_off = (long long)uniq.size();
-  g->row_ptr_h.assign(N + 1, 0);
-  g->col_idx_h.resize(uniq.size());
-  for (size_t k = 0; k < uniq.size(); ++k) {
-    g->row_ptr_h[(int)(uniq[k] >> 32) + 1]++;
-    g->col_idx_h[k] = (int)(uniq[k] & 0xffffffffu);
-    if (mult[k] > 1) g->has_dup_blocks = true;
-  }
-  for (int i = 0; i < N; ++i) g->row_ptr_h[i + 1] += g->row_ptr_h[i];
+  HostPattern pat;
+  build_pattern(N, E, edge_ids, pose_const, &pat);
+  g->active_h.swap(pat.active);
+  g->row_ptr_h.swap(pat.row_ptr);
+  g->col_idx_h.swap(pat.col_idx);
+  g->nnz_off = (long long)g->col_idx_h.size();
+  g->has_dup_blocks = pat.has_dup;
+  const std::vector<unsigned long long>& uniq = pat.uniq;
+  const std::vector<int>& mult = pat.mult;
   auto slot_of = [&](int r, int c) -> int {
     const unsigned long long key = ((unsigned long long)r << 32) | (unsigned)c;
     const size_t pos = std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin();
@@ -244,27 +297,28 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
 
   // ---- device allocations + uploads ----
-  G_TRY(dev_alloc(&g->poses, (size_t)N * 8));
-  G_TRY(dev_alloc(&g->poses_cand, (size_t)N * 8));
-  G_TRY(dev_alloc(&g->poses_snap, (size_t)N * 8));
-  G_TRY(dev_alloc(&g->scale, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->scale_eval, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->core, (size_t)std::max(T, 1)));
-  if (!g->identity_info) G_TRY(dev_alloc(&g->info, (size_t)std::max(T, 1)));
-  G_TRY(dev_alloc(&g->Hdiag, (size_t)N * 36));
-  G_TRY(dev_alloc(&g->Hoff, (size_t)g->nnz_off * 36));
-  G_TRY(dev_alloc(&g->row_ptr, (size_t)N + 1));
-  G_TRY(dev_alloc(&g->col_idx, (size_t)g->nnz_off));
-  G_TRY(dev_alloc(&g->grad, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->grad_unscaled, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->diagonal, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->dlm, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->Minv, (size_t)N * 36));
-  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb}) G_TRY(dev_alloc(v, (size_t)N * 6));
-  G_TRY(dev_alloc(&g->active, (size_t)N));
-  G_TRY(dev_alloc(&g->scalars, 1));
-  GC_TRY(cudaMallocHost(reinterpret_cast<void**>(&g->scalars_h), sizeof(DeviceScalars)));
-  G_TRY(dev_alloc(&g->barrier, 4));
+  G_TRY(dev_alloc(g, &g->poses, (size_t)N * 8));
+  G_TRY(dev_alloc(g, &g->poses_cand, (size_t)N * 8));
+  G_TRY(dev_alloc(g, &g->poses_snap, (size_t)N * 8));
+  G_TRY(dev_alloc(g, &g->scale, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->scale_eval, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->core, (size_t)std::max(T, 1)));
+  if (!g->identity_info) G_TRY(dev_alloc(g, &g->info, (size_t)std::max(T, 1)));
+  G_TRY(dev_alloc(g, &g->Hdiag, (size_t)N * 36));
+  G_TRY(dev_alloc(g, &g->Hoff, (size_t)g->nnz_off * 36));
+  G_TRY(dev_alloc(g, &g->row_ptr, (size_t)N + 1));
+  G_TRY(dev_alloc(g, &g->col_idx, (size_t)g->nnz_off));
+  G_TRY(dev_alloc(g, &g->grad, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->grad_unscaled, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->diagonal, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->dlm, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->Minv, (size_t)N * 36));
+  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb}) G_TRY(dev_alloc(g, v, (size_t)N * 6));
+  G_TRY(dev_alloc(g, &g->active, (size_t)N));
+  G_TRY(dev_alloc(g, &g->scalars, 1));
+  static_assert(sizeof(DeviceScalars) <= kPinnedBytes, "pinned scalars");
+  GC_TRY(pool_pinned(device, reinterpret_cast<void**>(&g->scalars_h)));
+  G_TRY(dev_alloc(g, &g->barrier, 4));
 
   GC_TRY(cudaMemcpyAsync(g->core, core_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
   if (!g->identity_info) GC_TRY(cudaMemcpyAsync(g->info, info_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
@@ -285,7 +339,7 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   int per_sm = 0;
   GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kPcgThreads, 0));
   g->pcg_max_ctas = std::max(1, std::min(per_sm, 4) * g->num_sms);
-  G_TRY(dev_alloc(&g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
+  G_TRY(dev_alloc(g, &g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
 
   *out = g;
   int rc = pgo_graph_set_poses(g, poses);
@@ -480,8 +534,9 @@ extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, do
   if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
   CUDA_TRY(cudaSetDevice(g->device));
   double *res_d = nullptr, *jac_d = nullptr;
-  PGO_TRY(dev_alloc(&res_d, (size_t)g->E * 6));
-  PGO_TRY(dev_alloc(&jac_d, (size_t)g->E * 72));
+  const size_t res_bytes = std::max<size_t>((size_t)g->E * 6, 1) * sizeof(double), jac_bytes = std::max<size_t>((size_t)g->E * 72, 1) * sizeof(double);
+  CUDA_TRY(pool_alloc(g->device, reinterpret_cast<void**>(&res_d), res_bytes));
+  CUDA_TRY(pool_alloc(g->device, reinterpret_cast<void**>(&jac_d), jac_bytes));
   int rc = PGO_OK;
   do {
     if ((rc = zero_system(g, false)) != PGO_OK) break;
@@ -499,7 +554,8 @@ extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, do
     if (ce == cudaSuccess && gradient) ce = cudaMemcpy(gradient, g->grad, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) rc = set_error(PGO_ERR_CUDA, "evaluate copy-back failed: %s", cudaGetErrorString(ce));
   } while (0);
-  cudaFree(res_d); cudaFree(jac_d);
+  cudaStreamSynchronize(g->stream);
+  pool_free(g->device, res_d, res_bytes); pool_free(g->device, jac_d, jac_bytes);
   return rc;
 }
 
@@ -581,7 +637,7 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
   if (t == PGO_LINEAR_AUTO || t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     if (!g->chol) {
       LevelChol* c = nullptr;
-      const int rc = level_chol_analyze(&c, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(),
+      const int rc = level_chol_analyze(&c, g->device, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(),
                                         t == PGO_LINEAR_AUTO ? 8.0 : 1e30, g->stream);
       if (rc == PGO_OK) g->chol = c;
       else if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return rc;
@@ -593,14 +649,20 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
   return PGO_LINEAR_PCG_BLOCK_JACOBI;
 }
 
-// Solve (H + diag(dlm)) x = b with the chosen solver; x -> g->vx, stats -> g->scalars (after fetch).
-static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b) {
-  if (g->world > 1) return pcg_multi(g, o, b);
-  if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
-    return level_chol_solve(g->chol, bsr_view(g), g->dlm, b, g->vx, g->vr, g->vu, g->vw, g->vp,
+// LevenbergMarquardtStrategy::ComputeStep: D = diagonal / radius (new, reused or given), then solve
+// (H + D) x = b with the chosen solver; x -> g->vx, stats -> g->scalars (after fetch).
+static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b, const LmDiagonal& lm) {
+  if (g->world == 1 && solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
+    // the LM diagonal is formed inside the factor kernel
+    return level_chol_solve(g->chol, bsr_view(g), lm, g->active, b, g->vx, g->vr, g->vu, g->vw, g->vp, g->vs,
                             std::min(o->pcg_max_iterations, 200), o->pcg_tolerance, o->pcg_num_ctas, g->scalars,
                             g->stream, &g->launches);
   }
+  const int tpb = 128;
+  lm_prepare_kernel<<<(g->N + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->N, g->Hdiag, g->active, lm.mode, lm.min_diag, lm.max_diag,
+                                                                   lm.radius, lm.diagonal, lm.dlm, g->Minv);
+  g->launches++;
+  if (g->world > 1) return pcg_multi(g, o, b);
   return launch_pcg(g, o, b);
 }
 
@@ -614,13 +676,10 @@ extern "C" int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* op
   if (solver < 0) return solver;
   CUDA_TRY(cudaMemcpyAsync(g->dlm, d, nv, cudaMemcpyHostToDevice, g->stream));
   CUDA_TRY(cudaMemcpyAsync(g->vb, b, nv, cudaMemcpyHostToDevice, g->stream));
-  const int tpb = 128;
-  lm_prepare_kernel<<<(g->N + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->N, g->Hdiag, g->active, 2, 0.0, 0.0, 1.0,
-                                                                   g->diagonal, g->dlm, g->Minv);
-  g->launches++;
   PGO_TRY(zero_scalars(g));
   CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
-  PGO_TRY(linear_solve_device(g, options, solver, g->vb));
+  const LmDiagonal lm = {2, 0.0, 0.0, 1.0, g->diagonal, g->dlm};
+  PGO_TRY(linear_solve_device(g, options, solver, g->vb, lm));
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
   PGO_TRY(fetch_scalars(g));
   CUDA_TRY(cudaMemcpy(y, g->vx, nv, cudaMemcpyDeviceToHost));
@@ -705,12 +764,10 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     { const double gm = it.gradient_max_norm, gn = it.gradient_norm; std::memset(&it, 0, sizeof it); it.iteration = iter; it.gradient_max_norm = gm; it.gradient_norm = gn; }
 
     // ---- LevenbergMarquardtStrategy::ComputeStep: D = diag / radius, solve (H + D) y = g, step = -y ----
-    lm_prepare_kernel<<<nblk, tpb, 0, g->stream>>>(N, g->Hdiag, g->active, reuse_diagonal ? 1 : 0, opt->min_lm_diagonal,
-                                                   opt->max_lm_diagonal, radius, g->diagonal, g->dlm, g->Minv);
-    g->launches++;
     PGO_TRY(zero_scalars(g));
     CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
-    PGO_TRY(linear_solve_device(g, opt, solver, g->grad));
+    const LmDiagonal lm = {reuse_diagonal ? 1 : 0, opt->min_lm_diagonal, opt->max_lm_diagonal, radius, g->diagonal, g->dlm};
+    PGO_TRY(linear_solve_device(g, opt, solver, g->grad, lm));
     CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
     reuse_diagonal = true;
     // ---- speculatively: candidate = Plus(x, -y .* scale), its cost, |step|, |x_cand| ----

@@ -1,25 +1,37 @@
 // pgo_level_chol.cuh -- level-scheduled sparse block Cholesky used as the PCG preconditioner.
 //
 // Why: the reference solves the damped normal equations exactly (SPARSE_NORMAL_CHOLESKY,
-// REF/test/pose_graph_ceres_plus_finial.cpp:505).  Odometry-chain pose graphs such as KITTI-00 are
+// REF/test/pose_graph_ceres_plus_finial.cpp:536).  Odometry-chain pose graphs such as KITTI-00 are
 // beam-like: at late LM radii block-Jacobi PCG needs 10^5 iterations to follow that exact path.
-// Here M = L L^T is the exact factor of H + D on a parallel elimination order, so PCG (whose
-// SpMV is still bsr6_row) converges in 1-3 iterations and acts as iterative refinement.
+// Here M = L L^T is the exact factor of H + D on a parallel elimination order, so the first PCG
+// iterate x1 = alpha M^-1 b already is the direct solution; further PCG iterations (whose SpMV is
+// still bsr6_row) act as iterative refinement and only run when ||b - A x1|| > tol ||b||.
 //
 // Host (once per graph): rounds of independent-set minimum-degree elimination -> levels; nodes of
 // a level are mutually non-adjacent, so their columns factor in parallel.  Structure of L, the
-// A->L scatter map, per-node Schur update tasks and per-node row lists are precomputed.
-// Device (one persistent cooperative kernel per solve): scatter A, factor level by level
-// (1 grid barrier per level when every column is short, 2 otherwise), then PCG whose M^-1 is a
-// forward + backward sweep over the levels (gather form, deterministic).
+// L<-A gather map, per-node Schur update tasks are precomputed.
+// Device (ONE persistent kernel per LM step):
+//   S   LM diagonal D = clamp(diag H) / radius (LevenbergMarquardtStrategy::ComputeStep), gather
+//       A + D into the factor storage, working rhs t = b
+//   F   level by level: 6x6 Cholesky of the pivot block, y_v = L_vv^-1 t_v, column scaling, Schur
+//       updates and the rhs fan-out t_u -= L_uv y_v (the forward substitution rides on the factor)
+//   B   level by level, descending: x_v = L_vv^-T (y_v - sum_u L_uv^T x_u)   (gather, deterministic)
+//   CG  q = A p, alpha, x/r/Ax update, ||r|| check -> done, else z = M^-1 r (F without factoring + B) ...
+// Two launch shapes share the kernel body: small graphs run as ONE thread-block cluster (16 CTAs on
+// 16 SMs of a GPC) whose level barrier is the hardware cluster barrier (~0.2 us); large graphs
+// run as a cooperative grid with an atomic-counter barrier.
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "pgo_kernels.cuh"
 
 namespace pgo {
+
+constexpr int kCholThreads = 512;   // per CTA, both launch shapes
+constexpr int kCholClusterMaxNodes = 60000;   // graphs up to this many variable poses use the cluster shape
 
 struct CholTask { int p; int q; int target; };   // target >= 0: L slot ; < 0: diagonal of node (-target-1)
 
@@ -32,31 +44,34 @@ struct LevelChol {
   int max_degree = 0;
   long long n_slots = 0, n_tasks = 0;
   // device
-  int* level_ptr = nullptr;     // [L+1] into order[]
-  int* level_split = nullptr;   // [L] 1 = two-phase level
-  int* order = nullptr;         // [n_nodes] pose ids in elimination order
-  int* col_ptr = nullptr;       // [n_nodes+1] by elimination position -> slots
+  int* level_ptr = nullptr;     // [L+1] into nodes[]
+  int* level_split = nullptr;   // [L] level mode: 8 / 16 / 32 lanes per node (staged), 1 = high-degree two-phase level
+  int4* nodes = nullptr;        // [n_nodes+1] by elimination position: {pose id, col0, col1, task0}
   int* col_row = nullptr;       // [n_slots] row pose id of each slot
-  int* row_ptr = nullptr;       // [N+1] by pose id -> row entries
-  int* row_slot = nullptr;      // [n_slots] slot
-  int* row_col = nullptr;       // [n_slots] column pose id
-  int* task_ptr = nullptr;      // [n_nodes+1] by elimination position
+  int* l2a = nullptr;           // [n_slots] BSR off-diagonal entry that seeds the slot, or -1 (pure fill)
   CholTask* tasks = nullptr;    // [n_tasks]
-  int* a2l = nullptr;           // [nnz_off] BSR off-diagonal entry -> slot or -1
   double* Lblk = nullptr;       // [n_slots][36] row-major (rows: row pose, cols: column pose)
   double* Ldiag = nullptr;      // [N][36] W_vv, then inverse of its lower Cholesky factor
-  double* vt = nullptr;         // [N][6] sweep workspace
+  double* vt = nullptr;         // [N][6] working rhs / y of the sweeps
   double* partials = nullptr;
   unsigned int* barrier = nullptr;
-  int max_ctas = 0;
+  int max_ctas = 0;             // cooperative-grid shape
+  int cluster_ctas = 0;         // cluster shape: CTAs per cluster (0 = unavailable)
+  std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
 };
 
-static void level_chol_destroy(LevelChol* c) {
+static void level_chol_destroy(LevelChol* c, int device) {
   if (!c) return;
-  void* ptrs[] = {c->level_ptr, c->level_split, c->order, c->col_ptr, c->col_row, c->row_ptr, c->row_slot, c->row_col,
-                  c->task_ptr, c->tasks, c->a2l, c->Lblk, c->Ldiag, c->vt, c->partials, c->barrier};
-  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& blk : c->blocks) pool_free(device, blk.first, blk.second);
   delete c;
+}
+
+template <typename Tp>
+static int chol_alloc(LevelChol* C, int device, Tp** dst, size_t count) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+  CUDA_TRY(pool_alloc(device, reinterpret_cast<void**>(dst), bytes));
+  C->blocks.emplace_back(static_cast<void*>(*dst), bytes);
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -64,88 +79,151 @@ static void level_chol_destroy(LevelChol* c) {
 // ---------------------------------------------------------------------------------------------
 struct CholParams {
   BsrView A;
-  const double* dlm;
+  // LM diagonal: mode 0 = new diagonal from H, 1 = reuse `diagonal`, 2 = dlm given
+  int lm_mode; double min_diag, max_diag, radius;
+  double* diagonal; double* dlm;
+  const unsigned char* active;
   const double* b;
-  double *x, *r, *z, *q, *p;   // PCG vectors [N][6]
+  double *x, *r, *z, *q, *p, *ax;   // PCG vectors [N][6]
   int num_levels, n_nodes;
-  const int *level_ptr, *level_split, *order, *col_ptr, *col_row, *row_ptr, *row_slot, *row_col, *task_ptr, *a2l;
+  const int *level_ptr, *level_split, *col_row, *l2a;
+  const int4* nodes;
   const CholTask* tasks;
   double *Lblk, *Ldiag, *vt;
   long long n_slots;
-  double* partials;
-  unsigned int* barrier;
+  double* partials;          // [8 regions][4 values][G]
+  unsigned int* barrier;     // [0] grid barrier counter, [1] factor-failure flag
   DeviceScalars* scalars;
   int max_iterations;
   double tolerance;
-  int do_factor;
+  unsigned long long* timeline;   // debug (PGO_TIMELINE=1): %globaltimer marks of CTA 0 / thread 0, [0] = count
 };
 
-// One warp: Cholesky of the 6x6 diagonal block of node v (every lane redundantly), store the inverse
-// of the lower factor, then scale the column: L_uv = W_uv * Linv^T (one lane per block row).
-__device__ __forceinline__ bool chol_node_factor(const CholParams& P, int k, int v, int lane) {
-  double A[6][6];
-  double* dv = P.Ldiag + 36 * (size_t)v;
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = 0; c < 6; ++c) A[r][c] = __ldcg(dv + r * 6 + c);
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double s = A[j][j];
-#pragma unroll
-    for (int t = 0; t < 6; ++t) if (t < j) s -= A[j][t] * A[j][t];
-    if (!(s > 0.0)) { ok = false; s = 1.0; }
-    const double l = sqrt(s), il = 1.0 / l;
-    A[j][j] = l;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) if (r > j) {
-      double t2 = A[r][j];
-#pragma unroll
-      for (int t = 0; t < 6; ++t) if (t < j) t2 -= A[r][t] * A[j][t];
-      A[r][j] = t2 * il;
-    }
+__device__ __forceinline__ void chol_mark(const CholParams& P, int tag) {
+  if (P.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long k = P.timeline[0];
+    if (k < 1000) { P.timeline[1 + 2 * k] = t; P.timeline[2 + 2 * k] = (unsigned long long)tag; P.timeline[0] = k + 1; }
   }
-  double Li[6][6];   // inverse of the lower factor
+}
+
+template <bool kCluster>
+__device__ __forceinline__ void chol_sync(unsigned int* counter, unsigned int& epoch) {
+  if constexpr (kCluster) {
+    // hardware barrier over every thread of the cluster; release/acquire orders the global-memory traffic
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    grid_barrier(counter, epoch);
+  }
+}
+
+// One warp, node at elimination position k.
+//   kFactor: Cholesky of the 6x6 pivot block (every lane redundantly), store the inverse of the lower factor,
+//            scale the column L_uv = W_uv Linv^T.
+//   always : y_v = Linv t_v (t = working rhs), store y_v, fan out t_u -= L_uv y_v to the later rows.
+template <bool kFactor>
+__device__ __forceinline__ bool chol_forward_node(const CholParams& P, int v, int p0, int p1, int lane) {
+  double Li[6][6];   // inverse of the lower factor (lower triangular)
+  double* dv = P.Ldiag + 36 * (size_t)v;
+  bool ok = true;
+  if (kFactor) {
+    double A[6][6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c)
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) if (c <= r) A[r][c] = __ldcg(dv + r * 6 + c);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double s = A[j][j];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) if (t < j) s -= A[j][t] * A[j][t];
+      if (!(s > 0.0)) { ok = false; s = 1.0; }
+      const double il = rsqrt(s);
+      A[j][j] = il;            // the diagonal keeps 1 / L_jj
+#pragma unroll
+      for (int r = 0; r < 6; ++r) if (r > j) {
+        double t2 = A[r][j];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) if (t < j) t2 -= A[r][t] * A[j][t];
+        A[r][j] = t2 * il;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        if (r < c) { Li[r][c] = 0.0; continue; }
+        double t = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int t3 = 0; t3 < 6; ++t3) if (t3 >= c && t3 < r) t -= A[r][t3] * Li[t3][c];
+        Li[r][c] = t * A[r][r];
+      }
+    __syncwarp();
+    if (lane < 6) {   // store Linv (row-major): lane = row
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double val = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) if (r == lane) val = Li[r][c];
+        dv[lane * 6 + c] = val;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Li[r][c] = (c <= r) ? __ldcg(dv + r * 6 + c) : 0.0;
+  }
+  // y_v = Linv t_v
+  double y[6];
+  {
+    double t[6];
+    double* tv = P.vt + 6 * (size_t)v;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t[c] = __ldcg(tv + c);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      if (r < c) { Li[r][c] = 0.0; continue; }
-      double t = (r == c) ? 1.0 : 0.0;
+      double s = 0.0;
 #pragma unroll
-      for (int t3 = 0; t3 < 6; ++t3) if (t3 >= c && t3 < r) t -= A[r][t3] * Li[t3][c];
-      Li[r][c] = t / A[r][r];
+      for (int c = 0; c < 6; ++c) if (c <= r) s = fma(Li[r][c], t[c], s);
+      y[r] = s;
     }
-  __syncwarp();
-  // store Linv (row-major) : lanes 0..5 write one row each
-  if (lane < 6) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
+    __syncwarp();
+    if (lane < 6) {
       double val = 0.0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) if (r == lane) val = Li[r][c];
-      dv[lane * 6 + c] = val;
+      for (int r = 0; r < 6; ++r) if (r == lane) val = y[r];
+      tv[lane] = val;
     }
   }
-  // column scaling: item = (block, row)
-  const int p0 = P.col_ptr[k], p1 = P.col_ptr[k + 1];
+  // column items: (block, row)
   const int items = (p1 - p0) * 6;
   for (int it = lane; it < items; it += 32) {
     const int blk = it / 6, r = it - blk * 6;
     double* w = P.Lblk + 36 * (size_t)(p0 + blk) + r * 6;
-    double wr[6], o[6];
+    double o[6];
+    if (kFactor) {
+      double wr[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) wr[c] = __ldcg(w + c);
+      for (int c = 0; c < 6; ++c) wr[c] = __ldcg(w + c);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double s = 0.0;
+      for (int c = 0; c < 6; ++c) {
+        double s = 0.0;
 #pragma unroll
-      for (int t = 0; t < 6; ++t) if (t <= c) s = fma(wr[t], Li[c][t], s);
-      o[c] = s;
+        for (int t = 0; t < 6; ++t) if (t <= c) s = fma(wr[t], Li[c][t], s);
+        o[c] = s;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) w[c] = o[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o[c] = __ldcg(w + c);
     }
+    double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) w[c] = o[c];
+    for (int c = 0; c < 6; ++c) s = fma(o[c], y[c], s);
+    atomicAdd(P.vt + 6 * (size_t)__ldg(P.col_row + p0 + blk) + r, -s);
   }
   return ok;
 }
@@ -167,11 +245,219 @@ __device__ __forceinline__ void chol_update_item(const CholParams& P, const Chol
   }
 }
 
-__global__ void __launch_bounds__(kPcgThreads) level_chol_pcg_kernel(const CholParams P) {
-  __shared__ double red[kPcgThreads / 32];
+// ---- shared-memory staging of one node's column (blocks, row ids, Schur tasks) per lane group ----
+constexpr int kStashBlocks = 16;    // per warp: 4 nodes x 4, 2 x 8 or 1 x 16 blocks
+constexpr int kStashTasks = 144;    // per warp: 4 x 36, 2 x 72 or 1 x 144 tasks (deg (deg + 1) / 2 <= 10 / 36 / 136)
+struct __align__(16) WarpStash {
+  double L[kStashBlocks][36];
+  CholTask task[kStashTasks];
+  int row[kStashBlocks];
+};
+constexpr int kCholSmemBytes = (kCholThreads / 32) * (int)sizeof(WarpStash);
+
+__device__ __forceinline__ void cp_async_cg16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Factor step for 32 / kLanes nodes per warp (positions kk .. kk + 32 / kLanes - 1 of one level, degree <= 128 / kLanes):
+// everything a node needs is fetched in ONE latency epoch (cp.async into the stash + broadcast loads of the pivot
+// block and rhs), the Cholesky, column scaling and Schur products then run out of registers / shared memory, and
+// results leave as plain stores and fire-and-forget fp64 RED atomics.
+template <int kLanes>
+__device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane) {
+  constexpr int kNpw = 32 / kLanes;
+  constexpr int kBlk = kStashBlocks / kNpw;
+  constexpr int kTsk = kStashTasks / kNpw;
+  const int sub = lane % kLanes, gi = lane / kLanes;
+  const int k = kk + gi;
+  const bool valid = k < k1;
+  int v = 0, p0 = 0, p1 = 0, t0 = 0, t1 = 0;
+  if (valid) {
+    const int4 nm = __ldg(P.nodes + k);
+    v = nm.x; p0 = nm.y; p1 = nm.z; t0 = nm.w;
+    t1 = __ldg(&P.nodes[k + 1].w);
+  }
+  const int deg = p1 - p0, ntask = t1 - t0;
+  double* SL = &st.L[gi * kBlk][0];
+  CholTask* ST = st.task + gi * kTsk;
+  int* SR = st.row + gi * kBlk;
+  {
+    const double* src = P.Lblk + 36 * (size_t)p0;
+    for (int c = sub; c < deg * 18; c += kLanes) cp_async_cg16(SL + 2 * c, src + 2 * c);
+    for (int j = sub; j < deg; j += kLanes) cp_async_ca4(SR + j, P.col_row + p0 + j);
+    const int* tsrc = reinterpret_cast<const int*>(P.tasks + t0);
+    for (int j = sub; j < ntask * 3; j += kLanes) cp_async_ca4(reinterpret_cast<int*>(ST) + j, tsrc + j);
+  }
+  double* dv = P.Ldiag + 36 * (size_t)v;
+  double* tv = P.vt + 6 * (size_t)v;
+  double A[6][6], t[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) if (c <= r) A[r][c] = valid ? __ldcg(dv + r * 6 + c) : (r == c ? 1.0 : 0.0);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t[c] = valid ? __ldcg(tv + c) : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) if (q < j) s -= A[j][q] * A[j][q];
+    if (!(s > 0.0)) { ok = false; s = 1.0; }
+    const double il = rsqrt(s);
+    A[j][j] = il;            // the diagonal keeps 1 / L_jj
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > j) {
+      double t2 = A[r][j];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) if (q < j) t2 -= A[r][q] * A[j][q];
+      A[r][j] = t2 * il;
+    }
+  }
+  double Li[6][6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r < c) { Li[r][c] = 0.0; continue; }
+      double x = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) if (q >= c && q < r) x -= A[r][q] * Li[q][c];
+      Li[r][c] = x * A[r][r];
+    }
+  double y[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) if (c <= r) s = fma(Li[r][c], t[c], s);
+    y[r] = s;
+  }
+  if (valid && sub < 6) {   // store Linv row `sub` and y[sub]
+    double yv = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double val = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) if (r == sub) val = Li[r][c];
+      dv[sub * 6 + c] = val;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r == sub) yv = y[r];
+    tv[sub] = yv;
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  // column scaling L_uv = W_uv Linv^T in the stash (+ write-through to global), rhs fan-out t_u -= L_uv y_v
+  for (int it = sub; it < deg * 6; it += kLanes) {
+    const int blk = it / 6, r = it - blk * 6;
+    double* w = SL + 36 * blk + 6 * r;
+    double wr[6], o[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) wr[c] = w[c];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) if (q <= c) s = fma(wr[q], Li[c][q], s);
+      o[c] = s;
+    }
+    double* gw_ = P.Lblk + 36 * (size_t)(p0 + blk) + 6 * r;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { w[c] = o[c]; gw_[c] = o[c]; s = fma(o[c], y[c], s); }
+    atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
+  }
+  __syncwarp();
+  // Schur updates: row r of target -= L_p L_q^T, operands from the stash
+  for (int it = sub; it < ntask * 6; it += kLanes) {
+    const int ti = it / 6, r = it - ti * 6;
+    const CholTask tk = ST[ti];
+    const double* lp = SL + 36 * (tk.p - p0) + 6 * r;
+    const double* lq = SL + 36 * (tk.q - p0);
+    double a[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a[c] = lp[c];
+    double* out = (tk.target >= 0) ? (P.Lblk + 36 * (size_t)tk.target + r * 6) : (P.Ldiag + 36 * (size_t)(-tk.target - 1) + r * 6);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s = fma(a[q], lq[c * 6 + q], s);
+      atomicAdd(out + c, -s);
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// Backward step for 32 / kLanes nodes per warp: x_v = Linv_v^T (y_v - sum_{u in col(v)} L_uv^T x_u).
+template <int kLanes>
+__device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk, int k1, int lane, double* dst, double* dst2) {
+  constexpr int kNpw = 32 / kLanes;
+  constexpr int kSub = kLanes / 6;                         // 6-lane column groups per node: 1, 2, 5
+  constexpr int kIter = (kStashBlocks / kNpw + kSub - 1) / kSub;   // blocks per column group: 4, 4, 4
+  const int sub = lane % kLanes, gi = lane / kLanes, base = lane - sub;
+  const int k = kk + gi;
+  const bool valid = k < k1;
+  int v = 0, p0 = 0, p1 = 0;
+  if (valid) { const int4 nm = __ldg(P.nodes + k); v = nm.x; p0 = nm.y; p1 = nm.z; }
+  const int sg = sub / 6, c = sub - 6 * sg;
+  const bool on = valid && sg < kSub;
+  int rows[kIter];
+#pragma unroll
+  for (int j = 0; j < kIter; ++j) {
+    const int p = p0 + sg + j * kSub;
+    rows[j] = (on && p < p1) ? __ldg(P.col_row + p) : -1;
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < kIter; ++j) {
+    if (rows[j] >= 0) {
+      const double* L = P.Lblk + 36 * (size_t)(p0 + sg + j * kSub) + c;
+      const double* xu = dst + 6 * (size_t)rows[j];
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) acc = fma(__ldcg(L + rr * 6), __ldcg(xu + rr), acc);
+    }
+  }
+  const int c6 = sub % 6;
+  double tot = 0.0;
+#pragma unroll
+  for (int g = 0; g < kSub; ++g) tot += __shfl_sync(0xffffffffu, acc, base + g * 6 + c6);
+  const double sv = __ldcg(P.vt + 6 * (size_t)v + c6) - tot;
+  double xv = 0.0;
+#pragma unroll
+  for (int rr = 0; rr < 6; ++rr) {
+    const double sr = __shfl_sync(0xffffffffu, sv, base + rr);
+    if (sub < 6 && rr >= sub) xv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + rr * 6 + sub), sr, xv);
+  }
+  if (valid && sub < 6) { dst[6 * (size_t)v + sub] = xv; if (dst2) dst2[6 * (size_t)v + sub] = xv; }
+}
+
+__device__ __forceinline__ double cta_sum_n(double v, double* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  const int nwarp = blockDim.x >> 5;
+  for (int k = 0; k < nwarp; ++k) t += red[k];
+  return t;
+}
+
+template <bool kCluster>
+__global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const CholParams P) {
+  __shared__ double red[kCholThreads / 32];
   __shared__ double bcast;
+  extern __shared__ __align__(16) unsigned char chol_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warps_per_cta = kPcgThreads / 32;
+  WarpStash& stash = reinterpret_cast<WarpStash*>(chol_smem)[warp];
+  const int warps_per_cta = kCholThreads / 32;
   const int gw = blockIdx.x * warps_per_cta + warp;
   const int nw = gridDim.x * warps_per_cta;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,192 +465,222 @@ __global__ void __launch_bounds__(kPcgThreads) level_chol_pcg_kernel(const CholP
   const int grp = lane / 6, r6 = lane - grp * 6;
   const bool lane_on = grp < kRowsPerWarp;
   const int n = P.A.n;
+  const int n6 = 6 * n;
   const int G = gridDim.x;
   unsigned int epoch = 0;
-  int fail = 0;
+  int region = 0;
+  auto next_region = [&]() -> double* { region = (region + 1) & 7; return P.partials + (size_t)region * 4 * G; };
 
-  if (P.do_factor) {
-    // ---- scatter A + D into the factor storage ----
-    for (long long i = gtid; i < P.n_slots * 36; i += gthreads) P.Lblk[i] = 0.0;
-    grid_barrier(P.barrier, epoch);
-    for (long long e = gtid; e < (long long)P.A.row_ptr[n] * 36; e += gthreads) {
-      const int pe = (int)(e / 36), k = (int)(e - 36LL * pe);
-      const int slot = P.a2l[pe];
-      if (slot >= 0) P.Lblk[36 * (size_t)slot + k] = P.A.Hoff[36 * (size_t)pe + pidx(k / 6, k % 6)];
+  // ---- S: LM diagonal, gather A + D into the factor storage, working rhs ----
+  chol_mark(P, 0);
+  for (int k = gtid; k < n6; k += gthreads) {
+    const int i = k / 6, c = k - 6 * i;
+    double dd;
+    if (P.lm_mode == 2) {
+      dd = P.dlm[k];
+    } else {
+      double dg;
+      if (P.lm_mode == 1) dg = P.diagonal[k];
+      else { dg = fmin(fmax(P.A.Hdiag[36 * (size_t)i + pidx(c, c)], P.min_diag), P.max_diag); P.diagonal[k] = dg; }
+      dd = dg / P.radius;
+      P.dlm[k] = dd;
     }
-    for (long long e = gtid; e < (long long)n * 36; e += gthreads) {
-      const int i = (int)(e / 36), k = (int)(e - 36LL * i);
-      const int rr = k / 6, cc = k % 6;
-      double v = P.A.Hdiag[36 * (size_t)i + pidx(rr, cc)];
-      if (rr == cc) v += P.dlm[6 * (size_t)i + rr];
-      P.Ldiag[e] = v;
+    P.vt[k] = P.b[k];
+    P.x[k] = 0.0; P.ax[k] = 0.0; P.r[k] = P.b[k];
+    // diagonal block row c of pose i
+    const double* hd = P.A.Hdiag + 36 * (size_t)i;
+    double* ld = P.Ldiag + 36 * (size_t)i + 6 * c;
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) ld[cc] = hd[pidx(c, cc)] + (cc == c ? dd : 0.0);
+  }
+  {
+    // factor storage <- A: four (slot, row) items per thread and pass so that their loads are in flight together
+    const double* __restrict__ hoff = P.A.Hoff;
+    const int* __restrict__ l2a = P.l2a;
+    double* __restrict__ lblk = P.Lblk;
+    const long long total = P.n_slots * 6;
+    for (long long e0 = gtid; e0 < total; e0 += 4LL * gthreads) {
+      int src[4];
+      double vals[4][6];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long e = e0 + (long long)j * gthreads;
+        src[j] = (e < total) ? __ldg(l2a + e / 6) : -2;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long e = e0 + (long long)j * gthreads;
+        const int rr = (int)(e % 6);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) vals[j][cc] = (src[j] >= 0) ? __ldg(hoff + 36 * (size_t)src[j] + pidx(rr, cc)) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long e = e0 + (long long)j * gthreads;
+        if (src[j] != -2) {
+          double* dst = lblk + 6 * e;
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) dst[cc] = vals[j][cc];
+        }
+      }
     }
-    grid_barrier(P.barrier, epoch);
-    // ---- numeric factorisation, level by level ----
+  }
+  chol_sync<kCluster>(P.barrier, epoch);
+  chol_mark(P, 1);
+
+  // forward sweep over the levels; kFactor also factors.  level_split[l] is the level's mode: 8 / 16 / 32 = lanes
+  // per node of the staged path (degree <= 4 / 8 / 16), 1 = high-degree level (global operands, tasks spread over
+  // the whole launch after an extra barrier).
+  auto forward = [&](auto factor_tag) {
+    constexpr bool kFactor = decltype(factor_tag)::value;
     for (int l = 0; l < P.num_levels; ++l) {
-      const int k0 = P.level_ptr[l], k1 = P.level_ptr[l + 1];
-      const bool split = P.level_split[l] != 0;
-      for (int k = k0 + gw; k < k1; k += nw) {
-        const int v = P.order[k];
-        if (!chol_node_factor(P, k, v, lane)) { fail = 1; if (lane == 0) atomicExch(P.barrier + 1, 1u); }
-        if (!split) {
-          __syncwarp();
-          const int t0 = P.task_ptr[k], t1 = P.task_ptr[k + 1];
-          for (int it = lane; it < (t1 - t0) * 6; it += 32) chol_update_item(P, P.tasks[t0 + it / 6], it % 6);
+      const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
+      const int mode = __ldg(P.level_split + l);
+      const bool split = kFactor && mode == 1;
+      if (kFactor && mode != 1) {
+        bool ok = true;
+        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8>(P, stash, kk, k1, lane); }
+        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16>(P, stash, kk, k1, lane); }
+        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32>(P, stash, kk, k1, lane); }
+        if (!ok) atomicExch(P.barrier + 1, 1u);
+      } else {
+        for (int k = k0 + gw; k < k1; k += nw) {
+          const int4 nm = __ldg(P.nodes + k);
+          const bool ok = chol_forward_node<kFactor>(P, nm.x, nm.y, nm.z, lane);
+          if (kFactor && !ok && lane == 0) atomicExch(P.barrier + 1, 1u);
         }
       }
       if (split) {
-        grid_barrier(P.barrier, epoch);
-        const long long t0 = P.task_ptr[k0], t1 = P.task_ptr[k1];
+        chol_sync<kCluster>(P.barrier, epoch);
+        const long long t0 = __ldg(&P.nodes[k0].w), t1 = __ldg(&P.nodes[k1].w);
         for (long long it = (long long)gtid; it < (t1 - t0) * 6; it += gthreads) chol_update_item(P, P.tasks[t0 + it / 6], (int)(it % 6));
       }
-      grid_barrier(P.barrier, epoch);
+      chol_mark(P, 100 + l);
+      chol_sync<kCluster>(P.barrier, epoch);
+      chol_mark(P, 200 + l);
     }
-  }
-
-  // z = (L L^T)^-1 src  (z also used as the backward-sweep output); inactive poses get 0.
-  auto apply_minv = [&](const double* src, double* dst) {
-    // forward: y_v = Linv_v (src_v - sum_{w earlier} L_vw y_w), levels ascending; y kept in vt
-    for (int l = 0; l < P.num_levels; ++l) {
-      const int k0 = P.level_ptr[l], k1 = P.level_ptr[l + 1];
-      for (int k = k0 + gw; k < k1; k += nw) {
-        const int v = P.order[k];
-        const int e0 = P.row_ptr[v], e1 = P.row_ptr[v + 1];
-        double acc = 0.0;   // lane (grp, r6): partial of row r6 over this group's blocks
-        if (lane_on) {
-          for (int e = e0 + grp; e < e1; e += kRowsPerWarp) {
-            const double* L = P.Lblk + 36 * (size_t)P.row_slot[e] + r6 * 6;
-            const double* y = P.vt + 6 * (size_t)P.row_col[e];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc = fma(__ldcg(L + c), __ldcg(y + c), acc);
-          }
-        }
-        // sum the 5 groups (fixed order)
-        double tot = 0.0;
-#pragma unroll
-        for (int gq = 0; gq < kRowsPerWarp; ++gq) tot += __shfl_sync(0xffffffffu, acc, gq * 6 + (lane % 6));
-        const double tv = __ldcg(src + 6 * (size_t)v + (lane % 6)) - tot;     // lanes 0..5 hold t_v[0..5]
-        double yv = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const double tc = __shfl_sync(0xffffffffu, tv, c);
-          if (lane < 6 && c <= lane) yv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + lane * 6 + c), tc, yv);
-        }
-        if (lane < 6) P.vt[6 * (size_t)v + lane] = yv;
-      }
-      grid_barrier(P.barrier, epoch);
-    }
-    // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending
+  };
+  // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending; writes dst (and dst2)
+  auto backward = [&](double* dst, double* dst2) {
     for (int l = P.num_levels - 1; l >= 0; --l) {
-      const int k0 = P.level_ptr[l], k1 = P.level_ptr[l + 1];
-      for (int k = k0 + gw; k < k1; k += nw) {
-        const int v = P.order[k];
-        const int p0 = P.col_ptr[k], p1 = P.col_ptr[k + 1];
-        double acc = 0.0;   // lane (grp, c = r6): sum_u sum_r L_uv[r][c] x_u[r]
-        if (lane_on) {
-          for (int p = p0 + grp; p < p1; p += kRowsPerWarp) {
-            const double* L = P.Lblk + 36 * (size_t)p + r6;
-            const double* xu = dst + 6 * (size_t)P.col_row[p];
+      const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
+      const int mode = __ldg(P.level_split + l);
+      if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) chol_backward_staged<8>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) chol_backward_staged<16>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 32) { for (int kk = k0 + gw; kk < k1; kk += nw) chol_backward_staged<32>(P, kk, k1, lane, dst, dst2); }
+      else {
+        for (int k = k0 + gw; k < k1; k += nw) {
+          const int4 nm = __ldg(P.nodes + k);
+          const int v = nm.x, p0 = nm.y, p1 = nm.z;
+          double acc = 0.0;   // lane (grp, c = r6): sum_u sum_r L_uv[r][c] x_u[r]
+          if (lane_on) {
+            for (int p = p0 + grp; p < p1; p += kRowsPerWarp) {
+              const double* L = P.Lblk + 36 * (size_t)p + r6;
+              const double* xu = dst + 6 * (size_t)__ldg(P.col_row + p);
 #pragma unroll
-            for (int rr = 0; rr < 6; ++rr) acc = fma(__ldcg(L + rr * 6), __ldcg(xu + rr), acc);
+              for (int rr = 0; rr < 6; ++rr) acc = fma(__ldcg(L + rr * 6), __ldcg(xu + rr), acc);
+            }
           }
-        }
-        double tot = 0.0;
+          double tot = 0.0;
 #pragma unroll
-        for (int gq = 0; gq < kRowsPerWarp; ++gq) tot += __shfl_sync(0xffffffffu, acc, gq * 6 + (lane % 6));
-        const double sv = __ldcg(P.vt + 6 * (size_t)v + (lane % 6)) - tot;
-        double xv = 0.0;
+          for (int gq = 0; gq < kRowsPerWarp; ++gq) tot += __shfl_sync(0xffffffffu, acc, gq * 6 + (lane % 6));
+          const double sv = __ldcg(P.vt + 6 * (size_t)v + (lane % 6)) - tot;
+          double xv = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < 6; ++rr) {
-          const double sr = __shfl_sync(0xffffffffu, sv, rr);
-          if (lane < 6 && rr >= lane) xv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + rr * 6 + lane), sr, xv);
+          for (int rr = 0; rr < 6; ++rr) {
+            const double sr = __shfl_sync(0xffffffffu, sv, rr);
+            if (lane < 6 && rr >= lane) xv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + rr * 6 + lane), sr, xv);
+          }
+          if (lane < 6) { dst[6 * (size_t)v + lane] = xv; if (dst2) dst2[6 * (size_t)v + lane] = xv; }
         }
-        if (lane < 6) dst[6 * (size_t)v + lane] = xv;
       }
-      grid_barrier(P.barrier, epoch);
+      chol_mark(P, 300 + l);
+      chol_sync<kCluster>(P.barrier, epoch);
+      chol_mark(P, 400 + l);
     }
   };
 
-  // ---- PCG: x = 0, r = b ----
-  const int n6 = 6 * n;
-  for (int k = gtid; k < n6; k += gthreads) { P.x[k] = 0.0; P.r[k] = P.b[k]; P.z[k] = 0.0; P.vt[k] = 0.0; }
-  grid_barrier(P.barrier, epoch);
-  apply_minv(P.r, P.z);
-  double acc = 0.0;
-  for (int k = gtid; k < n6; k += gthreads) { const double zv = __ldcg(P.z + k); P.p[k] = zv; acc = fma(P.r[k], zv, acc); }
-  acc = cta_sum(acc, red);
-  int slot = 0;
-  if (threadIdx.x == 0) P.partials[(size_t)slot * G + blockIdx.x] = acc;
-  grid_barrier(P.barrier, epoch);
-  const double rho0 = reduce_partials(P.partials + (size_t)slot * G, G, &bcast);
-  double rho = rho0;
-  int iter = 0, flag = 0;
-  (void)fail;
-  const double stop = P.tolerance * P.tolerance * rho0;
-  if (rho0 > 0.0 && isfinite(rho0)) {
-    for (;;) {
-      // q = A p ; pq = p.q
-      acc = 0.0;
-      for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
-        const int i = base + grp;
-        if (lane_on && i < n) {
-          const double qv = bsr6_row<true>(P.A.Hdiag, P.A.Hoff, P.A.row_ptr, P.A.col_idx, P.p, P.dlm, i, r6);
-          const size_t k = 6 * (size_t)i + r6;
-          P.q[k] = qv;
-          acc = fma(qv, __ldcg(P.p + k), acc);
-        }
+  // ---- F + B: z = p = M^-1 b (inactive poses keep 0: their z/p are zeroed here first) ----
+  for (int k = gtid; k < n6; k += gthreads) { P.z[k] = 0.0; P.p[k] = 0.0; }
+  forward(std::true_type{});
+  backward(P.z, P.p);
+
+  // ---- CG ----
+  double rho = 0.0, rho0 = 0.0, bb = 0.0, rr = 0.0;
+  double xtb = 0.0, xtAx = 0.0, xtDx = 0.0;
+  int iter = 0, flag = 0, norm_kind = 0;
+  for (;;) {
+    // q = A p ; pq = p.q ; (first pass also rho = r.z and bb = b.b)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
+      const int i = base + grp;
+      if (lane_on && i < n) {
+        const double qv = bsr6_row<true>(P.A.Hdiag, P.A.Hoff, P.A.row_ptr, P.A.col_idx, P.p, P.dlm, i, r6);
+        const size_t k = 6 * (size_t)i + r6;
+        P.q[k] = qv;
+        a0 = fma(qv, __ldcg(P.p + k), a0);
+        if (iter == 0) { const double bv = P.b[k]; a1 = fma(bv, __ldcg(P.z + k), a1); a2 = fma(bv, bv, a2); }
       }
-      acc = cta_sum(acc, red);
-      slot = (slot + 1) % 4;
-      if (threadIdx.x == 0) P.partials[(size_t)slot * G + blockIdx.x] = acc;
-      grid_barrier(P.barrier, epoch);
-      const double pq = reduce_partials(P.partials + (size_t)slot * G, G, &bcast);
-      if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
-      const double alpha = rho / pq;
-      ++iter;
-      for (int k = gtid; k < n6; k += gthreads) {
-        P.x[k] += alpha * __ldcg(P.p + k);
-        P.r[k] -= alpha * __ldcg(P.q + k);
-      }
-      grid_barrier(P.barrier, epoch);
-      apply_minv(P.r, P.z);
-      acc = 0.0;
-      for (int k = gtid; k < n6; k += gthreads) acc = fma(P.r[k], __ldcg(P.z + k), acc);
-      acc = cta_sum(acc, red);
-      slot = (slot + 1) % 4;
-      if (threadIdx.x == 0) P.partials[(size_t)slot * G + blockIdx.x] = acc;
-      grid_barrier(P.barrier, epoch);
-      const double rho_new = reduce_partials(P.partials + (size_t)slot * G, G, &bcast);
-      const double beta = rho_new / rho;
-      rho = rho_new;
-      if (fabs(rho) <= stop) break;
-      if (iter >= P.max_iterations) { flag = flag ? flag : 1; break; }
-      for (int k = gtid; k < n6; k += gthreads) P.p[k] = __ldcg(P.z + k) + beta * P.p[k];
-      grid_barrier(P.barrier, epoch);
     }
-  }
-  // ---- epilogue: x^T b, x^T (H + D) x, x^T D x ----
-  grid_barrier(P.barrier, epoch);
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int base = gw * kRowsPerWarp; base < n; base += nw * kRowsPerWarp) {
-    const int i = base + grp;
-    if (lane_on && i < n) {
-      const double ax = bsr6_row<true>(P.A.Hdiag, P.A.Hoff, P.A.row_ptr, P.A.col_idx, P.x, P.dlm, i, r6);
-      const size_t k = 6 * (size_t)i + r6;
-      const double xv = __ldcg(P.x + k);
-      a0 = fma(xv, P.b[k], a0); a1 = fma(xv, ax, a1); a2 = fma(xv * xv, P.dlm[k], a2);
+    a0 = cta_sum_n(a0, red);
+    if (iter == 0) { a1 = cta_sum_n(a1, red); a2 = cta_sum_n(a2, red); }
+    double* part = next_region();
+    if (threadIdx.x == 0) { part[blockIdx.x] = a0; if (iter == 0) { part[G + blockIdx.x] = a1; part[2 * G + blockIdx.x] = a2; } }
+    chol_sync<kCluster>(P.barrier, epoch);
+    chol_mark(P, 2);
+    const double pq = reduce_partials(part, G, &bcast);
+    if (iter == 0) {
+      rho0 = rho = reduce_partials(part + G, G, &bcast);
+      bb = reduce_partials(part + 2 * G, G, &bcast);
+      if (!(rho0 > 0.0) || !isfinite(rho0)) { flag = (rho0 == 0.0) ? 0 : 2; break; }
     }
+    if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
+    const double alpha = rho / pq;
+    ++iter;
+    // x += alpha p ; r -= alpha q ; Ax += alpha q ; rr = r.r ; x.b ; x.Ax ; x.D x
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int k = gtid; k < n6; k += gthreads) {
+      const double qv = __ldcg(P.q + k);
+      const double xv = P.x[k] + alpha * __ldcg(P.p + k);
+      const double rv = P.r[k] - alpha * qv;
+      const double av = P.ax[k] + alpha * qv;
+      P.x[k] = xv; P.r[k] = rv; P.ax[k] = av;
+      s0 = fma(rv, rv, s0); s1 = fma(xv, P.b[k], s1); s2 = fma(xv, av, s2); s3 = fma(xv * xv, P.dlm[k], s3);
+    }
+    s0 = cta_sum_n(s0, red); s1 = cta_sum_n(s1, red); s2 = cta_sum_n(s2, red); s3 = cta_sum_n(s3, red);
+    part = next_region();
+    if (threadIdx.x == 0) { part[blockIdx.x] = s0; part[G + blockIdx.x] = s1; part[2 * G + blockIdx.x] = s2; part[3 * G + blockIdx.x] = s3; }
+    chol_sync<kCluster>(P.barrier, epoch);
+    chol_mark(P, 3);
+    rr = reduce_partials(part, G, &bcast);
+    xtb = reduce_partials(part + G, G, &bcast);
+    xtAx = reduce_partials(part + 2 * G, G, &bcast);
+    xtDx = reduce_partials(part + 3 * G, G, &bcast);
+    if (rr <= P.tolerance * P.tolerance * bb) { norm_kind = 1; break; }          // ||b - A x|| <= tol ||b||
+    // z = M^-1 r
+    for (int k = gtid; k < n6; k += gthreads) { P.vt[k] = P.r[k]; }
+    chol_sync<kCluster>(P.barrier, epoch);
+    forward(std::false_type{});
+    backward(P.z, nullptr);
+    double t0 = 0.0;
+    for (int k = gtid; k < n6; k += gthreads) t0 = fma(P.r[k], __ldcg(P.z + k), t0);
+    t0 = cta_sum_n(t0, red);
+    part = next_region();
+    if (threadIdx.x == 0) part[blockIdx.x] = t0;
+    chol_sync<kCluster>(P.barrier, epoch);
+    const double rho_new = reduce_partials(part, G, &bcast);
+    const double beta = rho_new / rho;
+    rho = rho_new;
+    if (fabs(rho) <= P.tolerance * P.tolerance * rho0) break;                      // sqrt(r.M^-1 r) <= tol sqrt(b.M^-1 b)
+    if (iter >= P.max_iterations) { flag = 1; break; }
+    for (int k = gtid; k < n6; k += gthreads) P.p[k] = __ldcg(P.z + k) + beta * P.p[k];
+    chol_sync<kCluster>(P.barrier, epoch);
   }
-  a0 = cta_sum(a0, red); a1 = cta_sum(a1, red); a2 = cta_sum(a2, red);
-  double* pe = P.partials + (size_t)4 * G;
-  if (threadIdx.x == 0) { pe[blockIdx.x] = a0; pe[G + blockIdx.x] = a1; pe[2 * G + blockIdx.x] = a2; }
-  grid_barrier(P.barrier, epoch);
-  const double s0 = reduce_partials(pe, G, &bcast);
-  const double s1 = reduce_partials(pe + G, G, &bcast);
-  const double s2 = reduce_partials(pe + 2 * G, G, &bcast);
+  chol_mark(P, 4);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    P.scalars->xtb = s0; P.scalars->xtAx = s1; P.scalars->xtDx = s2;
-    P.scalars->pcg_gamma0 = rho0; P.scalars->pcg_gamma = fabs(rho);
+    P.scalars->xtb = xtb; P.scalars->xtAx = xtAx; P.scalars->xtDx = xtDx;
+    if (norm_kind == 1) { P.scalars->pcg_gamma0 = bb; P.scalars->pcg_gamma = rr; }
+    else { P.scalars->pcg_gamma0 = rho0; P.scalars->pcg_gamma = fabs(rho); }
     unsigned int failed;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(failed) : "l"(P.barrier + 1) : "memory");
     P.scalars->pcg_iterations = iter; P.scalars->pcg_flag = failed ? 3 : flag;
@@ -375,17 +691,24 @@ __global__ void __launch_bounds__(kPcgThreads) level_chol_pcg_kernel(const CholP
 // host side: symbolic analysis
 // ---------------------------------------------------------------------------------------------
 template <typename Tp>
-static int chol_upload(Tp** dst, const std::vector<Tp>& src, cudaStream_t stream) {
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(src.size(), 1) * sizeof(Tp)));
+static int chol_upload(LevelChol* C, int device, Tp** dst, const std::vector<Tp>& src, cudaStream_t stream) {
+  PGO_TRY(chol_alloc(C, device, dst, src.size()));
   if (!src.empty()) CUDA_TRY(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice, stream));
   return 0;
 }
 
-static int level_chol_analyze(LevelChol** out, int N, const unsigned char* active, const int* a_row_ptr,
-                              const int* a_col_idx, double max_fill_ratio, cudaStream_t stream) {
-  LevelChol* C = new LevelChol();
-  *out = C;
-  C->N = N;
+// Pure host part: elimination levels, structure of L, gather map, Schur tasks.
+struct LevelCholSymbolic {
+  bool usable = false;
+  int n_nodes = 0, num_levels = 0, max_degree = 0;
+  long long n_slots = 0;
+  std::vector<int> level_ptr, level_split, col_row, l2a;
+  std::vector<int4> nodes;
+  std::vector<CholTask> tasks;
+};
+
+static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char* active, const int* a_row_ptr,
+                               const int* a_col_idx, double max_fill_ratio) {
   std::vector<std::vector<int>> adj(N);
   int n_nodes = 0;
   long long a_off = 0;
@@ -395,23 +718,30 @@ static int level_chol_analyze(LevelChol** out, int N, const unsigned char* activ
     adj[i].assign(a_col_idx + a_row_ptr[i], a_col_idx + a_row_ptr[i + 1]);   // sorted, symmetric, active only
     a_off += (long long)adj[i].size();
   }
-  C->n_nodes = n_nodes;
+  S->n_nodes = n_nodes;
   if (n_nodes == 0) return 0;
   const long long fill_cap = (long long)std::min(max_fill_ratio * (double)(a_off / 2 + n_nodes) + 64.0, 4.0e9);
 
   std::vector<int> pos(N, -1), order;
   order.reserve(n_nodes);
-  std::vector<int> level_ptr(1, 0), level_split;
+  std::vector<int>& level_ptr = S->level_ptr;
+  std::vector<int>& level_split = S->level_split;
+  level_ptr.assign(1, 0);
   std::vector<std::vector<int>> col_rows(N);       // structure of L's column v (row pose ids, sorted by id)
   std::vector<unsigned char> alive(N, 0), blocked(N, 0);
   std::vector<int> alive_list;
   for (int i = 0; i < N; ++i) if (active[i]) { alive[i] = 1; alive_list.push_back(i); }
   std::vector<std::pair<int, int>> cand;
   std::vector<int> tmp, sel;
-  long long slots = 0;
+  long long slots = 0, work = 0;
+  const long long work_cap = 100LL * (a_off + n_nodes) + 32000000LL;   // symbolic effort bound (merged adjacency entries)
   while (!alive_list.empty()) {
     int dmin = 1 << 30;
-    for (int v : alive_list) dmin = std::min(dmin, (int)adj[v].size());
+    long long dsum = 0;
+    for (int v : alive_list) { dmin = std::min(dmin, (int)adj[v].size()); dsum += (long long)adj[v].size(); }
+    // mesh-like graphs (2-D grids, dense random loops) fill in quickly: give up as soon as the remaining
+    // graph is both large and dense instead of grinding through a factor that would not pay off
+    if (max_fill_ratio < 1e29 && alive_list.size() > 20000 && dsum > 16LL * (long long)alive_list.size()) return 0;
     const int thr = 2 * dmin + 2;
     cand.clear();
     for (int v : alive_list) if ((int)adj[v].size() <= thr) cand.emplace_back((int)adj[v].size(), v);
@@ -432,12 +762,13 @@ static int level_chol_analyze(LevelChol** out, int N, const unsigned char* activ
       slots += (long long)adj[v].size();
       lvl_maxdeg = std::max(lvl_maxdeg, (int)adj[v].size());
     }
-    if (slots > fill_cap || (int)level_ptr.size() > 8192) return 0;   // not usable (too much fill / too deep)
+    if (slots > fill_cap || (int)level_ptr.size() > 8192 || work > work_cap) return 0;   // not usable (fill / depth / effort)
     for (int v : sel) {
       const std::vector<int>& nb = col_rows[v];
       for (int u : nb) {
         // adj[u] = (adj[u] U nb) \ {u, v}
         tmp.clear();
+        work += (long long)(adj[u].size() + nb.size());
         std::set_union(adj[u].begin(), adj[u].end(), nb.begin(), nb.end(), std::back_inserter(tmp));
         adj[u].clear();
         for (int x : tmp) if (x != u && x != v) adj[u].push_back(x);
@@ -445,22 +776,22 @@ static int level_chol_analyze(LevelChol** out, int N, const unsigned char* activ
       alive[v] = 0;
       std::vector<int>().swap(adj[v]);
     }
-    // unblock
     for (auto& dv : cand) { blocked[dv.second] = 0; }
     for (int v : sel) for (int u : col_rows[v]) blocked[u] = 0;
     size_t w = 0;
     for (size_t k = 0; k < alive_list.size(); ++k) if (alive[alive_list[k]]) alive_list[w++] = alive_list[k];
     alive_list.resize(w);
     level_ptr.push_back((int)order.size());
-    level_split.push_back(lvl_maxdeg > 10 ? 1 : 0);
-    C->max_degree = std::max(C->max_degree, lvl_maxdeg);
+    level_split.push_back(lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : lvl_maxdeg <= 16 ? 32 : 1);
+    S->max_degree = std::max(S->max_degree, lvl_maxdeg);
   }
-  C->num_levels = (int)level_split.size();
-  C->n_slots = slots;
-  C->factor_blocks = slots + n_nodes;
+  S->num_levels = (int)level_split.size();
+  S->n_slots = slots;
 
   // column-major slots by elimination position
-  std::vector<int> col_ptr(n_nodes + 1, 0), col_row((size_t)slots);
+  std::vector<int> col_ptr(n_nodes + 1, 0);
+  std::vector<int>& col_row = S->col_row;
+  col_row.resize((size_t)slots);
   for (int k = 0; k < n_nodes; ++k) col_ptr[k + 1] = col_ptr[k] + (int)col_rows[order[k]].size();
   for (int k = 0; k < n_nodes; ++k) std::copy(col_rows[order[k]].begin(), col_rows[order[k]].end(), col_row.begin() + col_ptr[k]);
   auto slot_of = [&](int row, int col) -> int {   // block (row, col), col eliminated first
@@ -470,20 +801,12 @@ static int level_chol_analyze(LevelChol** out, int N, const unsigned char* activ
     const int* it = std::lower_bound(b, e, row);
     return (it != e && *it == row) ? (int)(it - col_row.data()) : -1;
   };
-  // row lists (by pose id)
-  std::vector<int> row_ptr(N + 1, 0), row_slot((size_t)slots), row_col((size_t)slots);
-  for (long long s = 0; s < slots; ++s) row_ptr[col_row[s] + 1]++;
-  for (int i = 0; i < N; ++i) row_ptr[i + 1] += row_ptr[i];
-  {
-    std::vector<int> fillp(row_ptr.begin(), row_ptr.end() - 1);
-    for (int k = 0; k < n_nodes; ++k)
-      for (int s = col_ptr[k]; s < col_ptr[k + 1]; ++s) { const int u = col_row[s]; row_slot[fillp[u]] = s; row_col[fillp[u]] = order[k]; fillp[u]++; }
-  }
   // Schur update tasks per node
-  std::vector<int> task_ptr(n_nodes + 1, 0);
-  std::vector<CholTask> tasks;
+  S->nodes.resize((size_t)n_nodes + 1);
+  std::vector<CholTask>& tasks = S->tasks;
   for (int k = 0; k < n_nodes; ++k) {
     const int p0 = col_ptr[k], p1 = col_ptr[k + 1];
+    S->nodes[k] = make_int4(order[k], p0, p1, (int)tasks.size());
     for (int p = p0; p < p1; ++p) {
       tasks.push_back({p, p, -col_row[p] - 1});                  // diagonal of row(p)
       for (int q = p0; q < p1; ++q) {
@@ -491,66 +814,143 @@ static int level_chol_analyze(LevelChol** out, int N, const unsigned char* activ
         const int u = col_row[p], w = col_row[q];
         if (pos[u] > pos[w]) {                                   // block (u, w): rows u, cols w = L_p L_q^T
           const int t = slot_of(u, w);
-          if (t < 0) { return set_error(PGO_ERR_NUMERICAL, "level Cholesky: missing fill slot"); }
+          if (t < 0) return set_error(PGO_ERR_NUMERICAL, "level Cholesky: missing fill slot");
           tasks.push_back({p, q, t});
         }
       }
     }
-    task_ptr[k + 1] = (int)tasks.size();
+    if (tasks.size() > 2000000000ull) return 0;
   }
-  C->n_tasks = (long long)tasks.size();
-  // A (BSR off-diagonal) -> L slot
-  std::vector<int> a2l((size_t)a_row_ptr[N], -1);
+  S->nodes[n_nodes] = make_int4(-1, (int)slots, (int)slots, (int)tasks.size());
+  // L slot <- A (BSR off-diagonal) entry
+  S->l2a.assign((size_t)slots, -1);
   for (int i = 0; i < N; ++i)
     for (int p = a_row_ptr[i]; p < a_row_ptr[i + 1]; ++p) {
       const int j = a_col_idx[p];
-      if (active[i] && active[j] && pos[j] < pos[i]) a2l[p] = slot_of(i, j);
+      if (active[i] && active[j] && pos[j] < pos[i]) {
+        const int s = slot_of(i, j);
+        if (s < 0) return set_error(PGO_ERR_NUMERICAL, "level Cholesky: missing slot for a Hessian block");
+        S->l2a[s] = p;
+      }
     }
+  S->usable = true;
+  return 0;
+}
 
-  PGO_TRY(chol_upload(&C->level_ptr, level_ptr, stream));
-  PGO_TRY(chol_upload(&C->level_split, level_split, stream));
-  PGO_TRY(chol_upload(&C->order, order, stream));
-  PGO_TRY(chol_upload(&C->col_ptr, col_ptr, stream));
-  PGO_TRY(chol_upload(&C->col_row, col_row, stream));
-  PGO_TRY(chol_upload(&C->row_ptr, row_ptr, stream));
-  PGO_TRY(chol_upload(&C->row_slot, row_slot, stream));
-  PGO_TRY(chol_upload(&C->row_col, row_col, stream));
-  PGO_TRY(chol_upload(&C->task_ptr, task_ptr, stream));
-  PGO_TRY(chol_upload(&C->tasks, tasks, stream));
-  PGO_TRY(chol_upload(&C->a2l, a2l, stream));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&C->Lblk), std::max<size_t>((size_t)slots * 36, 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&C->Ldiag), (size_t)N * 36 * sizeof(double)));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&C->vt), (size_t)N * 6 * sizeof(double)));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&C->barrier), 4 * sizeof(unsigned int)));
-  int dev = 0, sms = 0, per_sm = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel, kPcgThreads, 0));
-  C->max_ctas = std::max(1, std::min(per_sm, 2) * sms);
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&C->partials), (size_t)8 * C->max_ctas * sizeof(double)));
+static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned char* active, const int* a_row_ptr,
+                              const int* a_col_idx, double max_fill_ratio, cudaStream_t stream) {
+  LevelChol* C = new LevelChol();
+  *out = C;
+  C->N = N;
+  LevelCholSymbolic S;
+  PGO_TRY(level_chol_symbolic(&S, N, active, a_row_ptr, a_col_idx, max_fill_ratio));
+  C->n_nodes = S.n_nodes;
+  if (!S.usable) return 0;
+  C->num_levels = S.num_levels;
+  C->max_degree = S.max_degree;
+  C->n_slots = S.n_slots;
+  C->factor_blocks = S.n_slots + S.n_nodes;
+  C->n_tasks = (long long)S.tasks.size();
+  PGO_TRY(chol_upload(C, device, &C->level_ptr, S.level_ptr, stream));
+  PGO_TRY(chol_upload(C, device, &C->level_split, S.level_split, stream));
+  PGO_TRY(chol_upload(C, device, &C->nodes, S.nodes, stream));
+  PGO_TRY(chol_upload(C, device, &C->col_row, S.col_row, stream));
+  PGO_TRY(chol_upload(C, device, &C->l2a, S.l2a, stream));
+  PGO_TRY(chol_upload(C, device, &C->tasks, S.tasks, stream));
+  PGO_TRY(chol_alloc(C, device, &C->Lblk, (size_t)S.n_slots * 36));
+  PGO_TRY(chol_alloc(C, device, &C->Ldiag, (size_t)N * 36));
+  PGO_TRY(chol_alloc(C, device, &C->vt, (size_t)N * 6));
+  PGO_TRY(chol_alloc(C, device, &C->barrier, 4));
+  static int per_sm = -1, cluster_max = -1;   // launch-shape queries are per kernel, not per graph
+  const int sms = pool_num_sms(device);
+  if (per_sm < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<false>, kCholThreads, kCholSmemBytes));
+  }
+  C->max_ctas = std::max(1, std::min(per_sm, 1) * sms);
+  // cluster shape: the largest cluster (16, then 8) the device can co-schedule
+  C->cluster_ctas = 0;
+  if (S.n_nodes <= kCholClusterMaxNodes && cluster_max >= 0) C->cluster_ctas = cluster_max;
+  if (S.n_nodes <= kCholClusterMaxNodes && cluster_max < 0) {
+    cluster_max = 0;
+    cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    for (int cs : {16, 8}) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = kCholSmemBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, level_chol_pcg_kernel<true>, &cfg) == cudaSuccess && nclusters >= 1) {
+        C->cluster_ctas = cluster_max = cs;
+        break;
+      }
+      cudaGetLastError();
+    }
+  }
+  PGO_TRY(chol_alloc(C, device, &C->partials, (size_t)8 * 4 * std::max(C->max_ctas, 16)));
   CUDA_TRY(cudaStreamSynchronize(stream));
   C->usable = true;
   return 0;
 }
 
+struct LmDiagonal {           // LevenbergMarquardtStrategy::ComputeStep's D = sqrt(diagonal / radius), squared
+  int mode;                   // 0 new diagonal from H, 1 reuse, 2 dlm given
+  double min_diag, max_diag, radius;
+  double* diagonal; double* dlm;
+};
+
 // Factor (H + D) and solve (H + D) x = b by PCG preconditioned with the factor, one launch.
-static int level_chol_solve(LevelChol* C, BsrView A, const double* dlm, const double* b, double* x, double* r, double* z,
-                            double* q, double* p, int max_iterations, double tolerance, int num_ctas,
-                            DeviceScalars* scalars, cudaStream_t stream, long long* launches) {
+static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const unsigned char* active, const double* b,
+                            double* x, double* r, double* z, double* q, double* p, double* ax, int max_iterations,
+                            double tolerance, int num_ctas, DeviceScalars* scalars, cudaStream_t stream,
+                            long long* launches) {
   CholParams P;
-  P.A = A; P.dlm = dlm; P.b = b; P.x = x; P.r = r; P.z = z; P.q = q; P.p = p;
+  P.A = A; P.lm_mode = lm.mode; P.min_diag = lm.min_diag; P.max_diag = lm.max_diag; P.radius = lm.radius;
+  P.diagonal = lm.diagonal; P.dlm = lm.dlm; P.active = active;
+  P.b = b; P.x = x; P.r = r; P.z = z; P.q = q; P.p = p; P.ax = ax;
   P.num_levels = C->num_levels; P.n_nodes = C->n_nodes;
-  P.level_ptr = C->level_ptr; P.level_split = C->level_split; P.order = C->order; P.col_ptr = C->col_ptr;
-  P.col_row = C->col_row; P.row_ptr = C->row_ptr; P.row_slot = C->row_slot; P.row_col = C->row_col;
-  P.task_ptr = C->task_ptr; P.a2l = C->a2l; P.tasks = C->tasks; P.Lblk = C->Lblk; P.Ldiag = C->Ldiag; P.vt = C->vt;
+  P.level_ptr = C->level_ptr; P.level_split = C->level_split; P.col_row = C->col_row; P.l2a = C->l2a; P.nodes = C->nodes;
+  P.tasks = C->tasks; P.Lblk = C->Lblk; P.Ldiag = C->Ldiag; P.vt = C->vt;
   P.n_slots = C->n_slots; P.partials = C->partials; P.barrier = C->barrier; P.scalars = scalars;
-  P.max_iterations = max_iterations; P.tolerance = tolerance; P.do_factor = 1;
+  P.max_iterations = max_iterations; P.tolerance = tolerance;
+  static const bool want_timeline = getenv("PGO_TIMELINE") != nullptr;
+  static unsigned long long* timeline_d = nullptr;
+  P.timeline = nullptr;
+  if (want_timeline) {
+    if (!timeline_d) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&timeline_d), 2001 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(timeline_d, 0, 2001 * sizeof(unsigned long long), stream));
+    P.timeline = timeline_d;
+  }
   CUDA_TRY(cudaMemsetAsync(C->barrier, 0, 4 * sizeof(unsigned int), stream));
-  int grid = num_ctas > 0 ? num_ctas : std::max(1, (A.n + 39) / 40);
-  grid = std::max(1, std::min(grid, C->max_ctas));
-  void* args[] = {&P};
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel, dim3(grid), dim3(kPcgThreads), args, 0, stream));
+  if (C->cluster_ctas > 0 && num_ctas <= 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C->cluster_ctas); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = kCholSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, level_chol_pcg_kernel<true>, P));
+  } else {
+    int grid = num_ctas > 0 ? num_ctas : std::max(1, (A.n + 79) / 80);
+    grid = std::max(1, std::min(grid, C->max_ctas));
+    void* args[] = {&P};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<false>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
+  }
   if (launches) (*launches)++;
+  if (want_timeline) {
+    std::vector<unsigned long long> h(2001);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), timeline_d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    fprintf(stderr, "[pgo timeline] shape=%s ctas=%d levels=%d marks=%llu :", C->cluster_ctas > 0 && num_ctas <= 0 ? "cluster" : "grid",
+            C->cluster_ctas > 0 && num_ctas <= 0 ? C->cluster_ctas : -1, C->num_levels, h[0]);
+    for (unsigned long long k = 0; k < h[0] && k < 1000; ++k)
+      fprintf(stderr, " %llu@%.2f", h[2 + 2 * k], (double)(h[1 + 2 * k] - h[1]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 

@@ -1,0 +1,163 @@
+// pgo_pool.cuh -- per-device caches of the host runtime: device memory blocks, streams, events and
+// small pinned buffers survive pgo_graph_destroy and are handed to the next graph, so that the
+// one-shot entry point (pgo_solve_pose_graph: upload + solve + download, what ceres::Solve is for the
+// reference) does not pay cudaMalloc / cudaFree / cudaMallocHost / cudaStreamCreate on every call.
+// pgo_release_cached_memory() returns everything to the driver.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace pgo {
+
+struct DevicePool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;     // size -> device pointer
+  size_t cached_bytes = 0;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> events;
+  std::vector<void*> pinned;                    // kPinnedBytes each
+  int num_sms = 0;
+};
+
+constexpr size_t kPinnedBytes = 4096;
+constexpr int kMaxDevices = 64;
+
+inline DevicePool& device_pool(int device) {
+  static DevicePool pools[kMaxDevices];
+  return pools[device < 0 || device >= kMaxDevices ? 0 : device];
+}
+
+inline size_t pool_round(size_t bytes) {
+  if (bytes < 512) return 512;
+  return (bytes + 511) & ~(size_t)511;
+}
+
+// Device memory: exact-ish fit from the cache (<= 25% slack), else cudaMalloc (flushing the cache on failure).
+inline cudaError_t pool_alloc(int device, void** out, size_t bytes) {
+  DevicePool& P = device_pool(device);
+  const size_t want = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.free_blocks.lower_bound(want);
+    if (it != P.free_blocks.end() && it->first <= want + want / 4) {
+      *out = it->second;
+      P.cached_bytes -= it->first;
+      P.free_blocks.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> lk(P.mu);
+      for (auto& kv : P.free_blocks) drop.push_back(kv.second);
+      P.free_blocks.clear();
+      P.cached_bytes = 0;
+    }
+    for (void* p : drop) cudaFree(p);
+    e = cudaMalloc(out, want);
+  }
+  return e;
+}
+
+// The caller guarantees no work that touches the block is still in flight.
+inline void pool_free(int device, void* p, size_t bytes) {
+  if (!p) return;
+  DevicePool& P = device_pool(device);
+  const size_t sz = pool_round(bytes);
+  size_t free_b = 0, total_b = 0;
+  bool keep = true;
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (P.cached_bytes + sz > ((size_t)8 << 30)) keep = false;   // never sit on more than 8 GiB
+    if (keep) { P.free_blocks.emplace(sz, p); P.cached_bytes += sz; }
+  }
+  (void)free_b; (void)total_b;
+  if (!keep) cudaFree(p);
+}
+
+inline cudaError_t pool_stream(int device, cudaStream_t* s) {
+  DevicePool& P = device_pool(device);
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!P.streams.empty()) { *s = P.streams.back(); P.streams.pop_back(); return cudaSuccess; }
+  }
+  return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+inline void pool_stream_release(int device, cudaStream_t s) {
+  if (!s) return;
+  DevicePool& P = device_pool(device);
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.streams.push_back(s);
+}
+inline cudaError_t pool_event(int device, cudaEvent_t* ev) {
+  DevicePool& P = device_pool(device);
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!P.events.empty()) { *ev = P.events.back(); P.events.pop_back(); return cudaSuccess; }
+  }
+  return cudaEventCreate(ev);
+}
+inline void pool_event_release(int device, cudaEvent_t ev) {
+  if (!ev) return;
+  DevicePool& P = device_pool(device);
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.events.push_back(ev);
+}
+inline cudaError_t pool_pinned(int device, void** p) {
+  DevicePool& P = device_pool(device);
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!P.pinned.empty()) { *p = P.pinned.back(); P.pinned.pop_back(); return cudaSuccess; }
+  }
+  return cudaMallocHost(p, kPinnedBytes);
+}
+inline void pool_pinned_release(int device, void* p) {
+  if (!p) return;
+  DevicePool& P = device_pool(device);
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.pinned.push_back(p);
+}
+inline int pool_num_sms(int device) {
+  DevicePool& P = device_pool(device);
+  if (P.num_sms == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); n = 1; }
+    P.num_sms = n;
+  }
+  return P.num_sms;
+}
+
+// Return every cached resource of `device` (or of all devices when device < 0) to the driver.
+inline void pool_release(int device) {
+  for (int d = 0; d < kMaxDevices; ++d) {
+    if (device >= 0 && d != device) continue;
+    DevicePool& P = device_pool(d);
+    std::vector<void*> blocks, pins;
+    std::vector<cudaStream_t> st;
+    std::vector<cudaEvent_t> ev;
+    {
+      std::lock_guard<std::mutex> lk(P.mu);
+      for (auto& kv : P.free_blocks) blocks.push_back(kv.second);
+      P.free_blocks.clear(); P.cached_bytes = 0;
+      st.swap(P.streams); ev.swap(P.events); pins.swap(P.pinned);
+    }
+    if (blocks.empty() && st.empty() && ev.empty() && pins.empty()) continue;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d);
+    for (void* p : blocks) cudaFree(p);
+    for (void* p : pins) cudaFreeHost(p);
+    for (cudaStream_t s : st) cudaStreamDestroy(s);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    cudaSetDevice(prev);
+  }
+}
+
+}  // namespace pgo

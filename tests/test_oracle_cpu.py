@@ -217,7 +217,7 @@ def test_cabi_exports_every_declared_symbol(pgo):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     assert set(pgo.EXPORTED_SYMBOLS) == declared
-    assert lib.pgo_abi_version() == 1
+    assert lib.pgo_abi_version() == 2
 
 
 def test_cabi_defaults_mirror_ceres_and_reference(pgo):
@@ -226,6 +226,30 @@ def test_cabi_defaults_mirror_ceres_and_reference(pgo):
     assert (o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (1e-6, 1e-10, 1e-8)
     assert (o.initial_trust_region_radius, o.min_relative_decrease) == (1e4, 1e-3)
     assert o.loss_type == pgo.LOSS_HUBER and o.loss_a == 1.0 and o.jacobi_scaling == 1
+
+
+def test_host_structure_analysis(pgo, D):
+    """pgo_analyze_structure (host-only): block-CSR pattern size and the level-scheduled elimination order."""
+    g = D.kitti00()
+    info = pgo.analyze_structure(g.n_poses, g.edge_ids, g.pose_const)
+    assert info.variable_poses == 4540
+    pairs = {(min(a, b), max(a, b)) for a, b in g.edge_ids.tolist() if a != 0 and b != 0}
+    assert info.hessian_blocks == 2 * len(pairs) + g.n_poses
+    assert info.factor_usable == 1 and info.factor_levels <= 40            # a chain halves per level
+    assert info.factor_blocks < 4 * info.hessian_blocks                    # little fill on a beam-like graph
+    # a pure chain of n poses eliminates in about log2(n) levels with no fill beyond the chain itself
+    n = 1025
+    chain = np.stack([np.arange(1, n), np.arange(0, n - 1)], 1).astype(np.int32)
+    const = np.zeros(n, np.uint8)
+    const[0] = 1
+    ci = pgo.analyze_structure(n, chain, const)
+    assert ci.variable_poses == n - 1 and ci.factor_levels <= 12 and ci.factor_blocks <= ci.hessian_blocks
+    # dense random loops exceed a fill limit of 2x -> reported unusable, AUTO would fall back to block-Jacobi PCG
+    t = D.torus(3000, winds=20, loop_fraction=0.3)
+    ti = pgo.analyze_structure(t.n_poses, t.edge_ids, t.pose_const, max_fill_ratio=2.0)
+    assert ti.factor_usable == 0
+    with pytest.raises(pgo.PgoError):
+        pgo.analyze_structure(10, np.array([[0, 10]], np.int32))
 
 
 def test_no_cpu_fallback(pgo):
