@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -92,40 +93,46 @@ struct pgo_graph {
   long long launches = 0;
   double setup_s = 0.0;
   std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
+  std::vector<double> pose_stage;                 // host staging for the [N][7] <-> [N][8] pose layouts
 };
 
 // Host-only structure analysis shared by pgo_graph_create and pgo_analyze_structure: variable poses (used by an
 // edge and not constant) and the block-CSR pattern of the off-diagonal part of J^T J.
 struct HostPattern {
   std::vector<unsigned char> active;
-  std::vector<int> row_ptr, col_idx, mult;
-  std::vector<unsigned long long> uniq;   // (row << 32 | col), sorted
+  std::vector<int> row_ptr, col_idx;
+  std::vector<int> half_slot;             // [2E]: slot of block (a,b) at 2e, of (b,a) at 2e+1; -1 = none; <= -2: -(slot)-2, shared by several edges
   bool has_dup = false;
 };
 static void build_pattern(int N, int E, const int* edge_ids, const unsigned char* pose_const, HostPattern* out) {
   out->active.assign(N, 0);
   for (int e = 0; e < E; ++e) { out->active[edge_ids[2 * e]] = 1; out->active[edge_ids[2 * e + 1]] = 1; }
   if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) out->active[i] = 0;
-  std::vector<unsigned long long> sorted;
-  sorted.reserve(2 * (size_t)E);
+  struct Half { unsigned long long key; int idx; };
+  std::vector<Half> halves;
+  halves.reserve(2 * (size_t)E);
+  out->half_slot.assign(2 * (size_t)E, -1);
   for (int e = 0; e < E; ++e) {
     const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
     if (out->active[a] && out->active[b]) {
-      sorted.push_back(((unsigned long long)a << 32) | (unsigned)b);
-      sorted.push_back(((unsigned long long)b << 32) | (unsigned)a);
+      halves.push_back({((unsigned long long)a << 32) | (unsigned)b, 2 * e});
+      halves.push_back({((unsigned long long)b << 32) | (unsigned)a, 2 * e + 1});
     }
   }
-  std::sort(sorted.begin(), sorted.end());
-  out->uniq.reserve(sorted.size());
-  for (size_t k = 0; k < sorted.size(); ++k) {
-    if (k == 0 || sorted[k] != sorted[k - 1]) { out->uniq.push_back(sorted[k]); out->mult.push_back(1); }
-    else { out->mult.back()++; out->has_dup = true; }
-  }
+  std::sort(halves.begin(), halves.end(), [](const Half& x, const Half& y) { return x.key < y.key || (x.key == y.key && x.idx < y.idx); });
   out->row_ptr.assign(N + 1, 0);
-  out->col_idx.resize(out->uniq.size());
-  for (size_t k = 0; k < out->uniq.size(); ++k) {
-    out->row_ptr[(int)(out->uniq[k] >> 32) + 1]++;
-    out->col_idx[k] = (int)(out->uniq[k] & 0xffffffffu);
+  out->col_idx.clear();
+  out->col_idx.reserve(halves.size());
+  for (size_t k = 0; k < halves.size();) {
+    size_t k2 = k + 1;
+    while (k2 < halves.size() && halves[k2].key == halves[k].key) ++k2;
+    const int slot = (int)out->col_idx.size();
+    out->col_idx.push_back((int)(halves[k].key & 0xffffffffu));
+    out->row_ptr[(int)(halves[k].key >> 32) + 1]++;
+    const bool dup = k2 - k > 1;
+    if (dup) out->has_dup = true;
+    for (size_t q = k; q < k2; ++q) out->half_slot[halves[q].idx] = dup ? -slot - 2 : slot;
+    k = k2;
   }
   for (int i = 0; i < N; ++i) out->row_ptr[i + 1] += out->row_ptr[i];
 }
@@ -242,6 +249,9 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
   PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
   const double t0 = wall_s();
+  static const bool prof = getenv("PGO_PROFILE_HOST") != nullptr;
+  double tp = t0;
+  auto lap = [&](const char* what) { if (prof) { const double t = wall_s(); fprintf(stderr, "[pgo create] %-28s %8.1f us\n", what, 1e6 * (t - tp)); tp = t; } };
   CUDA_TRY(cudaSetDevice(device));
   pgo_graph* g = new pgo_graph();
   g->device = device;
@@ -259,25 +269,22 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   // ---- which poses are variables, identity information?, block-CSR pattern of the off-diagonal part ----
   g->identity_info = true;
   if (edge_sqrt_info) {
-    for (size_t k = 0; k < (size_t)E * 36 && g->identity_info; ++k) {
-      const int rc = (int)(k % 36);
-      if (edge_sqrt_info[k] != ((rc / 6 == rc % 6) ? 1.0 : 0.0)) g->identity_info = false;
-    }
+    static const double eye[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+    for (int e = 0; e < E && g->identity_info; ++e)
+      if (std::memcmp(edge_sqrt_info + 36 * (size_t)e, eye, sizeof eye) != 0) {
+        // memcmp also flags -0.0; confirm numerically
+        for (int k = 0; k < 36; ++k) if (edge_sqrt_info[36 * (size_t)e + k] != eye[k]) { g->identity_info = false; break; }
+      }
   }
+  lap("stream/events + identity scan");
   HostPattern pat;
   build_pattern(N, E, edge_ids, pose_const, &pat);
+  lap("block-CSR pattern");
   g->active_h.swap(pat.active);
   g->row_ptr_h.swap(pat.row_ptr);
   g->col_idx_h.swap(pat.col_idx);
   g->nnz_off = (long long)g->col_idx_h.size();
   g->has_dup_blocks = pat.has_dup;
-  const std::vector<unsigned long long>& uniq = pat.uniq;
-  const std::vector<int>& mult = pat.mult;
-  auto slot_of = [&](int r, int c) -> int {
-    const unsigned long long key = ((unsigned long long)r << 32) | (unsigned)c;
-    const size_t pos = std::lower_bound(uniq.begin(), uniq.end(), key) - uniq.begin();
-    return mult[pos] > 1 ? -(int)pos - 2 : (int)pos;
-  };
 
   // ---- edge tiles (field-major, one warp per tile) ----
   std::vector<EdgeCoreTile> core_h(std::max(T, 1));
@@ -289,13 +296,14 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
     const int l = e % kTile;
     const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
     t.a[l] = a; t.b[l] = b;
-    if (g->active_h[a] && g->active_h[b]) { t.slot_ab[l] = slot_of(a, b); t.slot_ba[l] = slot_of(b, a); }
-    else { t.slot_ab[l] = -1; t.slot_ba[l] = -1; }
+    t.slot_ab[l] = pat.half_slot[2 * (size_t)e];
+    t.slot_ba[l] = pat.half_slot[2 * (size_t)e + 1];
     for (int k = 0; k < 7; ++k) t.meas[k][l] = edge_meas[7 * (size_t)e + k];
     if (!g->identity_info) for (int k = 0; k < 36; ++k) info_h[e / kTile].S[k][l] = edge_sqrt_info[36 * (size_t)e + k];
   }
   for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
 
+  lap("edge tiles");
   // ---- device allocations + uploads ----
   G_TRY(dev_alloc(g, &g->poses, (size_t)N * 8));
   G_TRY(dev_alloc(g, &g->poses_cand, (size_t)N * 8));
@@ -320,6 +328,7 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   GC_TRY(pool_pinned(device, reinterpret_cast<void**>(&g->scalars_h)));
   G_TRY(dev_alloc(g, &g->barrier, 4));
 
+  lap("device allocations");
   GC_TRY(cudaMemcpyAsync(g->core, core_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
   if (!g->identity_info) GC_TRY(cudaMemcpyAsync(g->info, info_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
   GC_TRY(cudaMemcpyAsync(g->row_ptr, g->row_ptr_h.data(), ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
@@ -335,15 +344,17 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   GC_TRY(cudaMemsetAsync(g->Hoff, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
   GC_TRY(cudaStreamSynchronize(g->stream));
 
+  lap("uploads + memset");
   // persistent PCG grid: all CTAs must be co-resident (cooperative launch)
-  int per_sm = 0;
-  GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kPcgThreads, 0));
+  static int per_sm = 0;
+  if (per_sm == 0) GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kPcgThreads, 0));
   g->pcg_max_ctas = std::max(1, std::min(per_sm, 4) * g->num_sms);
   G_TRY(dev_alloc(g, &g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
 
   *out = g;
   int rc = pgo_graph_set_poses(g, poses);
   if (rc != PGO_OK) { *out = nullptr; return fail(rc); }
+  lap("poses");
   g->setup_s = wall_s() - t0;
   return PGO_OK;
 #undef G_TRY
@@ -364,10 +375,13 @@ extern "C" int pgo_graph_num_edges(const pgo_graph* g) { return g ? g->E : 0; }
 extern "C" int pgo_graph_set_poses(pgo_graph* g, const double* poses) {
   if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_set_poses: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
-  // [N][7] host -> [N][8] device (pitched copy), pad column zeroed once
-  CUDA_TRY(cudaMemsetAsync(g->poses, 0, (size_t)g->N * 8 * sizeof(double), g->stream));
-  CUDA_TRY(cudaMemcpy2DAsync(g->poses, 8 * sizeof(double), poses, 7 * sizeof(double), 7 * sizeof(double), g->N,
-                             cudaMemcpyHostToDevice, g->stream));
+  // [N][7] host -> [N][8] device: pad on the host, one contiguous copy (row-pitched DMA of 56-byte rows is slow)
+  g->pose_stage.resize((size_t)g->N * 8);
+  for (int i = 0; i < g->N; ++i) {
+    std::memcpy(&g->pose_stage[8 * (size_t)i], poses + 7 * (size_t)i, 7 * sizeof(double));
+    g->pose_stage[8 * (size_t)i + 7] = 0.0;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->poses, g->pose_stage.data(), (size_t)g->N * 8 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PGO_OK;
 }
@@ -375,9 +389,10 @@ extern "C" int pgo_graph_set_poses(pgo_graph* g, const double* poses) {
 extern "C" int pgo_graph_get_poses(pgo_graph* g, double* poses) {
   if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_get_poses: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
-  CUDA_TRY(cudaMemcpy2DAsync(poses, 7 * sizeof(double), g->poses, 8 * sizeof(double), 7 * sizeof(double), g->N,
-                             cudaMemcpyDeviceToHost, g->stream));
+  g->pose_stage.resize((size_t)g->N * 8);
+  CUDA_TRY(cudaMemcpyAsync(g->pose_stage.data(), g->poses, (size_t)g->N * 8 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
+  for (int i = 0; i < g->N; ++i) std::memcpy(poses + 7 * (size_t)i, &g->pose_stage[8 * (size_t)i], 7 * sizeof(double));
   return PGO_OK;
 }
 
@@ -767,8 +782,10 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     PGO_TRY(zero_scalars(g));
     CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
     const LmDiagonal lm = {reuse_diagonal ? 1 : 0, opt->min_lm_diagonal, opt->max_lm_diagonal, radius, g->diagonal, g->dlm};
+    const double th0 = wall_s();
     PGO_TRY(linear_solve_device(g, opt, solver, g->grad, lm));
     CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
+    const double th1 = wall_s();
     reuse_diagonal = true;
     // ---- speculatively: candidate = Plus(x, -y .* scale), its cost, |step|, |x_cand| ----
     plus_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
@@ -776,8 +793,12 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     PGO_TRY(cost_only(g, g->poses_cand, opt->loss_type, opt->loss_a));
     summary->num_cost_evaluations++;
     PGO_TRY(fetch_scalars(g));
+    const double th2 = wall_s();
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
     summary->time_linear_solver_ms += ms;
+    if (opt->verbose >= 2)
+      fprintf(stderr, "[pgo host] it %d: enqueue solver %.1f us, enqueue plus+cost + wait %.1f us, solver on GPU %.1f us\n", iter,
+              1e6 * (th1 - th0), 1e6 * (th2 - th1), 1e3 * ms);
     const DeviceScalars sc = *g->scalars_h;
     summary->total_pcg_iterations += sc.pcg_iterations;
     it.linear_solver_iterations = sc.pcg_iterations;

@@ -31,7 +31,8 @@
 namespace pgo {
 
 constexpr int kCholThreads = 512;   // per CTA, both launch shapes
-constexpr int kCholClusterMaxNodes = 60000;   // graphs up to this many variable poses use the cluster shape
+constexpr int kCholClusterMaxNodes = 60000;
+constexpr int kCholWideLevelNodes = 384;       // cluster shape: leading levels with at least this many nodes run grid-wide   // graphs up to this many variable poses use the cluster shape
 
 struct CholTask { int p; int q; int target; };   // target >= 0: L slot ; < 0: diagonal of node (-target-1)
 
@@ -55,6 +56,7 @@ struct LevelChol {
   double* vt = nullptr;         // [N][6] working rhs / y of the sweeps
   double* partials = nullptr;
   unsigned int* barrier = nullptr;
+  std::vector<int> level_ptr_h, level_mode_h;   // host copies for the wide-level launches
   int max_ctas = 0;             // cooperative-grid shape
   int cluster_ctas = 0;         // cluster shape: CTAs per cluster (0 = unavailable)
   std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
@@ -96,6 +98,7 @@ struct CholParams {
   DeviceScalars* scalars;
   int max_iterations;
   double tolerance;
+  int first_level;                // levels < first_level (and the S phase) were done by chol_wide_kernel launches
   unsigned long long* timeline;   // debug (PGO_TIMELINE=1): %globaltimer marks of CTA 0 / thread 0, [0] = count
 };
 
@@ -236,12 +239,13 @@ __device__ __forceinline__ void chol_update_item(const CholParams& P, const Chol
 #pragma unroll
   for (int c = 0; c < 6; ++c) a[c] = __ldcg(lp + c);
   double* out = (t.target >= 0) ? (P.Lblk + 36 * (size_t)t.target + r * 6) : (P.Ldiag + 36 * (size_t)(-t.target - 1) + r * 6);
+  const int cmax = (t.target >= 0) ? 5 : r;        // pivot blocks are symmetric: only their lower triangle is kept
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) s = fma(a[k], __ldcg(lq + c * 6 + k), s);
-    atomicAdd(out + c, -s);
+    if (c <= cmax) atomicAdd(out + c, -s);
   }
 }
 
@@ -383,12 +387,13 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
 #pragma unroll
     for (int c = 0; c < 6; ++c) a[c] = lp[c];
     double* out = (tk.target >= 0) ? (P.Lblk + 36 * (size_t)tk.target + r * 6) : (P.Ldiag + 36 * (size_t)(-tk.target - 1) + r * 6);
+    const int cmax = (tk.target >= 0) ? 5 : r;     // pivot blocks are symmetric: only their lower triangle is kept
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < 6; ++q) s = fma(a[q], lq[c * 6 + q], s);
-      atomicAdd(out + c, -s);
+      if (c <= cmax) atomicAdd(out + c, -s);
     }
   }
   __syncwarp();
@@ -450,29 +455,9 @@ __device__ __forceinline__ double cta_sum_n(double v, double* red) {
   return t;
 }
 
-template <bool kCluster>
-__global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const CholParams P) {
-  __shared__ double red[kCholThreads / 32];
-  __shared__ double bcast;
-  extern __shared__ __align__(16) unsigned char chol_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpStash& stash = reinterpret_cast<WarpStash*>(chol_smem)[warp];
-  const int warps_per_cta = kCholThreads / 32;
-  const int gw = blockIdx.x * warps_per_cta + warp;
-  const int nw = gridDim.x * warps_per_cta;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int gthreads = gridDim.x * blockDim.x;
-  const int grp = lane / 6, r6 = lane - grp * 6;
-  const bool lane_on = grp < kRowsPerWarp;
-  const int n = P.A.n;
-  const int n6 = 6 * n;
-  const int G = gridDim.x;
-  unsigned int epoch = 0;
-  int region = 0;
-  auto next_region = [&]() -> double* { region = (region + 1) & 7; return P.partials + (size_t)region * 4 * G; };
-
-  // ---- S: LM diagonal, gather A + D into the factor storage, working rhs ----
-  chol_mark(P, 0);
+// S phase: LM diagonal D = clamp(diag H) / radius, factor storage <- A + D, working rhs t = b, PCG vectors.
+__device__ __forceinline__ void chol_setup_phase(const CholParams& P, int gtid, int gthreads) {
+  const int n6 = 6 * P.A.n;
   for (int k = gtid; k < n6; k += gthreads) {
     const int i = k / 6, c = k - 6 * i;
     double dd;
@@ -525,6 +510,48 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       }
     }
   }
+}
+
+// Wide levels and the S phase as ordinary grid-wide launches: RED-atomic throughput is per SM (LSU bound), so the
+// levels that hold most of the nodes run on all SMs; the kernel boundary is their barrier.  phase 0 = S,
+// phase 1 = factor the nodes [k0, k1) of one level in `mode` (8 / 16 / 32 lanes per node).
+__global__ void __launch_bounds__(kCholThreads, 1) chol_wide_kernel(const CholParams P, int phase, int mode, int k0, int k1) {
+  extern __shared__ __align__(16) unsigned char chol_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (kCholThreads / 32) + warp, nw = gridDim.x * (kCholThreads / 32);
+  if (phase == 0) { chol_setup_phase(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); return; }
+  WarpStash& stash = reinterpret_cast<WarpStash*>(chol_smem)[warp];
+  bool ok = true;
+  if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8>(P, stash, kk, k1, lane); }
+  else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16>(P, stash, kk, k1, lane); }
+  else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32>(P, stash, kk, k1, lane); }
+  if (!ok) atomicExch(P.barrier + 1, 1u);
+}
+
+template <bool kCluster>
+__global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const CholParams P) {
+  __shared__ double red[kCholThreads / 32];
+  __shared__ double bcast;
+  extern __shared__ __align__(16) unsigned char chol_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpStash& stash = reinterpret_cast<WarpStash*>(chol_smem)[warp];
+  const int warps_per_cta = kCholThreads / 32;
+  const int gw = blockIdx.x * warps_per_cta + warp;
+  const int nw = gridDim.x * warps_per_cta;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gthreads = gridDim.x * blockDim.x;
+  const int grp = lane / 6, r6 = lane - grp * 6;
+  const bool lane_on = grp < kRowsPerWarp;
+  const int n = P.A.n;
+  const int n6 = 6 * n;
+  const int G = gridDim.x;
+  unsigned int epoch = 0;
+  int region = 0;
+  auto next_region = [&]() -> double* { region = (region + 1) & 7; return P.partials + (size_t)region * 4 * G; };
+
+  // ---- S: LM diagonal, gather A + D into the factor storage, working rhs ----
+  chol_mark(P, 0);
+  if (P.first_level == 0) chol_setup_phase(P, gtid, gthreads);
   chol_sync<kCluster>(P.barrier, epoch);
   chol_mark(P, 1);
 
@@ -533,7 +560,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   // the whole launch after an extra barrier).
   auto forward = [&](auto factor_tag) {
     constexpr bool kFactor = decltype(factor_tag)::value;
-    for (int l = 0; l < P.num_levels; ++l) {
+    for (int l = kFactor ? P.first_level : 0; l < P.num_levels; ++l) {
       const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
       const int mode = __ldg(P.level_split + l);
       const bool split = kFactor && mode == 1;
@@ -851,6 +878,8 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   C->n_slots = S.n_slots;
   C->factor_blocks = S.n_slots + S.n_nodes;
   C->n_tasks = (long long)S.tasks.size();
+  C->level_ptr_h = S.level_ptr;
+  C->level_mode_h = S.level_split;
   PGO_TRY(chol_upload(C, device, &C->level_ptr, S.level_ptr, stream));
   PGO_TRY(chol_upload(C, device, &C->level_split, S.level_split, stream));
   PGO_TRY(chol_upload(C, device, &C->nodes, S.nodes, stream));
@@ -866,6 +895,7 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   if (per_sm < 0) {
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(chol_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<false>, kCholThreads, kCholSmemBytes));
   }
   C->max_ctas = std::max(1, std::min(per_sm, 1) * sms);
@@ -926,7 +956,28 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     P.timeline = timeline_d;
   }
   CUDA_TRY(cudaMemsetAsync(C->barrier, 0, 4 * sizeof(unsigned int), stream));
-  if (C->cluster_ctas > 0 && num_ctas <= 0) {
+  const bool cluster = C->cluster_ctas > 0 && num_ctas <= 0;
+  P.first_level = 0;
+  if (cluster) {
+    // S phase and the leading wide levels as grid-wide launches (see chol_wide_kernel)
+    const int sms = C->max_ctas;   // one CTA per SM
+    int first = 0;
+    while (first < C->num_levels && C->level_mode_h[first] != 1 &&
+           C->level_ptr_h[first + 1] - C->level_ptr_h[first] >= kCholWideLevelNodes) ++first;
+    if (first > 0) {
+      const int s_items = (int)std::min<long long>(std::max<long long>((long long)A.n * 6, C->n_slots * 6 / 4), 1LL << 30);
+      const int s_ctas = std::max(1, std::min((s_items + kCholThreads - 1) / kCholThreads, 2 * sms));
+      chol_wide_kernel<<<s_ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 0, 0, 0, 0);
+      for (int l = 0; l < first; ++l) {
+        const int k0 = C->level_ptr_h[l], k1 = C->level_ptr_h[l + 1], mode = C->level_mode_h[l];
+        const int per_cta = (kCholThreads / 32) * (32 / mode);
+        const int ctas = std::max(1, std::min((k1 - k0 + per_cta - 1) / per_cta, sms));
+        chol_wide_kernel<<<ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 1, mode, k0, k1);
+      }
+      CUDA_TRY(cudaGetLastError());
+      if (launches) (*launches) += 1 + first;
+      P.first_level = first;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C->cluster_ctas); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = kCholSmemBytes; cfg.stream = stream;
     cudaLaunchAttribute at[1];

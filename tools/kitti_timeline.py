@@ -5,7 +5,8 @@ import os
 import sys
 import time
 
-os.environ["PGO_TIMELINE"] = "1"
+if os.environ.get("NO_TIMELINE") is None:
+    os.environ["PGO_TIMELINE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
@@ -14,6 +15,7 @@ import posegraph_ceres_b200 as P  # noqa: E402
 g = P.datasets.kitti00() if len(sys.argv) < 2 or sys.argv[1] == "kitti" else P.datasets.sphere()
 o = P.default_options()
 o.max_num_iterations = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+o.verbose = 2
 G = P.Graph.from_dataset(g)
 s, its = G.solve(o)
 print("iterations", s.num_iterations, "pcg", s.total_pcg_iterations, "solver ms", s.time_linear_solver_ms, flush=True)
