@@ -57,6 +57,8 @@ static double wall_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+namespace pgo { struct PcgMultiState; }
+
 struct pgo_graph {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -94,6 +96,9 @@ struct pgo_graph {
   double setup_s = 0.0;
   std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
   std::vector<double> pose_stage;                 // host staging for the [N][7] <-> [N][8] pose layouts
+  struct pgo::PcgMultiState* pcgm_state = nullptr;    // stream-ordered (multi-GPU) PCG
+  struct pgo::PcgMultiState* pcgm_state_h = nullptr;  // pinned
+  double *pcgm_part0 = nullptr, *pcgm_part1 = nullptr;
 };
 
 // Host-only structure analysis shared by pgo_graph_create and pgo_analyze_structure: variable poses (used by an
@@ -228,6 +233,7 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->chol) level_chol_destroy(g->chol, g->device);
   for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
   pool_pinned_release(g->device, g->scalars_h);
+  pool_pinned_release(g->device, g->pcgm_state_h);
   pool_event_release(g->device, g->ev0);
   pool_event_release(g->device, g->ev1);
   pool_stream_release(g->device, g->own_stream);
@@ -431,6 +437,17 @@ extern "C" int pgo_graph_init_comm(pgo_graph* g, const unsigned char unique_id[1
   std::memcpy(&id, unique_id, 128);
   NCCL_TRY(ncclCommInitRank(&g->comm, world_size, id, rank));
   g->rank = rank; g->world = world_size;
+  // A pose is a variable when ANY rank's shard uses it: make the active set (and the unit scaling derived from it) global.
+  NCCL_TRY(ncclAllReduce(g->active, g->active, (size_t)g->N, ncclUint8, ncclMax, g->comm, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->active_h.data(), g->active, (size_t)g->N, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  {
+    std::vector<double> se((size_t)g->N * 6);
+    for (int i = 0; i < g->N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
+    CUDA_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+  }
   return PGO_OK;
 }
 
@@ -488,6 +505,8 @@ static int zero_scalars(pgo_graph* g) {
   return PGO_OK;
 }
 static int fetch_scalars(pgo_graph* g) {
+  // every rank must take the same LM decisions: rank 0's scalars are authoritative
+  if (g->world > 1) NCCL_TRY(ncclBroadcast(g->scalars, g->scalars, sizeof(DeviceScalars), ncclUint8, 0, g->comm, g->stream));
   CUDA_TRY(cudaMemcpyAsync(g->scalars_h, g->scalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PGO_OK;
@@ -677,7 +696,8 @@ static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int so
   lm_prepare_kernel<<<(g->N + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->N, g->Hdiag, g->active, lm.mode, lm.min_diag, lm.max_diag,
                                                                    lm.radius, lm.diagonal, lm.dlm, g->Minv);
   g->launches++;
-  if (g->world > 1) return pcg_multi(g, o, b);
+  static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;   // tests: multi-GPU code path on one GPU
+  if (g->world > 1 || force_stream_pcg) return pcg_multi(g, o, b);
   return launch_pcg(g, o, b);
 }
 

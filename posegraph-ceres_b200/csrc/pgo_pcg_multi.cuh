@@ -10,9 +10,46 @@ struct PcgMultiState {
   int iter, done, flag, pad;
 };
 
-__global__ void __launch_bounds__(256) pcgm_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ Minv,
-                                                        double* x, double* r, double* u, double* p, double* s,
-                                                        PcgMultiState* st) {
+// Reductions are two-stage and fixed-order (per-CTA partial -> one CTA sums the partials): every rank computes
+// bit-identical scalars from bit-identical inputs, so all ranks take the same CG / LM decisions and issue the same
+// sequence of collectives.
+constexpr int kPcgmThreads = 256;
+__device__ __forceinline__ void pcgm_block_partial(double v, double* out) {
+  __shared__ double red[kPcgmThreads / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPcgmThreads / 32; ++k) t += red[k];
+    out[blockIdx.x] = t;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double pcgm_sum_partials(const double* part, int n) {   // one CTA, result on every thread
+  __shared__ double red[kPcgmThreads / 32];
+  __shared__ double total;
+  double t = 0.0;
+  for (int k = threadIdx.x; k < n; k += kPcgmThreads) t += part[k];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPcgmThreads / 32; ++k) s += red[k];
+    total = s;
+  }
+  __syncthreads();
+  const double r = total;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ Minv,
+                                                                 double* x, double* r, double* u, double* p, double* s,
+                                                                 double* part0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
   if (i < n) {
@@ -33,48 +70,48 @@ __global__ void __launch_bounds__(256) pcgm_init_kernel(int n, const double* __r
       acc += rv[k] * uv[k];
     }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(&st->acc0, acc);
+  pcgm_block_partial(acc, part0);
 }
 
-// delta = w.u (after the all-reduce of w)
-__global__ void __launch_bounds__(256) pcgm_dot_kernel(int n6, const double* __restrict__ w, const double* __restrict__ u,
-                                                       PcgMultiState* st) {
-  if (st->done) return;
+// delta = w.u (after the all-reduce of w): per-CTA partials
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_dot_kernel(int n6, const double* __restrict__ w, const double* __restrict__ u,
+                                                                const PcgMultiState* st, double* part1) {
   double acc = 0.0;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n6; k += gridDim.x * blockDim.x) acc = fma(w[k], u[k], acc);
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(&st->acc1, acc);
+  if (!st->done)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n6; k += gridDim.x * blockDim.x) acc = fma(w[k], u[k], acc);
+  pcgm_block_partial(acc, part1);
 }
 
-// scalar step between the reductions (1 thread)
-__global__ void pcgm_scalar_kernel(PcgMultiState* st, int phase, int max_iterations, double tol) {
+// scalar step between the reductions (one CTA): sums the partials in a fixed order, thread 0 updates the state
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_scalar_kernel(PcgMultiState* st, int phase, int max_iterations, double tol,
+                                                                   const double* part, int nparts) {
+  const double sum = pcgm_sum_partials(part, nparts);
+  if (threadIdx.x != 0) return;
   if (phase == 0) {           // after init: gamma0
-    st->gamma = st->gamma0 = st->acc0; st->acc0 = 0.0; st->iter = 0; st->flag = 0;
+    st->gamma = st->gamma0 = sum; st->iter = 0; st->flag = 0;
     st->done = (st->gamma0 > 0.0) ? 0 : 1;
   } else if (phase == 1) {    // after delta
     if (st->done) return;
-    st->delta = st->acc1; st->acc1 = 0.0;
+    st->delta = sum;
     if (st->iter == 0) { st->beta = 0.0; st->alpha = st->gamma / st->delta; }
     else { st->beta = st->gamma / st->gamma_old; st->alpha = st->gamma / (st->delta - st->beta * st->gamma / st->alpha); }
     if (!(st->alpha > 0.0) || !isfinite(st->alpha)) { st->flag = 2; st->done = 1; }
     else st->iter++;
   } else {                    // after the update: new gamma
     if (st->done) return;
-    st->gamma_old = st->gamma; st->gamma = st->acc0; st->acc0 = 0.0;
+    st->gamma_old = st->gamma; st->gamma = sum;
     if (st->gamma <= tol * tol * st->gamma0) { st->flag = 0; st->done = 1; }
     else if (st->iter >= max_iterations) { st->flag = 1; st->done = 1; }
   }
 }
 
-__global__ void __launch_bounds__(256) pcgm_update_kernel(int n, const double* __restrict__ Minv, const double* __restrict__ w,
-                                                          double* x, double* r, double* u, double* p, double* s,
-                                                          PcgMultiState* st) {
-  if (st->done) return;
-  const double alpha = st->alpha, beta = st->beta;
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_update_kernel(int n, const double* __restrict__ Minv, const double* __restrict__ w,
+                                                                   double* x, double* r, double* u, double* p, double* s,
+                                                                   const PcgMultiState* st, double* part0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  if (i < n) {
+  if (!st->done && i < n) {
+    const double alpha = st->alpha, beta = st->beta;
     double rv[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -95,22 +132,29 @@ __global__ void __launch_bounds__(256) pcgm_update_kernel(int n, const double* _
       acc += rv[k] * t;
     }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(&st->acc0, acc);
+  pcgm_block_partial(acc, part0);
 }
 
-// epilogue: x^T b, x^T A x (w = A x all-reduced), x^T D x -> DeviceScalars
-__global__ void __launch_bounds__(256) pcgm_final_kernel(int n6, const double* __restrict__ x, const double* __restrict__ b,
-                                                         const double* __restrict__ w, const double* __restrict__ d,
-                                                         const PcgMultiState* st, DeviceScalars* sc) {
+// epilogue: x^T b, x^T A x (w = A x all-reduced), x^T D x -> per-CTA partials, then one CTA -> DeviceScalars
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_final_kernel(int n6, const double* __restrict__ x, const double* __restrict__ b,
+                                                                  const double* __restrict__ w, const double* __restrict__ d,
+                                                                  double* part /* [3][gridDim.x] */) {
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n6; k += gridDim.x * blockDim.x) {
     const double xv = x[k];
     a0 = fma(xv, b[k], a0); a1 = fma(xv, w[k], a1); a2 = fma(xv * xv, d[k], a2);
   }
-  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sc->xtb, a0); atomicAdd(&sc->xtAx, a1); atomicAdd(&sc->xtDx, a2); }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  pcgm_block_partial(a0, part);
+  pcgm_block_partial(a1, part + gridDim.x);
+  pcgm_block_partial(a2, part + 2 * gridDim.x);
+}
+__global__ void __launch_bounds__(kPcgmThreads) pcgm_final_reduce_kernel(const double* part, int nparts, const PcgMultiState* st,
+                                                                         DeviceScalars* sc) {
+  const double e0 = pcgm_sum_partials(part, nparts);
+  const double e1 = pcgm_sum_partials(part + nparts, nparts);
+  const double e2 = pcgm_sum_partials(part + 2 * nparts, nparts);
+  if (threadIdx.x == 0) {
+    sc->xtb = e0; sc->xtAx = e1; sc->xtDx = e2;
     sc->pcg_gamma0 = st->gamma0; sc->pcg_gamma = st->gamma; sc->pcg_iterations = st->iter; sc->pcg_flag = st->flag;
   }
 }
@@ -121,21 +165,24 @@ __global__ void __launch_bounds__(256) pcgm_final_kernel(int n6, const double* _
 // kCheckEvery iterations (kernels after convergence are no-ops).
 static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b) {
   using namespace pgo;
-  static thread_local PcgMultiState* st = nullptr;
-  static thread_local PcgMultiState* st_h = nullptr;
-  if (!st) {
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&st), sizeof(PcgMultiState)));
-    CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&st_h), sizeof(PcgMultiState)));
-  }
   const int N = g->N, n6 = 6 * N;
-  const int nb = (N + 255) / 256;
+  const int nb = (N + kPcgmThreads - 1) / kPcgmThreads;
   const int warps = (N + kRowsPerWarp - 1) / kRowsPerWarp;
   const int sp_ctas = std::max(1, std::min((warps + 7) / 8, 8 * g->num_sms));
-  const int dot_ctas = std::max(1, std::min((n6 + 255) / 256, 4 * g->num_sms));
+  const int dot_ctas = std::max(1, std::min((n6 + kPcgmThreads - 1) / kPcgmThreads, 4 * g->num_sms));
+  if (!g->pcgm_state) {
+    PGO_TRY(dev_alloc(g, &g->pcgm_state, 1));
+    PGO_TRY(dev_alloc(g, &g->pcgm_part0, (size_t)nb));
+    PGO_TRY(dev_alloc(g, &g->pcgm_part1, (size_t)3 * dot_ctas));
+    CUDA_TRY(pool_pinned(g->device, reinterpret_cast<void**>(&g->pcgm_state_h)));
+  }
+  PcgMultiState* st = g->pcgm_state;
+  PcgMultiState* st_h = g->pcgm_state_h;
+  double *part0 = g->pcgm_part0, *part1 = g->pcgm_part1;
   const bool with_diag = (g->rank == 0);
   CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
-  pcgm_init_kernel<<<nb, 256, 0, g->stream>>>(N, b, g->Minv, g->vx, g->vr, g->vu, g->vp, g->vs, st);
-  pcgm_scalar_kernel<<<1, 1, 0, g->stream>>>(st, 0, o->pcg_max_iterations, o->pcg_tolerance);
+  pcgm_init_kernel<<<nb, kPcgmThreads, 0, g->stream>>>(N, b, g->Minv, g->vx, g->vr, g->vu, g->vp, g->vs, part0);
+  pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 0, o->pcg_max_iterations, o->pcg_tolerance, part0, nb);
   g->launches += 2;
   const int kCheckEvery = 32;
   int launched = 0;
@@ -143,13 +190,15 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
     for (int k = 0; k < kCheckEvery; ++k) {
       spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag);
       PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
-      pcgm_dot_kernel<<<dot_ctas, 256, 0, g->stream>>>(n6, g->vw, g->vu, st);
-      pcgm_scalar_kernel<<<1, 1, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance);
-      pcgm_update_kernel<<<nb, 256, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st);
-      pcgm_scalar_kernel<<<1, 1, 0, g->stream>>>(st, 2, o->pcg_max_iterations, o->pcg_tolerance);
+      pcgm_dot_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vw, g->vu, st, part1);
+      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, dot_ctas);
+      pcgm_update_kernel<<<nb, kPcgmThreads, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st, part0);
+      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 2, o->pcg_max_iterations, o->pcg_tolerance, part0, nb);
       g->launches += 5;
       ++launched;
     }
+    // the exit decision must be the same on every rank: rank 0's state is authoritative
+    if (g->world > 1) NCCL_TRY(ncclBroadcast(st, st, sizeof(PcgMultiState), ncclUint8, 0, g->comm, g->stream));
     CUDA_TRY(cudaMemcpyAsync(st_h, st, sizeof(PcgMultiState), cudaMemcpyDeviceToHost, g->stream));
     CUDA_TRY(cudaStreamSynchronize(g->stream));
     if (st_h->done || launched >= o->pcg_max_iterations + kCheckEvery) break;
@@ -157,8 +206,9 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
   // epilogue: w = A x (all-reduced) for the model cost change
   spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vx, g->dlm, g->vw, with_diag);
   PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
-  pcgm_final_kernel<<<dot_ctas, 256, 0, g->stream>>>(n6, g->vx, b, g->vw, g->dlm, st, g->scalars);
-  g->launches += 2;
+  pcgm_final_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vx, b, g->vw, g->dlm, part1);
+  pcgm_final_reduce_kernel<<<1, kPcgmThreads, 0, g->stream>>>(part1, dot_ctas, st, g->scalars);
+  g->launches += 3;
   CUDA_TRY(cudaGetLastError());
   return PGO_OK;
 }

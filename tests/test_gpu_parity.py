@@ -202,3 +202,24 @@ def test_empty_and_degenerate_inputs(pgo):
     s, its = G.solve()
     assert s.termination_type == 0 and np.array_equal(G.get_poses(), g.poses)
     G.close()
+
+
+def test_stream_ordered_pcg_of_the_multi_gpu_path(pgo):
+    """The multi-GPU solver path (stream-ordered PCG, deterministic two-stage reductions) on one GPU
+    (PGO_FORCE_STREAM_PCG=1: the all-reduce is a no-op at world size 1) reproduces the persistent PCG kernel."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("persistent", "stream"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "stream_pcg_check.py"), mode], capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[mode] = re.findall(r"(\w+): \w+ PCG: (\d+) LM iterations, (\d+) PCG iterations, [\d.]+ s, final cost ([\d.]+), checksum ([\d.]+)", r.stdout)
+        assert len(outs[mode]) == 2, r.stdout
+    for a, b in zip(outs["persistent"], outs["stream"]):
+        assert a[0] == b[0] and a[1] == b[1]                       # same LM iteration count
+        assert abs(float(a[3]) - float(b[3])) <= 1e-8 * float(a[3])  # same final cost
+        assert abs(float(a[4]) - float(b[4])) <= 1e-6              # same poses (sum |p|)
