@@ -460,14 +460,13 @@ static int allreduce_sum(pgo_graph* g, double* buf, size_t count) {
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers
 // ------------------------------------------------------------------------------------------------
-template <bool kIdent, int kMode>
+template <bool kIdent, int kMode, int kMinBlocks>
 static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
-  constexpr int stage = kCoreTileBytes + (kIdent ? 0 : kInfoTileBytes);
-  constexpr int smem = kLinWarps * 2 * stage + kLinWarps * 2 * 8;
-  auto kern = linearize_kernel<kIdent, kMode, true>;
+  constexpr int smem = lin_smem_bytes<kIdent>();
+  auto kern = linearize_kernel<kIdent, kMode, true, kMinBlocks>;
   static bool attr_set = false;
   if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
-  const int ctas = std::max(1, std::min((g->T + kLinWarps - 1) / kLinWarps, 2 * g->num_sms));
+  const int ctas = std::max(1, std::min((g->T + kLinWarps - 1) / kLinWarps, kMinBlocks * g->num_sms));
   kern<<<ctas, kLinWarps * 32, smem, g->stream>>>(p);
   g->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -481,14 +480,15 @@ static int launch_linearize(pgo_graph* g, int mode, const double* poses, const d
   p.Hdiag = g->Hdiag; p.Hoff = g->Hoff; p.grad = g->grad; p.scalars = g->scalars;
   p.loss_type = loss_type; p.loss_a = loss_a; p.res_out = res_out; p.jac_out = jac_out;
   if (g->E == 0) return PGO_OK;
+  static const int occ = getenv("PGO_LIN_OCC") ? atoi(getenv("PGO_LIN_OCC")) : 2;   // CTAs per SM of the full kernel (tuning knob)
   if (g->identity_info) {
-    if (mode == kLinFull) return launch_linearize_t<true, kLinFull>(g, p);
-    if (mode == kLinCost) return launch_linearize_t<true, kLinCost>(g, p);
-    return launch_linearize_t<true, kLinEval>(g, p);
+    if (mode == kLinFull) return occ >= 3 ? launch_linearize_t<true, kLinFull, 3>(g, p) : launch_linearize_t<true, kLinFull, 2>(g, p);
+    if (mode == kLinCost) return launch_linearize_t<true, kLinCost, 4>(g, p);
+    return launch_linearize_t<true, kLinEval, 2>(g, p);
   }
-  if (mode == kLinFull) return launch_linearize_t<false, kLinFull>(g, p);
-  if (mode == kLinCost) return launch_linearize_t<false, kLinCost>(g, p);
-  return launch_linearize_t<false, kLinEval>(g, p);
+  if (mode == kLinFull) return occ >= 3 ? launch_linearize_t<false, kLinFull, 3>(g, p) : launch_linearize_t<false, kLinFull, 2>(g, p);
+  if (mode == kLinCost) return launch_linearize_t<false, kLinCost, 4>(g, p);
+  return launch_linearize_t<false, kLinEval, 2>(g, p);
 }
 
 static int zero_system(pgo_graph* g, bool hessian) {

@@ -59,43 +59,88 @@ __device__ __forceinline__ void xty(const double (&X)[6][3], const double (&Y)[6
     }
 }
 
-template <bool kIdentityInfo, int kMode, bool kMerge>
-__global__ void __launch_bounds__(kLinWarps * 32, 2) linearize_kernel(const LinParams p) {
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// kStages-deep per-warp ring of edge tiles (bulk TMA); tile t+2 is in flight and tile t+1's pose / scale gathers
+// are prefetched into L1 while tile t is processed.
+constexpr int kLinStages = 3;
+
+constexpr int kLinInfoStages = 2;   // the 9 KB sqrt-information tiles are only double-buffered (shared-memory budget)
+
+template <bool kIdentityInfo>
+constexpr int lin_smem_bytes() {
+  return kLinWarps * (kLinStages * kCoreTileBytes + (kIdentityInfo ? kInfoTileBytes : kLinInfoStages * kInfoTileBytes)) +
+         kLinWarps * (kLinStages + kLinInfoStages) * 8 + kLinWarps * 64 * 4;
+}
+
+template <bool kIdentityInfo, int kMode, bool kMerge, int kMinBlocks>
+__global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(const LinParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int kStageBytes = kCoreTileBytes + (kIdentityInfo ? 0 : kInfoTileBytes);
+  // per warp: core ring, then the info ring; the output staging tile [32][36] aliases the CURRENT info stage (its
+  // sqrt-information is dead once the Jacobians are in registers) or, without information tiles, a dedicated buffer
+  constexpr int kWarpBytes = kLinStages * kCoreTileBytes + (kIdentityInfo ? kInfoTileBytes : kLinInfoStages * kInfoTileBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* wbase = smem_raw + (size_t)warp * 2 * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kLinWarps * 2 * kStageBytes) + warp * 2;
+  unsigned char* wbase = smem_raw + (size_t)warp * kWarpBytes;                 // core ring
+  unsigned char* ibase = wbase + kLinStages * kCoreTileBytes;                  // info ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kLinWarps * kWarpBytes) + warp * (kLinStages + kLinInfoStages);
+  uint64_t* ibars = bars + kLinStages;
+  int* sidx = reinterpret_cast<int*>(smem_raw + (size_t)kLinWarps * kWarpBytes + kLinWarps * (kLinStages + kLinInfoStages) * 8) + warp * 64;
 
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < kLinStages + kLinInfoStages; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
   }
   __syncwarp();
 
   const int gw = blockIdx.x * kLinWarps + warp;
   const int nw = gridDim.x * kLinWarps;
-  auto issue = [&](int tile, int stage) {
-    unsigned char* dst = wbase + (size_t)stage * kStageBytes;
-    mbar_expect_tx(&bars[stage], kStageBytes);
-    tma_load_1d(dst, p.core + tile, kCoreTileBytes, &bars[stage]);
-    if (!kIdentityInfo) tma_load_1d(dst + kCoreTileBytes, p.info + tile, kInfoTileBytes, &bars[stage]);
+  auto issue_core = [&](int tile, int st) {
+    mbar_expect_tx(&bars[st], kCoreTileBytes);
+    tma_load_1d(wbase + (size_t)st * kCoreTileBytes, p.core + tile, kCoreTileBytes, &bars[st]);
+  };
+  auto issue_info = [&](int tile, int st) {
+    if (!kIdentityInfo) {
+      // the stage doubled as the generic-proxy staging tile two iterations ago: order those accesses before the async-proxy write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&ibars[st], kInfoTileBytes);
+      tma_load_1d(ibase + (size_t)st * kInfoTileBytes, p.info + tile, kInfoTileBytes, &ibars[st]);
+    }
   };
 
-  int stage = 0;
-  uint32_t phase0 = 0, phase1 = 0;
+  int stage = 0, istage = 0;
+  uint32_t round = 0, iround = 0;   // completed trips around each ring = parity of the current stage's phase
   double cost_acc = 0.0;
-  if (gw < p.n_tiles && lane == 0) issue(gw, 0);
+  if (lane == 0) {
+    if (gw < p.n_tiles) { issue_core(gw, 0); issue_info(gw, 0); }
+    if (gw + nw < p.n_tiles) issue_core(gw + nw, 1);
+  }
+  auto prefetch_gathers = [&](int t, int st, uint32_t parity) {
+    mbar_wait(&bars[st], parity);
+    const EdgeCoreTile* nt = reinterpret_cast<const EdgeCoreTile*>(wbase + (size_t)st * kCoreTileBytes);
+    if (t * kTile + lane < p.n_edges) {
+      const int na = nt->a[lane], nbp = nt->b[lane];
+      prefetch_l1(p.poses + 8 * (size_t)na);
+      prefetch_l1(p.poses + 8 * (size_t)nbp);
+      if (kMode != kLinCost) { prefetch_l1(p.scale + 6 * (size_t)na); prefetch_l1(p.scale + 6 * (size_t)nbp); }
+    }
+  };
 
   for (int tile = gw; tile < p.n_tiles; tile += nw) {
-    const int next = tile + nw;
-    if (next < p.n_tiles && lane == 0) issue(next, stage ^ 1);
-    if (stage == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-    else            { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+    const int next = tile + nw, next2 = tile + 2 * nw;
+    const int stage1 = (stage + 1 == kLinStages) ? 0 : stage + 1;
+    const int stage2 = (stage1 + 1 == kLinStages) ? 0 : stage1 + 1;
+    if (lane == 0) {
+      if (next2 < p.n_tiles) issue_core(next2, stage2);
+      if (next < p.n_tiles) issue_info(next, istage ^ 1);
+    }
+    mbar_wait(&bars[stage], round & 1);
+    if (next < p.n_tiles) prefetch_gathers(next, stage1, (stage1 == 0 ? round + 1 : round) & 1);
+    if (!kIdentityInfo) mbar_wait(&ibars[istage], iround & 1);
 
-    const EdgeCoreTile* ct = reinterpret_cast<const EdgeCoreTile*>(wbase + (size_t)stage * kStageBytes);
-    const EdgeInfoTile* it = reinterpret_cast<const EdgeInfoTile*>(wbase + (size_t)stage * kStageBytes + kCoreTileBytes);
+    const EdgeCoreTile* ct = reinterpret_cast<const EdgeCoreTile*>(wbase + (size_t)stage * kCoreTileBytes);
+    const EdgeInfoTile* it = reinterpret_cast<const EdgeInfoTile*>(ibase + (size_t)istage * kInfoTileBytes);
+    double* stg = reinterpret_cast<double*>(ibase + (kIdentityInfo ? 0 : (size_t)istage * kInfoTileBytes));
     const int e = tile * kTile + lane;
     const bool valid = e < p.n_edges;
     const int a = valid ? ct->a[lane] : 0;
@@ -118,7 +163,10 @@ __global__ void __launch_bounds__(kLinWarps * 32, 2) linearize_kernel(const LinP
       const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
       if (valid) cost_acc += 0.5 * rho;
       __syncwarp();
-      stage ^= 1;
+      stage = stage1;
+      if (stage == 0) ++round;
+      istage ^= 1;
+      if (istage == 0) ++iround;
       continue;
     }
 
@@ -157,35 +205,40 @@ __global__ void __launch_bounds__(kLinWarps * 32, 2) linearize_kernel(const LinP
       }
     }
 
-    // ---- gradient J^T r (robustified: rho' J^T r), column-scaled ----
+    // ---- outputs.  Every lane owns one edge, but consecutive lanes must hit consecutive addresses for the L2 to
+    // see whole 32-byte sectors (fp64 RED and store throughput is per sector): each lane drops its block into a
+    // per-warp shared-memory staging tile [32 edges][36], the warp then walks the tile element-major and issues
+    // coalesced RED / stores (4 lanes per sector instead of 1).
     {
-      double g1[3], g2[3], gc[3];
+      __syncwarp();                                  // all lanes are done with the sqrt-information tile the staging aliases
+      auto rot36 = [](int x) -> int { return x >= 36 ? x - 36 : x; };
+      const int swz = lane >> 2;                     // row rotation: conflict-free 64-bit shared-memory writes
+      // ---- gradient J^T r (robustified: rho' J^T r), column-scaled: g_a = sa .* [-g1; gc], g_b = sb .* [g1; -g2] ----
+      {
+        double g1[3], g2[3], gc[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double s1 = 0.0, s2 = 0.0, sc = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          double s1 = 0.0, s2 = 0.0, sc = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { s1 = fma(L.B1[i][k], L.r[i], s1); s2 = fma(L.B2[i][k], L.r[i], s2); sc = fma(L.C[i][k], L.r[i], sc); }
-        g1[k] = rho1 * s1; g2[k] = rho1 * s2; gc[k] = rho1 * sc;
-      }
-      // g_a = sa .* [-g1; gc], g_b = sb .* [g1; -g2]. Merge lane+1's g_b into g_a when it hits the same pose.
-      const int b_next = __shfl_down_sync(0xffffffffu, b, 1);
-      const bool take = kMerge && lane < 31 && b_next == a;          // I absorb lane+1's b contribution
-      const int a_prev = __shfl_up_sync(0xffffffffu, a, 1);
-      const bool given = kMerge && lane > 0 && a_prev == b;          // lane-1 absorbed mine
-      double* ga = p.grad + 6 * (size_t)a;
-      double* gb = p.grad + 6 * (size_t)b;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double vb0 = sb[k] * g1[k], vb1 = -sb[3 + k] * g2[k];
-        double va0 = -sa[k] * g1[k], va1 = sa[3 + k] * gc[k];
-        if (kMerge) {
-          const double n0 = __shfl_down_sync(0xffffffffu, vb0, 1), n1 = __shfl_down_sync(0xffffffffu, vb1, 1);
-          if (take) { va0 += n0; va1 += n1; }
+          for (int i = 0; i < 6; ++i) { s1 = fma(L.B1[i][k], L.r[i], s1); s2 = fma(L.B2[i][k], L.r[i], s2); sc = fma(L.C[i][k], L.r[i], sc); }
+          g1[k] = rho1 * s1; g2[k] = rho1 * s2; gc[k] = rho1 * sc;
         }
-        if (valid) {
-          atomicAdd(ga + k, va0); atomicAdd(ga + 3 + k, va1);
-          if (!given) { atomicAdd(gb + k, vb0); atomicAdd(gb + 3 + k, vb1); }
+        sidx[lane] = valid ? a : -1;
+        sidx[32 + lane] = valid ? b : -1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          stg[lane * 6 + k] = -sa[k] * g1[k];        stg[lane * 6 + 3 + k] = sa[3 + k] * gc[k];
+          stg[192 + lane * 6 + k] = sb[k] * g1[k];   stg[192 + lane * 6 + 3 + k] = -sb[3 + k] * g2[k];
         }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const int item = j * 32 + lane;            // 0..383: [side][edge][6]
+          const int blk = item / 6, el = item - blk * 6;
+          const int t = sidx[blk];
+          if (t >= 0) atomicAdd(p.grad + 6 * (size_t)t + el, stg[item]);
+        }
+        __syncwarp();
       }
 
       if (kMode == kLinFull) {
@@ -204,58 +257,38 @@ __global__ void __launch_bounds__(kLinWarps * 32, 2) linearize_kernel(const LinP
         auto Hab = [&](int r, int c) -> double {
           return (r < 3) ? ((c < 3) ? -P11[r][c] : P12[r][c - 3]) : ((c < 3) ? P1C[c][r - 3] : -PC2[r - 3][c - 3]);
         };
-        double* da = p.Hdiag + 36 * (size_t)a;
-        double* db = p.Hdiag + 36 * (size_t)b;
+        // one block set: stage my 36 values (panel order, rotated row), then the warp drains the tile
+        auto emit = [&](auto value, int target, double* base, bool reduce_always) {
+          sidx[lane] = target;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+          for (int r = 0; r < 6; ++r)
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            const double hb = rho1 * sb[r] * sb[c] * Hbb(r, c);
-            double ha = rho1 * sa[r] * sa[c] * Haa(r, c);
-            if (kMerge) {
-              const double nb = __shfl_down_sync(0xffffffffu, hb, 1);
-              if (take) ha += nb;
-            }
-            if (valid) {
-              atomicAdd(da + pidx(r, c), ha);
-              if (!given) atomicAdd(db + pidx(r, c), hb);
-            }
+            for (int c = 0; c < 6; ++c) stg[lane * 36 + rot36(pidx(r, c) + swz)] = value(r, c);
+          __syncwarp();
+#pragma unroll 6
+          for (int j = 0; j < 36; ++j) {
+            const int item = j * 32 + lane;
+            const int blk = item / 36, el = item - blk * 36;
+            const int t = sidx[blk];
+            const double v = stg[blk * 36 + rot36(el + (blk >> 2))];
+            if (reduce_always) { if (t >= 0) atomicAdd(base + 36 * (size_t)t + el, v); }
+            else if (t >= 0) base[36 * (size_t)t + el] = v;
+            else if (t <= -2) atomicAdd(base + 36 * (size_t)(-t - 2) + el, v);
           }
-        // off-diagonal blocks: (a,b) = H_ab, (b,a) = H_ab^T
-        const int s_ab = valid ? ct->slot_ab[lane] : -1;
-        const int s_ba = valid ? ct->slot_ba[lane] : -1;
-        if (s_ab >= 0) {
-          double2* o = reinterpret_cast<double2*>(p.Hoff + 36 * (size_t)s_ab);
-#pragma unroll
-          for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-              o[cp * 6 + r] = make_double2(rho1 * sa[r] * sb[2 * cp] * Hab(r, 2 * cp), rho1 * sa[r] * sb[2 * cp + 1] * Hab(r, 2 * cp + 1));
-        } else if (s_ab <= -2) {
-          double* o = p.Hoff + 36 * (size_t)(-s_ab - 2);
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) atomicAdd(o + pidx(r, c), rho1 * sa[r] * sb[c] * Hab(r, c));
-        }
-        if (s_ba >= 0) {
-          double2* o = reinterpret_cast<double2*>(p.Hoff + 36 * (size_t)s_ba);
-#pragma unroll
-          for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-              o[cp * 6 + r] = make_double2(rho1 * sb[r] * sa[2 * cp] * Hab(2 * cp, r), rho1 * sb[r] * sa[2 * cp + 1] * Hab(2 * cp + 1, r));
-        } else if (s_ba <= -2) {
-          double* o = p.Hoff + 36 * (size_t)(-s_ba - 2);
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) atomicAdd(o + pidx(r, c), rho1 * sb[r] * sa[c] * Hab(c, r));
-        }
+          __syncwarp();
+        };
+        emit([&](int r, int c) { return rho1 * sa[r] * sa[c] * Haa(r, c); }, valid ? a : -1, p.Hdiag, true);
+        emit([&](int r, int c) { return rho1 * sb[r] * sb[c] * Hbb(r, c); }, valid ? b : -1, p.Hdiag, true);
+        // off-diagonal blocks: (a,b) = H_ab, (b,a) = H_ab^T; slot >= 0: sole producer (store), <= -2: shared slot (RED)
+        emit([&](int r, int c) { return rho1 * sa[r] * sb[c] * Hab(r, c); }, valid ? ct->slot_ab[lane] : -1, p.Hoff, false);
+        emit([&](int r, int c) { return rho1 * sb[r] * sa[c] * Hab(c, r); }, valid ? ct->slot_ba[lane] : -1, p.Hoff, false);
       }
     }
     __syncwarp();
-    stage ^= 1;
+    stage = stage1;
+    if (stage == 0) ++round;
+    istage ^= 1;
+    if (istage == 0) ++iround;
   }
   cost_acc = warp_sum(cost_acc);
   if (lane == 0 && cost_acc != 0.0) atomicAdd(&p.scalars->cost, cost_acc);
