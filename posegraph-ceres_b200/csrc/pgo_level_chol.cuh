@@ -32,6 +32,7 @@ namespace pgo {
 
 constexpr int kCholThreads = 512;   // per CTA, both launch shapes
 constexpr int kCholClusterMaxNodes = 60000;
+constexpr long long kCholClusterMaxTasks = 200000;
 constexpr int kCholWideLevelNodes = 384;       // cluster shape: leading levels with at least this many nodes run grid-wide   // graphs up to this many variable poses use the cluster shape
 
 struct CholTask { int p; int q; int target; };   // target >= 0: L slot ; < 0: diagonal of node (-target-1)
@@ -271,7 +272,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // everything a node needs is fetched in ONE latency epoch (cp.async into the stash + broadcast loads of the pivot
 // block and rhs), the Cholesky, column scaling and Schur products then run out of registers / shared memory, and
 // results leave as plain stores and fire-and-forget fp64 RED atomics.
-template <int kLanes>
+template <int kLanes, bool kFactor = true>
 __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane) {
   constexpr int kNpw = 32 / kLanes;
   constexpr int kBlk = kStashBlocks / kNpw;
@@ -293,8 +294,10 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     const double* src = P.Lblk + 36 * (size_t)p0;
     for (int c = sub; c < deg * 18; c += kLanes) cp_async_cg16(SL + 2 * c, src + 2 * c);
     for (int j = sub; j < deg; j += kLanes) cp_async_ca4(SR + j, P.col_row + p0 + j);
-    const int* tsrc = reinterpret_cast<const int*>(P.tasks + t0);
-    for (int j = sub; j < ntask * 3; j += kLanes) cp_async_ca4(reinterpret_cast<int*>(ST) + j, tsrc + j);
+    if (kFactor) {
+      const int* tsrc = reinterpret_cast<const int*>(P.tasks + t0);
+      for (int j = sub; j < ntask * 3; j += kLanes) cp_async_ca4(reinterpret_cast<int*>(ST) + j, tsrc + j);
+    }
   }
   double* dv = P.Ldiag + 36 * (size_t)v;
   double* tv = P.vt + 6 * (size_t)v;
@@ -306,33 +309,41 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
 #pragma unroll
   for (int c = 0; c < 6; ++c) t[c] = valid ? __ldcg(tv + c) : 0.0;
   bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double s = A[j][j];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) if (q < j) s -= A[j][q] * A[j][q];
-    if (!(s > 0.0)) { ok = false; s = 1.0; }
-    const double il = rsqrt(s);
-    A[j][j] = il;            // the diagonal keeps 1 / L_jj
-#pragma unroll
-    for (int r = 0; r < 6; ++r) if (r > j) {
-      double t2 = A[r][j];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) if (q < j) t2 -= A[r][q] * A[j][q];
-      A[r][j] = t2 * il;
-    }
-  }
   double Li[6][6];
+  if (kFactor) {
 #pragma unroll
-  for (int c = 0; c < 6; ++c)
+    for (int j = 0; j < 6; ++j) {
+      double s = A[j][j];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      if (r < c) { Li[r][c] = 0.0; continue; }
-      double x = (r == c) ? 1.0 : 0.0;
+      for (int q = 0; q < 6; ++q) if (q < j) s -= A[j][q] * A[j][q];
+      if (!(s > 0.0)) { ok = false; s = 1.0; }
+      const double il = rsqrt(s);
+      A[j][j] = il;            // the diagonal keeps 1 / L_jj
 #pragma unroll
-      for (int q = 0; q < 6; ++q) if (q >= c && q < r) x -= A[r][q] * Li[q][c];
-      Li[r][c] = x * A[r][r];
+      for (int r = 0; r < 6; ++r) if (r > j) {
+        double t2 = A[r][j];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (q < j) t2 -= A[r][q] * A[j][q];
+        A[r][j] = t2 * il;
+      }
     }
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        if (r < c) { Li[r][c] = 0.0; continue; }
+        double x = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (q >= c && q < r) x -= A[r][q] * Li[q][c];
+        Li[r][c] = x * A[r][r];
+      }
+  } else {
+    // refinement sweep: the pivot block already holds the inverse of its lower factor
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Li[r][c] = (c <= r) ? A[r][c] : 0.0;
+  }
   double y[6];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -343,12 +354,14 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
   }
   if (valid && sub < 6) {   // store Linv row `sub` and y[sub]
     double yv = 0.0;
+    if (kFactor) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double val = 0.0;
+      for (int c = 0; c < 6; ++c) {
+        double val = 0.0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) if (r == sub) val = Li[r][c];
-      dv[sub * 6 + c] = val;
+        for (int r = 0; r < 6; ++r) if (r == sub) val = Li[r][c];
+        dv[sub * 6 + c] = val;
+      }
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) if (r == sub) yv = y[r];
@@ -363,20 +376,28 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     double wr[6], o[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) wr[c] = w[c];
+    if (kFactor) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      double s = 0.0;
+      for (int c = 0; c < 6; ++c) {
+        double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) if (q <= c) s = fma(wr[q], Li[c][q], s);
-      o[c] = s;
+        for (int q = 0; q < 6; ++q) if (q <= c) s = fma(wr[q], Li[c][q], s);
+        o[c] = s;
+      }
+      double* gw_ = P.Lblk + 36 * (size_t)(p0 + blk) + 6 * r;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { w[c] = o[c]; gw_[c] = o[c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o[c] = wr[c];
     }
-    double* gw_ = P.Lblk + 36 * (size_t)(p0 + blk) + 6 * r;
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { w[c] = o[c]; gw_[c] = o[c]; s = fma(o[c], y[c], s); }
+    for (int c = 0; c < 6; ++c) s = fma(o[c], y[c], s);
     atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
   }
   __syncwarp();
+  if (!kFactor) return true;
   // Schur updates: row r of target -= L_p L_q^T, operands from the stash
   for (int it = sub; it < ntask * 6; it += kLanes) {
     const int ti = it / 6, r = it - ti * 6;
@@ -564,11 +585,11 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
       const int mode = __ldg(P.level_split + l);
       const bool split = kFactor && mode == 1;
-      if (kFactor && mode != 1) {
+      if (mode != 1) {
         bool ok = true;
-        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8>(P, stash, kk, k1, lane); }
-        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16>(P, stash, kk, k1, lane); }
-        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32>(P, stash, kk, k1, lane); }
+        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor>(P, stash, kk, k1, lane); }
+        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor>(P, stash, kk, k1, lane); }
+        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor>(P, stash, kk, k1, lane); }
         if (!ok) atomicExch(P.barrier + 1, 1u);
       } else {
         for (int k = k0 + gw; k < k1; k += nw) {
@@ -901,8 +922,10 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   C->max_ctas = std::max(1, std::min(per_sm, 1) * sms);
   // cluster shape: the largest cluster (16, then 8) the device can co-schedule
   C->cluster_ctas = 0;
-  if (S.n_nodes <= kCholClusterMaxNodes && cluster_max >= 0) C->cluster_ctas = cluster_max;
-  if (S.n_nodes <= kCholClusterMaxNodes && cluster_max < 0) {
+  // the cluster shape only pays when the whole factorisation is tiny (latency bound); otherwise all SMs are needed
+  const bool want_cluster = S.n_nodes <= kCholClusterMaxNodes && (long long)S.tasks.size() <= kCholClusterMaxTasks;
+  if (want_cluster && cluster_max >= 0) C->cluster_ctas = cluster_max;
+  if (want_cluster && cluster_max < 0) {
     cluster_max = 0;
     cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();

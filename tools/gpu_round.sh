@@ -9,6 +9,7 @@ tail -3 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -6 | tee gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 | tee gpurun_out/bench_reference.json
+timeout 600 python tools/config_runs.py 2>&1 | tee gpurun_out/config_runs.log
 if [ "$1" == "profile" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-large > gpurun_out/bench_under_ncu.log 2>&1
@@ -16,5 +17,7 @@ if [ "$1" == "profile" ]; then
       python tools/run_large_kernels.py 1000 > gpurun_out/prof_linearize.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:spmv_kernel -s 2 -c 1 -f -o gpurun_out/prof_spmv \
       python tools/run_large_kernels.py 1000 > gpurun_out/prof_spmv.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:level_chol_pcg_kernel -s 3 -c 1 -f -o gpurun_out/prof_chol \
+      python bench.py --steps 1 --warmup 3 --no-large > gpurun_out/prof_chol.log 2>&1
 fi
 ls -la gpurun_out
