@@ -237,8 +237,12 @@ def main():
         kname = "pcg_kernel"
     k_ms = solver_ms / n_solves
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic0 = {}
+    if os.path.exists(os.path.join(ROOT, "profiles", "ncu_traffic.json")):
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic0 = json.load(f)
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / hbm_peak, "traffic": traffic0.get(kname), "peak_source": peak_kind,
                 "ms_per_launch": k_ms, "share_of_step": solver_ms / max(total_ms, 1e-9),
                 "note": "dominant kernel of the KITTI-00 step (S + wide-level launches + cluster kernel, timed together with CUDA events); "
                         "4541-pose graph: latency/barrier bound, the 4.5 MB factor lives in L2, so the HBM fraction is not the "

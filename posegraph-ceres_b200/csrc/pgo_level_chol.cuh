@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "pgo_kernels.cuh"
@@ -35,7 +36,7 @@ constexpr int kCholClusterMaxNodes = 60000;
 constexpr long long kCholClusterMaxTasks = 200000;
 constexpr int kCholWideLevelNodes = 384;       // cluster shape: leading levels with at least this many nodes run grid-wide   // graphs up to this many variable poses use the cluster shape
 
-struct CholTask { int p; int q; int target; };   // target >= 0: L slot ; < 0: diagonal of node (-target-1)
+struct __align__(16) CholTask { int p; int q; int target; int pad; };   // target >= 0: L slot ; < 0: diagonal of node (-target-1)
 
 struct LevelChol {
   bool usable = false;
@@ -51,6 +52,8 @@ struct LevelChol {
   int4* nodes = nullptr;        // [n_nodes+1] by elimination position: {pose id, col0, col1, task0}
   int* col_row = nullptr;       // [n_slots] row pose id of each slot
   int* l2a = nullptr;           // [n_slots] BSR off-diagonal entry that seeds the slot, or -1 (pure fill)
+  int *pend_fwd = nullptr, *pend_bwd = nullptr, *pend_fwd_init = nullptr, *pend_bwd_init = nullptr, *rowp = nullptr, *rown = nullptr;
+  bool dataflow_ok = false;     // every level is a staged level (degree <= 16)
   CholTask* tasks = nullptr;    // [n_tasks]
   double* Lblk = nullptr;       // [n_slots][36] row-major (rows: row pose, cols: column pose)
   double* Ldiag = nullptr;      // [N][36] W_vv, then inverse of its lower Cholesky factor
@@ -100,6 +103,11 @@ struct CholParams {
   int max_iterations;
   double tolerance;
   int first_level;                // levels < first_level (and the S phase) were done by chol_wide_kernel launches
+  int setup_done;                 // the S phase ran as a chol_wide_kernel launch
+  // dataflow shape: per-node dependency counters instead of level barriers
+  int *pend_fwd, *pend_bwd;                      // [N] working counters
+  const int *pend_fwd_init, *pend_bwd_init;      // [N] sources of a node (earlier neighbours) ; degree + 1
+  const int *rowp, *rown;                        // [N+1], [n_slots]: for node u the earlier nodes v with u in col(v)
   unsigned long long* timeline;   // debug (PGO_TIMELINE=1): %globaltimer marks of CTA 0 / thread 0, [0] = count
 };
 
@@ -112,9 +120,29 @@ __device__ __forceinline__ void chol_mark(const CholParams& P, int tag) {
   }
 }
 
-template <bool kCluster>
+// launch shapes of the solver kernel
+enum CholShape { kShapeGrid = 0, kShapeCluster = 1, kShapeDataflow = 2 };
+
+// dataflow shape: wait until a node's dependency counter drains.  Bounded: a broken schedule must not hang the GPU.
+__device__ __forceinline__ void chol_wait(const int* ctr, unsigned int* err) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  if (v <= 0) return;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v <= 0) return;
+    unsigned int e;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(err) : "memory");
+    if (e != 0u) return;
+    if (clock64() - t0 > 3000000000LL) { atomicExch(err, 4u); return; }
+    __nanosleep(20);
+  }
+}
+
+template <int kShape>
 __device__ __forceinline__ void chol_sync(unsigned int* counter, unsigned int& epoch) {
-  if constexpr (kCluster) {
+  if constexpr (kShape == kShapeCluster) {
     // hardware barrier over every thread of the cluster; release/acquire orders the global-memory traffic
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   } else {
@@ -272,7 +300,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // everything a node needs is fetched in ONE latency epoch (cp.async into the stash + broadcast loads of the pivot
 // block and rhs), the Cholesky, column scaling and Schur products then run out of registers / shared memory, and
 // results leave as plain stores and fire-and-forget fp64 RED atomics.
-template <int kLanes, bool kFactor = true>
+template <int kLanes, bool kFactor = true, bool kDataflow = false>
 __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane) {
   constexpr int kNpw = 32 / kLanes;
   constexpr int kBlk = kStashBlocks / kNpw;
@@ -287,17 +315,27 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     t1 = __ldg(&P.nodes[k + 1].w);
   }
   const int deg = p1 - p0, ntask = t1 - t0;
+  double sink = 0.0;   // dataflow shape: sum of the values returned by this lane's update atomics
   double* SL = &st.L[gi * kBlk][0];
   CholTask* ST = st.task + gi * kTsk;
   int* SR = st.row + gi * kBlk;
   {
+    // static structure first (it does not depend on other nodes).  Only L1-bypassing copies (cp.async.cg) and plain
+    // loads are used: in the dataflow shape other warps of the SM execute gpu-scope fences (L1 invalidations) at any
+    // time, and cp.async.ca copies in flight through L1 were observed to deliver corrupt bytes under them.
+    for (int j = sub; j < deg; j += kLanes) SR[j] = __ldg(P.col_row + p0 + j);
+    if (kFactor) {
+      for (int j = sub; j < ntask; j += kLanes) cp_async_cg16(ST + j, P.tasks + t0 + j);
+    }
+    // ... then, in the dataflow shape, wait until every earlier neighbour has delivered its updates: lane 0 of the
+    // group acquires, the warp barrier + gpu-scope fence order every lane's loads behind it
+    if (kDataflow) {
+      if (valid && sub == 0) chol_wait(P.pend_fwd + v, P.barrier + 1);
+      __syncwarp();
+      __threadfence();
+    }
     const double* src = P.Lblk + 36 * (size_t)p0;
     for (int c = sub; c < deg * 18; c += kLanes) cp_async_cg16(SL + 2 * c, src + 2 * c);
-    for (int j = sub; j < deg; j += kLanes) cp_async_ca4(SR + j, P.col_row + p0 + j);
-    if (kFactor) {
-      const int* tsrc = reinterpret_cast<const int*>(P.tasks + t0);
-      for (int j = sub; j < ntask * 3; j += kLanes) cp_async_ca4(reinterpret_cast<int*>(ST) + j, tsrc + j);
-    }
   }
   double* dv = P.Ldiag + 36 * (size_t)v;
   double* tv = P.vt + 6 * (size_t)v;
@@ -394,10 +432,22 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) s = fma(o[c], y[c], s);
-    atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
+    if (kDataflow) sink += atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);   // returning form: see the publish step
+    else atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
   }
   __syncwarp();
-  if (!kFactor) return true;
+  if (!kFactor) {
+    if (kDataflow) {
+      if (sink == 0.123456789e-300) P.partials[0] = sink;
+      __threadfence();
+      __syncwarp();
+      __threadfence();
+      for (int j = sub; j < deg; j += kLanes) atomicSub(P.pend_fwd + SR[j], 1);
+      if (valid && sub == 0) atomicSub(P.pend_bwd + v, 1);
+      __syncwarp();
+    }
+    return true;
+  }
   // Schur updates: row r of target -= L_p L_q^T, operands from the stash
   for (int it = sub; it < ntask * 6; it += kLanes) {
     const int ti = it / 6, r = it - ti * 6;
@@ -414,15 +464,26 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < 6; ++q) s = fma(a[q], lq[c * 6 + q], s);
-      if (c <= cmax) atomicAdd(out + c, -s);
+      if (c <= cmax) { if (kDataflow) sink += atomicAdd(out + c, -s); else atomicAdd(out + c, -s); }
     }
+  }
+  if (kDataflow) {
+    // publish: my stores / atomics first, then one decrement per later neighbour and the backward-ready token.
+    // The updates use the RETURNING atomic (ATOM, not fire-and-forget RED): consuming the returned values below makes
+    // this lane wait until its updates have been performed at L2 -- a fence alone was observed not to wait for REDs.
+    if (sink == 0.123456789e-300) P.partials[0] = sink;
+    __threadfence();
+    __syncwarp();
+    __threadfence();
+    for (int j = sub; j < deg; j += kLanes) atomicSub(P.pend_fwd + SR[j], 1);
+    if (valid && sub == 0) atomicSub(P.pend_bwd + v, 1);
   }
   __syncwarp();
   return ok;
 }
 
 // Backward step for 32 / kLanes nodes per warp: x_v = Linv_v^T (y_v - sum_{u in col(v)} L_uv^T x_u).
-template <int kLanes>
+template <int kLanes, bool kDataflow = false>
 __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk, int k1, int lane, double* dst, double* dst2) {
   constexpr int kNpw = 32 / kLanes;
   constexpr int kSub = kLanes / 6;                         // 6-lane column groups per node: 1, 2, 5
@@ -434,6 +495,11 @@ __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk
   if (valid) { const int4 nm = __ldg(P.nodes + k); v = nm.x; p0 = nm.y; p1 = nm.z; }
   const int sg = sub / 6, c = sub - 6 * sg;
   const bool on = valid && sg < kSub;
+  if (kDataflow) {
+    if (valid && sub == 0) chol_wait(P.pend_bwd + v, P.barrier + 1);
+    __syncwarp();
+    __threadfence();
+  }
   int rows[kIter];
 #pragma unroll
   for (int j = 0; j < kIter; ++j) {
@@ -462,6 +528,15 @@ __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk
     if (sub < 6 && rr >= sub) xv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + rr * 6 + sub), sr, xv);
   }
   if (valid && sub < 6) { dst[6 * (size_t)v + sub] = xv; if (dst2) dst2[6 * (size_t)v + sub] = xv; }
+  if (kDataflow) {
+    __threadfence();
+    __syncwarp();
+    __threadfence();
+    if (valid) {
+      const int e1 = __ldg(P.rowp + v + 1);
+      for (int e = __ldg(P.rowp + v) + sub; e < e1; e += kLanes) atomicSub(P.pend_bwd + __ldg(P.rown + e), 1);
+    }
+  }
 }
 
 __device__ __forceinline__ double cta_sum_n(double v, double* red) {
@@ -492,7 +567,8 @@ __device__ __forceinline__ void chol_setup_phase(const CholParams& P, int gtid, 
       P.dlm[k] = dd;
     }
     P.vt[k] = P.b[k];
-    P.x[k] = 0.0; P.ax[k] = 0.0; P.r[k] = P.b[k];
+    P.x[k] = 0.0; P.ax[k] = 0.0; P.r[k] = P.b[k]; P.z[k] = 0.0; P.p[k] = 0.0;   // inactive poses keep z = p = 0
+    if (c == 0 && P.pend_fwd != nullptr) { P.pend_fwd[i] = P.pend_fwd_init[i]; P.pend_bwd[i] = P.pend_bwd_init[i]; }
     // diagonal block row c of pose i
     const double* hd = P.A.Hdiag + 36 * (size_t)i;
     double* ld = P.Ldiag + 36 * (size_t)i + 6 * c;
@@ -549,8 +625,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_wide_kernel(const CholPa
   if (!ok) atomicExch(P.barrier + 1, 1u);
 }
 
-template <bool kCluster>
+template <int kShape>
 __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const CholParams P) {
+  constexpr bool kDF = kShape == kShapeDataflow;
   __shared__ double red[kCholThreads / 32];
   __shared__ double bcast;
   extern __shared__ __align__(16) unsigned char chol_smem[];
@@ -572,8 +649,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
 
   // ---- S: LM diagonal, gather A + D into the factor storage, working rhs ----
   chol_mark(P, 0);
-  if (P.first_level == 0) chol_setup_phase(P, gtid, gthreads);
-  chol_sync<kCluster>(P.barrier, epoch);
+  if (!P.setup_done) chol_setup_phase(P, gtid, gthreads);
+  chol_sync<kShape>(P.barrier, epoch);
   chol_mark(P, 1);
 
   // forward sweep over the levels; kFactor also factors.  level_split[l] is the level's mode: 8 / 16 / 32 = lanes
@@ -587,9 +664,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       const bool split = kFactor && mode == 1;
       if (mode != 1) {
         bool ok = true;
-        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor>(P, stash, kk, k1, lane); }
-        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor>(P, stash, kk, k1, lane); }
-        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor>(P, stash, kk, k1, lane); }
+        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane); }
+        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane); }
+        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane); }
         if (!ok) atomicExch(P.barrier + 1, 1u);
       } else {
         for (int k = k0 + gw; k < k1; k += nw) {
@@ -599,13 +676,15 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
         }
       }
       if (split) {
-        chol_sync<kCluster>(P.barrier, epoch);
+        chol_sync<kShape>(P.barrier, epoch);
         const long long t0 = __ldg(&P.nodes[k0].w), t1 = __ldg(&P.nodes[k1].w);
         for (long long it = (long long)gtid; it < (t1 - t0) * 6; it += gthreads) chol_update_item(P, P.tasks[t0 + it / 6], (int)(it % 6));
       }
-      chol_mark(P, 100 + l);
-      chol_sync<kCluster>(P.barrier, epoch);
-      chol_mark(P, 200 + l);
+      if (!kDF) {
+        chol_mark(P, 100 + l);
+        chol_sync<kShape>(P.barrier, epoch);
+        chol_mark(P, 200 + l);
+      }
     }
   };
   // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending; writes dst (and dst2)
@@ -613,9 +692,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     for (int l = P.num_levels - 1; l >= 0; --l) {
       const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
       const int mode = __ldg(P.level_split + l);
-      if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) chol_backward_staged<8>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) chol_backward_staged<16>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 32) { for (int kk = k0 + gw; kk < k1; kk += nw) chol_backward_staged<32>(P, kk, k1, lane, dst, dst2); }
+      if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 32) { for (int kk = k0 + gw; kk < k1; kk += nw) chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2); }
       else {
         for (int k = k0 + gw; k < k1; k += nw) {
           const int4 nm = __ldg(P.nodes + k);
@@ -642,14 +721,16 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
           if (lane < 6) { dst[6 * (size_t)v + lane] = xv; if (dst2) dst2[6 * (size_t)v + lane] = xv; }
         }
       }
-      chol_mark(P, 300 + l);
-      chol_sync<kCluster>(P.barrier, epoch);
-      chol_mark(P, 400 + l);
+      if (!kDF) {
+        chol_mark(P, 300 + l);
+        chol_sync<kShape>(P.barrier, epoch);
+        chol_mark(P, 400 + l);
+      }
     }
+    if (kDF) { chol_mark(P, 300); chol_sync<kShape>(P.barrier, epoch); chol_mark(P, 400); }   // the one barrier of both sweeps
   };
 
-  // ---- F + B: z = p = M^-1 b (inactive poses keep 0: their z/p are zeroed here first) ----
-  for (int k = gtid; k < n6; k += gthreads) { P.z[k] = 0.0; P.p[k] = 0.0; }
+  // ---- F + B: z = p = M^-1 b ----
   forward(std::true_type{});
   backward(P.z, P.p);
 
@@ -674,7 +755,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     if (iter == 0) { a1 = cta_sum_n(a1, red); a2 = cta_sum_n(a2, red); }
     double* part = next_region();
     if (threadIdx.x == 0) { part[blockIdx.x] = a0; if (iter == 0) { part[G + blockIdx.x] = a1; part[2 * G + blockIdx.x] = a2; } }
-    chol_sync<kCluster>(P.barrier, epoch);
+    chol_sync<kShape>(P.barrier, epoch);
     chol_mark(P, 2);
     const double pq = reduce_partials(part, G, &bcast);
     if (iter == 0) {
@@ -698,7 +779,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     s0 = cta_sum_n(s0, red); s1 = cta_sum_n(s1, red); s2 = cta_sum_n(s2, red); s3 = cta_sum_n(s3, red);
     part = next_region();
     if (threadIdx.x == 0) { part[blockIdx.x] = s0; part[G + blockIdx.x] = s1; part[2 * G + blockIdx.x] = s2; part[3 * G + blockIdx.x] = s3; }
-    chol_sync<kCluster>(P.barrier, epoch);
+    chol_sync<kShape>(P.barrier, epoch);
     chol_mark(P, 3);
     rr = reduce_partials(part, G, &bcast);
     xtb = reduce_partials(part + G, G, &bcast);
@@ -707,7 +788,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     if (rr <= P.tolerance * P.tolerance * bb) { norm_kind = 1; break; }          // ||b - A x|| <= tol ||b||
     // z = M^-1 r
     for (int k = gtid; k < n6; k += gthreads) { P.vt[k] = P.r[k]; }
-    chol_sync<kCluster>(P.barrier, epoch);
+    if (kDF) for (int i = gtid; i < n; i += gthreads) { P.pend_fwd[i] = P.pend_fwd_init[i]; P.pend_bwd[i] = P.pend_bwd_init[i]; }
+    chol_sync<kShape>(P.barrier, epoch);
     forward(std::false_type{});
     backward(P.z, nullptr);
     double t0 = 0.0;
@@ -715,14 +797,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     t0 = cta_sum_n(t0, red);
     part = next_region();
     if (threadIdx.x == 0) part[blockIdx.x] = t0;
-    chol_sync<kCluster>(P.barrier, epoch);
+    chol_sync<kShape>(P.barrier, epoch);
     const double rho_new = reduce_partials(part, G, &bcast);
     const double beta = rho_new / rho;
     rho = rho_new;
     if (fabs(rho) <= P.tolerance * P.tolerance * rho0) break;                      // sqrt(r.M^-1 r) <= tol sqrt(b.M^-1 b)
     if (iter >= P.max_iterations) { flag = 1; break; }
     for (int k = gtid; k < n6; k += gthreads) P.p[k] = __ldcg(P.z + k) + beta * P.p[k];
-    chol_sync<kCluster>(P.barrier, epoch);
+    chol_sync<kShape>(P.barrier, epoch);
   }
   chol_mark(P, 4);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -751,6 +833,7 @@ struct LevelCholSymbolic {
   int n_nodes = 0, num_levels = 0, max_degree = 0;
   long long n_slots = 0;
   std::vector<int> level_ptr, level_split, col_row, l2a;
+  std::vector<int> pend_fwd_init, pend_bwd_init, rowp, rown;   // dataflow shape (by pose id)
   std::vector<int4> nodes;
   std::vector<CholTask> tasks;
 };
@@ -830,7 +913,8 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     for (size_t k = 0; k < alive_list.size(); ++k) if (alive[alive_list[k]]) alive_list[w++] = alive_list[k];
     alive_list.resize(w);
     level_ptr.push_back((int)order.size());
-    level_split.push_back(lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : lvl_maxdeg <= 16 ? 32 : 1);
+    static const bool force32 = getenv("PGO_CHOL_MODE32") != nullptr;   // debug
+    level_split.push_back(lvl_maxdeg > 16 ? 1 : force32 ? 32 : lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32);
     S->max_degree = std::max(S->max_degree, lvl_maxdeg);
   }
   S->num_levels = (int)level_split.size();
@@ -856,14 +940,14 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     const int p0 = col_ptr[k], p1 = col_ptr[k + 1];
     S->nodes[k] = make_int4(order[k], p0, p1, (int)tasks.size());
     for (int p = p0; p < p1; ++p) {
-      tasks.push_back({p, p, -col_row[p] - 1});                  // diagonal of row(p)
+      tasks.push_back({p, p, -col_row[p] - 1, 0});                  // diagonal of row(p)
       for (int q = p0; q < p1; ++q) {
         if (q == p) continue;
         const int u = col_row[p], w = col_row[q];
         if (pos[u] > pos[w]) {                                   // block (u, w): rows u, cols w = L_p L_q^T
           const int t = slot_of(u, w);
           if (t < 0) return set_error(PGO_ERR_NUMERICAL, "level Cholesky: missing fill slot");
-          tasks.push_back({p, q, t});
+          tasks.push_back({p, q, t, 0});
         }
       }
     }
@@ -881,6 +965,21 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
         S->l2a[s] = p;
       }
     }
+  // dependency counters and row lists of the dataflow shape
+  S->pend_fwd_init.assign(N, 0);
+  S->pend_bwd_init.assign(N, 0);
+  S->rowp.assign(N + 1, 0);
+  for (long long sl = 0; sl < slots; ++sl) S->rowp[col_row[sl] + 1]++;
+  for (int i = 0; i < N; ++i) { S->pend_fwd_init[i] = S->rowp[i + 1]; S->rowp[i + 1] += S->rowp[i]; }
+  S->rown.resize((size_t)slots);
+  {
+    std::vector<int> fill(S->rowp.begin(), S->rowp.end() - 1);
+    for (int k = 0; k < n_nodes; ++k) {
+      const int v = order[k];
+      S->pend_bwd_init[v] = col_ptr[k + 1] - col_ptr[k] + 1;
+      for (int pp = col_ptr[k]; pp < col_ptr[k + 1]; ++pp) S->rown[fill[col_row[pp]]++] = v;
+    }
+  }
   S->usable = true;
   return 0;
 }
@@ -907,6 +1006,13 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   PGO_TRY(chol_upload(C, device, &C->col_row, S.col_row, stream));
   PGO_TRY(chol_upload(C, device, &C->l2a, S.l2a, stream));
   PGO_TRY(chol_upload(C, device, &C->tasks, S.tasks, stream));
+  PGO_TRY(chol_upload(C, device, &C->pend_fwd_init, S.pend_fwd_init, stream));
+  PGO_TRY(chol_upload(C, device, &C->pend_bwd_init, S.pend_bwd_init, stream));
+  PGO_TRY(chol_upload(C, device, &C->rowp, S.rowp, stream));
+  PGO_TRY(chol_upload(C, device, &C->rown, S.rown, stream));
+  PGO_TRY(chol_alloc(C, device, &C->pend_fwd, (size_t)N));
+  PGO_TRY(chol_alloc(C, device, &C->pend_bwd, (size_t)N));
+  C->dataflow_ok = S.max_degree <= 16;
   PGO_TRY(chol_alloc(C, device, &C->Lblk, (size_t)S.n_slots * 36));
   PGO_TRY(chol_alloc(C, device, &C->Ldiag, (size_t)N * 36));
   PGO_TRY(chol_alloc(C, device, &C->vt, (size_t)N * 6));
@@ -914,10 +1020,11 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   static int per_sm = -1, cluster_max = -1;   // launch-shape queries are per kernel, not per graph
   const int sms = pool_num_sms(device);
   if (per_sm < 0) {
-    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeDataflow>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(chol_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<false>, kCholThreads, kCholSmemBytes));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<kShapeGrid>, kCholThreads, kCholSmemBytes));
   }
   C->max_ctas = std::max(1, std::min(per_sm, 1) * sms);
   // cluster shape: the largest cluster (16, then 8) the device can co-schedule
@@ -927,7 +1034,7 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   if (want_cluster && cluster_max >= 0) C->cluster_ctas = cluster_max;
   if (want_cluster && cluster_max < 0) {
     cluster_max = 0;
-    cudaFuncSetAttribute(level_chol_pcg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
     for (int cs : {16, 8}) {
       cudaLaunchConfig_t cfg = {};
@@ -937,7 +1044,7 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, level_chol_pcg_kernel<true>, &cfg) == cudaSuccess && nclusters >= 1) {
+      if (cudaOccupancyMaxActiveClusters(&nclusters, level_chol_pcg_kernel<kShapeCluster>, &cfg) == cudaSuccess && nclusters >= 1) {
         C->cluster_ctas = cluster_max = cs;
         break;
       }
@@ -976,21 +1083,45 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
   if (want_timeline) {
     if (!timeline_d) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&timeline_d), 2001 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(timeline_d, 0, 2001 * sizeof(unsigned long long), stream));
+
     P.timeline = timeline_d;
   }
   CUDA_TRY(cudaMemsetAsync(C->barrier, 0, 4 * sizeof(unsigned int), stream));
-  const bool cluster = C->cluster_ctas > 0 && num_ctas <= 0;
-  P.first_level = 0;
-  if (cluster) {
+  // launch shape: one cluster for tiny factorisations, else the cooperative grid.  PGO_CHOL_SHAPE=grid|cluster|dataflow
+  // overrides.  The dataflow shape (per-node dependency counters instead of level barriers) is EXPERIMENTAL and off by
+  // default: on B200 it still produces wrong factors on some graphs -- never selected automatically.
+  static const char* shape_env = getenv("PGO_CHOL_SHAPE");
+  int shape = C->cluster_ctas > 0 ? kShapeCluster : kShapeGrid;
+  if (shape_env) {
+    if (!strcmp(shape_env, "grid")) shape = kShapeGrid;
+    else if (!strcmp(shape_env, "cluster") && C->cluster_ctas > 0) shape = kShapeCluster;
+    else if (!strcmp(shape_env, "dataflow") && C->dataflow_ok) shape = kShapeDataflow;
+  }
+  if (num_ctas > 0 && shape == kShapeCluster) shape = kShapeGrid;
+  P.first_level = 0; P.setup_done = 0;
+  P.pend_fwd = C->pend_fwd; P.pend_bwd = C->pend_bwd; P.pend_fwd_init = C->pend_fwd_init; P.pend_bwd_init = C->pend_bwd_init;
+  P.rowp = C->rowp; P.rown = C->rown;
+  const int sms = C->max_ctas;   // one CTA per SM
+  auto launch_setup = [&]() {
+    const int s_items = (int)std::min<long long>(std::max<long long>((long long)A.n * 6, C->n_slots * 6 / 4), 1LL << 30);
+    const int s_ctas = std::max(1, std::min((s_items + kCholThreads - 1) / kCholThreads, 2 * sms));
+    chol_wide_kernel<<<s_ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 0, 0, 0, 0);
+    if (launches) (*launches)++;
+    P.setup_done = 1;
+  };
+  if (shape == kShapeDataflow) {
+    launch_setup();
+    int grid = num_ctas > 0 ? num_ctas : std::max(16, (C->n_nodes / 4 + (kCholThreads / 32) - 1) / (kCholThreads / 32));
+    grid = std::max(1, std::min(grid, C->max_ctas));
+    void* args[] = {&P};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<kShapeDataflow>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
+  } else if (shape == kShapeCluster) {
     // S phase and the leading wide levels as grid-wide launches (see chol_wide_kernel)
-    const int sms = C->max_ctas;   // one CTA per SM
     int first = 0;
     while (first < C->num_levels && C->level_mode_h[first] != 1 &&
            C->level_ptr_h[first + 1] - C->level_ptr_h[first] >= kCholWideLevelNodes) ++first;
     if (first > 0) {
-      const int s_items = (int)std::min<long long>(std::max<long long>((long long)A.n * 6, C->n_slots * 6 / 4), 1LL << 30);
-      const int s_ctas = std::max(1, std::min((s_items + kCholThreads - 1) / kCholThreads, 2 * sms));
-      chol_wide_kernel<<<s_ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 0, 0, 0, 0);
+      launch_setup();
       for (int l = 0; l < first; ++l) {
         const int k0 = C->level_ptr_h[l], k1 = C->level_ptr_h[l + 1], mode = C->level_mode_h[l];
         const int per_cta = (kCholThreads / 32) * (32 / mode);
@@ -998,7 +1129,7 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
         chol_wide_kernel<<<ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 1, mode, k0, k1);
       }
       CUDA_TRY(cudaGetLastError());
-      if (launches) (*launches) += 1 + first;
+      if (launches) (*launches) += first;
       P.first_level = first;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1007,20 +1138,19 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, level_chol_pcg_kernel<true>, P));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, level_chol_pcg_kernel<kShapeCluster>, P));
   } else {
     int grid = num_ctas > 0 ? num_ctas : std::max(1, (A.n + 79) / 80);
     grid = std::max(1, std::min(grid, C->max_ctas));
     void* args[] = {&P};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<false>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<kShapeGrid>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
   }
   if (launches) (*launches)++;
   if (want_timeline) {
     std::vector<unsigned long long> h(2001);
     CUDA_TRY(cudaMemcpyAsync(h.data(), timeline_d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    fprintf(stderr, "[pgo timeline] shape=%s ctas=%d levels=%d marks=%llu :", C->cluster_ctas > 0 && num_ctas <= 0 ? "cluster" : "grid",
-            C->cluster_ctas > 0 && num_ctas <= 0 ? C->cluster_ctas : -1, C->num_levels, h[0]);
+    fprintf(stderr, "[pgo timeline] shape=%d levels=%d marks=%llu :", shape, C->num_levels, h[0]);
     for (unsigned long long k = 0; k < h[0] && k < 1000; ++k)
       fprintf(stderr, " %llu@%.2f", h[2 + 2 * k], (double)(h[1 + 2 * k] - h[1]) * 1e-3);
     fprintf(stderr, "\n");
