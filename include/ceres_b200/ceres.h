@@ -198,6 +198,7 @@ struct Solver {
     int device_linear_solver = PGO_LINEAR_AUTO;   // pgo_linear_solver_type
     double pcg_tolerance = 1e-10;
     int pcg_max_iterations = 20000;
+    double direct_residual_accept = 1e-8;
   };
   struct IterationSummary {
     int iteration = 0;
@@ -450,6 +451,7 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   o.linear_solver_type = options.device_linear_solver;
   o.pcg_tolerance = options.pcg_tolerance;
   o.pcg_max_iterations = options.pcg_max_iterations;
+  o.direct_residual_accept = options.direct_residual_accept;
   const int cap = options.max_num_iterations + 2;
   std::vector<pgo_iteration_summary> log((size_t)std::max(cap, 2));
   std::memset(&summary->device, 0, sizeof summary->device);

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PGO_B200_ABI_VERSION 2
+#define PGO_B200_ABI_VERSION 3
 
 typedef enum {
   PGO_OK = 0,
@@ -81,6 +81,9 @@ typedef struct {
   int pcg_max_iterations;        /* per LM step */
   double pcg_tolerance;          /* stop when sqrt(r^T M^-1 r) <= tol * sqrt(b^T M^-1 b) */
   int pcg_num_ctas;              /* 0 = auto (persistent grid size of the PCG kernel) */
+  double direct_residual_accept; /* LEVEL_CHOLESKY: the direct solve (first PCG iterate) is accepted without refinement when
+                                    ||b - A x||_2 <= max(pcg_tolerance, this) * ||b||_2.  Default 1e-8: Ceres' own
+                                    SPARSE_NORMAL_CHOLESKY never refines; PCG refinement stays the safety net. */
   int verbose;
 } pgo_solver_options;
 

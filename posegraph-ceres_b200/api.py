@@ -39,7 +39,7 @@ class SolverOptions(C.Structure):
                 ("max_num_consecutive_invalid_steps", C.c_int), ("jacobi_scaling", C.c_int),
                 ("loss_type", C.c_int), ("loss_a", C.c_double), ("linear_solver_type", C.c_int),
                 ("pcg_max_iterations", C.c_int), ("pcg_tolerance", C.c_double), ("pcg_num_ctas", C.c_int),
-                ("verbose", C.c_int)]
+                ("direct_residual_accept", C.c_double), ("verbose", C.c_int)]
 
 
 class IterationSummary(C.Structure):

@@ -113,31 +113,42 @@ static void build_pattern(int N, int E, const int* edge_ids, const unsigned char
   out->active.assign(N, 0);
   for (int e = 0; e < E; ++e) { out->active[edge_ids[2 * e]] = 1; out->active[edge_ids[2 * e + 1]] = 1; }
   if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) out->active[i] = 0;
-  struct Half { unsigned long long key; int idx; };
-  std::vector<Half> halves;
-  halves.reserve(2 * (size_t)E);
-  out->half_slot.assign(2 * (size_t)E, -1);
+  // bucket the half-edges (row -> col) by row with a counting sort, then order each (short) row by column
+  struct Half { int col; int idx; };
+  std::vector<int> start(N + 1, 0);
+  size_t n_half = 0;
   for (int e = 0; e < E; ++e) {
     const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-    if (out->active[a] && out->active[b]) {
-      halves.push_back({((unsigned long long)a << 32) | (unsigned)b, 2 * e});
-      halves.push_back({((unsigned long long)b << 32) | (unsigned)a, 2 * e + 1});
+    if (out->active[a] && out->active[b]) { start[a + 1]++; start[b + 1]++; n_half += 2; }
+  }
+  for (int i = 0; i < N; ++i) start[i + 1] += start[i];
+  std::vector<Half> halves(n_half);
+  {
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int e = 0; e < E; ++e) {
+      const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+      if (out->active[a] && out->active[b]) { halves[fill[a]++] = {b, 2 * e}; halves[fill[b]++] = {a, 2 * e + 1}; }
     }
   }
-  std::sort(halves.begin(), halves.end(), [](const Half& x, const Half& y) { return x.key < y.key || (x.key == y.key && x.idx < y.idx); });
+  out->half_slot.assign(2 * (size_t)E, -1);
   out->row_ptr.assign(N + 1, 0);
   out->col_idx.clear();
-  out->col_idx.reserve(halves.size());
-  for (size_t k = 0; k < halves.size();) {
-    size_t k2 = k + 1;
-    while (k2 < halves.size() && halves[k2].key == halves[k].key) ++k2;
-    const int slot = (int)out->col_idx.size();
-    out->col_idx.push_back((int)(halves[k].key & 0xffffffffu));
-    out->row_ptr[(int)(halves[k].key >> 32) + 1]++;
-    const bool dup = k2 - k > 1;
-    if (dup) out->has_dup = true;
-    for (size_t q = k; q < k2; ++q) out->half_slot[halves[q].idx] = dup ? -slot - 2 : slot;
-    k = k2;
+  out->col_idx.reserve(n_half);
+  for (int i = 0; i < N; ++i) {
+    Half* hb = halves.data() + start[i];
+    Half* he = halves.data() + start[i + 1];
+    if (he - hb > 1) std::sort(hb, he, [](const Half& x, const Half& y) { return x.col < y.col || (x.col == y.col && x.idx < y.idx); });
+    for (Half* k = hb; k < he;) {
+      Half* k2 = k + 1;
+      while (k2 < he && k2->col == k->col) ++k2;
+      const int slot = (int)out->col_idx.size();
+      out->col_idx.push_back(k->col);
+      out->row_ptr[i + 1]++;
+      const bool dup = k2 - k > 1;
+      if (dup) out->has_dup = true;
+      for (Half* q = k; q < k2; ++q) out->half_slot[q->idx] = dup ? -slot - 2 : slot;
+      k = k2;
+    }
   }
   for (int i = 0; i < N; ++i) out->row_ptr[i + 1] += out->row_ptr[i];
 }
@@ -160,11 +171,13 @@ extern "C" int pgo_analyze_structure(int n_poses, int n_edges, const int* edge_i
   std::memset(info, 0, sizeof *info);
   HostPattern pat;
   build_pattern(n_poses, n_edges, edge_ids, pose_const, &pat);
+  const double t1 = wall_s();
   for (unsigned char a : pat.active) info->variable_poses += a;
   info->hessian_blocks = (long long)pat.col_idx.size() + n_poses;
   LevelCholSymbolic S;
   PGO_TRY(level_chol_symbolic(&S, n_poses, pat.active.data(), pat.row_ptr.data(), pat.col_idx.data(),
                               max_fill_ratio > 0.0 ? max_fill_ratio : 1e30));
+  if (getenv("PGO_PROFILE_HOST")) fprintf(stderr, "[pgo analyze] pattern %.1f us, symbolic %.1f us\n", 1e6 * (t1 - t0), 1e6 * (wall_s() - t1));
   info->factor_usable = S.usable ? 1 : 0;
   if (S.usable) {
     info->factor_blocks = S.n_slots + S.n_nodes;
@@ -213,6 +226,7 @@ extern "C" void pgo_default_options(pgo_solver_options* o) {
   o->pcg_max_iterations = 20000;
   o->pcg_tolerance = 1e-10;
   o->pcg_num_ctas = 0;
+  o->direct_residual_accept = 1e-8;
   o->verbose = 0;
 }
 
@@ -689,7 +703,8 @@ static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int so
   if (g->world == 1 && solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     // the LM diagonal is formed inside the factor kernel
     return level_chol_solve(g->chol, bsr_view(g), lm, g->active, b, g->vx, g->vr, g->vu, g->vw, g->vp, g->vs,
-                            std::min(o->pcg_max_iterations, 200), o->pcg_tolerance, o->pcg_num_ctas, g->scalars,
+                            std::min(o->pcg_max_iterations, 200), o->pcg_tolerance, std::max(o->pcg_tolerance, o->direct_residual_accept),
+                            o->pcg_num_ctas, g->scalars,
                             g->stream, &g->launches);
   }
   const int tpb = 128;

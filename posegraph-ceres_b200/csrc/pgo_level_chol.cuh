@@ -23,6 +23,7 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -102,6 +103,7 @@ struct CholParams {
   DeviceScalars* scalars;
   int max_iterations;
   double tolerance;
+  double accept;                  // 2-norm relative residual at which the direct solve is accepted without refinement
   int first_level;                // levels < first_level (and the S phase) were done by chol_wide_kernel launches
   int setup_done;                 // the S phase ran as a chol_wide_kernel launch
   // dataflow shape: per-node dependency counters instead of level barriers
@@ -785,7 +787,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     xtb = reduce_partials(part + G, G, &bcast);
     xtAx = reduce_partials(part + 2 * G, G, &bcast);
     xtDx = reduce_partials(part + 3 * G, G, &bcast);
-    if (rr <= P.tolerance * P.tolerance * bb) { norm_kind = 1; break; }          // ||b - A x|| <= tol ||b||
+    if (rr <= P.accept * P.accept * bb) { norm_kind = 1; break; }               // ||b - A x|| <= accept ||b||
     // z = M^-1 r
     for (int k = gtid; k < n6; k += gthreads) { P.vt[k] = P.r[k]; }
     if (kDF) for (int i = gtid; i < n; i += gthreads) { P.pend_fwd[i] = P.pend_fwd_init[i]; P.pend_bwd[i] = P.pend_bwd_init[i]; }
@@ -840,12 +842,17 @@ struct LevelCholSymbolic {
 
 static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char* active, const int* a_row_ptr,
                                const int* a_col_idx, double max_fill_ratio) {
+  const bool prof = getenv("PGO_PROFILE_HOST") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tp = now();
+  auto lap = [&](const char* what) { if (prof) { const double t = now(); fprintf(stderr, "[pgo symbolic] %-22s %8.1f us\n", what, 1e6 * (t - tp)); tp = t; } };
   std::vector<std::vector<int>> adj(N);
   int n_nodes = 0;
   long long a_off = 0;
   for (int i = 0; i < N; ++i) {
     if (!active[i]) continue;
     ++n_nodes;
+    adj[i].reserve((size_t)std::max(8, 2 * (a_row_ptr[i + 1] - a_row_ptr[i])));
     adj[i].assign(a_col_idx + a_row_ptr[i], a_col_idx + a_row_ptr[i + 1]);   // sorted, symmetric, active only
     a_off += (long long)adj[i].size();
   }
@@ -862,8 +869,9 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   std::vector<unsigned char> alive(N, 0), blocked(N, 0);
   std::vector<int> alive_list;
   for (int i = 0; i < N; ++i) if (active[i]) { alive[i] = 1; alive_list.push_back(i); }
-  std::vector<std::pair<int, int>> cand;
+  std::vector<unsigned long long> cand;   // (degree << 32 | pose)
   std::vector<int> tmp, sel;
+  alive_list.reserve(n_nodes); cand.reserve(n_nodes); sel.reserve(n_nodes); tmp.reserve(64);
   long long slots = 0, work = 0;
   const long long work_cap = 100LL * (a_off + n_nodes) + 32000000LL;   // symbolic effort bound (merged adjacency entries)
   while (!alive_list.empty()) {
@@ -874,40 +882,50 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     // graph is both large and dense instead of grinding through a factor that would not pay off
     if (max_fill_ratio < 1e29 && alive_list.size() > 20000 && dsum > 16LL * (long long)alive_list.size()) return 0;
     const int thr = 2 * dmin + 2;
-    cand.clear();
-    for (int v : alive_list) if ((int)adj[v].size() <= thr) cand.emplace_back((int)adj[v].size(), v);
-    std::sort(cand.begin(), cand.end());
+    // greedy independent set in order of increasing degree (then pose id): one pass over the alive list per degree
+    // value instead of a sort -- thr - dmin is small
     sel.clear();
-    for (auto& dv : cand) {
-      const int v = dv.second;
-      if (blocked[v]) continue;
-      sel.push_back(v);
-      blocked[v] = 1;
-      for (int u : adj[v]) blocked[u] = 1;
+    cand.clear();
+    for (int d = dmin; d <= thr; ++d) {
+      for (int v : alive_list) {
+        if ((int)adj[v].size() != d) continue;
+        cand.push_back((unsigned long long)(unsigned)v);
+        if (blocked[v]) continue;
+        sel.push_back(v);
+        blocked[v] = 1;
+        for (int u : adj[v]) blocked[u] = 1;
+      }
     }
     int lvl_maxdeg = 0;
     for (int v : sel) {
       pos[v] = (int)order.size();
       order.push_back(v);
-      col_rows[v] = adj[v];
       slots += (long long)adj[v].size();
       lvl_maxdeg = std::max(lvl_maxdeg, (int)adj[v].size());
+      col_rows[v].swap(adj[v]);
     }
     if (slots > fill_cap || (int)level_ptr.size() > 8192 || work > work_cap) return 0;   // not usable (fill / depth / effort)
     for (int v : sel) {
       const std::vector<int>& nb = col_rows[v];
       for (int u : nb) {
         // adj[u] = (adj[u] U nb) \ {u, v}
+        std::vector<int>& au = adj[u];
+        work += (long long)(au.size() + nb.size());
         tmp.clear();
-        work += (long long)(adj[u].size() + nb.size());
-        std::set_union(adj[u].begin(), adj[u].end(), nb.begin(), nb.end(), std::back_inserter(tmp));
-        adj[u].clear();
-        for (int x : tmp) if (x != u && x != v) adj[u].push_back(x);
+        size_t ia = 0, ib = 0;
+        const size_t na = au.size(), nbn = nb.size();
+        while (ia < na || ib < nbn) {
+          int x;
+          if (ib >= nbn || (ia < na && au[ia] < nb[ib])) x = au[ia++];
+          else if (ia >= na || nb[ib] < au[ia]) x = nb[ib++];
+          else { x = au[ia]; ++ia; ++ib; }
+          if (x != u && x != v) tmp.push_back(x);
+        }
+        au.swap(tmp);
       }
       alive[v] = 0;
-      std::vector<int>().swap(adj[v]);
     }
-    for (auto& dv : cand) { blocked[dv.second] = 0; }
+    for (unsigned long long dv : cand) blocked[(int)(dv & 0xffffffffu)] = 0;
     for (int v : sel) for (int u : col_rows[v]) blocked[u] = 0;
     size_t w = 0;
     for (size_t k = 0; k < alive_list.size(); ++k) if (alive[alive_list[k]]) alive_list[w++] = alive_list[k];
@@ -919,6 +937,7 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   }
   S->num_levels = (int)level_split.size();
   S->n_slots = slots;
+  lap("elimination rounds");
 
   // column-major slots by elimination position
   std::vector<int> col_ptr(n_nodes + 1, 0);
@@ -933,9 +952,15 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     const int* it = std::lower_bound(b, e, row);
     return (it != e && *it == row) ? (int)(it - col_row.data()) : -1;
   };
+  lap("column structure");
   // Schur update tasks per node
   S->nodes.resize((size_t)n_nodes + 1);
   std::vector<CholTask>& tasks = S->tasks;
+  {
+    size_t est = 0;
+    for (int k = 0; k < n_nodes; ++k) { const size_t d = col_rows[order[k]].size(); est += d * (d + 1) / 2; }
+    tasks.reserve(est);
+  }
   for (int k = 0; k < n_nodes; ++k) {
     const int p0 = col_ptr[k], p1 = col_ptr[k + 1];
     S->nodes[k] = make_int4(order[k], p0, p1, (int)tasks.size());
@@ -954,6 +979,7 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     if (tasks.size() > 2000000000ull) return 0;
   }
   S->nodes[n_nodes] = make_int4(-1, (int)slots, (int)slots, (int)tasks.size());
+  lap("tasks");
   // L slot <- A (BSR off-diagonal) entry
   S->l2a.assign((size_t)slots, -1);
   for (int i = 0; i < N; ++i)
@@ -965,7 +991,10 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
         S->l2a[s] = p;
       }
     }
-  // dependency counters and row lists of the dataflow shape
+  lap("l2a");
+  // dependency counters and row lists of the (experimental, opt-in) dataflow shape
+  static const bool want_dataflow = getenv("PGO_CHOL_SHAPE") != nullptr && !strcmp(getenv("PGO_CHOL_SHAPE"), "dataflow");
+  if (!want_dataflow) { S->usable = true; return 0; }
   S->pend_fwd_init.assign(N, 0);
   S->pend_bwd_init.assign(N, 0);
   S->rowp.assign(N + 1, 0);
@@ -980,6 +1009,7 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
       for (int pp = col_ptr[k]; pp < col_ptr[k + 1]; ++pp) S->rown[fill[col_row[pp]]++] = v;
     }
   }
+  lap("dataflow lists");
   S->usable = true;
   return 0;
 }
@@ -1006,13 +1036,15 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned
   PGO_TRY(chol_upload(C, device, &C->col_row, S.col_row, stream));
   PGO_TRY(chol_upload(C, device, &C->l2a, S.l2a, stream));
   PGO_TRY(chol_upload(C, device, &C->tasks, S.tasks, stream));
-  PGO_TRY(chol_upload(C, device, &C->pend_fwd_init, S.pend_fwd_init, stream));
-  PGO_TRY(chol_upload(C, device, &C->pend_bwd_init, S.pend_bwd_init, stream));
-  PGO_TRY(chol_upload(C, device, &C->rowp, S.rowp, stream));
-  PGO_TRY(chol_upload(C, device, &C->rown, S.rown, stream));
-  PGO_TRY(chol_alloc(C, device, &C->pend_fwd, (size_t)N));
-  PGO_TRY(chol_alloc(C, device, &C->pend_bwd, (size_t)N));
-  C->dataflow_ok = S.max_degree <= 16;
+  if (!S.rowp.empty()) {
+    PGO_TRY(chol_upload(C, device, &C->pend_fwd_init, S.pend_fwd_init, stream));
+    PGO_TRY(chol_upload(C, device, &C->pend_bwd_init, S.pend_bwd_init, stream));
+    PGO_TRY(chol_upload(C, device, &C->rowp, S.rowp, stream));
+    PGO_TRY(chol_upload(C, device, &C->rown, S.rown, stream));
+    PGO_TRY(chol_alloc(C, device, &C->pend_fwd, (size_t)N));
+    PGO_TRY(chol_alloc(C, device, &C->pend_bwd, (size_t)N));
+    C->dataflow_ok = S.max_degree <= 16;
+  }
   PGO_TRY(chol_alloc(C, device, &C->Lblk, (size_t)S.n_slots * 36));
   PGO_TRY(chol_alloc(C, device, &C->Ldiag, (size_t)N * 36));
   PGO_TRY(chol_alloc(C, device, &C->vt, (size_t)N * 6));
@@ -1066,7 +1098,7 @@ struct LmDiagonal {           // LevenbergMarquardtStrategy::ComputeStep's D = s
 // Factor (H + D) and solve (H + D) x = b by PCG preconditioned with the factor, one launch.
 static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const unsigned char* active, const double* b,
                             double* x, double* r, double* z, double* q, double* p, double* ax, int max_iterations,
-                            double tolerance, int num_ctas, DeviceScalars* scalars, cudaStream_t stream,
+                            double tolerance, double accept, int num_ctas, DeviceScalars* scalars, cudaStream_t stream,
                             long long* launches) {
   CholParams P;
   P.A = A; P.lm_mode = lm.mode; P.min_diag = lm.min_diag; P.max_diag = lm.max_diag; P.radius = lm.radius;
@@ -1076,7 +1108,7 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
   P.level_ptr = C->level_ptr; P.level_split = C->level_split; P.col_row = C->col_row; P.l2a = C->l2a; P.nodes = C->nodes;
   P.tasks = C->tasks; P.Lblk = C->Lblk; P.Ldiag = C->Ldiag; P.vt = C->vt;
   P.n_slots = C->n_slots; P.partials = C->partials; P.barrier = C->barrier; P.scalars = scalars;
-  P.max_iterations = max_iterations; P.tolerance = tolerance;
+  P.max_iterations = max_iterations; P.tolerance = tolerance; P.accept = accept;
   static const bool want_timeline = getenv("PGO_TIMELINE") != nullptr;
   static unsigned long long* timeline_d = nullptr;
   P.timeline = nullptr;

@@ -125,6 +125,7 @@ def test_linear_solve_matches_oracle_cholesky(pgo, oracle, graphs, name, solver)
     o = pgo.default_options()
     o.linear_solver_type = solver
     o.pcg_tolerance = 1e-12
+    o.direct_residual_accept = 0.0        # the requested tolerance rules (forces refinement iterations)
     o.pcg_max_iterations = 20000
     y, iters, rel, ms = G.linear_solve(d, grad, o)
     assert rel <= 1e-10
@@ -173,6 +174,19 @@ def test_solve_kitti00_matches_oracle(pgo, oracle, graphs):
     """configs[1]: KITTI-00, 4541 poses / 5179 edges, reference settings (Huber(1.0), 1000 iterations)."""
     s, its = _compare_solves(pgo, oracle, graphs["kitti00"], 2)
     assert s.termination_type == 0
+
+
+def test_solve_kitti00_default_options_matches_oracle(pgo, oracle, graphs):
+    """the configuration bench.py times: pgo_default_options() untouched (direct solves accepted at 1e-8 relative residual)."""
+    g = graphs["kitti00"]
+    ref, rs, rits = oracle.solve(g)
+    poses, s, its = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
+    assert s.termination_type == rs.termination_type and len(its) == len(rits)
+    for a, b in zip(its, rits):
+        assert a.step_is_successful == b.step_is_successful
+        assert abs(a.cost - b.cost) <= 1e-7 * max(1.0, abs(b.cost))
+    assert np.abs(poses[:, :3] - ref[:, :3]).max() <= 1e-4                      # north_star: <= 1e-4 m
+    assert rot_angle_between(poses[:, 3:], ref[:, 3:]).max() <= 1e-4            # north_star: <= 1e-4 rad
 
 
 def test_e2e_host_buffers(pgo, oracle, graphs):
