@@ -638,6 +638,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   const int warps_per_cta = kCholThreads / 32;
   const int gw = blockIdx.x * warps_per_cta + warp;
   const int nw = gridDim.x * warps_per_cta;
+  // level work is dealt CTA-minor (node j -> CTA j mod G): a narrow level then spreads over all SMs instead of filling
+  // the first CTAs -- the fp64 RED throughput that bounds a node's Schur updates is per SM
+  const int gwx = warp * (int)gridDim.x + (int)blockIdx.x;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
   const int grp = lane / 6, r6 = lane - grp * 6;
@@ -666,12 +669,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       const bool split = kFactor && mode == 1;
       if (mode != 1) {
         bool ok = true;
-        if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane); }
-        else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane); }
-        else { for (int kk = k0 + gw; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane); }
+        if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane); }
+        else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane); }
+        else { for (int kk = k0 + gwx; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane); }
         if (!ok) atomicExch(P.barrier + 1, 1u);
       } else {
-        for (int k = k0 + gw; k < k1; k += nw) {
+        for (int k = k0 + gwx; k < k1; k += nw) {
           const int4 nm = __ldg(P.nodes + k);
           const bool ok = chol_forward_node<kFactor>(P, nm.x, nm.y, nm.z, lane);
           if (kFactor && !ok && lane == 0) atomicExch(P.barrier + 1, 1u);
@@ -694,11 +697,11 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     for (int l = P.num_levels - 1; l >= 0; --l) {
       const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
       const int mode = __ldg(P.level_split + l);
-      if (mode == 8) { for (int kk = k0 + gw * 4; kk < k1; kk += nw * 4) chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 16) { for (int kk = k0 + gw * 2; kk < k1; kk += nw * 2) chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 32) { for (int kk = k0 + gw; kk < k1; kk += nw) chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2); }
+      if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2); }
+      else if (mode == 32) { for (int kk = k0 + gwx; kk < k1; kk += nw) chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2); }
       else {
-        for (int k = k0 + gw; k < k1; k += nw) {
+        for (int k = k0 + gwx; k < k1; k += nw) {
           const int4 nm = __ldg(P.nodes + k);
           const int v = nm.x, p0 = nm.y, p1 = nm.z;
           double acc = 0.0;   // lane (grp, c = r6): sum_u sum_r L_uv[r][c] x_u[r]
