@@ -303,7 +303,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // block and rhs), the Cholesky, column scaling and Schur products then run out of registers / shared memory, and
 // results leave as plain stores and fire-and-forget fp64 RED atomics.
 template <int kLanes, bool kFactor = true, bool kDataflow = false>
-__device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane) {
+__device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane,
+                                                   bool pre = false, int4 pre0 = int4(), int4 pre1 = int4()) {   // pre0/1: this lane's node records k, k+1 (prefetched)
   constexpr int kNpw = 32 / kLanes;
   constexpr int kBlk = kStashBlocks / kNpw;
   constexpr int kTsk = kStashTasks / kNpw;
@@ -312,9 +313,9 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
   const bool valid = k < k1;
   int v = 0, p0 = 0, p1 = 0, t0 = 0, t1 = 0;
   if (valid) {
-    const int4 nm = __ldg(P.nodes + k);
+    const int4 nm = pre ? pre0 : __ldg(P.nodes + k);
     v = nm.x; p0 = nm.y; p1 = nm.z; t0 = nm.w;
-    t1 = __ldg(&P.nodes[k + 1].w);
+    t1 = pre ? pre1.w : __ldg(&P.nodes[k + 1].w);
   }
   const int deg = p1 - p0, ntask = t1 - t0;
   double sink = 0.0;   // dataflow shape: sum of the values returned by this lane's update atomics
@@ -486,7 +487,8 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
 
 // Backward step for 32 / kLanes nodes per warp: x_v = Linv_v^T (y_v - sum_{u in col(v)} L_uv^T x_u).
 template <int kLanes, bool kDataflow = false>
-__device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk, int k1, int lane, double* dst, double* dst2) {
+__device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk, int k1, int lane, double* dst, double* dst2,
+                                                     bool pre = false, int4 pre0 = int4()) {
   constexpr int kNpw = 32 / kLanes;
   constexpr int kSub = kLanes / 6;                         // 6-lane column groups per node: 1, 2, 5
   constexpr int kIter = (kStashBlocks / kNpw + kSub - 1) / kSub;   // blocks per column group: 4, 4, 4
@@ -494,7 +496,7 @@ __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk
   const int k = kk + gi;
   const bool valid = k < k1;
   int v = 0, p0 = 0, p1 = 0;
-  if (valid) { const int4 nm = __ldg(P.nodes + k); v = nm.x; p0 = nm.y; p1 = nm.z; }
+  if (valid) { const int4 nm = pre ? pre0 : __ldg(P.nodes + k); v = nm.x; p0 = nm.y; p1 = nm.z; }
   const int sg = sub / 6, c = sub - 6 * sg;
   const bool on = valid && sg < kSub;
   if (kDataflow) {
@@ -651,6 +653,29 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   unsigned int epoch = 0;
   int region = 0;
   auto next_region = [&]() -> double* { region = (region + 1) & 7; return P.partials + (size_t)region * 4 * G; };
+  // level table in shared memory (one L2 round trip less per level) and node-record prefetch across the level barrier
+  constexpr int kMaxLv = 1024;
+  __shared__ int s_lptr[kMaxLv + 1];
+  __shared__ int s_lmode[kMaxLv];
+  const bool lv_smem = P.num_levels <= kMaxLv;
+  if (lv_smem) {
+    for (int l = threadIdx.x; l <= P.num_levels; l += blockDim.x) { s_lptr[l] = __ldg(P.level_ptr + l); if (l < P.num_levels) s_lmode[l] = __ldg(P.level_split + l); }
+    __syncthreads();
+  }
+  auto lv_ptr = [&](int l) -> int { return lv_smem ? s_lptr[l] : __ldg(P.level_ptr + l); };
+  auto lv_mode = [&](int l) -> int { return lv_smem ? s_lmode[l] : __ldg(P.level_split + l); };
+  int4 pre0 = make_int4(0, 0, 0, 0), pre1 = make_int4(0, 0, 0, 0);
+  bool have_pre = false;
+  // fetch this lane's node records for the first group this warp will own in level l
+  auto prefetch_level = [&](int l) {
+    have_pre = false;
+    if (l < 0 || l >= P.num_levels) return;
+    const int m = lv_mode(l);
+    if (m == 1) return;
+    const int k = lv_ptr(l) + gwx * (32 / m) + lane / m;
+    if (k < lv_ptr(l + 1)) { pre0 = __ldg(P.nodes + k); pre1 = __ldg(P.nodes + k + 1); }
+    have_pre = true;
+  };
 
   // ---- S: LM diagonal, gather A + D into the factor storage, working rhs ----
   chol_mark(P, 0);
@@ -663,15 +688,18 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   // the whole launch after an extra barrier).
   auto forward = [&](auto factor_tag) {
     constexpr bool kFactor = decltype(factor_tag)::value;
-    for (int l = kFactor ? P.first_level : 0; l < P.num_levels; ++l) {
-      const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
-      const int mode = __ldg(P.level_split + l);
+    const int l0 = kFactor ? P.first_level : 0;
+    prefetch_level(l0);
+    for (int l = l0; l < P.num_levels; ++l) {
+      const int k0 = lv_ptr(l), k1 = lv_ptr(l + 1);
+      const int mode = lv_mode(l);
       const bool split = kFactor && mode == 1;
       if (mode != 1) {
         bool ok = true;
-        if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane); }
-        else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane); }
-        else { for (int kk = k0 + gwx; kk < k1; kk += nw) ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane); }
+        bool pp = have_pre;   // only the first group of the level was prefetched
+        if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
+        else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
+        else { for (int kk = k0 + gwx; kk < k1; kk += nw) { ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
         if (!ok) atomicExch(P.barrier + 1, 1u);
       } else {
         for (int k = k0 + gwx; k < k1; k += nw) {
@@ -685,6 +713,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
         const long long t0 = __ldg(&P.nodes[k0].w), t1 = __ldg(&P.nodes[k1].w);
         for (long long it = (long long)gtid; it < (t1 - t0) * 6; it += gthreads) chol_update_item(P, P.tasks[t0 + it / 6], (int)(it % 6));
       }
+      prefetch_level(l + 1);       // static structure: its latency hides behind the barrier
       if (!kDF) {
         chol_mark(P, 100 + l);
         chol_sync<kShape>(P.barrier, epoch);
@@ -694,12 +723,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   };
   // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending; writes dst (and dst2)
   auto backward = [&](double* dst, double* dst2) {
+    prefetch_level(P.num_levels - 1);
     for (int l = P.num_levels - 1; l >= 0; --l) {
-      const int k0 = __ldg(P.level_ptr + l), k1 = __ldg(P.level_ptr + l + 1);
-      const int mode = __ldg(P.level_split + l);
-      if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2); }
-      else if (mode == 32) { for (int kk = k0 + gwx; kk < k1; kk += nw) chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2); }
+      const int k0 = lv_ptr(l), k1 = lv_ptr(l + 1);
+      const int mode = lv_mode(l);
+      bool pp = have_pre;
+      if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
+      else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
+      else if (mode == 32) { for (int kk = k0 + gwx; kk < k1; kk += nw) { chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
       else {
         for (int k = k0 + gwx; k < k1; k += nw) {
           const int4 nm = __ldg(P.nodes + k);
@@ -726,6 +757,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
           if (lane < 6) { dst[6 * (size_t)v + lane] = xv; if (dst2) dst2[6 * (size_t)v + lane] = xv; }
         }
       }
+      prefetch_level(l - 1);
       if (!kDF) {
         chol_mark(P, 300 + l);
         chol_sync<kShape>(P.barrier, epoch);
