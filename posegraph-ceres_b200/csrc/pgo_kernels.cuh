@@ -263,17 +263,29 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
 #pragma unroll
           for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) stg[lane * 36 + rot36(pidx(r, c) + swz)] = value(r, c);
+            for (int c = 0; c < 6; ++c) {
+              // swz <= 7: the rotation can only wrap for the last elements of the row (decided at compile time)
+              const int idx = (pidx(r, c) + 7 < 36) ? pidx(r, c) + swz : rot36(pidx(r, c) + swz);
+              stg[lane * 36 + idx] = value(r, c);
+            }
           __syncwarp();
-#pragma unroll 6
-          for (int j = 0; j < 36; ++j) {
-            const int item = j * 32 + lane;
-            const int blk = item / 36, el = item - blk * 36;
-            const int t = sidx[blk];
-            const double v = stg[blk * 36 + rot36(el + (blk >> 2))];
+          auto out = [&](int t, int el, double v) {
             if (reduce_always) { if (t >= 0) atomicAdd(base + 36 * (size_t)t + el, v); }
             else if (t >= 0) base[36 * (size_t)t + el] = v;
             else if (t <= -2) atomicAdd(base + 36 * (size_t)(-t - 2) + el, v);
+          };
+          // drain, element-major: pass 1 -- lane l owns element l of every block (32 lanes = 8 whole sectors);
+          // pass 2 -- elements 32..35, four lanes per block (one sector), eight blocks per instruction
+#pragma unroll 8
+          for (int blk = 0; blk < 32; ++blk) {
+            const int t = sidx[blk];
+            out(t, lane, stg[blk * 36 + rot36(lane + (blk >> 2))]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int blk = j * 8 + (lane >> 2), el = 32 + (lane & 3);
+            const int t = sidx[blk];
+            out(t, el, stg[blk * 36 + rot36(el + (blk >> 2))]);
           }
           __syncwarp();
         };

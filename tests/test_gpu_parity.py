@@ -237,3 +237,47 @@ def test_stream_ordered_pcg_of_the_multi_gpu_path(pgo):
         assert a[0] == b[0] and a[1] == b[1]                       # same LM iteration count
         assert abs(float(a[3]) - float(b[3])) <= 1e-8 * float(a[3])  # same final cost
         assert abs(float(a[4]) - float(b[4])) <= 1e-6              # same poses (sum |p|)
+
+
+def test_full_size_properties_1m_pose_grid(pgo):
+    """BASELINE configs[3] at full size (1M poses / 2.05M edges), where the oracle is out of reach: size-independent
+    properties of the assembled system -- symmetry and positive semi-definiteness of H through the block-SpMV kernel,
+    and gradient = derivative of the cost along a random tangent direction (central difference through Plus)."""
+    D = pgo.datasets
+    g = D.manhattan_grid(1000, 1000, 50000)
+    G = pgo.Graph.from_dataset(g)
+    cost0, _ = G.linearize(loss_type=1, loss_a=1.0)
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(g.n_poses, 6))
+    y = rng.normal(size=(g.n_poses, 6))
+    Hx, _ = G.spmv(x)
+    Hy, _ = G.spmv(y)
+    xHy, yHx = float((x * Hy).sum()), float((y * Hx).sum())
+    assert abs(xHy - yHx) <= 1e-10 * max(abs(xHy), abs(yHx))            # symmetry
+    assert float((x * Hx).sum()) > 0.0 and float((y * Hy).sum()) > 0.0  # J^T J is PSD
+    # the first pose is constant: its row and column of H and its gradient entries vanish
+    assert np.abs(Hx[0]).max() == 0.0
+    # gradient check: d/d eps cost(Plus(x, eps d)) at 0 == g . d
+    cost, _, grad, _ = G.evaluate(loss_type=1, loss_a=1.0, want_jacobians=False)
+    assert abs(cost - cost0) <= 1e-12 * cost0
+    d = rng.normal(size=(g.n_poses, 6))
+    d[0] = 0.0
+    eps = 1e-6
+
+    def plus(p, delta):   # EigenQuaternionParameterization::Plus, vectorised
+        out = p.copy()
+        out[:, :3] += delta[:, :3]
+        n = np.linalg.norm(delta[:, 3:], axis=1, keepdims=True)
+        k = np.where(n > 0, np.sin(n) / np.maximum(n, 1e-300), 1.0)
+        dq = np.concatenate([k * delta[:, 3:], np.cos(n)], axis=1)
+        out[:, 3:] = D.qmul(dq, p[:, 3:])
+        return out
+
+    G.set_poses(plus(g.poses, eps * d))
+    cp = G.evaluate(loss_type=1, loss_a=1.0, want_jacobians=False)[0]
+    G.set_poses(plus(g.poses, -eps * d))
+    cm = G.evaluate(loss_type=1, loss_a=1.0, want_jacobians=False)[0]
+    fd = (cp - cm) / (2 * eps)
+    gd = float((grad * d).sum())
+    assert abs(fd - gd) <= 1e-5 * max(1.0, abs(gd)), (fd, gd)
+    G.close()
