@@ -550,6 +550,8 @@ static BsrView bsr_view(const pgo_graph* g) {
   return A;
 }
 
+constexpr int kStreamPcgMinPoses = 200000;
+
 static int pcg_grid(const pgo_graph* g, const pgo_solver_options* o) {
   int want = (g->N + (kPcgThreads / 32) * kRowsPerWarp - 1) / ((kPcgThreads / 32) * kRowsPerWarp);
   if (o && o->pcg_num_ctas > 0) want = o->pcg_num_ctas;
@@ -712,7 +714,9 @@ static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int so
                                                                    lm.radius, lm.diagonal, lm.dlm, g->Minv);
   g->launches++;
   static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;   // tests: multi-GPU code path on one GPU
-  if (g->world > 1 || force_stream_pcg) return pcg_multi(g, o, b);
+  // large graphs: separate launches at full occupancy beat the persistent kernel (whose grid barriers only pay when an
+  // iteration is a few microseconds long)
+  if (g->world > 1 || force_stream_pcg || g->N >= kStreamPcgMinPoses) return pcg_multi(g, o, b);
   return launch_pcg(g, o, b);
 }
 

@@ -369,20 +369,38 @@ struct BsrView {
   const int* col_idx;
 };
 
-// y = (H + diag(d)) x ; grid-stride over groups of 5 rows per warp.
+// y = (H + diag(d)) x ; grid-stride over groups of 5 rows per warp.  dot_part (optional): per-CTA partial of y . x
+// in a fixed summation order (the CG step length of the stream-ordered PCG rides on the SpMV).
 __global__ void __launch_bounds__(256) spmv_kernel(const BsrView A, const double* __restrict__ x,
                                                    const double* __restrict__ d, double* __restrict__ y,
-                                                   bool with_diag) {
+                                                   bool with_diag, double* __restrict__ dot_part = nullptr,
+                                                   const int* __restrict__ skip = nullptr) {
+  __shared__ double red[8];
+  const bool idle = skip != nullptr && *skip != 0;   // stream-ordered PCG: converged, keep the vectors frozen
   const int lane = threadIdx.x & 31;
   const int grp = lane / 6, r = lane - grp * 6;
   const int warps_per_cta = blockDim.x >> 5;
   const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
   const int nw = gridDim.x * warps_per_cta;
-  for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
-    const int i = base + grp;
-    if (grp < kRowsPerWarp && i < A.n) {
-      const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, r, with_diag);
-      y[6 * (size_t)i + r] = v;
+  double acc = 0.0;
+  if (!idle) {
+    for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
+      const int i = base + grp;
+      if (grp < kRowsPerWarp && i < A.n) {
+        const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, r, with_diag);
+        y[6 * (size_t)i + r] = v;
+        if (dot_part != nullptr) acc = fma(v, __ldg(x + 6 * (size_t)i + r), acc);
+      }
+    }
+  }
+  if (dot_part != nullptr) {
+    acc = warp_sum(acc);
+    if (lane == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < warps_per_cta; ++k) t += red[k];
+      dot_part[blockIdx.x] = t;
     }
   }
 }

@@ -105,32 +105,36 @@ __global__ void __launch_bounds__(kPcgmThreads) pcgm_scalar_kernel(PcgMultiState
   }
 }
 
+// p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, u = Minv r, partial of r.u.  Six lanes per pose (lane =
+// component), five poses per warp: the vector traffic is contiguous and a Minv row is three 128-bit loads.
 __global__ void __launch_bounds__(kPcgmThreads) pcgm_update_kernel(int n, const double* __restrict__ Minv, const double* __restrict__ w,
                                                                    double* x, double* r, double* u, double* p, double* s,
                                                                    const PcgMultiState* st, double* part0) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc = 0.0;
-  if (!st->done && i < n) {
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / 6, c6 = lane - grp * 6;
+  const int warps_per_cta = kPcgmThreads / 32;
+  const int i = (blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * kRowsPerWarp + grp;
+  const bool on = !st->done && grp < kRowsPerWarp && i < n;
+  double acc = 0.0, rv = 0.0;
+  const size_t q = 6 * (size_t)(on ? i : 0) + c6;
+  if (on) {
     const double alpha = st->alpha, beta = st->beta;
-    double rv[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const size_t q = 6 * (size_t)i + k;
-      const double pv = u[q] + beta * p[q];
-      const double sv = w[q] + beta * s[q];
-      p[q] = pv; s[q] = sv;
-      x[q] += alpha * pv;
-      rv[k] = r[q] - alpha * sv;
-      r[q] = rv[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double t = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) t = fma(Minv[36 * (size_t)i + 6 * k + c], rv[c], t);
-      u[6 * (size_t)i + k] = t;
-      acc += rv[k] * t;
-    }
+    const double pv = u[q] + beta * p[q];
+    const double sv = w[q] + beta * s[q];
+    p[q] = pv; s[q] = sv;
+    x[q] += alpha * pv;
+    rv = r[q] - alpha * sv;
+    r[q] = rv;
+  }
+  const int g0 = grp * 6;
+  const double r0 = __shfl_sync(0xffffffffu, rv, g0), r1 = __shfl_sync(0xffffffffu, rv, g0 + 1), r2 = __shfl_sync(0xffffffffu, rv, g0 + 2);
+  const double r3 = __shfl_sync(0xffffffffu, rv, g0 + 3), r4 = __shfl_sync(0xffffffffu, rv, g0 + 4), r5 = __shfl_sync(0xffffffffu, rv, g0 + 5);
+  if (on) {
+    const double2* mi = reinterpret_cast<const double2*>(Minv + 36 * (size_t)i + 6 * c6);
+    const double2 m0 = __ldg(mi), m1 = __ldg(mi + 1), m2 = __ldg(mi + 2);
+    const double t = m0.x * r0 + m0.y * r1 + m1.x * r2 + m1.y * r3 + m2.x * r4 + m2.y * r5;
+    u[q] = t;
+    acc = rv * t;
   }
   pcgm_block_partial(acc, part0);
 }
@@ -167,13 +171,14 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
   using namespace pgo;
   const int N = g->N, n6 = 6 * N;
   const int nb = (N + kPcgmThreads - 1) / kPcgmThreads;
+  const int nbu = (N + (kPcgmThreads / 32) * kRowsPerWarp - 1) / ((kPcgmThreads / 32) * kRowsPerWarp);   // update kernel: 5 poses per warp
   const int warps = (N + kRowsPerWarp - 1) / kRowsPerWarp;
   const int sp_ctas = std::max(1, std::min((warps + 7) / 8, 8 * g->num_sms));
   const int dot_ctas = std::max(1, std::min((n6 + kPcgmThreads - 1) / kPcgmThreads, 4 * g->num_sms));
   if (!g->pcgm_state) {
     PGO_TRY(dev_alloc(g, &g->pcgm_state, 1));
-    PGO_TRY(dev_alloc(g, &g->pcgm_part0, (size_t)nb));
-    PGO_TRY(dev_alloc(g, &g->pcgm_part1, (size_t)3 * dot_ctas));
+    PGO_TRY(dev_alloc(g, &g->pcgm_part0, (size_t)std::max(nb, nbu)));
+    PGO_TRY(dev_alloc(g, &g->pcgm_part1, (size_t)std::max(3 * dot_ctas, sp_ctas)));
     CUDA_TRY(pool_pinned(g->device, reinterpret_cast<void**>(&g->pcgm_state_h)));
   }
   PcgMultiState* st = g->pcgm_state;
@@ -188,13 +193,21 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
   int launched = 0;
   for (;;) {
     for (int k = 0; k < kCheckEvery; ++k) {
-      spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag);
-      PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
-      pcgm_dot_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vw, g->vu, st, part1);
-      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, dot_ctas);
-      pcgm_update_kernel<<<nb, kPcgmThreads, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st, part0);
-      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 2, o->pcg_max_iterations, o->pcg_tolerance, part0, nb);
-      g->launches += 5;
+      if (g->world > 1) {
+        // the SpMV product is a sum over ranks: all-reduce it, then w . u on the summed vector
+        spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, nullptr, &st->done);
+        PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
+        pcgm_dot_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vw, g->vu, st, part1);
+        pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, dot_ctas);
+        g->launches += 1;
+      } else {
+        // one GPU: w . u rides on the SpMV (per-CTA partials in a fixed order)
+        spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
+        pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, sp_ctas);
+      }
+      pcgm_update_kernel<<<nbu, kPcgmThreads, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st, part0);
+      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 2, o->pcg_max_iterations, o->pcg_tolerance, part0, nbu);
+      g->launches += 4;
       ++launched;
     }
     // the exit decision must be the same on every rank: rank 0's state is authoritative
