@@ -367,7 +367,7 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   lap("uploads + memset");
   // persistent PCG grid: all CTAs must be co-resident (cooperative launch)
   static int per_sm = 0;
-  if (per_sm == 0) GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel, kPcgThreads, 0));
+  if (per_sm == 0) GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, kPcgThreads, 0));
   g->pcg_max_ctas = std::max(1, std::min(per_sm, 4) * g->num_sms);
   G_TRY(dev_alloc(g, &g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
 
@@ -551,6 +551,7 @@ static BsrView bsr_view(const pgo_graph* g) {
 }
 
 constexpr int kStreamPcgMinPoses = 200000;
+constexpr int kClusterPcgMaxPoses = 400;   // measured: at 2500 poses the 16-SM cluster is already 2.5x slower than the full grid
 
 static int pcg_grid(const pgo_graph* g, const pgo_solver_options* o) {
   int want = (g->N + (kPcgThreads / 32) * kRowsPerWarp - 1) / ((kPcgThreads / 32) * kRowsPerWarp);
@@ -567,9 +568,37 @@ static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b
   P.partials = g->partials; P.barrier = g->barrier; P.scalars = g->scalars;
   P.max_iterations = o->pcg_max_iterations; P.tolerance = o->pcg_tolerance;
   CUDA_TRY(cudaMemsetAsync(g->barrier, 0, 4 * sizeof(unsigned int), g->stream));
-  void* args[] = {&P};
-  const int grid = pcg_grid(g, o);
-  CUDA_TRY(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(kPcgThreads), args, 0, g->stream));
+  // small graphs: one 16-CTA cluster, hardware barrier (an iteration is a few microseconds, the barrier dominates)
+  static int cluster_ctas = -1;
+  if (cluster_ctas < 0) {
+    cluster_ctas = 0;
+    cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    for (int cs : {16, 8}) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kPcgThreads);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, pcg_kernel<true>, &cfg) == cudaSuccess && ncl >= 1) { cluster_ctas = cs; break; }
+      cudaGetLastError();
+    }
+  }
+  if (cluster_ctas > 0 && g->N <= kClusterPcgMaxPoses && o->pcg_num_ctas <= 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_ctas); cfg.blockDim = dim3(kPcgThreads); cfg.stream = g->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, pcg_kernel<true>, P));
+  } else {
+    void* args[] = {&P};
+    const int grid = pcg_grid(g, o);
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)pcg_kernel<false>, dim3(grid), dim3(kPcgThreads), args, 0, g->stream));
+  }
   g->launches++;
   return PGO_OK;
 }
@@ -687,8 +716,11 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
   if (t == PGO_LINEAR_AUTO || t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     if (!g->chol) {
       LevelChol* c = nullptr;
+      // AUTO takes the factor only when it is cheap: chain-like graphs (<= 64 levels, node degree <= 16, fill <= 8x);
+      // mesh-like graphs (sphere, grids, dense random loops) go to block-Jacobi PCG
+      const bool autosel = t == PGO_LINEAR_AUTO;
       const int rc = level_chol_analyze(&c, g->device, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(),
-                                        t == PGO_LINEAR_AUTO ? 8.0 : 1e30, g->stream);
+                                        autosel ? 8.0 : 1e30, autosel ? 64 : 8192, autosel ? 16 : (1 << 30), g->stream);
       if (rc == PGO_OK) g->chol = c;
       else if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return rc;
     }

@@ -464,6 +464,15 @@ __device__ __forceinline__ double reduce_partials(const double* part, int n, dou
 }
 
 
+// kCluster: the whole launch is ONE thread-block cluster (small graphs) and the two barriers per iteration are the
+// hardware cluster barrier instead of the atomic-counter grid barrier.
+template <bool kCluster>
+__device__ __forceinline__ void pcg_sync(unsigned int* counter, unsigned int& epoch) {
+  if constexpr (kCluster) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else grid_barrier(counter, epoch);
+}
+
+template <bool kCluster>
 __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   __shared__ double red[kPcgThreads / 32];
   __shared__ double bcast;
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   }
   acc = cta_sum(acc, red);
   if (threadIdx.x == 0) P.partials[0 * 3 * G + 0 * G + blockIdx.x] = acc;
-  grid_barrier(P.barrier, epoch);
+  pcg_sync<kCluster>(P.barrier, epoch);
   const double gamma0 = reduce_partials(P.partials + 0, G, &bcast);
   double gamma = gamma0, gamma_old = 0.0, alpha = 0.0, beta = 0.0;
   int iter = 0;
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
       }
       acc = cta_sum(acc, red);
       if (threadIdx.x == 0) part[1 * G + blockIdx.x] = acc;
-      grid_barrier(P.barrier, epoch);
+      pcg_sync<kCluster>(P.barrier, epoch);
       const double delta = reduce_partials(part + 1 * G, G, &bcast);
       // ---- scalars (identical on every thread) ----
       if (iter == 0) { beta = 0.0; alpha = gamma / delta; }
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
       acc = cta_sum(acc, red);
       double* partn = P.partials + (size_t)(iter & 1) * 3 * G;
       if (threadIdx.x == 0) partn[0 * G + blockIdx.x] = acc;
-      grid_barrier(P.barrier, epoch);
+      pcg_sync<kCluster>(P.barrier, epoch);
       gamma_old = gamma;
       gamma = reduce_partials(partn + 0 * G, G, &bcast);
       if (gamma <= stop) { flag = 0; break; }
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   a0 = cta_sum(a0, red); a1 = cta_sum(a1, red); a2 = cta_sum(a2, red);
   double* parte = P.partials + (size_t)((iter + 1) & 1) * 3 * G;
   if (threadIdx.x == 0) { parte[0 * G + blockIdx.x] = a0; parte[1 * G + blockIdx.x] = a1; parte[2 * G + blockIdx.x] = a2; }
-  grid_barrier(P.barrier, epoch);
+  pcg_sync<kCluster>(P.barrier, epoch);
   const double e0 = reduce_partials(parte + 0 * G, G, &bcast);
   const double e1 = reduce_partials(parte + 1 * G, G, &bcast);
   const double e2 = reduce_partials(parte + 2 * G, G, &bcast);

@@ -875,8 +875,10 @@ struct LevelCholSymbolic {
   std::vector<CholTask> tasks;
 };
 
+// max_levels / max_node_degree: AUTO only accepts a "cheap" factor (few levels, every level a low-degree staged level);
+// the analysis gives up as soon as a limit is exceeded.
 static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char* active, const int* a_row_ptr,
-                               const int* a_col_idx, double max_fill_ratio) {
+                               const int* a_col_idx, double max_fill_ratio, int max_levels = 8192, int max_node_degree = 1 << 30) {
   const bool prof = getenv("PGO_PROFILE_HOST") != nullptr;
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tp = now();
@@ -939,7 +941,7 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
       lvl_maxdeg = std::max(lvl_maxdeg, (int)adj[v].size());
       col_rows[v].swap(adj[v]);
     }
-    if (slots > fill_cap || (int)level_ptr.size() > 8192 || work > work_cap) return 0;   // not usable (fill / depth / effort)
+    if (slots > fill_cap || (int)level_ptr.size() > max_levels || lvl_maxdeg > max_node_degree || work > work_cap) return 0;   // not usable
     for (int v : sel) {
       const std::vector<int>& nb = col_rows[v];
       for (int u : nb) {
@@ -1050,12 +1052,12 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
 }
 
 static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned char* active, const int* a_row_ptr,
-                              const int* a_col_idx, double max_fill_ratio, cudaStream_t stream) {
+                              const int* a_col_idx, double max_fill_ratio, int max_levels, int max_node_degree, cudaStream_t stream) {
   LevelChol* C = new LevelChol();
   *out = C;
   C->N = N;
   LevelCholSymbolic S;
-  PGO_TRY(level_chol_symbolic(&S, N, active, a_row_ptr, a_col_idx, max_fill_ratio));
+  PGO_TRY(level_chol_symbolic(&S, N, active, a_row_ptr, a_col_idx, max_fill_ratio, max_levels, max_node_degree));
   C->n_nodes = S.n_nodes;
   if (!S.usable) return 0;
   C->num_levels = S.num_levels;
