@@ -698,7 +698,7 @@ extern "C" int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, do
   const int ctas = std::max(1, std::min((warps + 7) / 8, 8 * g->num_sms));
   CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
   for (int k = 0; k < std::max(repeats, 1); ++k) {
-    spmv_kernel<<<ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, d ? g->dlm : nullptr, g->vw, g->rank == 0);
+    spmv_kernel<false><<<ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, d ? g->dlm : nullptr, g->vw, g->rank == 0);
     g->launches++;
   }
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));

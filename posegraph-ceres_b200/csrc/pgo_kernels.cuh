@@ -371,12 +371,13 @@ struct BsrView {
 
 // y = (H + diag(d)) x ; grid-stride over groups of 5 rows per warp.  dot_part (optional): per-CTA partial of y . x
 // in a fixed summation order (the CG step length of the stream-ordered PCG rides on the SpMV).
+template <bool kDot>
 __global__ void __launch_bounds__(256) spmv_kernel(const BsrView A, const double* __restrict__ x,
                                                    const double* __restrict__ d, double* __restrict__ y,
                                                    bool with_diag, double* __restrict__ dot_part = nullptr,
                                                    const int* __restrict__ skip = nullptr) {
   __shared__ double red[8];
-  const bool idle = skip != nullptr && *skip != 0;   // stream-ordered PCG: converged, keep the vectors frozen
+  const bool idle = kDot && skip != nullptr && *skip != 0;   // stream-ordered PCG: converged, keep the vectors frozen
   const int lane = threadIdx.x & 31;
   const int grp = lane / 6, r = lane - grp * 6;
   const int warps_per_cta = blockDim.x >> 5;
@@ -389,11 +390,11 @@ __global__ void __launch_bounds__(256) spmv_kernel(const BsrView A, const double
       if (grp < kRowsPerWarp && i < A.n) {
         const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, r, with_diag);
         y[6 * (size_t)i + r] = v;
-        if (dot_part != nullptr) acc = fma(v, __ldg(x + 6 * (size_t)i + r), acc);
+        if (kDot) acc = fma(v, __ldg(x + 6 * (size_t)i + r), acc);
       }
     }
   }
-  if (dot_part != nullptr) {
+  if (kDot) {
     acc = warp_sum(acc);
     if (lane == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();

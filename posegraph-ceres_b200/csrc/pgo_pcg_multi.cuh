@@ -195,14 +195,14 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
     for (int k = 0; k < kCheckEvery; ++k) {
       if (g->world > 1) {
         // the SpMV product is a sum over ranks: all-reduce it, then w . u on the summed vector
-        spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, nullptr, &st->done);
+        spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
         PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
         pcgm_dot_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vw, g->vu, st, part1);
         pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, dot_ctas);
         g->launches += 1;
       } else {
         // one GPU: w . u rides on the SpMV (per-CTA partials in a fixed order)
-        spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
+        spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
         pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, sp_ctas);
       }
       pcgm_update_kernel<<<nbu, kPcgmThreads, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st, part0);
@@ -217,7 +217,7 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
     if (st_h->done || launched >= o->pcg_max_iterations + kCheckEvery) break;
   }
   // epilogue: w = A x (all-reduced) for the model cost change
-  spmv_kernel<<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vx, g->dlm, g->vw, with_diag);
+  spmv_kernel<false><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vx, g->dlm, g->vw, with_diag);
   PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
   pcgm_final_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vx, b, g->vw, g->dlm, part1);
   pcgm_final_reduce_kernel<<<1, kPcgmThreads, 0, g->stream>>>(part1, dot_ctas, st, g->scalars);
