@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -96,6 +98,10 @@ struct pgo_graph {
   double setup_s = 0.0;
   std::vector<std::pair<void*, size_t>> blocks;   // device memory borrowed from the per-device pool
   std::vector<double> pose_stage;                 // host staging for the [N][7] <-> [N][8] pose layouts
+  // symbolic factor analysis started on a helper thread by the one-shot entry point (overlaps upload + iteration zero)
+  std::future<int> sym_future;
+  std::unique_ptr<LevelCholSymbolic> sym;
+  int sym_solver_type = -1;
   struct pgo::PcgMultiState* pcgm_state = nullptr;    // stream-ordered (multi-GPU) PCG
   struct pgo::PcgMultiState* pcgm_state_h = nullptr;  // pinned
   double *pcgm_part0 = nullptr, *pcgm_part1 = nullptr;
@@ -241,6 +247,7 @@ static int dev_alloc(pgo_graph* g, Tp** p, size_t count) {
 extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
+  if (g->sym_future.valid()) g->sym_future.get();
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->own_stream && g->own_stream != g->stream) cudaStreamSynchronize(g->own_stream);
   if (g->comm) ncclCommDestroy(g->comm);
@@ -255,6 +262,9 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
 }
 
 extern "C" void pgo_release_cached_memory(int device) { pool_release(device); }
+
+static thread_local int g_symbolic_hint = -1;   // set by pgo_solve_pose_graph around its pgo_graph_create call
+static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S);
 
 extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
                                 const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
@@ -305,6 +315,14 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   g->col_idx_h.swap(pat.col_idx);
   g->nnz_off = (long long)g->col_idx_h.size();
   g->has_dup_blocks = pat.has_dup;
+  if (g_symbolic_hint == PGO_LINEAR_AUTO || g_symbolic_hint == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
+    // the pattern is final: analyse the elimination order on a helper thread while this thread packs and uploads
+    g->sym.reset(new LevelCholSymbolic());
+    g->sym_solver_type = g_symbolic_hint;
+    pgo_graph* gp = g;
+    const int t = g_symbolic_hint;
+    g->sym_future = std::async(std::launch::async, [gp, t]() { return run_symbolic(gp, t, gp->sym.get()); });
+  }
 
   // ---- edge tiles (field-major, one warp per tile) ----
   std::vector<EdgeCoreTile> core_h(std::max(T, 1));
@@ -710,19 +728,32 @@ extern "C" int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, do
   return PGO_OK;
 }
 
+// Host-only symbolic analysis for solver type t.  AUTO takes the factor only when it is cheap: chain-like graphs (<= 64
+// levels, node degree <= 16, fill <= 8x); mesh-like graphs (sphere, grids, dense random loops) go to block-Jacobi PCG.
+static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S) {
+  const bool autosel = t == PGO_LINEAR_AUTO;
+  return level_chol_symbolic(S, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(), autosel ? 8.0 : 1e30,
+                             autosel ? 64 : 8192, autosel ? 16 : (1 << 30));
+}
+
 static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
   int t = o->linear_solver_type;
   if (g->world > 1) return PGO_LINEAR_PCG_BLOCK_JACOBI;  // the factor is not distributed
   if (t == PGO_LINEAR_AUTO || t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     if (!g->chol) {
       LevelChol* c = nullptr;
-      // AUTO takes the factor only when it is cheap: chain-like graphs (<= 64 levels, node degree <= 16, fill <= 8x);
-      // mesh-like graphs (sphere, grids, dense random loops) go to block-Jacobi PCG
-      const bool autosel = t == PGO_LINEAR_AUTO;
-      const int rc = level_chol_analyze(&c, g->device, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(),
-                                        autosel ? 8.0 : 1e30, autosel ? 64 : 8192, autosel ? 16 : (1 << 30), g->stream);
+      int rc = PGO_OK;
+      if (g->sym_future.valid() && g->sym_solver_type == t) {
+        rc = g->sym_future.get();                      // started by pgo_solve_pose_graph
+      } else {
+        if (g->sym_future.valid()) g->sym_future.get();
+        g->sym.reset(new LevelCholSymbolic());
+        rc = run_symbolic(g, t, g->sym.get());
+      }
+      if (rc == PGO_OK) rc = level_chol_analyze(&c, g->device, g->N, *g->sym, g->stream);
+      g->sym.reset();
       if (rc == PGO_OK) g->chol = c;
-      else if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return rc;
+      else { if (c) level_chol_destroy(c, g->device); if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return rc; }
     }
     if (g->chol && g->chol->usable) return PGO_LINEAR_PCG_LEVEL_CHOLESKY;
     if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return set_error(PGO_ERR_NUMERICAL, "level Cholesky analysis failed");
@@ -959,10 +990,13 @@ extern "C" int pgo_solve_pose_graph(int device, int n_poses, double* poses, int 
                                     const unsigned char* pose_const, const pgo_solver_options* options,
                                     pgo_solver_summary* summary, pgo_iteration_summary* iteration_log,
                                     int iteration_log_capacity) {
-  pgo_graph* g = nullptr;
-  PGO_TRY(pgo_graph_create(&g, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const));
   pgo_solver_options defaults;
   if (!options) { pgo_default_options(&defaults); options = &defaults; }
+  pgo_graph* g = nullptr;
+  g_symbolic_hint = options->linear_solver_type;     // pgo_graph_create starts the symbolic analysis on a helper thread
+  const int crc = pgo_graph_create(&g, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const);
+  g_symbolic_hint = -1;
+  PGO_TRY(crc);
   int rc = pgo_graph_solve(g, options, summary, iteration_log, iteration_log_capacity);
   if (rc == PGO_OK) rc = pgo_graph_get_poses(g, poses);
   pgo_graph_destroy(g);

@@ -1051,13 +1051,12 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   return 0;
 }
 
-static int level_chol_analyze(LevelChol** out, int device, int N, const unsigned char* active, const int* a_row_ptr,
-                              const int* a_col_idx, double max_fill_ratio, int max_levels, int max_node_degree, cudaStream_t stream) {
+// Device half of the analysis: upload the symbolic structure `S` (computed by level_chol_symbolic, possibly on a helper
+// thread while the graph was being uploaded) and size the launch shapes.
+static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCholSymbolic& S, cudaStream_t stream) {
   LevelChol* C = new LevelChol();
   *out = C;
   C->N = N;
-  LevelCholSymbolic S;
-  PGO_TRY(level_chol_symbolic(&S, N, active, a_row_ptr, a_col_idx, max_fill_ratio, max_levels, max_node_degree));
   C->n_nodes = S.n_nodes;
   if (!S.usable) return 0;
   C->num_levels = S.num_levels;
