@@ -495,7 +495,7 @@ static int allreduce_sum(pgo_graph* g, double* buf, size_t count) {
 template <bool kIdent, int kMode, int kMinBlocks>
 static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
   constexpr int smem = lin_smem_bytes<kIdent>();
-  auto kern = linearize_kernel<kIdent, kMode, true, kMinBlocks>;
+  auto kern = linearize_kernel<kIdent, kMode, kMinBlocks>;
   static bool attr_set = false;
   if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
   const int ctas = std::max(1, std::min((g->T + kLinWarps - 1) / kLinWarps, kMinBlocks * g->num_sms));

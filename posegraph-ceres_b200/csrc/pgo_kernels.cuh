@@ -2,12 +2,15 @@
 //
 //  linearize_kernel   : per edge residual + both 6x6 Jacobians + J^T J blocks + J^T r, fused.
 //                       Edge tiles are staged global->shared by 1-D bulk TMA (cp.async.bulk +
-//                       mbarrier, double buffered per warp); poses are gathered with 128-bit loads;
-//                       diagonal blocks shared by neighbouring lanes are merged with warp shuffles
-//                       before fp64 RED atomics into the block-CSR Hessian.
-//  pcg_kernel         : persistent block-Jacobi PCG (Chronopoulos-Gear form, 2 grid barriers per
-//                       iteration); its SpMV is bsr6_row() -- 6 lanes per 6x6 block row.
-//  spmv_kernel        : the same bsr6_row() as a stand-alone launch (tests, bench, multi-GPU path).
+//                       mbarrier, 3-deep ring per warp) with L1 prefetch of the next tile's pose
+//                       gathers; poses are gathered with 128-bit loads; every output block goes
+//                       through a per-warp shared-memory staging tile so that the fp64 RED atomics
+//                       (block-CSR diagonal, gradient) and the off-diagonal stores hit whole sectors.
+//  pcg_kernel         : persistent block-Jacobi PCG (Chronopoulos-Gear form, 2 barriers per
+//                       iteration: atomic grid barrier, or the cluster barrier for tiny graphs);
+//                       its SpMV is bsr6_row() -- 6 lanes per 6x6 block row.
+//  spmv_kernel        : the same bsr6_row() as a stand-alone launch (tests, bench, and the
+//                       stream-ordered PCG of large / multi-GPU solves, with w.u fused in).
 #pragma once
 
 #include "pgo_common.cuh"
@@ -73,7 +76,7 @@ constexpr int lin_smem_bytes() {
          kLinWarps * (kLinStages + kLinInfoStages) * 8 + kLinWarps * 64 * 4;
 }
 
-template <bool kIdentityInfo, int kMode, bool kMerge, int kMinBlocks>
+template <bool kIdentityInfo, int kMode, int kMinBlocks>
 __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(const LinParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // per warp: core ring, then the info ring; the output staging tile [32][36] aliases the CURRENT info stage (its
