@@ -281,3 +281,19 @@ def test_full_size_properties_1m_pose_grid(pgo):
     gd = float((grad * d).sum())
     assert abs(fd - gd) <= 1e-5 * max(1.0, abs(gd)), (fd, gd)
     G.close()
+
+
+def test_solve_iteration_limit_and_rejected_steps(pgo, oracle, graphs):
+    """LM bookkeeping paths of ceres::Solve beyond the happy path: NO_CONVERGENCE at max_num_iterations, and a run with
+    rejected steps (huge initial trust region on a badly initialised sphere) -- same decisions as the oracle."""
+    g = graphs["sphere"]
+    # iteration limit
+    s, its = _compare_solves(pgo, oracle, g, 0, max_num_iterations=3)
+    assert s.termination_type == pgo.NO_CONVERGENCE and len(its) == 4
+    # rejected steps: bad initial guess + very large radius
+    D = pgo.datasets
+    bad = D.sphere(8, 12, None, init_sigma_t=4.0, init_sigma_r=1.5, seed=11)    # the oracle rejects 8 of its 31 steps here
+    for solver in (0, 1):
+        s, its = _compare_solves(pgo, oracle, bad, solver, initial_trust_region_radius=1e9, pos_tol=1e-3, rot_tol=1e-3)
+        assert s.num_unsuccessful_steps >= 1, "the case is meant to exercise the step-rejection path"
+        assert any(not it.step_is_successful for it in its[1:])
