@@ -79,6 +79,7 @@ struct pgo_graph {
   EdgeCoreTile* core = nullptr;
   EdgeInfoTile* info = nullptr;
   double *Hdiag = nullptr, *Hoff = nullptr;
+  double *Hdiag_alt = nullptr, *Hoff_alt = nullptr, *grad_alt = nullptr;   // second system for the speculative linearisation
   int *row_ptr = nullptr, *col_idx = nullptr;
   double *grad = nullptr, *grad_unscaled = nullptr;
   double *diagonal = nullptr, *dlm = nullptr, *Minv = nullptr;
@@ -88,7 +89,7 @@ struct pgo_graph {
   DeviceScalars* scalars_h = nullptr;  // pinned
   double* partials = nullptr;
   unsigned int* barrier = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -257,6 +258,8 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   pool_pinned_release(g->device, g->pcgm_state_h);
   pool_event_release(g->device, g->ev0);
   pool_event_release(g->device, g->ev1);
+  pool_event_release(g->device, g->ev2);
+  pool_event_release(g->device, g->ev3);
   pool_stream_release(g->device, g->own_stream);
   delete g;
 }
@@ -294,6 +297,8 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   g->stream = g->own_stream;
   GC_TRY(pool_event(device, &g->ev0));
   GC_TRY(pool_event(device, &g->ev1));
+  GC_TRY(pool_event(device, &g->ev2));
+  GC_TRY(pool_event(device, &g->ev3));
   g->num_sms = pool_num_sms(device);
 
   // ---- which poses are variables, identity information?, block-CSR pattern of the off-diagonal part ----
@@ -556,7 +561,15 @@ static int linearize_full(pgo_graph* g, const double* poses, const double* scale
   return PGO_OK;
 }
 
-static int cost_only(pgo_graph* g, const double* poses, int loss_type, double loss_a) {
+// The LM loop linearises speculatively at every candidate point into the alternate system (H, g) while the current one
+// stays intact: an accepted step keeps the swap, a rejected one swaps back.  One stream synchronisation per iteration.
+static void swap_system(pgo_graph* g) {
+  std::swap(g->Hdiag, g->Hdiag_alt);
+  std::swap(g->Hoff, g->Hoff_alt);
+  std::swap(g->grad, g->grad_alt);
+}
+
+[[maybe_unused]] static int cost_only(pgo_graph* g, const double* poses, int loss_type, double loss_a) {
   PGO_TRY(launch_linearize(g, kLinCost, poses, g->scale, loss_type, loss_a));
   if (g->world > 1) PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
   return PGO_OK;
@@ -828,6 +841,11 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   const int solver = resolve_linear_solver(g, opt);
   if (solver < 0) return solver;
   summary->linear_solver_used = solver;
+  if (!g->Hdiag_alt) {
+    PGO_TRY(dev_alloc(g, &g->Hdiag_alt, (size_t)N * 36));
+    PGO_TRY(dev_alloc(g, &g->Hoff_alt, (size_t)g->nnz_off * 36));
+    PGO_TRY(dev_alloc(g, &g->grad_alt, (size_t)N * 6));
+  }
   summary->hessian_blocks = g->nnz_off + g->N;
   if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) { summary->factor_blocks = g->chol->factor_blocks; summary->factor_levels = g->chol->num_levels; }
   summary->time_setup_s = g->setup_s;
@@ -889,17 +907,24 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
     const double th1 = wall_s();
     reuse_diagonal = true;
-    // ---- speculatively: candidate = Plus(x, -y .* scale), its cost, |step|, |x_cand| ----
+    // ---- candidate = Plus(x, -y .* scale), |step|, |x_cand|, and -- speculatively -- the full linearisation at the
+    //      candidate (cost, H, g, gradient norms) into the alternate system: everything the decision needs in one sync
     plus_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
     g->launches++;
-    PGO_TRY(cost_only(g, g->poses_cand, opt->loss_type, opt->loss_a));
-    summary->num_cost_evaluations++;
+    swap_system(g);
+    CUDA_TRY(cudaEventRecord(g->ev2, g->stream));
+    PGO_TRY(linearize_full(g, g->poses_cand, g->scale, opt->loss_type, opt->loss_a));
+    CUDA_TRY(cudaEventRecord(g->ev3, g->stream));
+    summary->num_linearizations++;
+    gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses_cand, g->grad, g->scale, g->active, nullptr, g->scalars);
+    g->launches++;
     PGO_TRY(fetch_scalars(g));
     const double th2 = wall_s();
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
     summary->time_linear_solver_ms += ms;
+    { float ms2 = 0.f; CUDA_TRY(cudaEventElapsedTime(&ms2, g->ev2, g->ev3)); summary->time_linearize_ms += ms2; }
     if (opt->verbose >= 2)
-      fprintf(stderr, "[pgo host] it %d: enqueue solver %.1f us, enqueue plus+cost + wait %.1f us, solver on GPU %.1f us\n", iter,
+      fprintf(stderr, "[pgo host] it %d: enqueue solver %.1f us, enqueue plus+linearize + wait %.1f us, solver on GPU %.1f us\n", iter,
               1e6 * (th1 - th0), 1e6 * (th2 - th1), 1e3 * ms);
     const DeviceScalars sc = *g->scalars_h;
     summary->total_pcg_iterations += sc.pcg_iterations;
@@ -909,11 +934,12 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
 
     // model_cost_change = -(J step)^T (r + J step / 2) = y^T g - y^T H y / 2
     const double model_cost_change = sc.xtb - 0.5 * (sc.xtAx - sc.xtDx);
-    bool step_valid = sc.pcg_flag != 2 && std::isfinite(model_cost_change) && model_cost_change > 0.0;
+    bool step_valid = sc.pcg_flag < 2 && std::isfinite(model_cost_change) && model_cost_change > 0.0;   // 2: CG breakdown, 3: pivot failure
     if (opt->verbose)
       fprintf(stderr, "[pgo] it %d radius %.3e pcg %d (flag %d, rel %.2e) model %.6e\n", iter, radius, sc.pcg_iterations,
               sc.pcg_flag, it.pcg_relative_residual, model_cost_change);
     if (!step_valid) {
+      swap_system(g);   // discard the speculative system
       it.step_is_valid = 0; it.cost = x_cost;
       if (++num_consecutive_invalid >= opt->max_num_consecutive_invalid_steps) {
         summary->termination_type = PGO_FAILURE;
@@ -935,6 +961,7 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
       summary->termination_type = PGO_CONVERGENCE;
       snprintf(summary->message, sizeof summary->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", step_norm / (x_norm + opt->parameter_tolerance), opt->parameter_tolerance);
+      swap_system(g);
       it.cost = x_cost; push_log(it);
       break;
     }
@@ -943,28 +970,19 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     if (std::fabs(cost_change) <= opt->function_tolerance * x_cost) {
       summary->termination_type = PGO_CONVERGENCE;
       snprintf(summary->message, sizeof summary->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(cost_change) / x_cost, opt->function_tolerance);
+      swap_system(g);
       it.cost = x_cost; push_log(it);
       break;
     }
     const double relative_decrease = cost_change / model_cost_change;
     it.relative_decrease = relative_decrease;
     if (relative_decrease > opt->min_relative_decrease) {
-      // HandleSuccessfulStep: x = candidate, re-linearize there
+      // HandleSuccessfulStep: x = candidate; its linearisation is already the current system
       std::swap(g->poses, g->poses_cand);
       x_norm = std::sqrt(sc.x_norm2);
-      PGO_TRY(zero_scalars(g));
-      CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
-      PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
-      CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-      summary->num_linearizations++;
-      gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
-      g->launches++;
-      PGO_TRY(fetch_scalars(g));
-      CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
-      summary->time_linearize_ms += ms;
-      x_cost = g->scalars_h->cost;
-      { long long bits = (long long)g->scalars_h->gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
-      it.gradient_norm = std::sqrt(g->scalars_h->gnorm2);
+      x_cost = sc.cost;
+      { long long bits = (long long)sc.gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
+      it.gradient_norm = std::sqrt(sc.gnorm2);
       it.step_is_successful = 1; it.cost = x_cost;
       summary->num_successful_steps++;
       double t = 2.0 * relative_decrease - 1.0;
@@ -973,6 +991,7 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
       radius = std::min(radius / t, opt->max_trust_region_radius);
       decrease_factor = 2.0; reuse_diagonal = false;
     } else {
+      swap_system(g);   // HandleUnsuccessfulStep: discard the speculative system
       it.step_is_successful = 0; it.cost = x_cost;
       summary->num_unsuccessful_steps++;
       radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
