@@ -104,9 +104,9 @@ def run_reference(args, rank, world):
     v = iters / dt
     line = {"impl": "reference", "metric": "lm_iterations_per_sec_kitti00", "value": v, "unit": "LM iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (fixture from the reference's own "
-                                   "trajectory_origin/edges_for_loop files; loop measurements synthesised), "
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference fixture (KITTI-00 graph) + synthetic 1M-pose grid",
+            "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (the reference's own "
+                                   "trajectory_origin/edges_for_loop files; loop measurements recovered from its optimised trajectory), "
                                    "Huber(1.0), LM to Ceres' default tolerances"},
             "cpu_baseline": {"value": v, "unit": "LM iterations/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} full KITTI-00 solves with oracle/pgo_oracle.c (edge evaluation on {cores} threads, serial sparse Cholesky)"},
@@ -269,9 +269,9 @@ def main():
             "ms_per_solve": 1e3 * c_dt / n_cpu}
         line = {"metric": "lm_iterations_per_sec_kitti00", "value": value, "unit": "LM iterations/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (fixture from the reference's own "
-                                       "trajectory_origin/edges_for_loop files; loop measurements synthesised), "
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference fixture (KITTI-00 graph) + synthetic 1M-pose grid",
+                "config": {"workload": "KITTI-00 pose graph, 4541 poses / 5179 edges (the reference's own "
+                                       "trajectory_origin/edges_for_loop files; loop measurements recovered from its optimised trajectory), "
                                        "Huber(1.0), LM to Ceres' default tolerances, one full solve per step",
                            "lm_iterations_per_solve": lm_iterations(last), "linear_solver": kname,
                            "pcg_iterations_per_solve": int(last.total_pcg_iterations),

@@ -4,8 +4,8 @@
  * Every function cites the reference line (or the Ceres Solver component the reference calls)
  * it restates.  REF = /root/reference/src/POSE_GRAPH_CERES_PLUS.
  *
- * PARITY UNPINNED: no real Ceres run is available to check the iterate sequence against
- * (DESIGN.md "Oracle" lists the partial pins that do exist).
+ * PARITY PARTIALLY PINNED: no real Ceres run is available to check the iterate sequence against; the cost
+ * function and the end result are pinned against the reference's own Ceres output (pgo_oracle.h).
  */
 #include "pgo_oracle.h"
 

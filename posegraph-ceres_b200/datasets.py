@@ -107,29 +107,33 @@ def _sqrt_info_from_sigmas(n, sigma_t, sigma_r, rng=None, correlated=False):
 
 
 # ---------------------------------------------------------------- configs[1]: KITTI-00
-def kitti00(loop_sigma_t: float = 0.02, loop_sigma_r: float = 0.002, seed: int = 0) -> PoseGraph:
+def kitti00(synthetic_loops: bool = False, loop_sigma_t: float = 0.02, loop_sigma_r: float = 0.002, seed: int = 0) -> PoseGraph:
     """KITTI-00 pose graph as the reference builds it (4541 poses, 4540 odometry + 639 loop edges).
 
     Vertices: trajectory_origin.txt (the reference's own dump of the initial poses).
     Odometry edge for frame i>0: begin=i, end=i-1, t_be = Tcw_i * Twc_{i-1}, information = I
-      (REF/test/pose_graph_ceres_plus_finial.cpp:184-199).
+      (REF/test/pose_graph_ceres_plus_finial.cpp:206-224).
     Loop edges: the 639 (begin, end) pairs the reference accepted (edges_for_loop.txt), all of them
-      members of Edge_Candidates_index.txt.  Their PnP measurements are not in the reference tree;
-      they are synthesised here as the relative pose in the reference's own optimised trajectory
-      (trajectory_update_y_not_constant.txt) plus seeded noise.  Edge order follows the reference:
-      per frame, the odometry edge then that frame's loop edges.
+      members of Edge_Candidates_index.txt.  Their PnP measurements are not in the reference tree; the
+      fixture holds the values RECOVERED from the reference's own Ceres output (stationarity of
+      trajectory_update_y_not_constant.txt, see tests/golden/make_kitti00_fixture.py).
+      synthetic_loops=True instead draws them as the optimised relative pose plus seeded noise.
+    Edge order follows the reference: per frame, the odometry edge then that frame's loop edge.
     """
     fx = np.load(os.path.join(_GOLDEN, "kitti00_fixture.npz"))
     before = fx["poses_before"].copy()
     after = fx["poses_after"]
     loops = fx["loop_edges"]
     n = before.shape[0]
-    rng = np.random.default_rng(seed)
     odo_ids = np.stack([np.arange(1, n), np.arange(0, n - 1)], axis=1).astype(np.int32)
     odo_meas = relative_pose(before[odo_ids[:, 0]], before[odo_ids[:, 1]])
-    loop_meas = relative_pose(after[loops[:, 0]], after[loops[:, 1]])
-    loop_meas[:, 3:7] /= np.linalg.norm(loop_meas[:, 3:7], axis=1, keepdims=True)
-    loop_meas = perturb(loop_meas, rng, loop_sigma_t, loop_sigma_r)
+    if synthetic_loops:
+        rng = np.random.default_rng(seed)
+        loop_meas = relative_pose(after[loops[:, 0]], after[loops[:, 1]])
+        loop_meas[:, 3:7] /= np.linalg.norm(loop_meas[:, 3:7], axis=1, keepdims=True)
+        loop_meas = perturb(loop_meas, rng, loop_sigma_t, loop_sigma_r)
+    else:
+        loop_meas = fx["loop_meas"].copy()
     ids = np.concatenate([odo_ids, loops.astype(np.int32)], axis=0)
     meas = np.concatenate([odo_meas, loop_meas], axis=0)
     # reference order: sort by begin frame, odometry (end = begin-1) first
@@ -137,7 +141,7 @@ def kitti00(loop_sigma_t: float = 0.02, loop_sigma_r: float = 0.002, seed: int =
     order = np.argsort(key, kind="stable")
     ids, meas = ids[order], meas[order]
     const = np.zeros(n, np.uint8)
-    const[0] = 1   # SetParameterBlockConstant(poses->begin()), :495-496
+    const[0] = 1   # SetParameterBlockConstant(poses->begin()), :525-527
     return PoseGraph("kitti00", before, ids, meas, _identity_sqrt_info(len(ids)), const, truth=after.copy())
 
 

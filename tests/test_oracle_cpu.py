@@ -69,13 +69,52 @@ def test_reference_ceres_output_is_stationary_for_the_oracle(D, oracle, fixture)
     assert np.median(gn[has_loop]) >= 20 * np.median(gn[free])
 
 
-def test_oracle_solve_moves_towards_reference_output(D, oracle, fixture):
+def test_recovered_loop_measurements_are_validated_by_the_end_poses(D, oracle, fixture):
+    """The fixture's loop measurements were fitted to the six stationarity equations at each loop edge's BEGIN pose
+    (make_kitti00_fixture.py).  The six equations at the END pose were not used: with the recovered measurements the
+    oracle's gradient at the reference's optimised trajectory must vanish there as well (to the files' rounding) --
+    a pin of the loop-edge Jacobians w.r.t. both poses, of the edge direction and of the loss weighting against a
+    real Ceres output."""
     g = D.kitti00()
+    after, loops = fixture["poses_after"], fixture["loop_edges"]
+    assert len(set(loops[:, 0].tolist())) == len(loops) and not (set(loops[:, 0].tolist()) & set(loops[:, 1].tolist()))
+    cost, res, grad, _ = oracle.evaluate(g, poses=after)
+    gn = np.linalg.norm(grad, axis=1)
+    begin = np.zeros(g.n_poses, bool)
+    begin[loops[:, 0]] = True
+    end = np.zeros(g.n_poses, bool)
+    end[loops[:, 1]] = True
+    free = ~begin & ~end
+    free[0] = False
+    assert gn[begin].max() <= 1e-10                    # fitted
+    assert gn[end].max() <= 6e-3                       # NOT fitted: validation (file rounding level, like the free poses)
+    assert gn[free].max() <= 5e-3
+    assert np.median(gn[end]) <= 2e-3
+    # none of the reference's loop edges sits in the Huber region at the optimum
+    odo = (g.edge_ids[:, 0] - g.edge_ids[:, 1]) == 1
+    assert np.linalg.norm(res[~odo], axis=1).max() < 1.0
+
+
+def test_oracle_solve_reproduces_the_reference_trajectory(D, oracle, fixture):
+    """End-to-end pin against the reference's own Ceres run: from trajectory_origin.txt, with the reference's edge
+    topology and the recovered loop measurements, the oracle's LM lands on trajectory_update_y_not_constant.txt --
+    within 2.5 cm (max) / 1 cm (mean) of it, after moving the poses by 3.6 m on average (7.1 m max).  The residual gap
+    is the 6-digit rounding of the files acting on a beam-like (ill-conditioned) graph plus the 1e-6 function tolerance
+    at which both solvers stop."""
+    g = D.kitti00()
+    after = fixture["poses_after"]
     poses, s, its = oracle.solve(g)
-    assert s.termination_type == 0 and s.final_cost < 0.05 * s.initial_cost
-    err_after = np.linalg.norm(poses[:, :3] - fixture["poses_after"][:, :3], axis=1)
-    err_before = np.linalg.norm(g.poses[:, :3] - fixture["poses_after"][:, :3], axis=1)
-    assert err_after.mean() < 0.35 * err_before.mean()
+    assert s.termination_type == 0
+    moved = np.linalg.norm(g.poses[:, :3] - after[:, :3], axis=1)
+    err = np.linalg.norm(poses[:, :3] - after[:, :3], axis=1)
+    assert moved.mean() > 3.0 and moved.max() > 7.0
+    assert err.max() <= 0.025 and err.mean() <= 0.010
+    qa = after[:, 3:] / np.linalg.norm(after[:, 3:], axis=1, keepdims=True)
+    qp = poses[:, 3:] / np.linalg.norm(poses[:, 3:], axis=1, keepdims=True)
+    ang = 2 * np.arccos(np.abs((qa * qp).sum(1)).clip(0, 1))
+    assert ang.max() <= 1e-3
+    # the cost at the oracle's solution is not above the cost at the reference's (rounded) solution
+    assert s.final_cost <= oracle.evaluate(g, poses=after, want_jac=False)[0] * (1 + 1e-6)
     costs = [it.cost for it in its if it.step_is_successful]
     assert all(b <= a for a, b in zip(costs, costs[1:]))
 
