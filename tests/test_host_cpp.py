@@ -119,3 +119,19 @@ def test_example_matches_oracle(pgo, oracle, D, example, tmp_path, name):
     assert rot_angle_between(got[:, 4:8], ref[:, 3:]).max() <= 1e-4
     before = np.loadtxt(str(tmp_path / "before.txt"))
     assert np.abs(before[:, 1:] - g.poses).max() <= 1e-15
+
+
+@pytest.mark.gpu
+def test_example_reproduces_the_reference_trajectory(D, example, tmp_path):
+    """The reference-facing C++ surface end to end on the reference's own problem: KITTI-00 as a g2o file ->
+    ceres_b200::Problem / Solve (the patched BuildOptimizationProblem / SolveOptimizationProblem) -> OutputPoses;
+    the written trajectory is within 2.5 cm / 1e-3 rad of the reference's result/trajectory/trajectory_update_y_not_constant.txt."""
+    g = D.kitti00()
+    path, out = str(tmp_path / "kitti00.g2o"), str(tmp_path / "trajectory_update.txt")
+    D.write_g2o(g, path)
+    r = subprocess.run([example, path, str(tmp_path / "trajectory_origin.txt"), out], capture_output=True, text=True)
+    assert r.returncode == 0 and "Optimizing Suscessfully!" in r.stdout, r.stdout + r.stderr
+    got = np.loadtxt(out)
+    err = np.linalg.norm(got[:, 1:4] - g.truth[:, :3], axis=1)
+    assert err.max() <= 0.025 and err.mean() <= 0.010
+    assert rot_angle_between(got[:, 4:8], g.truth[:, 3:]).max() <= 1e-3
