@@ -112,8 +112,9 @@ typedef struct {
   int num_iterations;            /* rows produced for the iteration log (incl. iteration 0) */
   int termination_type;          /* pgo_termination_type */
   char message[160];
-  int num_linearizations;        /* residual + Jacobian + Hessian kernel launches */
-  int num_cost_evaluations;      /* residual-only kernel launches */
+  int num_linearizations;        /* residual + Jacobian + Hessian kernel launches (one per LM iteration: the candidate is
+                                    linearised speculatively, so its cost, H and g arrive with the step statistics) */
+  int num_cost_evaluations;      /* residual-only kernel launches (0 since the speculative linearisation) */
   long long total_pcg_iterations;
   long long kernel_launches;     /* kernels of this library launched by the call */
   double time_total_s;           /* host wall clock of the call */

@@ -520,11 +520,9 @@ static int launch_linearize(pgo_graph* g, int mode, const double* poses, const d
   static const int occ = getenv("PGO_LIN_OCC") ? atoi(getenv("PGO_LIN_OCC")) : 2;   // CTAs per SM of the full kernel (tuning knob)
   if (g->identity_info) {
     if (mode == kLinFull) return occ >= 3 ? launch_linearize_t<true, kLinFull, 3>(g, p) : launch_linearize_t<true, kLinFull, 2>(g, p);
-    if (mode == kLinCost) return launch_linearize_t<true, kLinCost, 4>(g, p);
     return launch_linearize_t<true, kLinEval, 2>(g, p);
   }
   if (mode == kLinFull) return occ >= 3 ? launch_linearize_t<false, kLinFull, 3>(g, p) : launch_linearize_t<false, kLinFull, 2>(g, p);
-  if (mode == kLinCost) return launch_linearize_t<false, kLinCost, 4>(g, p);
   return launch_linearize_t<false, kLinEval, 2>(g, p);
 }
 
@@ -567,12 +565,6 @@ static void swap_system(pgo_graph* g) {
   std::swap(g->Hdiag, g->Hdiag_alt);
   std::swap(g->Hoff, g->Hoff_alt);
   std::swap(g->grad, g->grad_alt);
-}
-
-[[maybe_unused]] static int cost_only(pgo_graph* g, const double* poses, int loss_type, double loss_a) {
-  PGO_TRY(launch_linearize(g, kLinCost, poses, g->scale, loss_type, loss_a));
-  if (g->world > 1) PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
-  return PGO_OK;
 }
 
 static BsrView bsr_view(const pgo_graph* g) {

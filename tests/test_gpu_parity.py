@@ -310,3 +310,22 @@ def test_cuda_solve_reproduces_the_reference_ceres_trajectory(pgo, graphs):
     err = np.linalg.norm(poses[:, :3] - g.truth[:, :3], axis=1)
     assert err.max() <= 0.025 and err.mean() <= 0.010
     assert rot_angle_between(poses[:, 3:], g.truth[:, 3:]).max() <= 1e-3
+
+
+def test_one_shot_calls_reuse_cached_device_memory(pgo, graphs):
+    """pgo_solve_pose_graph in a loop: the per-device pool hands the blocks of destroyed graphs to the next call, so
+    device memory does not grow, results are identical, and pgo_release_cached_memory gives everything back."""
+    import torch
+    g = graphs["manhattan"]
+    ref, _, _ = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(20):
+        poses, s, _ = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
+        assert np.array_equal(poses, ref) or np.abs(poses - ref).max() <= 1e-9
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 <= 8 * 1024 * 1024            # no growth beyond allocator granularity
+    pgo.release_cached_memory()
+    free2, _ = torch.cuda.mem_get_info()
+    assert free2 >= free1
