@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PGO_B200_ABI_VERSION 3
+#define PGO_B200_ABI_VERSION 4
 
 typedef enum {
   PGO_OK = 0,
@@ -220,6 +220,15 @@ int pgo_solve_pose_graph(int device, int n_poses, double* poses, int n_edges, co
                          const unsigned char* pose_const, const pgo_solver_options* options,
                          pgo_solver_summary* summary, pgo_iteration_summary* iteration_log,
                          int iteration_log_capacity);
+
+/* Loop-edge candidate search, the caller side of the path: what getCandidatesIndex() / isInSearchRange() of
+ * REF/test/generate_edges_from_trajectory_origion.cpp:58-110 compute into config/Edge_Candidates_index.txt (read back by
+ * getEdegsCandidateIndex(), REF/include/ReadEdges.h:9-48).  positions [n_frames][3] camera centres (rounded to float like
+ * the reference's CV_32F poses); for frame c = 1..n-1 the candidates are c-1 followed, in ascending order, by every
+ * i < c - min_frame_gap with !(|p_i - p_c|^2 > radius^2) in float arithmetic -- bit-exact with the reference's file.
+ * row_ptr [n_frames+1] (frame 0 has no entry); candidates may be NULL to query *total first. */
+int pgo_edge_candidates(int device, int n_frames, const double* positions, double search_radius, int min_frame_gap,
+                        long long* row_ptr, int* candidates, long long capacity, long long* total);
 
 #ifdef __cplusplus
 }

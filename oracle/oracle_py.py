@@ -58,6 +58,7 @@ def lib():
         _lib.oracle_evaluate.restype = C.c_int
         _lib.oracle_solve.restype = C.c_int
         _lib.oracle_normal_solve.restype = C.c_int
+        _lib.oracle_edge_candidates.restype = C.c_longlong
     return _lib
 
 
@@ -121,3 +122,15 @@ def normal_solve(g, jac, d, rhs, ordering=1):
                                    _p(np.ascontiguousarray(d, np.float64)), _p(np.ascontiguousarray(rhs, np.float64)),
                                    _p(y), C.c_int(ordering))
     return rc, y.reshape(-1, 6)
+
+
+def edge_candidates(positions, search_radius=6.0, min_frame_gap=100):
+    """(row_ptr[n+1], candidates): the lists generate_edges_from_trajectory_origion.cpp writes per frame."""
+    pos = np.ascontiguousarray(positions, np.float64)
+    n = int(pos.shape[0])
+    row_ptr = np.zeros(n + 1, np.int64)
+    args = (C.c_int(n), _p(pos), C.c_double(search_radius), C.c_int(min_frame_gap), _p(row_ptr, C.c_longlong))
+    total = lib().oracle_edge_candidates(*args, None, C.c_longlong(0))
+    idx = np.zeros(max(total, 1), np.int32)
+    lib().oracle_edge_candidates(*args, _p(idx, C.c_int), C.c_longlong(idx.size))
+    return row_ptr, idx[:total]

@@ -926,3 +926,41 @@ done:
   free(rhs); free(step); free(delta); free(cand); free(active);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Loop-edge candidate lists: generate_edges_from_trajectory_origion.cpp:58-110.
+ * For frame c: first c-1 (:61), then, if c > gap, every i in [0, c-gap) (:65, the inner "c - i > gap" test :70 is
+ * implied) whose centre is in range.  isInSearchRange (:84-110) works on float (CV_32F) coordinates:
+ * dist = dA*dA + dB*dB + dC*dC, each operation rounded to float (x86-64 build of the reference: no FMA), and the
+ * frame is rejected when dist > radius*radius.  volatile keeps this compiler from contracting into FMAs.
+ * ------------------------------------------------------------------------------------------------ */
+static int oracle_in_search_range(const float* c, const float* p, float r2) {
+  volatile float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2];
+  volatile float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+  volatile float s = xx + yy;
+  volatile float dist = s + zz;
+  return !(dist > r2);
+}
+
+long long oracle_edge_candidates(int n_frames, const double* positions, double search_radius, int min_frame_gap,
+                                 long long* row_ptr, int* candidates, long long capacity) {
+  float* pf = (float*)malloc(sizeof(float) * 3 * (size_t)(n_frames > 0 ? n_frames : 1));
+  const float r = (float)search_radius;
+  const float r2 = r * r;
+  long long total = 0;
+  for (int i = 0; i < 3 * n_frames; ++i) pf[i] = (float)positions[i];
+  row_ptr[0] = 0;
+  if (n_frames > 0) row_ptr[1] = 0;               /* frame 0 has no line in the file (:38 starts at id = 1) */
+  for (int c = 1; c < n_frames; ++c) {
+    if (candidates && total < capacity) candidates[total] = c - 1;
+    ++total;
+    for (int i = 0; i < c - min_frame_gap; ++i)
+      if (oracle_in_search_range(pf + 3 * c, pf + 3 * i, r2)) {
+        if (candidates && total < capacity) candidates[total] = i;
+        ++total;
+      }
+    row_ptr[c + 1] = total;
+  }
+  free(pf);
+  return total;
+}

@@ -13,7 +13,7 @@
  *
  * PARITY PARTIALLY PINNED: Ceres is not installable in this image, so the LM
  * iterate sequence cannot be compared with a real Ceres run step by step.  What IS pinned against the
- * reference's own Ceres output (result/trajectory/*.txt): the cost function's stationarity at the reference's
+ * reference's own Ceres output (the result/trajectory text files): the cost function's stationarity at the reference's
  * optimised trajectory on every pose (free poses; loop-edge END poses with measurements recovered from the
  * BEGIN poses only), and the end result -- from the reference's initial trajectory the oracle's LM lands
  * within 2.3 cm (max) / 0.8 cm (mean) of the reference's optimised trajectory (tests/test_oracle_cpu.py).
@@ -121,6 +121,14 @@ int oracle_solve(int n_poses, double* poses, const unsigned char* pose_const,
 int oracle_normal_solve(int n_poses, const unsigned char* pose_const, int n_edges,
                         const int* edge_ids, const double* jac, const double* d,
                         const double* rhs, double* y, int ordering);
+
+/* Loop-edge candidate lists, the caller side of the path -- PINNED bit-exactly against the reference's own
+ * config/Edge_Candidates_index.txt (tests/golden/kitti00_fixture.npz cand_*; tests/test_oracle_cpu.py).
+ * getCandidatesIndex()  /root/reference/src/POSE_GRAPH_CERES_PLUS/test/generate_edges_from_trajectory_origion.cpp:58-82
+ * isInSearchRange()     same file :84-110 (float arithmetic on CV_32F poses, radius from config "search_radius").
+ * positions [n][3]; row_ptr [n+1]; candidates (capacity entries) may be NULL to count only.  Returns the total. */
+long long oracle_edge_candidates(int n_frames, const double* positions, double search_radius, int min_frame_gap,
+                                 long long* row_ptr, int* candidates, long long capacity);
 
 #ifdef __cplusplus
 }

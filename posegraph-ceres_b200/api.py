@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "pgo_graph_get_poses", "pgo_graph_snapshot_poses", "pgo_graph_restore_poses", "pgo_nccl_unique_id",
     "pgo_graph_init_comm", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
-    "pgo_analyze_structure", "pgo_release_cached_memory",
+    "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates",
 ]
 
 
@@ -131,6 +131,22 @@ def analyze_structure(n_poses, edge_ids, pose_const=None, max_fill_ratio: float 
                                        pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None,
                                        C.c_double(max_fill_ratio), C.byref(info)))
     return info
+
+
+def edge_candidates(positions, search_radius: float = 6.0, min_frame_gap: int = 100, device: int = 0):
+    """Loop-edge candidates per frame (pgo_edge_candidates): returns (row_ptr[n+1], candidates) -- frame c's list is
+    candidates[row_ptr[c]:row_ptr[c+1]] = [c-1, then every i < c - min_frame_gap within the search radius, ascending]."""
+    pos = np.ascontiguousarray(positions, np.float64)
+    n = int(pos.shape[0])
+    row_ptr = np.zeros(n + 1, np.int64)
+    total = C.c_longlong()
+    _check(lib().pgo_edge_candidates(C.c_int(device), C.c_int(n), _dp(pos), C.c_double(search_radius), C.c_int(min_frame_gap),
+                                     row_ptr.ctypes.data_as(C.POINTER(C.c_longlong)), None, C.c_longlong(0), C.byref(total)))
+    idx = np.zeros(max(total.value, 1), np.int32)
+    _check(lib().pgo_edge_candidates(C.c_int(device), C.c_int(n), _dp(pos), C.c_double(search_radius), C.c_int(min_frame_gap),
+                                     row_ptr.ctypes.data_as(C.POINTER(C.c_longlong)), idx.ctypes.data_as(C.POINTER(C.c_int)),
+                                     C.c_longlong(idx.size), C.byref(total)))
+    return row_ptr, idx[:total.value]
 
 
 def release_cached_memory(device: int = -1):

@@ -54,6 +54,7 @@ static int set_error(int code, const char* fmt, ...) {
   } while (0)
 
 #include "pgo_level_chol.cuh"
+#include "pgo_candidates.cuh"
 
 static double wall_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -993,6 +994,68 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   summary->final_cost = x_cost;
   summary->kernel_launches = g->launches - launches0;
   summary->time_total_s = wall_s() - t_begin;
+  return PGO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loop-edge candidate search (the caller side of the path): REF/test/generate_edges_from_trajectory_origion.cpp
+// ------------------------------------------------------------------------------------------------
+extern "C" int pgo_edge_candidates(int device, int n_frames, const double* positions, double search_radius, int min_frame_gap,
+                                   long long* row_ptr, int* candidates, long long capacity, long long* total) {
+  if (n_frames <= 0 || !positions || !row_ptr || !total || min_frame_gap < 0 || !(search_radius >= 0.0))
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_edge_candidates: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(PGO_ERR_NO_DEVICE, "pgo_edge_candidates: no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  const int n = n_frames;
+  // the reference keeps poses in CV_32F matrices: positions are rounded to float before the search
+  std::vector<float> soa(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) soa[(size_t)k * n + i] = (float)positions[3 * (size_t)i + k];
+  const float r = (float)search_radius;
+  const float r2 = r * r;
+  cudaStream_t stream = nullptr;
+  CUDA_TRY(pool_stream(device, &stream));
+  float* d_pos = nullptr; int* d_counts = nullptr; long long* d_ptr = nullptr; int* d_idx = nullptr;
+  const size_t pos_bytes = soa.size() * sizeof(float), cnt_bytes = (size_t)n * sizeof(int), ptr_bytes = ((size_t)n + 1) * sizeof(long long);
+  size_t idx_bytes = 0;
+  int rc = PGO_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(stream);
+    pool_free(device, d_pos, pos_bytes); pool_free(device, d_counts, cnt_bytes); pool_free(device, d_ptr, ptr_bytes);
+    if (d_idx) pool_free(device, d_idx, idx_bytes);
+    pool_stream_release(device, stream);
+  };
+#define CAND_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rc = set_error(PGO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); cleanup(); return rc; } } while (0)
+  CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_pos), pos_bytes));
+  CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_counts), cnt_bytes));
+  CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_ptr), ptr_bytes));
+  CAND_TRY(cudaMemcpyAsync(d_pos, soa.data(), pos_bytes, cudaMemcpyHostToDevice, stream));
+  const int sms = pool_num_sms(device);
+  const int ctas = std::max(1, std::min((n + 7) / 8, 8 * sms));
+  edge_candidates_kernel<false><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, d_counts, nullptr, nullptr);
+  CAND_TRY(cudaGetLastError());
+  std::vector<int> counts(n);
+  CAND_TRY(cudaMemcpyAsync(counts.data(), d_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
+  CAND_TRY(cudaStreamSynchronize(stream));
+  row_ptr[0] = 0;
+  for (int c = 0; c < n; ++c) row_ptr[c + 1] = row_ptr[c] + counts[c];
+  *total = row_ptr[n];
+  if (candidates != nullptr) {
+    if (capacity < *total) { cleanup(); return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_edge_candidates: capacity %lld < %lld candidates", capacity, *total); }
+    idx_bytes = std::max<size_t>((size_t)*total, 1) * sizeof(int);
+    CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_idx), idx_bytes));
+    CAND_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ptr_bytes, cudaMemcpyHostToDevice, stream));
+    edge_candidates_kernel<true><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, nullptr, d_ptr, d_idx);
+    CAND_TRY(cudaGetLastError());
+    if (*total > 0) CAND_TRY(cudaMemcpyAsync(candidates, d_idx, (size_t)*total * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CAND_TRY(cudaStreamSynchronize(stream));
+  }
+#undef CAND_TRY
+  cleanup();
   return PGO_OK;
 }
 

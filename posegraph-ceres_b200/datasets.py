@@ -338,3 +338,29 @@ def shard_edges(g: PoseGraph, rank: int, world: int) -> PoseGraph:
     hi = (e * (rank + 1)) // world
     return PoseGraph(f"{g.name}[{rank}/{world}]", g.poses.copy(), g.edge_ids[lo:hi], g.edge_meas[lo:hi],
                      g.edge_sqrt_info[lo:hi], g.pose_const, g.truth)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config/Edge_Candidates_index.txt: "cur cand cand ..." per line for frames 1..n-1, written by
+# REF/src/POSE_GRAPH_CERES_PLUS/test/generate_edges_from_trajectory_origion.cpp:36-52 and read back by
+# getEdegsCandidateIndex(), REF/src/POSE_GRAPH_CERES_PLUS/include/ReadEdges.h:9-48.
+# ---------------------------------------------------------------------------------------------------------------
+def write_edge_candidates(row_ptr, candidates, path: str):
+    with open(path, "w") as f:
+        for c in range(1, len(row_ptr) - 1):
+            f.write(" ".join([str(c)] + [str(int(i)) for i in candidates[row_ptr[c]:row_ptr[c + 1]]]) + "\n")
+
+
+def read_edge_candidates(path: str):
+    """-> (row_ptr[n+1], candidates) in the layout pgo_edge_candidates returns (frame 0 has no line)."""
+    row_ptr, idx = [0, 0], []
+    with open(path) as f:
+        for line in f:
+            tok = [int(t) for t in line.split()]
+            if not tok:
+                continue
+            if tok[0] != len(row_ptr) - 1:
+                raise ValueError(f"{path}: expected frame {len(row_ptr) - 1}, found {tok[0]}")
+            idx.extend(tok[1:])
+            row_ptr.append(len(idx))
+    return np.asarray(row_ptr, np.int64), np.asarray(idx, np.int32)

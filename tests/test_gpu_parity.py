@@ -329,3 +329,40 @@ def test_one_shot_calls_reuse_cached_device_memory(pgo, graphs):
     pgo.release_cached_memory()
     free2, _ = torch.cuda.mem_get_info()
     assert free2 >= free1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# loop-edge candidate search (integer/index work: bit-exact)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_edge_candidates_match_the_reference_file_exactly(pgo):
+    """pgo_edge_candidates on trajectory_origin.txt == the reference's config/Edge_Candidates_index.txt, entry for entry."""
+    import os
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti00_fixture.npz"))
+    ptr, idx = pgo.edge_candidates(f["poses_before"][:, :3], 6.0, 100)
+    assert np.array_equal(ptr[1:], f["cand_ptr"]) and np.array_equal(idx, f["cand_idx"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,radius,gap,seed", [(1, 6.0, 100, 0), (2, 6.0, 100, 1), (101, 6.0, 100, 2), (102, 50.0, 100, 3),
+                                               (3000, 6.0, 100, 4), (3000, 0.0, 100, 5), (2000, 25.0, 0, 6), (20000, 4.0, 100, 7)])
+def test_edge_candidates_vs_oracle(pgo, oracle, n, radius, gap, seed):
+    """random-walk trajectories that revisit themselves; float rounding decides membership near the radius, so the
+    comparison is exact (same ordered lists), including empty / single-frame / gap-0 / radius-0 cases."""
+    rng = np.random.default_rng(seed)
+    pos = np.cumsum(rng.normal(0, 0.8, (n, 3)), axis=0) % 40.0
+    if radius == 0.0:
+        pos[n // 2:] = pos[: n - n // 2]            # exact revisits so that radius 0 still has hits
+    ptr, idx = pgo.edge_candidates(pos, radius, gap)
+    optr, oidx = oracle.edge_candidates(pos, radius, gap)
+    assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+    if n > 200:
+        assert idx.size > n                        # the case does exercise the radius test
+
+
+@pytest.mark.gpu
+def test_edge_candidates_argument_errors(pgo):
+    with pytest.raises(pgo.PgoError):
+        pgo.edge_candidates(np.zeros((4, 3)), -1.0, 100)
+    with pytest.raises(pgo.PgoError):
+        pgo.edge_candidates(np.zeros((4, 3)), 6.0, 100, device=99)

@@ -256,7 +256,7 @@ def test_cabi_exports_every_declared_symbol(pgo):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     assert set(pgo.EXPORTED_SYMBOLS) == declared
-    assert lib.pgo_abi_version() == 3
+    assert lib.pgo_abi_version() == 4
 
 
 def test_cabi_defaults_mirror_ceres_and_reference(pgo):
@@ -300,3 +300,47 @@ def test_no_cpu_fallback(pgo):
         pgo.Graph.from_dataset(g)
     with pytest.raises(pgo.PgoError, match="no CUDA device"):
         pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
+
+
+def test_oracle_edge_candidates_match_the_reference_file_exactly(oracle, fixture):
+    """Golden vector: config/Edge_Candidates_index.txt of the reference (written by
+    generate_edges_from_trajectory_origion.cpp from trajectory_origin.txt, search_radius 6) is reproduced bit-exactly."""
+    ptr, idx = oracle.edge_candidates(fixture["poses_before"][:, :3], 6.0, 100)
+    assert np.array_equal(fixture["cand_cur"], np.arange(1, len(ptr) - 1))
+    assert ptr[1] == 0 and np.array_equal(ptr[1:], fixture["cand_ptr"])
+    assert np.array_equal(idx, fixture["cand_idx"])
+
+
+def test_oracle_edge_candidates_edge_cases(oracle):
+    ptr, idx = oracle.edge_candidates(np.zeros((1, 3)))
+    assert ptr.tolist() == [0, 0] and idx.size == 0
+    pos = np.zeros((150, 3))                                        # all frames at one point: every i < c - 100 qualifies
+    ptr, idx = oracle.edge_candidates(pos, 0.0, 100)
+    for c in (1, 100, 101, 149):
+        assert idx[ptr[c]:ptr[c + 1]].tolist() == [c - 1] + list(range(0, max(c - 100, 0)))
+    pos[:, 0] = np.arange(150) * 10.0                               # a straight line: only the odometry neighbour
+    ptr, idx = oracle.edge_candidates(pos, 6.0, 100)
+    assert np.array_equal(idx, np.arange(149)) and np.array_equal(ptr[1:], np.arange(150))
+    ptr, idx = oracle.edge_candidates(pos, 6.0, 0)                  # gap 0: i < c, so c - 1 appears twice when in range
+    assert idx[ptr[5]:ptr[6]].tolist() == [4]
+    pos[:, 0] = np.arange(150) * 6.0                                # distance exactly the radius is IN range (dist > r^2 rejects)
+    ptr, idx = oracle.edge_candidates(pos, 6.0, 0)
+    assert idx[ptr[5]:ptr[6]].tolist() == [4, 4]
+
+
+def test_edge_candidate_file_round_trip(oracle, fixture, tmp_path):
+    import posegraph_ceres_b200.datasets as D
+    ptr, idx = oracle.edge_candidates(fixture["poses_before"][:, :3])
+    path = str(tmp_path / "Edge_Candidates_index.txt")
+    D.write_edge_candidates(ptr, idx, path)
+    ptr2, idx2 = D.read_edge_candidates(path)
+    assert np.array_equal(ptr, ptr2) and np.array_equal(idx, idx2)
+    first = open(path).readline().split()
+    assert first == ["1", "0"]
+
+
+def test_edge_candidates_fail_loudly_without_gpu(pgo):
+    if pgo.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(pgo.PgoError, match="no CUDA device"):
+        pgo.edge_candidates(np.zeros((4, 3)))
