@@ -1035,8 +1035,15 @@ extern "C" int pgo_edge_candidates(int device, int n_frames, const double* posit
   CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_ptr), ptr_bytes));
   CAND_TRY(cudaMemcpyAsync(d_pos, soa.data(), pos_bytes, cudaMemcpyHostToDevice, stream));
   const int sms = pool_num_sms(device);
-  const int ctas = std::max(1, std::min((n + 7) / 8, 8 * sms));
-  edge_candidates_kernel<false><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, d_counts, nullptr, nullptr);
+  // short trajectories: one frame per warp (parallelism); long ones: eight frames per warp (L2 traffic / 8)
+  const bool blocked = n >= 16 * 8 * sms;
+  const int groups = blocked ? (n + 7) / 8 : n;
+  int per_sm = 1;   // grid = what is resident: groups are dealt longest first, a queued CTA would start late with a long one
+  CAND_TRY(blocked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_candidates_kernel<true, 8>, 256, 0)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_candidates_kernel<true, 1>, 256, 0));
+  const int ctas = std::max(1, std::min((groups + 7) / 8, std::max(per_sm, 1) * sms));
+  if (blocked) edge_candidates_kernel<false, 8><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, d_counts, nullptr, nullptr);
+  else edge_candidates_kernel<false, 1><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, d_counts, nullptr, nullptr);
   CAND_TRY(cudaGetLastError());
   std::vector<int> counts(n);
   CAND_TRY(cudaMemcpyAsync(counts.data(), d_counts, cnt_bytes, cudaMemcpyDeviceToHost, stream));
@@ -1049,7 +1056,8 @@ extern "C" int pgo_edge_candidates(int device, int n_frames, const double* posit
     idx_bytes = std::max<size_t>((size_t)*total, 1) * sizeof(int);
     CAND_TRY(pool_alloc(device, reinterpret_cast<void**>(&d_idx), idx_bytes));
     CAND_TRY(cudaMemcpyAsync(d_ptr, row_ptr, ptr_bytes, cudaMemcpyHostToDevice, stream));
-    edge_candidates_kernel<true><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, nullptr, d_ptr, d_idx);
+    if (blocked) edge_candidates_kernel<true, 8><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, nullptr, d_ptr, d_idx);
+    else edge_candidates_kernel<true, 1><<<ctas, 256, 0, stream>>>(n, d_pos, d_pos + n, d_pos + 2 * (size_t)n, r2, min_frame_gap, nullptr, d_ptr, d_idx);
     CAND_TRY(cudaGetLastError());
     if (*total > 0) CAND_TRY(cudaMemcpyAsync(candidates, d_idx, (size_t)*total * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CAND_TRY(cudaStreamSynchronize(stream));

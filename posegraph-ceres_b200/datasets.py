@@ -348,7 +348,8 @@ def shard_edges(g: PoseGraph, rank: int, world: int) -> PoseGraph:
 def write_edge_candidates(row_ptr, candidates, path: str):
     with open(path, "w") as f:
         for c in range(1, len(row_ptr) - 1):
-            f.write(" ".join([str(c)] + [str(int(i)) for i in candidates[row_ptr[c]:row_ptr[c + 1]]]) + "\n")
+            # every token is followed by one blank, like the reference's "outFile << v << \" \"" (:43-48)
+            f.write("".join(f"{int(v)} " for v in [c, *candidates[row_ptr[c]:row_ptr[c + 1]]]) + "\n")
 
 
 def read_edge_candidates(path: str):

@@ -335,12 +335,18 @@ def test_one_shot_calls_reuse_cached_device_memory(pgo, graphs):
 # loop-edge candidate search (integer/index work: bit-exact)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-def test_edge_candidates_match_the_reference_file_exactly(pgo):
+def test_edge_candidates_match_the_reference_file_exactly(pgo, tmp_path):
     """pgo_edge_candidates on trajectory_origin.txt == the reference's config/Edge_Candidates_index.txt, entry for entry."""
     import os
     f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti00_fixture.npz"))
     ptr, idx = pgo.edge_candidates(f["poses_before"][:, :3], 6.0, 100)
     assert np.array_equal(ptr[1:], f["cand_ptr"]) and np.array_equal(idx, f["cand_idx"])
+    import hashlib
+    import posegraph_ceres_b200.datasets as D
+    from test_oracle_cpu import REF_CANDIDATE_FILE_SHA256
+    path = str(tmp_path / "Edge_Candidates_index.txt")
+    D.write_edge_candidates(ptr, idx, path)            # the file the reference's tool writes, byte for byte
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == REF_CANDIDATE_FILE_SHA256
 
 
 @pytest.mark.gpu
