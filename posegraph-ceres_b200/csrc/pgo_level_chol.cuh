@@ -34,6 +34,7 @@ namespace pgo {
 
 constexpr int kCholThreads = 512;   // per CTA, both launch shapes
 constexpr int kCholClusterMaxNodes = 60000;
+constexpr int kCholBlockMaxNodes = 256;       // at most this many nodes: one CTA with block barriers (measured on Manhattan-100)
 constexpr long long kCholClusterMaxTasks = 200000;
 constexpr int kCholWideLevelNodes = 384;       // cluster shape: leading levels with at least this many nodes run grid-wide   // graphs up to this many variable poses use the cluster shape
 
@@ -122,8 +123,14 @@ __device__ __forceinline__ void chol_mark(const CholParams& P, int tag) {
   }
 }
 
+#ifdef PGO_CHOL_FINE_MARKS   // debug build only: stage marks inside the staged factor step
+#define CHOL_FINE(tag) chol_mark(P, tag)
+#else
+#define CHOL_FINE(tag) ((void)0)
+#endif
+
 // launch shapes of the solver kernel
-enum CholShape { kShapeGrid = 0, kShapeCluster = 1, kShapeDataflow = 2 };
+enum CholShape { kShapeGrid = 0, kShapeCluster = 1, kShapeDataflow = 2, kShapeBlock = 3 };
 
 // dataflow shape: wait until a node's dependency counter drains.  Bounded: a broken schedule must not hang the GPU.
 __device__ __forceinline__ void chol_wait(const int* ctr, unsigned int* err) {
@@ -147,6 +154,8 @@ __device__ __forceinline__ void chol_sync(unsigned int* counter, unsigned int& e
   if constexpr (kShape == kShapeCluster) {
     // hardware barrier over every thread of the cluster; release/acquire orders the global-memory traffic
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else if constexpr (kShape == kShapeBlock) {
+    __syncthreads();   // one CTA: the block barrier orders its global-memory traffic (all mutable operands are read past L1)
   } else {
     grid_barrier(counter, epoch);
   }
@@ -317,6 +326,7 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     v = nm.x; p0 = nm.y; p1 = nm.z; t0 = nm.w;
     t1 = pre ? pre1.w : __ldg(&P.nodes[k + 1].w);
   }
+  if (kFactor) CHOL_FINE(500);
   const int deg = p1 - p0, ntask = t1 - t0;
   double sink = 0.0;   // dataflow shape: sum of the values returned by this lane's update atomics
   double* SL = &st.L[gi * kBlk][0];
@@ -340,6 +350,7 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     const double* src = P.Lblk + 36 * (size_t)p0;
     for (int c = sub; c < deg * 18; c += kLanes) cp_async_cg16(SL + 2 * c, src + 2 * c);
   }
+  if (kFactor) CHOL_FINE(501);
   double* dv = P.Ldiag + 36 * (size_t)v;
   double* tv = P.vt + 6 * (size_t)v;
   double A[6][6], t[6];
@@ -408,8 +419,10 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     for (int r = 0; r < 6; ++r) if (r == sub) yv = y[r];
     tv[sub] = yv;
   }
+  if (kFactor) CHOL_FINE(502);
   cp_async_wait_all();
   __syncwarp();
+  if (kFactor) CHOL_FINE(503);
   // column scaling L_uv = W_uv Linv^T in the stash (+ write-through to global), rhs fan-out t_u -= L_uv y_v
   for (int it = sub; it < deg * 6; it += kLanes) {
     const int blk = it / 6, r = it - blk * 6;
@@ -451,6 +464,7 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     }
     return true;
   }
+  CHOL_FINE(504);
   // Schur updates: row r of target -= L_p L_q^T, operands from the stash
   for (int it = sub; it < ntask * 6; it += kLanes) {
     const int ti = it / 6, r = it - ti * 6;
@@ -470,6 +484,7 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
       if (c <= cmax) { if (kDataflow) sink += atomicAdd(out + c, -s); else atomicAdd(out + c, -s); }
     }
   }
+  CHOL_FINE(505);
   if (kDataflow) {
     // publish: my stores / atomics first, then one decrement per later neighbour and the backward-ready token.
     // The updates use the RETURNING atomic (ATOM, not fire-and-forget RED): consuming the returned values below makes
@@ -969,7 +984,14 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     alive_list.resize(w);
     level_ptr.push_back((int)order.size());
     static const bool force32 = getenv("PGO_CHOL_MODE32") != nullptr;   // debug
-    level_split.push_back(lvl_maxdeg > 16 ? 1 : force32 ? 32 : lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32);
+    static const bool no_widen = getenv("PGO_CHOL_NO_WIDEN") != nullptr;   // debug: lanes per node from the degree only
+    // lanes per node: what the degree needs (stash capacity), widened on narrow levels -- a level with fewer nodes than
+    // the launch has warps is bound by one warp's walk through the node's Schur products, so give the node all 32 lanes
+    const int launch_warps = (n_nodes <= kCholBlockMaxNodes ? 1 : 16) * (kCholThreads / 32);   // block / cluster shape
+    const int lvl_nodes = (int)sel.size();
+    int lanes = lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32;
+    if (!no_widen) lanes = std::max(lanes, lvl_nodes <= launch_warps ? 32 : lvl_nodes <= 2 * launch_warps ? 16 : 8);
+    level_split.push_back(lvl_maxdeg > 16 ? 1 : force32 ? 32 : lanes);
     S->max_degree = std::max(S->max_degree, lvl_maxdeg);
   }
   S->num_levels = (int)level_split.size();
@@ -1091,6 +1113,7 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCho
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeDataflow>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(chol_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<kShapeGrid>, kCholThreads, kCholSmemBytes));
   }
@@ -1159,13 +1182,17 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
   // overrides.  The dataflow shape (per-node dependency counters instead of level barriers) is EXPERIMENTAL and off by
   // default: on B200 it still produces wrong factors on some graphs -- never selected automatically.
   static const char* shape_env = getenv("PGO_CHOL_SHAPE");
+  static const int block_max_nodes = getenv("PGO_CHOL_BLOCK_MAX") ? atoi(getenv("PGO_CHOL_BLOCK_MAX")) : kCholBlockMaxNodes;
   int shape = C->cluster_ctas > 0 ? kShapeCluster : kShapeGrid;
+  // a factorisation of a few hundred nodes cannot use more than one SM's warps per level: one CTA, block barriers
+  if (C->n_nodes <= block_max_nodes) shape = kShapeBlock;
   if (shape_env) {
     if (!strcmp(shape_env, "grid")) shape = kShapeGrid;
+    else if (!strcmp(shape_env, "block")) shape = kShapeBlock;
     else if (!strcmp(shape_env, "cluster") && C->cluster_ctas > 0) shape = kShapeCluster;
     else if (!strcmp(shape_env, "dataflow") && C->dataflow_ok) shape = kShapeDataflow;
   }
-  if (num_ctas > 0 && shape == kShapeCluster) shape = kShapeGrid;
+  if (num_ctas > 0 && (shape == kShapeCluster || shape == kShapeBlock)) shape = kShapeGrid;
   P.first_level = 0; P.setup_done = 0;
   P.pend_fwd = C->pend_fwd; P.pend_bwd = C->pend_bwd; P.pend_fwd_init = C->pend_fwd_init; P.pend_bwd_init = C->pend_bwd_init;
   P.rowp = C->rowp; P.rown = C->rown;
@@ -1183,6 +1210,9 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     grid = std::max(1, std::min(grid, C->max_ctas));
     void* args[] = {&P};
     CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<kShapeDataflow>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
+  } else if (shape == kShapeBlock) {
+    level_chol_pcg_kernel<kShapeBlock><<<1, kCholThreads, kCholSmemBytes, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
   } else if (shape == kShapeCluster) {
     // S phase and the leading wide levels as grid-wide launches (see chol_wide_kernel)
     int first = 0;
