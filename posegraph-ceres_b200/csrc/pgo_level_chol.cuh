@@ -987,8 +987,11 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     static const bool no_widen = getenv("PGO_CHOL_NO_WIDEN") != nullptr;   // debug: lanes per node from the degree only
     // lanes per node: what the degree needs (stash capacity), widened on narrow levels -- a level with fewer nodes than
     // the launch has warps is bound by one warp's walk through the node's Schur products, so give the node all 32 lanes
-    const int launch_warps = (n_nodes <= kCholBlockMaxNodes ? 1 : 16) * (kCholThreads / 32);   // block / cluster shape
+    // warps of the launch that will run this level: one CTA (block shape), the 16-CTA cluster, or one CTA per SM
+    // (grid shape, and the wide levels of a cluster-shape factorisation that go out as chol_wide_kernel launches)
     const int lvl_nodes = (int)sel.size();
+    const int launch_ctas = n_nodes <= kCholBlockMaxNodes ? 1 : (n_nodes > kCholClusterMaxNodes || lvl_nodes >= kCholWideLevelNodes) ? 148 : 16;
+    const int launch_warps = launch_ctas * (kCholThreads / 32);
     int lanes = lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32;
     if (!no_widen) lanes = std::max(lanes, lvl_nodes <= launch_warps ? 32 : lvl_nodes <= 2 * launch_warps ? 16 : 8);
     level_split.push_back(lvl_maxdeg > 16 ? 1 : force32 ? 32 : lanes);
