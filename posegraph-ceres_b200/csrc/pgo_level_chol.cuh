@@ -682,11 +682,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   int4 pre0 = make_int4(0, 0, 0, 0), pre1 = make_int4(0, 0, 0, 0);
   bool have_pre = false;
   // fetch this lane's node records for the first group this warp will own in level l
-  auto prefetch_level = [&](int l) {
+  auto prefetch_level = [&](int l, bool bwd = false) {
     have_pre = false;
     if (l < 0 || l >= P.num_levels) return;
-    const int m = lv_mode(l);
-    if (m == 1) return;
+    const int raw = lv_mode(l);
+    if (raw == 1) return;
+    const int m = bwd ? (raw >> 8) : (raw & 0xff);
     const int k = lv_ptr(l) + gwx * (32 / m) + lane / m;
     if (k < lv_ptr(l + 1)) { pre0 = __ldg(P.nodes + k); pre1 = __ldg(P.nodes + k + 1); }
     have_pre = true;
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     prefetch_level(l0);
     for (int l = l0; l < P.num_levels; ++l) {
       const int k0 = lv_ptr(l), k1 = lv_ptr(l + 1);
-      const int mode = lv_mode(l);
+      const int mode = lv_mode(l) & 0xff;
       const bool split = kFactor && mode == 1;
       if (mode != 1) {
         bool ok = true;
@@ -738,10 +739,11 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   };
   // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending; writes dst (and dst2)
   auto backward = [&](double* dst, double* dst2) {
-    prefetch_level(P.num_levels - 1);
+    prefetch_level(P.num_levels - 1, true);
     for (int l = P.num_levels - 1; l >= 0; --l) {
       const int k0 = lv_ptr(l), k1 = lv_ptr(l + 1);
-      const int mode = lv_mode(l);
+      const int raw_mode = lv_mode(l);
+      const int mode = raw_mode == 1 ? 1 : (raw_mode >> 8);
       bool pp = have_pre;
       if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
       else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
           if (lane < 6) { dst[6 * (size_t)v + lane] = xv; if (dst2) dst2[6 * (size_t)v + lane] = xv; }
         }
       }
-      prefetch_level(l - 1);
+      prefetch_level(l - 1, true);
       if (!kDF) {
         chol_mark(P, 300 + l);
         chol_sync<kShape>(P.barrier, epoch);
@@ -994,7 +996,15 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     const int launch_warps = launch_ctas * (kCholThreads / 32);
     int lanes = lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32;
     if (!no_widen) lanes = std::max(lanes, lvl_nodes <= launch_warps ? 32 : lvl_nodes <= 2 * launch_warps ? 16 : 8);
-    level_split.push_back(lvl_maxdeg > 16 ? 1 : force32 ? 32 : lanes);
+    // the backward sweep of every level runs inside the solver kernel (no wide launches): its lanes are widened against
+    // that launch only.  Packed: bits 0-7 forward lanes, bits 8-15 backward lanes; 1 = high-degree level.
+    static const bool no_bwd_split = getenv("PGO_CHOL_NO_BWD_SPLIT") != nullptr;   // debug
+    const int bwd_warps = (n_nodes <= kCholBlockMaxNodes ? 1 : n_nodes > kCholClusterMaxNodes ? 148 : 16) * (kCholThreads / 32);
+    int bwd_lanes = lvl_maxdeg <= 4 ? 8 : lvl_maxdeg <= 8 ? 16 : 32;
+    if (!no_widen) bwd_lanes = std::max(bwd_lanes, lvl_nodes <= bwd_warps ? 32 : lvl_nodes <= 2 * bwd_warps ? 16 : 8);
+    if (force32) lanes = bwd_lanes = 32;
+    if (no_bwd_split) bwd_lanes = lanes;
+    level_split.push_back(lvl_maxdeg > 16 ? 1 : (lanes | (bwd_lanes << 8)));
     S->max_degree = std::max(S->max_degree, lvl_maxdeg);
   }
   S->num_levels = (int)level_split.size();
@@ -1224,7 +1234,7 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     if (first > 0) {
       launch_setup();
       for (int l = 0; l < first; ++l) {
-        const int k0 = C->level_ptr_h[l], k1 = C->level_ptr_h[l + 1], mode = C->level_mode_h[l];
+        const int k0 = C->level_ptr_h[l], k1 = C->level_ptr_h[l + 1], mode = C->level_mode_h[l] & 0xff;
         const int per_cta = (kCholThreads / 32) * (32 / mode);
         const int ctas = std::max(1, std::min((k1 - k0 + per_cta - 1) / per_cta, sms));
         chol_wide_kernel<<<ctas, kCholThreads, kCholSmemBytes, stream>>>(P, 1, mode, k0, k1);
