@@ -54,8 +54,6 @@ struct LevelChol {
   int4* nodes = nullptr;        // [n_nodes+1] by elimination position: {pose id, col0, col1, task0}
   int* col_row = nullptr;       // [n_slots] row pose id of each slot
   int* l2a = nullptr;           // [n_slots] BSR off-diagonal entry that seeds the slot, or -1 (pure fill)
-  int *pend_fwd = nullptr, *pend_bwd = nullptr, *pend_fwd_init = nullptr, *pend_bwd_init = nullptr, *rowp = nullptr, *rown = nullptr;
-  bool dataflow_ok = false;     // every level is a staged level (degree <= 16)
   CholTask* tasks = nullptr;    // [n_tasks]
   double* Lblk = nullptr;       // [n_slots][36] row-major (rows: row pose, cols: column pose)
   double* Ldiag = nullptr;      // [N][36] W_vv, then inverse of its lower Cholesky factor
@@ -107,10 +105,6 @@ struct CholParams {
   double accept;                  // 2-norm relative residual at which the direct solve is accepted without refinement
   int first_level;                // levels < first_level (and the S phase) were done by chol_wide_kernel launches
   int setup_done;                 // the S phase ran as a chol_wide_kernel launch
-  // dataflow shape: per-node dependency counters instead of level barriers
-  int *pend_fwd, *pend_bwd;                      // [N] working counters
-  const int *pend_fwd_init, *pend_bwd_init;      // [N] sources of a node (earlier neighbours) ; degree + 1
-  const int *rowp, *rown;                        // [N+1], [n_slots]: for node u the earlier nodes v with u in col(v)
   unsigned long long* timeline;   // debug (PGO_TIMELINE=1): %globaltimer marks of CTA 0 / thread 0, [0] = count
 };
 
@@ -130,24 +124,7 @@ __device__ __forceinline__ void chol_mark(const CholParams& P, int tag) {
 #endif
 
 // launch shapes of the solver kernel
-enum CholShape { kShapeGrid = 0, kShapeCluster = 1, kShapeDataflow = 2, kShapeBlock = 3 };
-
-// dataflow shape: wait until a node's dependency counter drains.  Bounded: a broken schedule must not hang the GPU.
-__device__ __forceinline__ void chol_wait(const int* ctr, unsigned int* err) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-  if (v <= 0) return;
-  const long long t0 = clock64();
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if (v <= 0) return;
-    unsigned int e;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(err) : "memory");
-    if (e != 0u) return;
-    if (clock64() - t0 > 3000000000LL) { atomicExch(err, 4u); return; }
-    __nanosleep(20);
-  }
-}
+enum CholShape { kShapeGrid = 0, kShapeCluster = 1, kShapeBlock = 3 };
 
 template <int kShape>
 __device__ __forceinline__ void chol_sync(unsigned int* counter, unsigned int& epoch) {
@@ -311,7 +288,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // everything a node needs is fetched in ONE latency epoch (cp.async into the stash + broadcast loads of the pivot
 // block and rhs), the Cholesky, column scaling and Schur products then run out of registers / shared memory, and
 // results leave as plain stores and fire-and-forget fp64 RED atomics.
-template <int kLanes, bool kFactor = true, bool kDataflow = false>
+template <int kLanes, bool kFactor = true>
 __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStash& st, int kk, int k1, int lane,
                                                    bool pre = false, int4 pre0 = int4(), int4 pre1 = int4()) {   // pre0/1: this lane's node records k, k+1 (prefetched)
   constexpr int kNpw = 32 / kLanes;
@@ -328,24 +305,15 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
   }
   if (kFactor) CHOL_FINE(500);
   const int deg = p1 - p0, ntask = t1 - t0;
-  double sink = 0.0;   // dataflow shape: sum of the values returned by this lane's update atomics
   double* SL = &st.L[gi * kBlk][0];
   CholTask* ST = st.task + gi * kTsk;
   int* SR = st.row + gi * kBlk;
   {
-    // static structure first (it does not depend on other nodes).  Only L1-bypassing copies (cp.async.cg) and plain
-    // loads are used: in the dataflow shape other warps of the SM execute gpu-scope fences (L1 invalidations) at any
-    // time, and cp.async.ca copies in flight through L1 were observed to deliver corrupt bytes under them.
+    // static structure first (it does not depend on other nodes), then the node's column; L1-bypassing copies
+    // (cp.async.cg): the blocks were updated by other SMs' RED atomics at L2
     for (int j = sub; j < deg; j += kLanes) SR[j] = __ldg(P.col_row + p0 + j);
     if (kFactor) {
       for (int j = sub; j < ntask; j += kLanes) cp_async_cg16(ST + j, P.tasks + t0 + j);
-    }
-    // ... then, in the dataflow shape, wait until every earlier neighbour has delivered its updates: lane 0 of the
-    // group acquires, the warp barrier + gpu-scope fence order every lane's loads behind it
-    if (kDataflow) {
-      if (valid && sub == 0) chol_wait(P.pend_fwd + v, P.barrier + 1);
-      __syncwarp();
-      __threadfence();
     }
     const double* src = P.Lblk + 36 * (size_t)p0;
     for (int c = sub; c < deg * 18; c += kLanes) cp_async_cg16(SL + 2 * c, src + 2 * c);
@@ -448,22 +416,10 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
     double s = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) s = fma(o[c], y[c], s);
-    if (kDataflow) sink += atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);   // returning form: see the publish step
-    else atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
+    atomicAdd(P.vt + 6 * (size_t)SR[blk] + r, -s);
   }
   __syncwarp();
-  if (!kFactor) {
-    if (kDataflow) {
-      if (sink == 0.123456789e-300) P.partials[0] = sink;
-      __threadfence();
-      __syncwarp();
-      __threadfence();
-      for (int j = sub; j < deg; j += kLanes) atomicSub(P.pend_fwd + SR[j], 1);
-      if (valid && sub == 0) atomicSub(P.pend_bwd + v, 1);
-      __syncwarp();
-    }
-    return true;
-  }
+  if (!kFactor) return true;
   CHOL_FINE(504);
   // Schur updates: row r of target -= L_p L_q^T, operands from the stash
   for (int it = sub; it < ntask * 6; it += kLanes) {
@@ -481,27 +437,16 @@ __device__ __forceinline__ bool chol_factor_staged(const CholParams& P, WarpStas
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < 6; ++q) s = fma(a[q], lq[c * 6 + q], s);
-      if (c <= cmax) { if (kDataflow) sink += atomicAdd(out + c, -s); else atomicAdd(out + c, -s); }
+      if (c <= cmax) atomicAdd(out + c, -s);
     }
   }
   CHOL_FINE(505);
-  if (kDataflow) {
-    // publish: my stores / atomics first, then one decrement per later neighbour and the backward-ready token.
-    // The updates use the RETURNING atomic (ATOM, not fire-and-forget RED): consuming the returned values below makes
-    // this lane wait until its updates have been performed at L2 -- a fence alone was observed not to wait for REDs.
-    if (sink == 0.123456789e-300) P.partials[0] = sink;
-    __threadfence();
-    __syncwarp();
-    __threadfence();
-    for (int j = sub; j < deg; j += kLanes) atomicSub(P.pend_fwd + SR[j], 1);
-    if (valid && sub == 0) atomicSub(P.pend_bwd + v, 1);
-  }
   __syncwarp();
   return ok;
 }
 
 // Backward step for 32 / kLanes nodes per warp: x_v = Linv_v^T (y_v - sum_{u in col(v)} L_uv^T x_u).
-template <int kLanes, bool kDataflow = false>
+template <int kLanes>
 __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk, int k1, int lane, double* dst, double* dst2,
                                                      bool pre = false, int4 pre0 = int4()) {
   constexpr int kNpw = 32 / kLanes;
@@ -514,11 +459,6 @@ __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk
   if (valid) { const int4 nm = pre ? pre0 : __ldg(P.nodes + k); v = nm.x; p0 = nm.y; p1 = nm.z; }
   const int sg = sub / 6, c = sub - 6 * sg;
   const bool on = valid && sg < kSub;
-  if (kDataflow) {
-    if (valid && sub == 0) chol_wait(P.pend_bwd + v, P.barrier + 1);
-    __syncwarp();
-    __threadfence();
-  }
   int rows[kIter];
 #pragma unroll
   for (int j = 0; j < kIter; ++j) {
@@ -547,15 +487,6 @@ __device__ __forceinline__ void chol_backward_staged(const CholParams& P, int kk
     if (sub < 6 && rr >= sub) xv = fma(__ldcg(P.Ldiag + 36 * (size_t)v + rr * 6 + sub), sr, xv);
   }
   if (valid && sub < 6) { dst[6 * (size_t)v + sub] = xv; if (dst2) dst2[6 * (size_t)v + sub] = xv; }
-  if (kDataflow) {
-    __threadfence();
-    __syncwarp();
-    __threadfence();
-    if (valid) {
-      const int e1 = __ldg(P.rowp + v + 1);
-      for (int e = __ldg(P.rowp + v) + sub; e < e1; e += kLanes) atomicSub(P.pend_bwd + __ldg(P.rown + e), 1);
-    }
-  }
 }
 
 __device__ __forceinline__ double cta_sum_n(double v, double* red) {
@@ -587,7 +518,6 @@ __device__ __forceinline__ void chol_setup_phase(const CholParams& P, int gtid, 
     }
     P.vt[k] = P.b[k];
     P.x[k] = 0.0; P.ax[k] = 0.0; P.r[k] = P.b[k]; P.z[k] = 0.0; P.p[k] = 0.0;   // inactive poses keep z = p = 0
-    if (c == 0 && P.pend_fwd != nullptr) { P.pend_fwd[i] = P.pend_fwd_init[i]; P.pend_bwd[i] = P.pend_bwd_init[i]; }
     // diagonal block row c of pose i
     const double* hd = P.A.Hdiag + 36 * (size_t)i;
     double* ld = P.Ldiag + 36 * (size_t)i + 6 * c;
@@ -646,7 +576,6 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_wide_kernel(const CholPa
 
 template <int kShape>
 __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const CholParams P) {
-  constexpr bool kDF = kShape == kShapeDataflow;
   __shared__ double red[kCholThreads / 32];
   __shared__ double bcast;
   extern __shared__ __align__(16) unsigned char chol_smem[];
@@ -713,9 +642,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       if (mode != 1) {
         bool ok = true;
         bool pp = have_pre;   // only the first group of the level was prefetched
-        if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { ok &= chol_factor_staged<8, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
-        else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { ok &= chol_factor_staged<16, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
-        else { for (int kk = k0 + gwx; kk < k1; kk += nw) { ok &= chol_factor_staged<32, kFactor, kDF>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
+        if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { ok &= chol_factor_staged<8, kFactor>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
+        else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { ok &= chol_factor_staged<16, kFactor>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
+        else { for (int kk = k0 + gwx; kk < k1; kk += nw) { ok &= chol_factor_staged<32, kFactor>(P, stash, kk, k1, lane, pp, pre0, pre1); pp = false; } }
         if (!ok) atomicExch(P.barrier + 1, 1u);
       } else {
         for (int k = k0 + gwx; k < k1; k += nw) {
@@ -730,11 +659,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
         for (long long it = (long long)gtid; it < (t1 - t0) * 6; it += gthreads) chol_update_item(P, P.tasks[t0 + it / 6], (int)(it % 6));
       }
       prefetch_level(l + 1);       // static structure: its latency hides behind the barrier
-      if (!kDF) {
-        chol_mark(P, 100 + l);
-        chol_sync<kShape>(P.barrier, epoch);
-        chol_mark(P, 200 + l);
-      }
+      chol_mark(P, 100 + l);
+      chol_sync<kShape>(P.barrier, epoch);
+      chol_mark(P, 200 + l);
     }
   };
   // backward: x_v = Linv_v^T (y_v - sum_{u later} L_uv^T x_u), levels descending; writes dst (and dst2)
@@ -745,9 +672,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
       const int raw_mode = lv_mode(l);
       const int mode = raw_mode == 1 ? 1 : (raw_mode >> 8);
       bool pp = have_pre;
-      if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { chol_backward_staged<8, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
-      else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { chol_backward_staged<16, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
-      else if (mode == 32) { for (int kk = k0 + gwx; kk < k1; kk += nw) { chol_backward_staged<32, kDF>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
+      if (mode == 8) { for (int kk = k0 + gwx * 4; kk < k1; kk += nw * 4) { chol_backward_staged<8>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
+      else if (mode == 16) { for (int kk = k0 + gwx * 2; kk < k1; kk += nw * 2) { chol_backward_staged<16>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
+      else if (mode == 32) { for (int kk = k0 + gwx; kk < k1; kk += nw) { chol_backward_staged<32>(P, kk, k1, lane, dst, dst2, pp, pre0); pp = false; } }
       else {
         for (int k = k0 + gwx; k < k1; k += nw) {
           const int4 nm = __ldg(P.nodes + k);
@@ -775,13 +702,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
         }
       }
       prefetch_level(l - 1, true);
-      if (!kDF) {
-        chol_mark(P, 300 + l);
-        chol_sync<kShape>(P.barrier, epoch);
-        chol_mark(P, 400 + l);
-      }
+      chol_mark(P, 300 + l);
+      chol_sync<kShape>(P.barrier, epoch);
+      chol_mark(P, 400 + l);
     }
-    if (kDF) { chol_mark(P, 300); chol_sync<kShape>(P.barrier, epoch); chol_mark(P, 400); }   // the one barrier of both sweeps
   };
 
   // ---- F + B: z = p = M^-1 b ----
@@ -842,7 +766,6 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
     if (rr <= P.accept * P.accept * bb) { norm_kind = 1; break; }               // ||b - A x|| <= accept ||b||
     // z = M^-1 r
     for (int k = gtid; k < n6; k += gthreads) { P.vt[k] = P.r[k]; }
-    if (kDF) for (int i = gtid; i < n; i += gthreads) { P.pend_fwd[i] = P.pend_fwd_init[i]; P.pend_bwd[i] = P.pend_bwd_init[i]; }
     chol_sync<kShape>(P.barrier, epoch);
     forward(std::false_type{});
     backward(P.z, nullptr);
@@ -887,7 +810,6 @@ struct LevelCholSymbolic {
   int n_nodes = 0, num_levels = 0, max_degree = 0;
   long long n_slots = 0;
   std::vector<int> level_ptr, level_split, col_row, l2a;
-  std::vector<int> pend_fwd_init, pend_bwd_init, rowp, rown;   // dataflow shape (by pose id)
   std::vector<int4> nodes;
   std::vector<CholTask> tasks;
 };
@@ -1064,24 +986,6 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
       }
     }
   lap("l2a");
-  // dependency counters and row lists of the (experimental, opt-in) dataflow shape
-  static const bool want_dataflow = getenv("PGO_CHOL_SHAPE") != nullptr && !strcmp(getenv("PGO_CHOL_SHAPE"), "dataflow");
-  if (!want_dataflow) { S->usable = true; return 0; }
-  S->pend_fwd_init.assign(N, 0);
-  S->pend_bwd_init.assign(N, 0);
-  S->rowp.assign(N + 1, 0);
-  for (long long sl = 0; sl < slots; ++sl) S->rowp[col_row[sl] + 1]++;
-  for (int i = 0; i < N; ++i) { S->pend_fwd_init[i] = S->rowp[i + 1]; S->rowp[i + 1] += S->rowp[i]; }
-  S->rown.resize((size_t)slots);
-  {
-    std::vector<int> fill(S->rowp.begin(), S->rowp.end() - 1);
-    for (int k = 0; k < n_nodes; ++k) {
-      const int v = order[k];
-      S->pend_bwd_init[v] = col_ptr[k + 1] - col_ptr[k] + 1;
-      for (int pp = col_ptr[k]; pp < col_ptr[k + 1]; ++pp) S->rown[fill[col_row[pp]]++] = v;
-    }
-  }
-  lap("dataflow lists");
   S->usable = true;
   return 0;
 }
@@ -1107,15 +1011,6 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCho
   PGO_TRY(chol_upload(C, device, &C->col_row, S.col_row, stream));
   PGO_TRY(chol_upload(C, device, &C->l2a, S.l2a, stream));
   PGO_TRY(chol_upload(C, device, &C->tasks, S.tasks, stream));
-  if (!S.rowp.empty()) {
-    PGO_TRY(chol_upload(C, device, &C->pend_fwd_init, S.pend_fwd_init, stream));
-    PGO_TRY(chol_upload(C, device, &C->pend_bwd_init, S.pend_bwd_init, stream));
-    PGO_TRY(chol_upload(C, device, &C->rowp, S.rowp, stream));
-    PGO_TRY(chol_upload(C, device, &C->rown, S.rown, stream));
-    PGO_TRY(chol_alloc(C, device, &C->pend_fwd, (size_t)N));
-    PGO_TRY(chol_alloc(C, device, &C->pend_bwd, (size_t)N));
-    C->dataflow_ok = S.max_degree <= 16;
-  }
   PGO_TRY(chol_alloc(C, device, &C->Lblk, (size_t)S.n_slots * 36));
   PGO_TRY(chol_alloc(C, device, &C->Ldiag, (size_t)N * 36));
   PGO_TRY(chol_alloc(C, device, &C->vt, (size_t)N * 6));
@@ -1125,7 +1020,6 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCho
   if (per_sm < 0) {
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeDataflow>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(chol_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<kShapeGrid>, kCholThreads, kCholSmemBytes));
@@ -1191,9 +1085,8 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     P.timeline = timeline_d;
   }
   CUDA_TRY(cudaMemsetAsync(C->barrier, 0, 4 * sizeof(unsigned int), stream));
-  // launch shape: one cluster for tiny factorisations, else the cooperative grid.  PGO_CHOL_SHAPE=grid|cluster|dataflow
-  // overrides.  The dataflow shape (per-node dependency counters instead of level barriers) is EXPERIMENTAL and off by
-  // default: on B200 it still produces wrong factors on some graphs -- never selected automatically.
+  // launch shape: one CTA for tiny factorisations, one cluster for small ones, else the cooperative grid.
+  // PGO_CHOL_SHAPE=grid|cluster|block overrides (measurement aid).
   static const char* shape_env = getenv("PGO_CHOL_SHAPE");
   static const int block_max_nodes = getenv("PGO_CHOL_BLOCK_MAX") ? atoi(getenv("PGO_CHOL_BLOCK_MAX")) : kCholBlockMaxNodes;
   int shape = C->cluster_ctas > 0 ? kShapeCluster : kShapeGrid;
@@ -1203,12 +1096,9 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     if (!strcmp(shape_env, "grid")) shape = kShapeGrid;
     else if (!strcmp(shape_env, "block")) shape = kShapeBlock;
     else if (!strcmp(shape_env, "cluster") && C->cluster_ctas > 0) shape = kShapeCluster;
-    else if (!strcmp(shape_env, "dataflow") && C->dataflow_ok) shape = kShapeDataflow;
   }
   if (num_ctas > 0 && (shape == kShapeCluster || shape == kShapeBlock)) shape = kShapeGrid;
   P.first_level = 0; P.setup_done = 0;
-  P.pend_fwd = C->pend_fwd; P.pend_bwd = C->pend_bwd; P.pend_fwd_init = C->pend_fwd_init; P.pend_bwd_init = C->pend_bwd_init;
-  P.rowp = C->rowp; P.rown = C->rown;
   const int sms = C->max_ctas;   // one CTA per SM
   auto launch_setup = [&]() {
     const int s_items = (int)std::min<long long>(std::max<long long>((long long)A.n * 6, C->n_slots * 6 / 4), 1LL << 30);
@@ -1217,13 +1107,7 @@ static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const
     if (launches) (*launches)++;
     P.setup_done = 1;
   };
-  if (shape == kShapeDataflow) {
-    launch_setup();
-    int grid = num_ctas > 0 ? num_ctas : std::max(16, (C->n_nodes / 4 + (kCholThreads / 32) - 1) / (kCholThreads / 32));
-    grid = std::max(1, std::min(grid, C->max_ctas));
-    void* args[] = {&P};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)level_chol_pcg_kernel<kShapeDataflow>, dim3(grid), dim3(kCholThreads), args, kCholSmemBytes, stream));
-  } else if (shape == kShapeBlock) {
+  if (shape == kShapeBlock) {
     level_chol_pcg_kernel<kShapeBlock><<<1, kCholThreads, kCholSmemBytes, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
   } else if (shape == kShapeCluster) {
