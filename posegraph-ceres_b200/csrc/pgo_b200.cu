@@ -302,17 +302,8 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   GC_TRY(pool_event(device, &g->ev3));
   g->num_sms = pool_num_sms(device);
 
-  // ---- which poses are variables, identity information?, block-CSR pattern of the off-diagonal part ----
-  g->identity_info = true;
-  if (edge_sqrt_info) {
-    static const double eye[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
-    for (int e = 0; e < E && g->identity_info; ++e)
-      if (std::memcmp(edge_sqrt_info + 36 * (size_t)e, eye, sizeof eye) != 0) {
-        // memcmp also flags -0.0; confirm numerically
-        for (int k = 0; k < 36; ++k) if (edge_sqrt_info[36 * (size_t)e + k] != eye[k]) { g->identity_info = false; break; }
-      }
-  }
-  lap("stream/events + identity scan");
+  // ---- which poses are variables, block-CSR pattern of the off-diagonal part ----
+  lap("stream/events");
   HostPattern pat;
   build_pattern(N, E, edge_ids, pose_const, &pat);
   lap("block-CSR pattern");
@@ -330,6 +321,17 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
     g->sym_future = std::async(std::launch::async, [gp, t]() { return run_symbolic(gp, t, gp->sym.get()); });
   }
 
+  // ---- identity information? (after the helper thread is off: the symbolic analysis is the longer leg) ----
+  g->identity_info = true;
+  if (edge_sqrt_info) {
+    static const double eye[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+    for (int e = 0; e < E && g->identity_info; ++e)
+      if (std::memcmp(edge_sqrt_info + 36 * (size_t)e, eye, sizeof eye) != 0) {
+        // memcmp also flags -0.0; confirm numerically
+        for (int k = 0; k < 36; ++k) if (edge_sqrt_info[36 * (size_t)e + k] != eye[k]) { g->identity_info = false; break; }
+      }
+  }
+  lap("identity scan");
   // ---- edge tiles (field-major, one warp per tile) ----
   std::vector<EdgeCoreTile> core_h(std::max(T, 1));
   std::memset(core_h.data(), 0, core_h.size() * sizeof(EdgeCoreTile));
@@ -383,10 +385,9 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
     for (int i = 0; i < N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
     GC_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
     GC_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-    GC_TRY(cudaStreamSynchronize(g->stream));
   }
+  // (pageable sources: cudaMemcpyAsync returns once they are staged, so the host vectors may go; the stream orders the rest)
   GC_TRY(cudaMemsetAsync(g->Hoff, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
-  GC_TRY(cudaStreamSynchronize(g->stream));
 
   lap("uploads + memset");
   // persistent PCG grid: all CTAs must be co-resident (cooperative launch)

@@ -822,15 +822,26 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double tp = now();
   auto lap = [&](const char* what) { if (prof) { const double t = now(); fprintf(stderr, "[pgo symbolic] %-22s %8.1f us\n", what, 1e6 * (t - tp)); tp = t; } };
-  std::vector<std::vector<int>> adj(N);
+  // adjacency lists live in one arena (offset / size / capacity per pose): no per-node allocations, and the column
+  // structure of an eliminated node is simply its frozen list
+  struct AdjList { long long off; int n, cap; };
+  std::vector<AdjList> adj(N, AdjList{0, 0, 0});
+  std::vector<int> pool;
   int n_nodes = 0;
   long long a_off = 0;
-  for (int i = 0; i < N; ++i) {
-    if (!active[i]) continue;
-    ++n_nodes;
-    adj[i].reserve((size_t)std::max(8, 2 * (a_row_ptr[i + 1] - a_row_ptr[i])));
-    adj[i].assign(a_col_idx + a_row_ptr[i], a_col_idx + a_row_ptr[i + 1]);   // sorted, symmetric, active only
-    a_off += (long long)adj[i].size();
+  {
+    long long need = 0;
+    for (int i = 0; i < N; ++i) if (active[i]) need += std::max(8, 2 * (a_row_ptr[i + 1] - a_row_ptr[i]));
+    pool.reserve((size_t)(need + need / 2 + 1024));
+    for (int i = 0; i < N; ++i) {
+      if (!active[i]) continue;
+      ++n_nodes;
+      const int deg = a_row_ptr[i + 1] - a_row_ptr[i];
+      adj[i] = AdjList{(long long)pool.size(), deg, std::max(8, 2 * deg)};
+      pool.resize(pool.size() + (size_t)adj[i].cap);
+      std::copy(a_col_idx + a_row_ptr[i], a_col_idx + a_row_ptr[i + 1], pool.begin() + adj[i].off);   // sorted, symmetric, active only
+      a_off += deg;
+    }
   }
   S->n_nodes = n_nodes;
   if (n_nodes == 0) return 0;
@@ -841,55 +852,60 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   std::vector<int>& level_ptr = S->level_ptr;
   std::vector<int>& level_split = S->level_split;
   level_ptr.assign(1, 0);
-  std::vector<std::vector<int>> col_rows(N);       // structure of L's column v (row pose ids, sorted by id)
+  // structure of L's column v (row pose ids, sorted by id) = adj[v] at the moment v is eliminated
   std::vector<unsigned char> alive(N, 0), blocked(N, 0);
   std::vector<int> alive_list;
   for (int i = 0; i < N; ++i) if (active[i]) { alive[i] = 1; alive_list.push_back(i); }
   std::vector<unsigned long long> cand;   // (degree << 32 | pose)
   std::vector<int> tmp, sel;
+  std::vector<std::vector<int>> buckets;
   alive_list.reserve(n_nodes); cand.reserve(n_nodes); sel.reserve(n_nodes); tmp.reserve(64);
   long long slots = 0, work = 0;
   const long long work_cap = 100LL * (a_off + n_nodes) + 32000000LL;   // symbolic effort bound (merged adjacency entries)
   while (!alive_list.empty()) {
     int dmin = 1 << 30;
     long long dsum = 0;
-    for (int v : alive_list) { dmin = std::min(dmin, (int)adj[v].size()); dsum += (long long)adj[v].size(); }
+    for (int v : alive_list) { dmin = std::min(dmin, adj[v].n); dsum += (long long)adj[v].n; }
     // mesh-like graphs (2-D grids, dense random loops) fill in quickly: give up as soon as the remaining
     // graph is both large and dense instead of grinding through a factor that would not pay off
     if (max_fill_ratio < 1e29 && alive_list.size() > 20000 && dsum > 16LL * (long long)alive_list.size()) return 0;
     const int thr = 2 * dmin + 2;
-    // greedy independent set in order of increasing degree (then pose id): one pass over the alive list per degree
-    // value instead of a sort -- thr - dmin is small
+    // greedy independent set in order of increasing degree (then pose id): degree buckets instead of a sort
     sel.clear();
     cand.clear();
+    if ((int)buckets.size() < thr - dmin + 1) buckets.resize((size_t)(thr - dmin + 1));
+    for (int d = dmin; d <= thr; ++d) buckets[d - dmin].clear();
+    for (int v : alive_list) if (adj[v].n <= thr) buckets[adj[v].n - dmin].push_back(v);
     for (int d = dmin; d <= thr; ++d) {
-      for (int v : alive_list) {
-        if ((int)adj[v].size() != d) continue;
+      for (int v : buckets[d - dmin]) {
         cand.push_back((unsigned long long)(unsigned)v);
         if (blocked[v]) continue;
         sel.push_back(v);
         blocked[v] = 1;
-        for (int u : adj[v]) blocked[u] = 1;
+        const int* av = pool.data() + adj[v].off;
+        for (int j = 0; j < adj[v].n; ++j) blocked[av[j]] = 1;
       }
     }
     int lvl_maxdeg = 0;
     for (int v : sel) {
       pos[v] = (int)order.size();
       order.push_back(v);
-      slots += (long long)adj[v].size();
-      lvl_maxdeg = std::max(lvl_maxdeg, (int)adj[v].size());
-      col_rows[v].swap(adj[v]);
+      slots += (long long)adj[v].n;
+      lvl_maxdeg = std::max(lvl_maxdeg, adj[v].n);
     }
     if (slots > fill_cap || (int)level_ptr.size() > max_levels || lvl_maxdeg > max_node_degree || work > work_cap) return 0;   // not usable
     for (int v : sel) {
-      const std::vector<int>& nb = col_rows[v];
-      for (int u : nb) {
+      const int nbn = adj[v].n;
+      for (int jn = 0; jn < nbn; ++jn) {
         // adj[u] = (adj[u] U nb) \ {u, v}
-        std::vector<int>& au = adj[u];
-        work += (long long)(au.size() + nb.size());
+        const int* nb = pool.data() + adj[v].off;      // re-read: the arena may have grown
+        const int u = nb[jn];
+        AdjList& au_l = adj[u];
+        const int* au = pool.data() + au_l.off;
+        const int na = au_l.n;
+        work += (long long)(na + nbn);
         tmp.clear();
-        size_t ia = 0, ib = 0;
-        const size_t na = au.size(), nbn = nb.size();
+        int ia = 0, ib = 0;
         while (ia < na || ib < nbn) {
           int x;
           if (ib >= nbn || (ia < na && au[ia] < nb[ib])) x = au[ia++];
@@ -897,12 +913,18 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
           else { x = au[ia]; ++ia; ++ib; }
           if (x != u && x != v) tmp.push_back(x);
         }
-        au.swap(tmp);
+        if ((int)tmp.size() > au_l.cap) {               // move the list to the end of the arena
+          au_l.cap = 2 * (int)tmp.size();
+          au_l.off = (long long)pool.size();
+          pool.resize(pool.size() + (size_t)au_l.cap);
+        }
+        au_l.n = (int)tmp.size();
+        std::copy(tmp.begin(), tmp.end(), pool.begin() + au_l.off);
       }
       alive[v] = 0;
     }
     for (unsigned long long dv : cand) blocked[(int)(dv & 0xffffffffu)] = 0;
-    for (int v : sel) for (int u : col_rows[v]) blocked[u] = 0;
+    for (int v : sel) { const int* cv = pool.data() + adj[v].off; for (int j = 0; j < adj[v].n; ++j) blocked[cv[j]] = 0; }
     size_t w = 0;
     for (size_t k = 0; k < alive_list.size(); ++k) if (alive[alive_list[k]]) alive_list[w++] = alive_list[k];
     alive_list.resize(w);
@@ -937,8 +959,8 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   std::vector<int> col_ptr(n_nodes + 1, 0);
   std::vector<int>& col_row = S->col_row;
   col_row.resize((size_t)slots);
-  for (int k = 0; k < n_nodes; ++k) col_ptr[k + 1] = col_ptr[k] + (int)col_rows[order[k]].size();
-  for (int k = 0; k < n_nodes; ++k) std::copy(col_rows[order[k]].begin(), col_rows[order[k]].end(), col_row.begin() + col_ptr[k]);
+  for (int k = 0; k < n_nodes; ++k) col_ptr[k + 1] = col_ptr[k] + adj[order[k]].n;
+  for (int k = 0; k < n_nodes; ++k) std::copy(pool.begin() + adj[order[k]].off, pool.begin() + adj[order[k]].off + adj[order[k]].n, col_row.begin() + col_ptr[k]);
   auto slot_of = [&](int row, int col) -> int {   // block (row, col), col eliminated first
     const int k = pos[col];
     const int* b = col_row.data() + col_ptr[k];
@@ -952,7 +974,7 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
   std::vector<CholTask>& tasks = S->tasks;
   {
     size_t est = 0;
-    for (int k = 0; k < n_nodes; ++k) { const size_t d = col_rows[order[k]].size(); est += d * (d + 1) / 2; }
+    for (int k = 0; k < n_nodes; ++k) { const size_t d = (size_t)adj[order[k]].n; est += d * (d + 1) / 2; }
     tasks.reserve(est);
   }
   for (int k = 0; k < n_nodes; ++k) {
@@ -986,6 +1008,14 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
       }
     }
   lap("l2a");
+  if (prof) {   // fingerprint of the whole symbolic result (regression aid for changes to this function)
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* ptr, size_t bytes) { const unsigned char* b = (const unsigned char*)ptr; for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    mix(S->level_ptr.data(), S->level_ptr.size() * sizeof(int)); mix(S->level_split.data(), S->level_split.size() * sizeof(int));
+    mix(S->col_row.data(), S->col_row.size() * sizeof(int)); mix(S->l2a.data(), S->l2a.size() * sizeof(int));
+    mix(S->nodes.data(), S->nodes.size() * sizeof(int4)); mix(S->tasks.data(), S->tasks.size() * sizeof(CholTask));
+    fprintf(stderr, "[pgo symbolic] fingerprint %016llx (%d levels, %lld slots, %zu tasks)\n", h, S->num_levels, S->n_slots, S->tasks.size());
+  }
   S->usable = true;
   return 0;
 }
