@@ -10,6 +10,7 @@ from helpers import rot_angle_between
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXAMPLE = os.path.join(ROOT, "examples", "pose_graph_b200")
+CANDIDATES_EXAMPLE = os.path.join(ROOT, "examples", "edge_candidates_b200")
 
 
 @pytest.fixture(scope="module")
@@ -135,3 +136,35 @@ def test_example_reproduces_the_reference_trajectory(D, example, tmp_path):
     err = np.linalg.norm(got[:, 1:4] - g.truth[:, :3], axis=1)
     assert err.max() <= 0.025 and err.mean() <= 0.010
     assert rot_angle_between(got[:, 4:8], g.truth[:, 3:]).max() <= 1e-3
+
+
+def _write_trajectory(path, with_ids=False):
+    f = np.load(os.path.join(ROOT, "tests", "golden", "kitti00_fixture.npz"))
+    poses = f["poses_before"]
+    if with_ids:
+        poses = np.column_stack([np.arange(len(poses)), poses])
+    np.savetxt(path, poses, fmt="%.17g")
+
+
+def test_candidates_example_fails_loudly_without_gpu(pgo, example, tmp_path):
+    if pgo.device_count() > 0:
+        pytest.skip("GPU present")
+    _write_trajectory(str(tmp_path / "trajectory.txt"))
+    r = subprocess.run([CANDIDATES_EXAMPLE, str(tmp_path / "trajectory.txt"), str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+    r = subprocess.run([CANDIDATES_EXAMPLE, str(tmp_path / "missing.txt"), str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_ids", [False, True])
+def test_candidates_example_writes_the_reference_file(example, tmp_path, with_ids):
+    """examples/edge_candidates_b200 (the reference's generate_edges_from_trajectory_origion with the CUDA search) on the
+    reference's trajectory_origin poses: the written Edge_Candidates_index.txt is byte-identical to the reference's."""
+    import hashlib
+    from test_oracle_cpu import REF_CANDIDATE_FILE_SHA256
+    traj, out = str(tmp_path / "trajectory.txt"), str(tmp_path / "Edge_Candidates_index.txt")
+    _write_trajectory(traj, with_ids)
+    r = subprocess.run([CANDIDATES_EXAMPLE, traj, out], capture_output=True, text=True)
+    assert r.returncode == 0 and "4541 frames, 20499 candidates" in r.stdout, r.stdout + r.stderr
+    assert hashlib.sha256(open(out, "rb").read()).hexdigest() == REF_CANDIDATE_FILE_SHA256
