@@ -329,6 +329,27 @@ def main():
         except Exception as ex:  # the headline line must still be printed
             if line is not None:
                 line["kernels_large_graph"] = {"error": str(ex)[:200]}
+    # ---------------- loop-edge candidate search (the producer of the path's edge topology), rank 0 only ----------------
+    if rank == 0 and line is not None:
+        try:
+            fx = np.load(os.path.join(ROOT, "tests", "golden", "kitti00_fixture.npz"))
+            pos = np.ascontiguousarray(fx["poses_before"][:, :3])
+            P.edge_candidates(pos, 6.0, 100, device=local_rank)          # warm-up
+            t0 = time.perf_counter()
+            reps = 20
+            for _ in range(reps):
+                ptr, idx = P.edge_candidates(pos, 6.0, 100, device=local_rank)
+            c_ms = 1e3 * (time.perf_counter() - t0) / reps
+            exact = bool(np.array_equal(ptr[1:], fx["cand_ptr"]) and np.array_equal(idx, fx["cand_idx"]))
+            entry = {"workload": "KITTI-00 trajectory_origin, 4541 frames, radius 6, gap 100 (host buffers in and out)",
+                     "ms_per_call": c_ms, "candidates": int(idx.size), "bit_exact_vs_reference_file": exact}
+            if world == 1:
+                t0 = time.perf_counter()
+                O.edge_candidates(pos, 6.0, 100)
+                entry["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+            line["edge_candidates"] = entry
+        except Exception as ex:
+            line["edge_candidates"] = {"error": str(ex)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
