@@ -1008,6 +1008,14 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
       }
     }
   lap("l2a");
+  if (prof && getenv("PGO_PROFILE_LEVELS")) {
+    for (int l = 0; l < S->num_levels; ++l) {
+      int mx = 0; long long sum = 0;
+      for (int k = level_ptr[l]; k < level_ptr[l + 1]; ++k) { const int nt = S->nodes[k + 1].w - S->nodes[k].w; mx = std::max(mx, nt); sum += nt; }
+      fprintf(stderr, "[pgo level] %3d nodes %5d lanes fwd %2d bwd %2d tasks max %4d mean %.1f\n", l, level_ptr[l + 1] - level_ptr[l],
+              level_split[l] & 0xff, level_split[l] >> 8, mx, (double)sum / std::max(1, level_ptr[l + 1] - level_ptr[l]));
+    }
+  }
   if (prof) {   // fingerprint of the whole symbolic result (regression aid for changes to this function)
     unsigned long long h = 1469598103934665603ull;
     auto mix = [&](const void* ptr, size_t bytes) { const unsigned char* b = (const unsigned char*)ptr; for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; } };

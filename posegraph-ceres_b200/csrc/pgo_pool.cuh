@@ -71,14 +71,12 @@ inline void pool_free(int device, void* p, size_t bytes) {
   if (!p) return;
   DevicePool& P = device_pool(device);
   const size_t sz = pool_round(bytes);
-  size_t free_b = 0, total_b = 0;
   bool keep = true;
   {
     std::lock_guard<std::mutex> lk(P.mu);
     if (P.cached_bytes + sz > ((size_t)8 << 30)) keep = false;   // never sit on more than 8 GiB
     if (keep) { P.free_blocks.emplace(sz, p); P.cached_bytes += sz; }
   }
-  (void)free_b; (void)total_b;
   if (!keep) cudaFree(p);
 }
 
