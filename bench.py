@@ -139,6 +139,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, where exactly one JSON line is expected
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_kind = load_peaks()
     args.warmup = max(args.warmup, 3)
