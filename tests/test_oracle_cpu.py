@@ -348,3 +348,15 @@ def test_edge_candidates_fail_loudly_without_gpu(pgo):
         pytest.skip("GPU present")
     with pytest.raises(pgo.PgoError, match="no CUDA device"):
         pgo.edge_candidates(np.zeros((4, 3)))
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/pgo_b200.h is the FFI surface: it must compile as C99 (no C++ or torch types in the signatures)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "pgo_b200.h"\nint main(void) { pgo_solver_options o; pgo_solver_summary s; (void)o; (void)s; '
+                   'return pgo_abi_version() == PGO_B200_ABI_VERSION ? 0 : 1; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
