@@ -134,3 +134,39 @@ def edge_candidates(positions, search_radius=6.0, min_frame_gap=100):
     idx = np.zeros(max(total, 1), np.int32)
     lib().oracle_edge_candidates(*args, _p(idx, C.c_int), C.c_longlong(idx.size))
     return row_ptr, idx[:total]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the REFERENCE's own cost functor (PoseGraph3dError.h compiled from /root/reference, see ref_functor.cpp)
+# ---------------------------------------------------------------------------------------------------------------
+_REF_LIB = os.path.join(_HERE, "_ref", "libref_functor.so")
+_REF_HEADER = "/root/reference/src/POSE_GRAPH_CERES_PLUS/include/PoseGraph3dError.h"
+_ref = None
+
+
+def ref_functor():
+    """ctypes handle of oracle/_ref/libref_functor.so, built on demand when the reference tree is present; None otherwise."""
+    global _ref
+    if _ref is None:
+        if os.path.exists(_REF_HEADER):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        if not os.path.exists(_REF_LIB):
+            return None
+        _ref = C.CDLL(_REF_LIB)
+    return _ref
+
+
+def ref_edge_jacobian(pose_a, pose_b, meas, sqrt_info):
+    """(residual[6], jacobian[6][14]) of one edge from the reference's functor; the Jacobian is w.r.t. the ambient
+    parameters (p_a[3], q_a[4], p_b[3], q_b[4]), as AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4> sees them."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (pose_a, pose_b, meas, sqrt_info)]
+    res, jac = np.zeros(6), np.zeros((6, 14))
+    ref_functor().ref_edge_jacobian(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(res), _p(jac))
+    return res, jac
+
+
+def ref_edge_residual(pose_a, pose_b, meas, sqrt_info):
+    a = [np.ascontiguousarray(v, np.float64) for v in (pose_a, pose_b, meas, sqrt_info)]
+    res = np.zeros(6)
+    ref_functor().ref_edge_residual(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(res))
+    return res

@@ -5,7 +5,9 @@
  * it restates.  REF = /root/reference/src/POSE_GRAPH_CERES_PLUS.
  *
  * PARITY PARTIALLY PINNED: no real Ceres run is available to check the iterate sequence against; the cost
- * function and the end result are pinned against the reference's own Ceres output (pgo_oracle.h).
+ * function is pinned against the reference's own functor source (oracle/_ref, ref_functor.cpp) and against the
+ * reference's Ceres output, the end result against that output, the candidate search against the reference's
+ * committed file (pgo_oracle.h).
  */
 #include "pgo_oracle.h"
 

@@ -12,7 +12,10 @@
  * SPARSE_NORMAL_CHOLESKY (here: block min-degree ordering + block up-looking Cholesky).
  *
  * PARITY PARTIALLY PINNED: Ceres is not installable in this image, so the LM
- * iterate sequence cannot be compared with a real Ceres run step by step.  What IS pinned against the
+ * iterate sequence cannot be compared with a real Ceres run step by step.  The COST FUNCTION is pinned against the
+ * reference's own source: oracle/_ref/libref_functor.so compiles PoseGraph3dErrorTerm::operator() unmodified from
+ * /root/reference (ref_functor.cpp, minimal Eigen/Ceres stand-ins in ref_shim/) and oracle_evaluate's residuals and
+ * Jacobians agree with it to rounding on random edges.  What is pinned against the
  * reference's own Ceres output (the result/trajectory text files): the cost function's stationarity at the reference's
  * optimised trajectory on every pose (free poses; loop-edge END poses with measurements recovered from the
  * BEGIN poses only), and the end result -- from the reference's initial trajectory the oracle's LM lands

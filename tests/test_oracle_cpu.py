@@ -360,3 +360,58 @@ def test_c_abi_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the oracle's cost function against the reference's OWN functor source (oracle/_ref, built from /root/reference)
+# ---------------------------------------------------------------------------------------------------------------
+def _quaternion_plus_jacobian(q):
+    """EigenQuaternionParameterization::ComputeJacobian (ceres 1.13 local_parameterization.cc), 4 x 3, q = x y z w"""
+    x, y, z, w = q
+    return np.array([[w, z, -y], [-z, w, x], [y, -x, w], [-x, -y, -z]])
+
+
+@pytest.fixture(scope="module")
+def ref_functor(oracle):
+    if oracle.ref_functor() is None:
+        pytest.skip("/root/reference is not present and oracle/_ref was not prebuilt")
+    return oracle
+
+
+def test_oracle_residual_and_jacobian_match_the_reference_functor(ref_functor):
+    """PoseGraph3dErrorTerm::operator() compiled from the reference's header (T = double and T = a 14-wide Jet) versus
+    oracle_evaluate on random edges with random full sqrt-information: residuals to 1e-14, local Jacobians
+    (ambient Jacobian x the parameterization's plus-Jacobian) to 1e-13."""
+    import posegraph_ceres_b200.datasets as D
+    O = ref_functor
+    rng = np.random.default_rng(11)
+    unit = lambda q: q / np.linalg.norm(q)  # noqa: E731
+    for trial in range(300):
+        pa = np.concatenate([rng.normal(0, 5, 3), unit(rng.normal(size=4))])
+        pb = np.concatenate([rng.normal(0, 5, 3), unit(rng.normal(size=4))])
+        m = np.concatenate([rng.normal(0, 5, 3), unit(rng.normal(size=4))])
+        S = rng.normal(size=(6, 6)) if trial % 3 else np.eye(6)
+        res, jac = O.ref_edge_jacobian(pa, pb, m, S)
+        assert np.array_equal(res, O.ref_edge_residual(pa, pb, m, S))
+        g = D.PoseGraph("one_edge", np.stack([pa, pb]), np.array([[0, 1]], np.int32), m[None, :], S.reshape(1, 36), np.zeros(2, np.uint8))
+        _, r, _, J = O.evaluate(g, loss_type=O.LOSS_TRIVIAL)
+        scale = max(1.0, np.abs(jac).max())
+        assert np.abs(r.reshape(-1) - res).max() <= 1e-14 * max(1.0, np.abs(res).max())
+        Ja = np.hstack([jac[:, 0:3], jac[:, 3:7] @ _quaternion_plus_jacobian(pa[3:])])
+        Jb = np.hstack([jac[:, 7:10], jac[:, 10:14] @ _quaternion_plus_jacobian(pb[3:])])
+        Jo = J.reshape(2, 6, 6)
+        assert np.abs(Jo[0] - Ja).max() <= 1e-13 * scale and np.abs(Jo[1] - Jb).max() <= 1e-13 * scale
+
+
+def test_oracle_kitti_cost_matches_the_reference_functor(ref_functor):
+    """Initial cost of the reference's own problem: 1/2 sum rho_Huber(|r_e|^2) with r_e from the reference's functor on all
+    5 179 KITTI-00 edges equals oracle_evaluate's cost (and the 286.0912 the solver tests start from)."""
+    import posegraph_ceres_b200.datasets as D
+    O = ref_functor
+    g = D.kitti00()
+    s = np.array([np.sum(O.ref_edge_residual(g.poses[a], g.poses[b], g.edge_meas[e], g.edge_sqrt_info[e]) ** 2)
+                  for e, (a, b) in enumerate(g.edge_ids)])
+    rho = np.where(s <= 1.0, s, 2.0 * np.sqrt(s) - 1.0)          # HuberLoss(1.0): rho(s) = s or 2 sqrt(s) - 1
+    cost, _, _, _ = O.evaluate(g, want_jac=False)
+    assert abs(0.5 * rho.sum() - cost) <= 1e-12 * cost
+    assert abs(cost - 286.0912) < 1e-3
