@@ -372,3 +372,36 @@ def test_edge_candidates_argument_errors(pgo):
         pgo.edge_candidates(np.zeros((4, 3)), -1.0, 100)
     with pytest.raises(pgo.PgoError):
         pgo.edge_candidates(np.zeros((4, 3)), 6.0, 100, device=99)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the CUDA kernel against the reference's OWN functor source (oracle/_ref/libref_functor.so, prebuilt: it travels)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere", "kitti00"])
+def test_evaluate_matches_the_reference_functor(pgo, oracle, graphs, name):
+    """residuals and both local Jacobian blocks of every edge from linearize_kernel vs PoseGraph3dErrorTerm::operator()
+    compiled from the reference's header (double and Jets), trivial loss so that nothing but the functor is compared."""
+    if oracle.ref_functor() is None:
+        pytest.skip("oracle/_ref/libref_functor.so was not built (needs /root/reference at build time)")
+    g = graphs[name]
+    G = pgo.Graph.from_dataset(g)
+    _, res, _, jac = G.evaluate(loss_type=0, loss_a=1.0)
+    G.close()
+
+    def plus_jacobian(q):   # EigenQuaternionParameterization::ComputeJacobian, q = x y z w
+        x, y, z, w = q
+        return np.array([[w, z, -y], [-z, w, x], [y, -x, w], [-x, -y, -z]])
+
+    rng = np.random.default_rng(5)
+    edges = rng.choice(g.n_edges, size=min(g.n_edges, 600), replace=False)
+    worst_r = worst_j = 0.0
+    for e in edges:
+        a, b = g.edge_ids[e]
+        r, J = oracle.ref_edge_jacobian(g.poses[a], g.poses[b], g.edge_meas[e], g.edge_sqrt_info[e])
+        Ja = np.hstack([J[:, 0:3], J[:, 3:7] @ plus_jacobian(g.poses[a][3:])]) * (0.0 if g.pose_const[a] else 1.0)
+        Jb = np.hstack([J[:, 7:10], J[:, 10:14] @ plus_jacobian(g.poses[b][3:])]) * (0.0 if g.pose_const[b] else 1.0)
+        je = np.asarray(jac[e]).reshape(2, 6, 6)
+        worst_r = max(worst_r, np.abs(np.asarray(res[e]) - r).max() / max(1.0, np.abs(r).max()))
+        worst_j = max(worst_j, max(np.abs(je[0] - Ja).max(), np.abs(je[1] - Jb).max()) / max(1.0, np.abs(J).max()))
+    assert worst_r <= 1e-12 and worst_j <= 1e-12, (worst_r, worst_j)
