@@ -170,3 +170,25 @@ def ref_edge_residual(pose_a, pose_b, meas, sqrt_info):
     res = np.zeros(6)
     ref_functor().ref_edge_residual(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(res))
     return res
+
+
+_REF_READER = os.path.join(_HERE, "_ref", "ref_read_edges")
+
+
+def ref_read_edge_candidates(candidate_file):
+    """Parse `candidate_file` with the REFERENCE's own reader (ReadEdges.h:9-48 compiled into oracle/_ref/ref_read_edges):
+    returns {key: [candidates]} exactly as getEdegsCandidateIndex() does, or None when oracle/_ref is unavailable."""
+    import shutil
+    import tempfile
+    if ref_functor() is None or not os.path.exists(_REF_READER):
+        return None
+    with tempfile.TemporaryDirectory() as d:            # the reader opens ../config/Edge_Candidates_index.txt
+        os.makedirs(os.path.join(d, "bin"))
+        os.makedirs(os.path.join(d, "config"))
+        shutil.copy(candidate_file, os.path.join(d, "config", "Edge_Candidates_index.txt"))
+        out = subprocess.run([_REF_READER], cwd=os.path.join(d, "bin"), capture_output=True, text=True, check=True).stdout
+    result = {}
+    for line in out.splitlines():
+        key, _, rest = line.partition(":")
+        result[int(key)] = [int(t) for t in rest.split()]
+    return result

@@ -415,3 +415,19 @@ def test_oracle_kitti_cost_matches_the_reference_functor(ref_functor):
     cost, _, _, _ = O.evaluate(g, want_jac=False)
     assert abs(0.5 * rho.sum() - cost) <= 1e-12 * cost
     assert abs(cost - 286.0912) < 1e-3
+
+
+def test_candidate_file_is_read_back_by_the_reference_reader(ref_functor, fixture, tmp_path):
+    """The file written from the candidate search, parsed by the reference's own getEdegsCandidateIndex()
+    (include/ReadEdges.h compiled from /root/reference): frame c maps to exactly the candidates of frame c; the reader's
+    trailing empty entry (it reads one line past the end) is the only extra key."""
+    import posegraph_ceres_b200.datasets as D
+    O = ref_functor
+    ptr, idx = O.edge_candidates(fixture["poses_before"][:, :3])
+    path = str(tmp_path / "Edge_Candidates_index.txt")
+    D.write_edge_candidates(ptr, idx, path)
+    parsed = O.ref_read_edge_candidates(path)
+    n = len(ptr) - 1
+    assert sorted(parsed) == list(range(1, n + 1)) and parsed[n] == []
+    for c in range(1, n):
+        assert parsed[c] == idx[ptr[c]:ptr[c + 1]].tolist()
