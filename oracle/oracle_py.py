@@ -192,3 +192,39 @@ def ref_read_edge_candidates(candidate_file):
         key, _, rest = line.partition(":")
         result[int(key)] = [int(t) for t in rest.split()]
     return result
+
+
+_REF_GENERATOR = os.path.join(_HERE, "_ref", "ref_generate_edges")
+
+
+def ref_generate_edge_candidates(positions, search_radius=6, want_file=False):
+    """Run the REFERENCE's own candidate generator (test/generate_edges_from_trajectory_origion.cpp compiled into
+    oracle/_ref/ref_generate_edges, stand-ins for OpenCV / yaml under ref_shim/gen) on `positions` [n][3].
+    Returns (row_ptr[n+1], candidates) in pgo_edge_candidates' layout (and the raw file bytes with want_file), or None
+    when oracle/_ref is unavailable.  The radius is an integer (Config::get<int>), the frame gap is the reference's 100."""
+    import tempfile
+    if ref_functor() is None or not os.path.exists(_REF_GENERATOR):
+        return None
+    pos = np.ascontiguousarray(positions, np.float64)
+    n = int(pos.shape[0])
+    with tempfile.TemporaryDirectory() as d:            # the program writes ../config/Edge_Candidates_index.txt
+        os.makedirs(os.path.join(d, "bin"))
+        os.makedirs(os.path.join(d, "config"))
+        traj = os.path.join(d, "trajectory.txt")        # format 1: x y z q_x q_y q_z q_w
+        np.savetxt(traj, np.hstack([pos, np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))]), fmt="%.17g")
+        env = dict(os.environ, REF_TRAJECTORY=traj, REF_SEQUENCE_LENGTH=str(n), REF_SEARCH_RADIUS=str(int(search_radius)))
+        subprocess.run([_REF_GENERATOR], cwd=os.path.join(d, "bin"), env=env, stdout=subprocess.DEVNULL, check=True)
+        with open(os.path.join(d, "config", "Edge_Candidates_index.txt"), "rb") as f:
+            raw = f.read()
+    row_ptr, idx = [0, 0], []
+    for line in raw.decode().splitlines():
+        tok = [int(t) for t in line.split()]
+        if not tok:
+            continue
+        assert tok[0] == len(row_ptr) - 1
+        idx.extend(tok[1:])
+        row_ptr.append(len(idx))
+    while len(row_ptr) < n + 1:
+        row_ptr.append(len(idx))
+    out = (np.asarray(row_ptr, np.int64), np.asarray(idx, np.int32))
+    return out + (raw,) if want_file else out

@@ -405,3 +405,17 @@ def test_evaluate_matches_the_reference_functor(pgo, oracle, graphs, name):
         worst_r = max(worst_r, np.abs(np.asarray(res[e]) - r).max() / max(1.0, np.abs(r).max()))
         worst_j = max(worst_j, max(np.abs(je[0] - Ja).max(), np.abs(je[1] - Jb).max()) / max(1.0, np.abs(J).max()))
     assert worst_r <= 1e-12 and worst_j <= 1e-12, (worst_r, worst_j)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,radius,seed", [(150, 6, 0), (3000, 5, 1), (3000, 11, 2)])
+def test_edge_candidates_match_the_reference_generator_source(pgo, oracle, n, radius, seed):
+    """pgo_edge_candidates vs the reference's own generate_edges_from_trajectory_origion.cpp (oracle/_ref/ref_generate_edges,
+    prebuilt from /root/reference) on random self-revisiting trajectories: identical lists."""
+    rng = np.random.default_rng(seed)
+    pos = np.cumsum(rng.normal(0, 0.7, (n, 3)), axis=0) % 30.0
+    ref = oracle.ref_generate_edge_candidates(pos, radius)
+    if ref is None:
+        pytest.skip("oracle/_ref/ref_generate_edges was not built (needs /root/reference at build time)")
+    ptr, idx = pgo.edge_candidates(pos, float(radius), 100)
+    assert np.array_equal(ptr, ref[0]) and np.array_equal(idx, ref[1])

@@ -431,3 +431,28 @@ def test_candidate_file_is_read_back_by_the_reference_reader(ref_functor, fixtur
     assert sorted(parsed) == list(range(1, n + 1)) and parsed[n] == []
     for c in range(1, n):
         assert parsed[c] == idx[ptr[c]:ptr[c + 1]].tolist()
+
+
+def test_reference_generator_source_reproduces_its_committed_file(ref_functor, fixture):
+    """generate_edges_from_trajectory_origion.cpp compiled from /root/reference (stand-ins only for OpenCV / yaml / the
+    pose loader) and run on trajectory_origin: its output is the reference's committed Edge_Candidates_index.txt, byte for
+    byte -- which validates the stand-ins -- and equals the oracle's lists."""
+    O = ref_functor
+    ptr, idx, raw = O.ref_generate_edge_candidates(fixture["poses_before"][:, :3], 6, want_file=True)
+    assert hashlib.sha256(raw).hexdigest() == REF_CANDIDATE_FILE_SHA256
+    optr, oidx = O.edge_candidates(fixture["poses_before"][:, :3], 6.0, 100)
+    assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+
+
+@pytest.mark.parametrize("n,radius,seed", [(90, 6, 0), (101, 6, 1), (102, 30, 2), (1500, 5, 3), (1500, 9, 4), (2500, 3, 5)])
+def test_oracle_edge_candidates_match_the_reference_generator_source(ref_functor, n, radius, seed):
+    """the oracle's restatement against the reference's own program on random self-revisiting trajectories
+    (float rounding decides membership near the radius: the lists must be identical)"""
+    O = ref_functor
+    rng = np.random.default_rng(seed)
+    pos = np.cumsum(rng.normal(0, 0.7, (n, 3)), axis=0) % 30.0
+    ptr, idx = O.ref_generate_edge_candidates(pos, radius)
+    optr, oidx = O.edge_candidates(pos, float(radius), 100)
+    assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+    if n > 1000:
+        assert idx.size > 2 * n
