@@ -148,7 +148,9 @@ void pgo_default_options(pgo_solver_options* options);
 
 /* Host-only: variable poses, block-CSR Hessian pattern and the level-scheduled elimination order that
  * pgo_graph_create / pgo_graph_solve would use for this topology (what Ceres' program preprocessing and
- * symbolic factorisation do inside ceres::Solve).  max_fill_ratio <= 0: no fill limit. */
+ * symbolic factorisation do inside ceres::Solve).  max_fill_ratio <= 0: the full analysis, no limits (what an explicit
+ * PGO_LINEAR_PCG_LEVEL_CHOLESKY request runs); > 0: the "cheap factor only" analysis of PGO_LINEAR_AUTO with this fill
+ * limit (AUTO uses 8) plus its limits of 64 levels and node degree 16 -- it gives up early on mesh-like graphs. */
 int pgo_analyze_structure(int n_poses, int n_edges, const int* edge_ids, const unsigned char* pose_const,
                           double max_fill_ratio, pgo_structure_info* info);
 

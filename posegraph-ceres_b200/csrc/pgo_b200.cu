@@ -183,8 +183,10 @@ extern "C" int pgo_analyze_structure(int n_poses, int n_edges, const int* edge_i
   for (unsigned char a : pat.active) info->variable_poses += a;
   info->hessian_blocks = (long long)pat.col_idx.size() + n_poses;
   LevelCholSymbolic S;
+  // max_fill_ratio > 0: the "cheap factor only" analysis PGO_LINEAR_AUTO runs (run_symbolic), with this fill limit
+  const bool cheap_only = max_fill_ratio > 0.0;
   PGO_TRY(level_chol_symbolic(&S, n_poses, pat.active.data(), pat.row_ptr.data(), pat.col_idx.data(),
-                              max_fill_ratio > 0.0 ? max_fill_ratio : 1e30));
+                              cheap_only ? max_fill_ratio : 1e30, cheap_only ? 64 : 8192, cheap_only ? 16 : (1 << 30)));
   if (getenv("PGO_PROFILE_HOST")) fprintf(stderr, "[pgo analyze] pattern %.1f us, symbolic %.1f us\n", 1e6 * (t1 - t0), 1e6 * (wall_s() - t1));
   info->factor_usable = S.usable ? 1 : 0;
   if (S.usable) {

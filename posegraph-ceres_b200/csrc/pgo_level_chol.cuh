@@ -868,7 +868,12 @@ static int level_chol_symbolic(LevelCholSymbolic* S, int N, const unsigned char*
     for (int v : alive_list) { dmin = std::min(dmin, adj[v].n); dsum += (long long)adj[v].n; }
     // mesh-like graphs (2-D grids, dense random loops) fill in quickly: give up as soon as the remaining
     // graph is both large and dense instead of grinding through a factor that would not pay off
+    if (prof && getenv("PGO_PROFILE_LEVELS")) fprintf(stderr, "[pgo round] %3zu alive %8zu mean degree %.2f min %d\n", level_ptr.size() - 1, alive_list.size(), (double)dsum / (double)alive_list.size(), dmin);
     if (max_fill_ratio < 1e29 && alive_list.size() > 20000 && dsum > 16LL * (long long)alive_list.size()) return 0;
+    // "cheap factor only" callers (AUTO: a node-degree limit is set): a chain-like graph keeps its mean degree near 2-3
+    // while thousands of nodes are alive (KITTI-00: <= 3.1 above 1 000 alive nodes); a mesh is past 8 after one or two
+    // rounds and will break the degree limit later anyway -- stop now instead of after seconds of merging
+    if (max_node_degree < (1 << 30) && alive_list.size() > 1024 && dsum > (long long)(max_node_degree / 2) * (long long)alive_list.size()) return 0;
     const int thr = 2 * dmin + 2;
     // greedy independent set in order of increasing degree (then pose id): degree buckets instead of a sort
     sel.clear();

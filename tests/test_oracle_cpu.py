@@ -290,6 +290,15 @@ def test_host_structure_analysis(pgo, D):
     assert ti.factor_usable == 0
     with pytest.raises(pgo.PgoError):
         pgo.analyze_structure(10, np.array([[0, 10]], np.int32))
+    # the analysis PGO_LINEAR_AUTO runs (fill limit 8, <= 64 levels, node degree <= 16): same factor for the chain-like
+    # KITTI-00 graph; mesh-like graphs are turned down after a round or two, not after seconds of symbolic elimination
+    ai = pgo.analyze_structure(g.n_poses, g.edge_ids, g.pose_const, max_fill_ratio=8.0)
+    assert ai.factor_usable == 1 and ai.factor_levels == info.factor_levels and ai.factor_blocks == info.factor_blocks
+    import time
+    for mesh in (D.manhattan_grid(300, 300, 3000), D.sphere()):
+        t0 = time.perf_counter()
+        mi = pgo.analyze_structure(mesh.n_poses, mesh.edge_ids, mesh.pose_const, max_fill_ratio=8.0)
+        assert mi.factor_usable == 0 and time.perf_counter() - t0 < 1.0
 
 
 def test_no_cpu_fallback(pgo):
