@@ -465,3 +465,12 @@ def test_oracle_edge_candidates_match_the_reference_generator_source(ref_functor
     assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
     if n > 1000:
         assert idx.size > 2 * n
+
+
+def test_tools_and_entry_points_compile():
+    """hygiene: every script the GPU rounds run must at least byte-compile on the CPU box"""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]:
+        py_compile.compile(path, doraise=True)
