@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PGO_B200_ABI_VERSION 4
+#define PGO_B200_ABI_VERSION 5
 
 typedef enum {
   PGO_OK = 0,
@@ -57,7 +57,11 @@ typedef enum { PGO_CONVERGENCE = 0, PGO_NO_CONVERGENCE = 1, PGO_FAILURE = 2 } pg
 typedef enum {
   PGO_LINEAR_PCG_BLOCK_JACOBI = 0,   /* 6x6 block-Jacobi preconditioned CG (block-SpMV kernel)        */
   PGO_LINEAR_PCG_LEVEL_CHOLESKY = 1, /* PCG preconditioned by a level-scheduled block Cholesky factor */
-  PGO_LINEAR_AUTO = 2                /* LEVEL_CHOLESKY when the symbolic fill is small, else BLOCK_JACOBI */
+  PGO_LINEAR_AUTO = 2,               /* LEVEL_CHOLESKY when the symbolic fill is small (chain-like graphs), else AMG
+                                        (mesh-like graphs; tiny ones stay with BLOCK_JACOBI) */
+  PGO_LINEAR_PCG_AMG = 3             /* PCG preconditioned by an aggregation-multigrid V-cycle on rigid-body modes of pose
+                                        patches: every level is again a 6x6 block system swept by the block-SpMV kernel.
+                                        The solver of every multi-GPU (row-partitioned) solve. */
 } pgo_linear_solver_type;
 
 /* Mirrors the ceres::Solver::Options fields that matter on this path; defaults = Ceres defaults
@@ -125,6 +129,12 @@ typedef struct {
   long long hessian_blocks;      /* 6x6 blocks in the block-CSR Hessian (diag + off-diag) */
   long long factor_blocks;       /* 6x6 blocks in the level-Cholesky factor (0 if unused) */
   int factor_levels;
+  int amg_levels;                /* levels of the multilevel preconditioner (0 if unused) */
+  long long amg_blocks;          /* 6x6 blocks over all its levels stored on this rank */
+  long long comm_calls;          /* multi-GPU: NCCL calls issued by this rank during the solve */
+  long long comm_bytes;          /*            payload bytes this rank sent */
+  long long comm_bytes_per_pcg_iteration;   /* halo + gather + scalar payload this rank sends per PCG iteration */
+  int comm_calls_per_pcg_iteration;
 } pgo_solver_summary;
 
 /* Result of the host-side structure analysis (no GPU needed). */
@@ -177,11 +187,47 @@ int pgo_graph_get_poses(pgo_graph* g, double* poses);         /* device -> host 
 int pgo_graph_snapshot_poses(pgo_graph* g);
 int pgo_graph_restore_poses(pgo_graph* g);
 
-/* Multi-GPU: this rank holds an edge shard and a replica of all poses; J^T r, the Hessian
- * diagonal and every PCG SpMV product are all-reduced over NCCL.  unique_id is the 128-byte
- * ncclUniqueId produced by rank 0 (pgo_nccl_unique_id) and distributed by the caller. */
+/* Multi-GPU (one process per GPU): owner-computes row partition.  EVERY rank passes the same global graph; rank r keeps
+ * the block rows of the poses [n r / W, n (r+1) / W) -- contiguous index ranges, pose graphs are trajectory-ordered --,
+ * every edge that touches one of them (a cut edge is evaluated by both owners, each keeps its own rows of J^T J and J^T r)
+ * and halo copies of the other endpoints.  Per PCG iteration only halo slices of the vectors move between neighbours plus
+ * one all-reduce of two scalars; per LM iteration the halo poses and five scalars.  unique_id is the 128-byte ncclUniqueId
+ * produced by rank 0 (pgo_nccl_unique_id) and distributed by the caller.  The calls below that take or return per-pose
+ * arrays keep the GLOBAL layout on every rank and are collective: all ranks must make them in the same order. */
 int pgo_nccl_unique_id(unsigned char unique_id[128]);
-int pgo_graph_init_comm(pgo_graph* g, const unsigned char unique_id[128], int rank, int world_size);
+int pgo_graph_create_partitioned(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
+                                 const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
+                                 const unsigned char* pose_const, const unsigned char unique_id[128], int rank,
+                                 int world_size);
+int pgo_graph_rank(const pgo_graph* g);
+int pgo_graph_world_size(const pgo_graph* g);
+int pgo_graph_num_local_poses(const pgo_graph* g);   /* block rows owned by this rank */
+int pgo_graph_num_halo_poses(const pgo_graph* g);    /* copies of other ranks' poses held for the cut edges */
+int pgo_graph_num_local_edges(const pgo_graph* g);   /* edges evaluated here (cut edges count on both sides) */
+
+/* Host-only: what pgo_graph_create_partitioned would set up for `rank` of `world_size` -- the partition, the halo
+ * exchange plan and the multilevel hierarchy (no GPU needed; CPU tests cover the N > 1 host logic with it). */
+typedef struct {
+  int n_own, n_halo, n_local_edges, n_cut_edges;
+  int n_neighbours;
+  int send_total, recv_total;            /* level-0 halo plan */
+  int send_to[64], recv_from[64];        /* per peer rank (world_size <= 64) */
+  int amg_levels;
+  int level_nodes[16];                   /* global nodes per level */
+  int level_own[16], level_halo[16];     /* this rank's rows / halo columns per level */
+  int level_replicated[16];
+  long long level_blocks[16];            /* 6x6 blocks stored by this rank per level */
+  int level_send[16], level_recv[16];
+  unsigned long long plan_checksum;      /* order-dependent hash of send lists: the receiver-side hash must match */
+  unsigned long long recv_checksum;
+  int consistent;                        /* internal invariants hold (aggregates do not cross ranks, gather lists complete, ...) */
+} pgo_partition_info;
+int pgo_analyze_partition(int n_poses, int n_edges, const double* poses, const int* edge_ids,
+                          const unsigned char* pose_const, int rank, int world_size, pgo_partition_info* info);
+/* Host-only: the aggregation hierarchy itself.  level_nodes[16]; agg_out = concatenation over the levels 0..L-2 of the
+ * aggregate (node id on the next level, -1 = not a variable) of every node; agg_out may be NULL to query the sizes. */
+int pgo_amg_aggregates(int n_poses, int n_edges, const double* poses, const int* edge_ids, const unsigned char* pose_const,
+                       int world_size, int* n_levels, int* level_nodes, int* agg_out, long long agg_capacity);
 
 /* ceres::Problem::Evaluate on the device: cost, robustified residuals [n_edges][6], gradient
  * [n_poses][6] (unscaled, zero for constant poses), per-edge local Jacobians [n_edges][2][36]

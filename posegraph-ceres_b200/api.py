@@ -17,14 +17,15 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(_CSRC, "libpgo_b200.so")
 
 LOSS_TRIVIAL, LOSS_HUBER, LOSS_CAUCHY = 0, 1, 2
-LINEAR_PCG_BLOCK_JACOBI, LINEAR_PCG_LEVEL_CHOLESKY, LINEAR_AUTO = 0, 1, 2
+LINEAR_PCG_BLOCK_JACOBI, LINEAR_PCG_LEVEL_CHOLESKY, LINEAR_AUTO, LINEAR_PCG_AMG = 0, 1, 2, 3
 CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "pgo_last_error", "pgo_abi_version", "pgo_device_count", "pgo_default_options", "pgo_graph_create",
     "pgo_graph_destroy", "pgo_graph_set_stream", "pgo_graph_num_poses", "pgo_graph_num_edges", "pgo_graph_set_poses",
     "pgo_graph_get_poses", "pgo_graph_snapshot_poses", "pgo_graph_restore_poses", "pgo_nccl_unique_id",
-    "pgo_graph_init_comm", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
+    "pgo_graph_create_partitioned", "pgo_graph_rank", "pgo_graph_world_size", "pgo_graph_num_local_poses",
+    "pgo_graph_num_halo_poses", "pgo_graph_num_local_edges", "pgo_analyze_partition", "pgo_amg_aggregates", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
     "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates",
 ]
@@ -57,13 +58,26 @@ class SolverSummary(C.Structure):
                 ("total_pcg_iterations", C.c_longlong), ("kernel_launches", C.c_longlong),
                 ("time_total_s", C.c_double), ("time_setup_s", C.c_double), ("time_linearize_ms", C.c_double),
                 ("time_linear_solver_ms", C.c_double), ("linear_solver_used", C.c_int),
-                ("hessian_blocks", C.c_longlong), ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int)]
+                ("hessian_blocks", C.c_longlong), ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int),
+                ("amg_levels", C.c_int), ("amg_blocks", C.c_longlong), ("comm_calls", C.c_longlong),
+                ("comm_bytes", C.c_longlong), ("comm_bytes_per_pcg_iteration", C.c_longlong),
+                ("comm_calls_per_pcg_iteration", C.c_int)]
 
 
 class StructureInfo(C.Structure):
     _fields_ = [("variable_poses", C.c_int), ("hessian_blocks", C.c_longlong), ("factor_usable", C.c_int),
                 ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int), ("factor_max_degree", C.c_int),
                 ("factor_tasks", C.c_longlong), ("analysis_seconds", C.c_double)]
+
+
+class PartitionInfo(C.Structure):
+    _fields_ = [("n_own", C.c_int), ("n_halo", C.c_int), ("n_local_edges", C.c_int), ("n_cut_edges", C.c_int),
+                ("n_neighbours", C.c_int), ("send_total", C.c_int), ("recv_total", C.c_int),
+                ("send_to", C.c_int * 64), ("recv_from", C.c_int * 64), ("amg_levels", C.c_int),
+                ("level_nodes", C.c_int * 16), ("level_own", C.c_int * 16), ("level_halo", C.c_int * 16),
+                ("level_replicated", C.c_int * 16), ("level_blocks", C.c_longlong * 16),
+                ("level_send", C.c_int * 16), ("level_recv", C.c_int * 16),
+                ("plan_checksum", C.c_ulonglong), ("recv_checksum", C.c_ulonglong), ("consistent", C.c_int)]
 
 
 class PgoError(RuntimeError):
@@ -133,6 +147,37 @@ def analyze_structure(n_poses, edge_ids, pose_const=None, max_fill_ratio: float 
     return info
 
 
+def analyze_partition(g, rank: int, world: int) -> PartitionInfo:
+    """Host-only: the row partition, halo plan and multilevel hierarchy rank `rank` of `world` would build (no GPU)."""
+    poses = np.ascontiguousarray(g.poses, np.float64)
+    ids = np.ascontiguousarray(g.edge_ids, np.int32)
+    pc = np.ascontiguousarray(g.pose_const, np.uint8)
+    info = PartitionInfo()
+    _check(lib().pgo_analyze_partition(C.c_int(poses.shape[0]), C.c_int(ids.shape[0]), _dp(poses), ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                       pc.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(rank), C.c_int(world), C.byref(info)))
+    return info
+
+
+def amg_aggregates(g, world: int = 1):
+    """Host-only: [agg_0, agg_1, ...] -- for every level but the last, the aggregate (next-level node) of every node."""
+    poses = np.ascontiguousarray(g.poses, np.float64)
+    ids = np.ascontiguousarray(g.edge_ids, np.int32)
+    pc = np.ascontiguousarray(g.pose_const, np.uint8)
+    nl = C.c_int()
+    nodes = (C.c_int * 16)()
+    args = (C.c_int(poses.shape[0]), C.c_int(ids.shape[0]), _dp(poses), ids.ctypes.data_as(C.POINTER(C.c_int)),
+            pc.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(world), C.byref(nl), nodes)
+    _check(lib().pgo_amg_aggregates(*args, None, C.c_longlong(0)))
+    sizes = [nodes[l] for l in range(nl.value)]
+    out = np.zeros(max(1, sum(sizes[:-1])), np.int32)
+    _check(lib().pgo_amg_aggregates(*args, out.ctypes.data_as(C.POINTER(C.c_int)), C.c_longlong(out.size)))
+    res, k = [], 0
+    for n in sizes[:-1]:
+        res.append(out[k:k + n].copy())
+        k += n
+    return sizes, res
+
+
 def edge_candidates(positions, search_radius: float = 6.0, min_frame_gap: int = 100, device: int = 0):
     """Loop-edge candidates per frame (pgo_edge_candidates): returns (row_ptr[n+1], candidates) -- frame c's list is
     candidates[row_ptr[c]:row_ptr[c+1]] = [c-1, then every i < c - min_frame_gap within the search radius, ascending]."""
@@ -162,7 +207,9 @@ def nccl_unique_id() -> bytes:
 class Graph:
     """A pose graph resident in HBM (pgo_graph)."""
 
-    def __init__(self, poses, edge_ids, edge_meas, edge_sqrt_info=None, pose_const=None, device: int = 0):
+    def __init__(self, poses, edge_ids, edge_meas, edge_sqrt_info=None, pose_const=None, device: int = 0,
+                 unique_id: bytes | None = None, rank: int = 0, world: int = 1):
+        """world > 1: every rank passes the same global graph and keeps its row slice (pgo_graph_create_partitioned)."""
         self._h = C.c_void_p()
         poses = np.ascontiguousarray(poses, np.float64)
         edge_ids = np.ascontiguousarray(edge_ids, np.int32)
@@ -170,13 +217,23 @@ class Graph:
         self.n_poses, self.n_edges = int(poses.shape[0]), int(edge_ids.shape[0])
         si = None if edge_sqrt_info is None else np.ascontiguousarray(edge_sqrt_info, np.float64)
         pc = None if pose_const is None else np.ascontiguousarray(pose_const, np.uint8)
-        _check(lib().pgo_graph_create(C.byref(self._h), C.c_int(device), C.c_int(self.n_poses), C.c_int(self.n_edges),
-                                      _dp(poses), edge_ids.ctypes.data_as(C.POINTER(C.c_int)), _dp(edge_meas), _dp(si),
-                                      pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None))
+        args = (C.byref(self._h), C.c_int(device), C.c_int(self.n_poses), C.c_int(self.n_edges),
+                _dp(poses), edge_ids.ctypes.data_as(C.POINTER(C.c_int)), _dp(edge_meas), _dp(si),
+                pc.ctypes.data_as(C.POINTER(C.c_ubyte)) if pc is not None else None)
+        if world > 1:
+            buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+            _check(lib().pgo_graph_create_partitioned(*args, buf, C.c_int(rank), C.c_int(world)))
+        else:
+            _check(lib().pgo_graph_create(*args))
 
     @classmethod
-    def from_dataset(cls, g, device: int = 0):
-        return cls(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, device)
+    def from_dataset(cls, g, device: int = 0, unique_id: bytes | None = None, rank: int = 0, world: int = 1):
+        return cls(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, device, unique_id, rank, world)
+
+    def local_sizes(self):
+        """(owned poses, halo poses, local edges) of this rank's slice"""
+        L = lib()
+        return int(L.pgo_graph_num_local_poses(self._h)), int(L.pgo_graph_num_halo_poses(self._h)), int(L.pgo_graph_num_local_edges(self._h))
 
     def close(self):
         if self._h:
@@ -205,10 +262,6 @@ class Graph:
 
     def restore_poses(self):
         _check(lib().pgo_graph_restore_poses(self._h))
-
-    def init_comm(self, unique_id: bytes, rank: int, world: int):
-        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
-        _check(lib().pgo_graph_init_comm(self._h, buf, C.c_int(rank), C.c_int(world)))
 
     def evaluate(self, loss_type=LOSS_HUBER, loss_a=1.0, want_jacobians=True):
         cost = C.c_double()

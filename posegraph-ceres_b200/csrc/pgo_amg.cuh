@@ -1,0 +1,838 @@
+// pgo_amg.cuh -- PCG for the damped normal equations preconditioned by an aggregation multigrid V-cycle whose coarse
+// spaces are the rigid-body modes of pose patches (hierarchy: pgo_amg_host.hpp).  Solver type PGO_LINEAR_PCG_AMG: the
+// solver of mesh-like graphs (sphere, grids, dense random loops) and of every multi-GPU solve.  Included by pgo_b200.cu.
+//
+// Per LM step (amg_setup_numeric): patch centroids from the current poses, the Galerkin operators A_{l+1} = P^T A_l P
+// gathered block by block in a fixed order (no atomics: every rank computes bit-identical replicated levels), 6x6
+// block-Jacobi inverses, and the dense inverse of the coarsest system.
+// Per PCG iteration (Chronopoulos-Gear form, ONE reduction per iteration): V-cycle u = M^-1 r, halo exchange of u,
+// w = A u with the partial sums of r.u and w.u in its epilogue, all-reduce of the two scalars, vector update fused with
+// the first pre-smoothing sweep of the next V-cycle.
+//
+// Prolongator of fine node i in aggregate I (d = p_i - c_I, c_I the patch centroid, S the Jacobi column scaling):
+//   P_i = S_i^-1 [[I, X], [0, I]],  X = -2 [d]x      (a patch rotation delta moves p_i by 2 delta x d: the local rotation
+//   coordinates of EigenQuaternionParameterization are HALF rotation vectors applied on the left, i.e. in the world frame)
+// so P is never stored: restriction and prolongation cost one cross product per node.
+#pragma once
+
+#include "pgo_amg_host.hpp"
+
+namespace pgo {
+
+constexpr int kAmgThreads = 256;
+constexpr int kAmgDenseMaxNodes = 16;      // coarsest level: explicit dense inverse in the shared memory of one CTA
+
+struct AmgLevelDev {
+  bool replicated = false;
+  int n_own = 0, n_halo = 0;
+  // operator of the stored rows (panel layout, like the graph's Hessian); level 0 aliases the graph's arrays
+  double* Adiag = nullptr;
+  double* Aoff = nullptr;
+  int* row_ptr = nullptr;
+  int* col_idx = nullptr;
+  long long nnz = 0;
+  double* Dinv = nullptr;                  // [n_own][36] row-major inverses of the diagonal blocks (level 0: Minv)
+  double *r = nullptr, *x = nullptr, *y = nullptr;   // [n_own + n_halo][6]
+  double* pos = nullptr;                   // [n_own + n_halo][pos_stride] (level 0: the pose array)
+  int pos_stride = 3;
+  // coarsening towards the next level
+  int* agg = nullptr;
+  int c_row0 = 0, c_row1 = 0, c_slot0 = 0, n_cblk = 0;
+  int *mem_ptr = nullptr, *mem_idx = nullptr, *gal_ptr = nullptr, *gal_row = nullptr, *gal_slot = nullptr;
+  // exchange plans (host copies drive the NCCL calls)
+  std::vector<int> nbr, send_ptr, recv_ptr, gather_off, gather_slot_off;
+  int* send_idx = nullptr;
+};
+
+struct Amg {
+  int num_levels = 0;
+  std::vector<AmgLevelDev> lv;
+  double* dense_inv = nullptr;             // [6 n][6 n] of the coarsest level (n <= kAmgDenseMaxNodes), else nullptr
+  double omega = 0.7;
+  int nu = 1;
+  int coarse_sweeps = 4;
+  PcgMultiState* state = nullptr;
+  PcgMultiState* state_h = nullptr;        // pinned, two slots
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double* part = nullptr;                  // per-CTA partial sums
+  int part_cap = 0;
+  double* red = nullptr;                   // [8] reduced scalars (all-reduced across ranks)
+  long long blocks_all_levels = 0;
+  long long comm_bytes_per_iteration = 0;  // payload this rank sends per PCG iteration (halo + gathers + scalars)
+  int comm_calls_per_iteration = 0;
+};
+
+// --------------------------------------------------------------------------------------------
+// kernels
+// --------------------------------------------------------------------------------------------
+// B(k, r) of the mode matrix [[I, X], [0, I]], X = -2 [d]x
+__device__ __forceinline__ double amg_mode(const double* d, int k, int r) {
+  if (k == r) return 1.0;
+  if (k < 3 && r >= 3) {
+    const int c = r - 3;
+    // X = [[0, 2dz, -2dy], [-2dz, 0, 2dx], [2dy, -2dx, 0]]
+    if (k == 0) return c == 1 ? 2.0 * d[2] : (c == 2 ? -2.0 * d[1] : 0.0);
+    if (k == 1) return c == 0 ? -2.0 * d[2] : (c == 2 ? 2.0 * d[0] : 0.0);
+    return c == 0 ? 2.0 * d[1] : (c == 1 ? -2.0 * d[0] : 0.0);
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ void amg_delta(const double* pos, int stride, int i, const double* cpos, int I, double* d) {
+  d[0] = pos[(size_t)stride * i] - cpos[3 * (size_t)I];
+  d[1] = pos[(size_t)stride * i + 1] - cpos[3 * (size_t)I + 1];
+  d[2] = pos[(size_t)stride * i + 2] - cpos[3 * (size_t)I + 2];
+}
+
+// centroids of the computed coarse rows
+__global__ void amg_centroid_kernel(int ncomp, int c_row0, const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx,
+                                    const double* __restrict__ pos, int stride, double* __restrict__ cpos) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncomp) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const int m0 = mem_ptr[k], m1 = mem_ptr[k + 1];
+  for (int m = m0; m < m1; ++m) {
+    const int i = mem_idx[m];
+    s0 += pos[(size_t)stride * i]; s1 += pos[(size_t)stride * i + 1]; s2 += pos[(size_t)stride * i + 2];
+  }
+  const double inv = 1.0 / (double)max(m1 - m0, 1);
+  double* o = cpos + 3 * (size_t)(c_row0 + k);
+  o[0] = s0 * inv; o[1] = s1 * inv; o[2] = s2 * inv;
+}
+
+struct GalerkinParams {
+  int n_cblk, ncomp, c_row0, c_slot0;
+  const int *gal_ptr, *gal_row, *gal_slot;
+  const double *Adiag, *Aoff;
+  const int* col_idx;
+  const double* dlm;        // level 0: LM diagonal added to the diagonal blocks; else nullptr
+  const double* scale;      // level 0: Jacobi column scaling [n_loc][6]; else nullptr (identity)
+  const int* agg;
+  const double* pos; int pos_stride;
+  const double* cpos;
+  double *Cdiag, *Coff;
+};
+
+// One thread per element (r, c) of a coarse block: Z(r,c) = sum over the fine blocks of the gather list of
+// sum_{k,m} P_i(k,r) A(k,m) P_j(m,c), summed in list order (deterministic).
+__global__ void __launch_bounds__(288) amg_galerkin_kernel(const GalerkinParams P) {
+  const int cb = blockIdx.x * 8 + threadIdx.x / 36;
+  if (cb >= P.n_cblk) return;
+  const int e = threadIdx.x % 36, r = e / 6, c = e - r * 6;
+  double acc = 0.0;
+  const int q0 = P.gal_ptr[cb], q1 = P.gal_ptr[cb + 1];
+  for (int q = q0; q < q1; ++q) {
+    const int i = P.gal_row[q], p = P.gal_slot[q];
+    const int j = p < 0 ? i : P.col_idx[p];
+    const double* A = p < 0 ? P.Adiag + 36 * (size_t)i : P.Aoff + 36 * (size_t)p;
+    double di[3], dj[3];
+    amg_delta(P.pos, P.pos_stride, i, P.cpos, P.agg[i], di);
+    amg_delta(P.pos, P.pos_stride, j, P.cpos, P.agg[j], dj);
+    // rows k of A that reach coarse row r: k = r, and k = 0..2 when r >= 3 (through X_i); likewise columns m for c
+    double t = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = kk == 0 ? r : kk - 1;
+      if (kk > 0 && r < 3) continue;
+      double bi = amg_mode(di, k, r);
+      if (P.scale) { const double s = P.scale[6 * (size_t)i + k]; bi = s > 0.0 ? bi / s : 0.0; }
+      if (bi == 0.0) continue;
+      double u = 0.0;
+#pragma unroll
+      for (int mm = 0; mm < 4; ++mm) {
+        const int m = mm == 0 ? c : mm - 1;
+        if (mm > 0 && c < 3) continue;
+        double bj = amg_mode(dj, m, c);
+        if (P.scale) { const double s = P.scale[6 * (size_t)j + m]; bj = s > 0.0 ? bj / s : 0.0; }
+        if (bj == 0.0) continue;
+        double a = A[pidx(k, m)];
+        if (p < 0 && P.dlm && k == m) a += P.dlm[6 * (size_t)i + k];
+        u = fma(a, bj, u);
+      }
+      t = fma(bi, u, t);
+    }
+    acc += t;
+  }
+  double* out = cb < P.ncomp ? P.Cdiag + 36 * (size_t)(P.c_row0 + cb) : P.Coff + 36 * (size_t)(P.c_slot0 + cb - P.ncomp);
+  out[pidx(r, c)] = acc;
+}
+
+// inverse of a symmetric positive definite 6x6 block by Cholesky; false when a pivot is not positive
+__device__ __forceinline__ bool spd6_inverse(double (&A)[6][6], double* out /* row-major 36 */) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < j) s -= A[j][k] * A[j][k];
+    if (!(s > 0.0)) { ok = false; s = 1.0; }
+    const double l = sqrt(s);
+    A[j][j] = l;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > j) {
+      double t = A[r][j];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k < j) t -= A[r][k] * A[j][k];
+      A[r][j] = t / l;
+    }
+  }
+  double Li[6][6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      if (r < c) { Li[r][c] = 0.0; continue; }
+      double t = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k >= c && k < r) t -= A[r][k] * Li[k][c];
+      Li[r][c] = t / A[r][r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k >= r && k >= c) t += Li[k][r] * Li[k][c];
+      out[r * 6 + c] = t;
+    }
+  return ok;
+}
+
+// block-Jacobi inverses of a coarse level
+__global__ void amg_block_inverse_kernel(int n, const double* __restrict__ Adiag, double* __restrict__ Dinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double A[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[r][c] = Adiag[36 * (size_t)i + pidx(r, c)];
+  double inv[36];
+  const bool ok = spd6_inverse(A, inv);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) Dinv[36 * (size_t)i + k] = ok ? inv[k] : 0.0;
+}
+
+// Dense inverse of the coarsest operator (n <= kAmgDenseMaxNodes nodes) by Gauss-Jordan in shared memory, one CTA.
+__global__ void __launch_bounds__(kAmgThreads) amg_dense_inverse_kernel(int n, const double* __restrict__ Adiag, const double* __restrict__ Aoff,
+                                                                        const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                                                        double* __restrict__ inv) {
+  extern __shared__ double M[];
+  const int m = 6 * n;
+  for (int k = threadIdx.x; k < m * m; k += blockDim.x) M[k] = 0.0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n * 36; t += blockDim.x) {
+    const int i = t / 36, e = t - i * 36, r = e / 6, c = e - r * 6;
+    M[(6 * i + r) * m + 6 * i + c] = Adiag[36 * (size_t)i + pidx(r, c)];
+  }
+  const int nnz = row_ptr[n];
+  for (int t = threadIdx.x; t < nnz * 36; t += blockDim.x) {
+    const int p = t / 36, e = t - p * 36, r = e / 6, c = e - r * 6;
+    // row of slot p
+    int i = 0;
+    while (row_ptr[i + 1] <= p) ++i;
+    M[(6 * i + r) * m + 6 * col_idx[p] + c] = Aoff[36 * (size_t)p + pidx(r, c)];
+  }
+  __syncthreads();
+  __shared__ double piv_s;
+  for (int k = 0; k < m; ++k) {
+    if (threadIdx.x == 0) { const double d = M[k * m + k]; piv_s = d != 0.0 ? 1.0 / d : 0.0; }
+    __syncthreads();
+    const double piv = piv_s;
+    // scale the pivot row (except the pivot)
+    for (int j = threadIdx.x; j < m; j += blockDim.x) if (j != k) M[k * m + j] *= piv;
+    __syncthreads();
+    for (int t = threadIdx.x; t < m * m; t += blockDim.x) {
+      const int i = t / m, j = t - i * m;
+      if (i != k && j != k) M[t] -= M[i * m + k] * M[k * m + j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      if (i != k) M[i * m + k] = -M[i * m + k] * piv;
+      else M[k * m + k] = piv;
+    }
+    __syncthreads();
+  }
+  for (int k = threadIdx.x; k < m * m; k += blockDim.x) inv[k] = M[k];
+}
+
+// x = inv * r on the coarsest level (one CTA)
+__global__ void __launch_bounds__(kAmgThreads) amg_dense_solve_kernel(int m, const double* __restrict__ inv, const double* __restrict__ r,
+                                                                      double* __restrict__ x, const int* skip) {
+  if (skip && *skip) return;
+  __shared__ double rs[6 * kAmgDenseMaxNodes];
+  for (int k = threadIdx.x; k < m; k += blockDim.x) rs[k] = r[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < m; ++k) s = fma(inv[i * m + k], rs[k], s);
+    x[i] = s;
+  }
+}
+
+// six lanes per block row, five rows per warp (the lane layout of bsr6_row)
+struct RowLane {
+  int i, c, g0;
+  bool on;
+};
+__device__ __forceinline__ RowLane amg_row_lane(int n) {
+  const int lane = threadIdx.x & 31, grp = lane / 6;
+  RowLane L;
+  L.c = lane - grp * 6;
+  L.g0 = grp * 6;
+  L.i = (blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5)) * kRowsPerWarp + grp;
+  L.on = grp < kRowsPerWarp && L.i < n;
+  return L;
+}
+// row c of a row-major 6x6 block times the 6-vector spread over the lanes of the group
+__device__ __forceinline__ double amg_block_row_dot(const double* blk, int c, int g0, double v) {
+  const unsigned m = 0xffffffffu;
+  const double v0 = __shfl_sync(m, v, g0), v1 = __shfl_sync(m, v, g0 + 1), v2 = __shfl_sync(m, v, g0 + 2);
+  const double v3 = __shfl_sync(m, v, g0 + 3), v4 = __shfl_sync(m, v, g0 + 4), v5 = __shfl_sync(m, v, g0 + 5);
+  if (blk == nullptr) return 0.0;
+  const double2* b = reinterpret_cast<const double2*>(blk + 6 * c);
+  const double2 m0 = __ldg(b), m1 = __ldg(b + 1), m2 = __ldg(b + 2);
+  return m0.x * v0 + m0.y * v1 + m1.x * v2 + m1.y * v3 + m2.x * v4 + m2.y * v5;
+}
+
+// x = omega * Dinv r   (first smoothing sweep from a zero guess)
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth0_kernel(int n, const double* __restrict__ Dinv, const double* __restrict__ r,
+                                                                  double omega, double* __restrict__ x, const int* skip) {
+  if (skip && *skip) return;
+  const RowLane L = amg_row_lane(n);
+  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
+  const double rv = L.on ? r[q] : 0.0;
+  const double t = amg_block_row_dot(L.on ? Dinv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
+  if (L.on) x[q] = omega * t;
+}
+
+// y = x + omega * Dinv (r - A x)
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ Dinv,
+                                                                 const double* __restrict__ r, const double* __restrict__ x, double omega,
+                                                                 double* __restrict__ y, const int* skip) {
+  if (skip && *skip) return;
+  const RowLane L = amg_row_lane(A.n);
+  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
+  double t = 0.0;
+  if (L.on) t = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, L.i, L.c);
+  const double z = amg_block_row_dot(L.on ? Dinv + 36 * (size_t)L.i : nullptr, L.c, L.g0, t);
+  if (L.on) y[q] = x[q] + omega * z;
+}
+
+// rc_I = sum_{i in I} P_i^T (r_i - (A x)_i) for the computed coarse rows: six lanes per coarse row walk its members.
+__global__ void __launch_bounds__(kAmgThreads) amg_residual_restrict_kernel(const BsrView A, const double* __restrict__ d,
+                                                                            const double* __restrict__ r, const double* __restrict__ x,
+                                                                            int ncomp, int c_row0, const int* __restrict__ mem_ptr,
+                                                                            const int* __restrict__ mem_idx, const double* __restrict__ pos,
+                                                                            int pos_stride, const double* __restrict__ cpos,
+                                                                            const double* __restrict__ scale, double* __restrict__ rc,
+                                                                            const int* skip) {
+  if (skip && *skip) return;
+  const RowLane L = amg_row_lane(ncomp);      // L.i = computed coarse row (relative)
+  const unsigned full = 0xffffffffu;
+  int m0 = 0, m1 = 0;
+  if (L.on) { m0 = mem_ptr[L.i]; m1 = mem_ptr[L.i + 1]; }
+  int cnt = m1 - m0;
+  int maxcnt = cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(full, maxcnt, o));
+  const int I = c_row0 + (L.on ? L.i : 0);
+  double acc = 0.0;
+  for (int k = 0; k < maxcnt; ++k) {
+    const bool on = L.on && k < cnt;
+    double u = 0.0;
+    double dd[3] = {0.0, 0.0, 0.0};
+    if (on) {
+      const int i = mem_idx[m0 + k];
+      const double t = r[6 * (size_t)i + L.c] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, L.c);
+      double s = 1.0;
+      if (scale) { const double sv = scale[6 * (size_t)i + L.c]; s = sv > 0.0 ? 1.0 / sv : 0.0; }
+      u = s * t;
+      amg_delta(pos, pos_stride, i, cpos, I, dd);
+    }
+    const double u0 = __shfl_sync(full, u, L.g0), u1 = __shfl_sync(full, u, L.g0 + 1), u2 = __shfl_sync(full, u, L.g0 + 2);
+    if (on) {
+      // (P^T t)[c] = u_c, plus for the rotation rows X^T u_p = 2 d x u_p
+      double v = u;
+      if (L.c == 3) v += 2.0 * (dd[1] * u2 - dd[2] * u1);
+      else if (L.c == 4) v += 2.0 * (dd[2] * u0 - dd[0] * u2);
+      else if (L.c == 5) v += 2.0 * (dd[0] * u1 - dd[1] * u0);
+      acc += v;
+    }
+  }
+  if (L.on) rc[6 * (size_t)I + L.c] = acc;
+}
+
+// x_i += P_i e_{agg(i)} over the stored rows
+__global__ void __launch_bounds__(kAmgThreads) amg_prolong_kernel(int n, const int* __restrict__ agg, const double* __restrict__ pos,
+                                                                  int pos_stride, const double* __restrict__ cpos,
+                                                                  const double* __restrict__ scale, const double* __restrict__ ec,
+                                                                  double* __restrict__ x, const int* skip) {
+  if (skip && *skip) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t / 6, c = t - i * 6;
+  if (i >= n) return;
+  const int I = agg[i];
+  if (I < 0) return;
+  const double* e = ec + 6 * (size_t)I;
+  double v = e[c];
+  if (c < 3) {
+    double dd[3];
+    amg_delta(pos, pos_stride, i, cpos, I, dd);
+    // X e_r = -2 d x e_r
+    const double e3 = e[3], e4 = e[4], e5 = e[5];
+    if (c == 0) v -= 2.0 * (dd[1] * e5 - dd[2] * e4);
+    else if (c == 1) v -= 2.0 * (dd[2] * e3 - dd[0] * e5);
+    else v -= 2.0 * (dd[0] * e4 - dd[1] * e3);
+  }
+  if (scale) { const double sv = scale[6 * (size_t)i + c]; v = sv > 0.0 ? v / sv : 0.0; }
+  x[6 * (size_t)i + c] += v;
+}
+
+// ---- PCG pieces (Chronopoulos-Gear with a general preconditioner) ----
+// init: x = 0, r = b, p = s = 0, x0 = omega Minv r (first pre-smoothing sweep of the first V-cycle)
+__global__ void __launch_bounds__(kAmgThreads) amg_pcg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ Minv,
+                                                                   double omega, double* x, double* r, double* p, double* s, double* x0) {
+  const RowLane L = amg_row_lane(n);
+  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
+  const double rv = L.on ? b[q] : 0.0;
+  const double t = amg_block_row_dot(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
+  if (L.on) { x[q] = 0.0; r[q] = rv; p[q] = 0.0; s[q] = 0.0; x0[q] = omega * t; }
+}
+
+// w = (A + D) u over the owned rows; per-CTA partials of w.u and r.u in a fixed order
+__global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ u,
+                                                                    const double* __restrict__ r, double* __restrict__ w,
+                                                                    double* __restrict__ part /* [2][gridDim.x] */, const int* skip) {
+  __shared__ double red0[kAmgThreads / 32], red1[kAmgThreads / 32];
+  const bool idle = skip && *skip;
+  double a0 = 0.0, a1 = 0.0;
+  if (!idle) {
+    const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6;
+    const int wpc = kAmgThreads / 32;
+    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
+    for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
+      const int i = base + grp;
+      if (grp < kRowsPerWarp && i < A.n) {
+        const size_t q = 6 * (size_t)i + c;
+        const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, u, d, i, c);
+        w[q] = v;
+        const double uv = __ldg(u + q);
+        a0 = fma(v, uv, a0);
+        a1 = fma(__ldg(r + q), uv, a1);
+      }
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5] = a0; red1[threadIdx.x >> 5] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAmgThreads / 32; ++k) { t0 += red0[k]; t1 += red1[k]; }
+    part[blockIdx.x] = t0;
+    part[gridDim.x + blockIdx.x] = t1;
+  }
+}
+
+// sums nq quantities of per-CTA partials (part[q * nparts + k]) into out[q] in a fixed order (one CTA)
+__global__ void __launch_bounds__(kAmgThreads) amg_reduce_kernel(const double* __restrict__ part, int nparts, int nq, double* __restrict__ out) {
+  __shared__ double red[kAmgThreads / 32];
+  for (int q = 0; q < nq; ++q) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += kAmgThreads) t += part[(size_t)q * nparts + k];
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < kAmgThreads / 32; ++k) s += red[k];
+      out[q] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// scalar step: red[0] = w.u (delta), red[1] = r.u (gamma)
+__global__ void amg_pcg_scalar_kernel(PcgMultiState* st, const double* __restrict__ red, int max_iterations, double tol) {
+  if (threadIdx.x != 0 || st->done) return;
+  const double delta = red[0], gamma = red[1];
+  if (st->iter == 0) { st->gamma0 = gamma; st->gamma = gamma; }
+  else { st->gamma_old = st->gamma; st->gamma = gamma; }
+  if (!(st->gamma0 > 0.0)) { st->flag = 0; st->done = 1; return; }
+  if (st->iter > 0 && gamma <= tol * tol * st->gamma0) { st->flag = 0; st->done = 1; return; }
+  if (st->iter >= max_iterations) { st->flag = 1; st->done = 1; return; }
+  st->delta = delta;
+  if (st->iter == 0) { st->beta = 0.0; st->alpha = gamma / delta; }
+  else { st->beta = gamma / st->gamma_old; st->alpha = gamma / (delta - st->beta * gamma / st->alpha); }
+  if (!(st->alpha > 0.0) || !isfinite(st->alpha)) { st->flag = 2; st->done = 1; return; }
+  st->iter++;
+}
+
+// p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, x0 = omega Minv r
+__global__ void __launch_bounds__(kAmgThreads) amg_pcg_update_kernel(int n, const double* __restrict__ Minv, const double* __restrict__ u,
+                                                                     const double* __restrict__ w, double omega, double* x, double* r,
+                                                                     double* p, double* s, double* x0, const PcgMultiState* st) {
+  if (st->done) return;
+  const RowLane L = amg_row_lane(n);
+  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
+  double rv = 0.0;
+  if (L.on) {
+    const double alpha = st->alpha, beta = st->beta;
+    const double pv = u[q] + beta * p[q];
+    const double sv = w[q] + beta * s[q];
+    p[q] = pv; s[q] = sv;
+    x[q] += alpha * pv;
+    rv = r[q] - alpha * sv;
+    r[q] = rv;
+  }
+  const double t = amg_block_row_dot(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
+  if (L.on) x0[q] = omega * t;
+}
+
+// epilogue partials over the owned rows: x.b, x.w (w = A x), x.D x
+__global__ void __launch_bounds__(kAmgThreads) amg_final_kernel(int n6, const double* __restrict__ x, const double* __restrict__ b,
+                                                                const double* __restrict__ w, const double* __restrict__ d,
+                                                                double* __restrict__ part /* [3][gridDim.x] */) {
+  __shared__ double red[3][kAmgThreads / 32];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n6; k += gridDim.x * blockDim.x) {
+    const double xv = x[k];
+    a0 = fma(xv, b[k], a0); a1 = fma(xv, w[k], a1); a2 = fma(xv * xv, d[k], a2);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; red[2][threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAmgThreads / 32; ++k) t += red[threadIdx.x][k];
+    part[threadIdx.x * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void amg_final_store_kernel(const double* __restrict__ red, const PcgMultiState* st, DeviceScalars* sc) {
+  if (threadIdx.x != 0) return;
+  sc->xtb = red[0]; sc->xtAx = red[1]; sc->xtDx = red[2];
+  sc->pcg_gamma0 = st->gamma0; sc->pcg_gamma = st->gamma; sc->pcg_iterations = st->iter; sc->pcg_flag = st->flag;
+}
+
+}  // namespace pgo
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static void amg_destroy(pgo::Amg* M, int device) {
+  if (!M) return;
+  pgo::pool_pinned_release(device, M->state_h);
+  pgo::pool_event_release(device, M->ev[0]);
+  pgo::pool_event_release(device, M->ev[1]);
+  delete M;   // device blocks were borrowed through dev_alloc and go back with the graph's
+}
+
+template <typename Tp>
+static int amg_upload(pgo_graph* g, Tp** dst, const std::vector<Tp>& src) {
+  PGO_TRY(dev_alloc(g, dst, src.size()));
+  if (!src.empty()) CUDA_TRY(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice, g->stream));
+  return PGO_OK;
+}
+
+static int amg_rows_grid(int n) { return std::max(1, (n + (pgo::kAmgThreads / 32) * pgo::kRowsPerWarp - 1) / ((pgo::kAmgThreads / 32) * pgo::kRowsPerWarp)); }
+
+// Halo exchange of a per-node vector on a distributed level (see halo_exchange in pgo_b200.cu).
+static int amg_exchange(pgo_graph* g, pgo::Amg* M, const pgo::AmgLevelDev& L, double* v, int width, int stride, const int* skip) {
+  (void)M;
+  if (g->world <= 1 || L.replicated || L.nbr.empty()) return PGO_OK;
+  if (stride != width) return set_error(PGO_ERR_INVALID_ARGUMENT, "amg_exchange: strided vectors are not supported");
+  return halo_exchange(g, L.nbr, L.send_ptr, L.recv_ptr, L.send_idx, L.n_own, v, width, skip);
+}
+
+// All-gather of rank-owned ranges of a replicated array (`unit` doubles per item, item ranges off[r]..off[r+1]).
+static int amg_gather(pgo_graph* g, double* v, const std::vector<int>& off, int unit) {
+  if (g->world <= 1 || off.empty()) return PGO_OK;
+  NCCL_TRY(ncclGroupStart());
+  for (int r = 0; r < g->world; ++r) {
+    const size_t cnt = (size_t)(off[r + 1] - off[r]) * unit;
+    if (cnt == 0) continue;
+    double* p = v + (size_t)off[r] * unit;
+    NCCL_TRY(ncclBroadcast(p, p, cnt, ncclDouble, r, g->comm, g->stream));
+  }
+  NCCL_TRY(ncclGroupEnd());
+  g->comm_calls++;
+  g->comm_bytes += (long long)(off[g->rank + 1] - off[g->rank]) * unit * 8;
+  return PGO_OK;
+}
+
+static int amg_allreduce(pgo_graph* g, double* buf, int count) { return allreduce_sum(g, buf, (size_t)count); }
+
+// Build the hierarchy for this graph (host analysis + uploads).  pos0: [N_global][3] setup-time positions.
+static int amg_create(pgo_graph* g, pgo::Amg** out) {
+  using namespace pgo;
+  Amg* M = new Amg();
+  *out = M;
+  AmgHostParams prm;
+  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
+  if (const char* e = getenv("PGO_AMG_REPLICATE_MAX")) prm.replicate_max = atoi(e);
+  if (const char* e = getenv("PGO_AMG_OMEGA")) M->omega = atof(e);
+  if (const char* e = getenv("PGO_AMG_NU")) M->nu = std::max(1, atoi(e));
+  if (const char* e = getenv("PGO_AMG_COARSE_SWEEPS")) M->coarse_sweeps = std::max(1, atoi(e));
+  std::vector<AmgGlobalLevel> G;
+  std::vector<AmgLocalLevel> Lh;
+  const double t0 = wall_s();
+  PGO_TRY(graph_amg_hierarchy(g, prm, &G, &Lh));
+  const double t1 = wall_s();
+  const int nl = (int)Lh.size();
+  M->num_levels = nl;
+  M->lv.assign(nl, AmgLevelDev());
+  size_t max_send = 0;
+  for (int l = 0; l < nl; ++l) {
+    const AmgLocalLevel& H = Lh[l];
+    AmgLevelDev& D = M->lv[l];
+    D.replicated = H.replicated;
+    D.n_own = H.n_own; D.n_halo = H.n_halo;
+    const size_t n_loc = (size_t)H.n_own + H.n_halo;
+    if (l == 0) {
+      D.row_ptr = g->row_ptr; D.col_idx = g->col_idx; D.nnz = g->nnz_off;
+      D.pos_stride = 8;
+    } else {
+      D.nnz = (long long)H.col_idx.size();
+      PGO_TRY(amg_upload(g, &D.row_ptr, H.row_ptr));
+      PGO_TRY(amg_upload(g, &D.col_idx, H.col_idx));
+      PGO_TRY(dev_alloc(g, &D.Adiag, (size_t)H.n_own * 36));
+      PGO_TRY(dev_alloc(g, &D.Aoff, (size_t)D.nnz * 36));
+      PGO_TRY(dev_alloc(g, &D.Dinv, (size_t)H.n_own * 36));
+      PGO_TRY(dev_alloc(g, &D.r, n_loc * 6));
+      PGO_TRY(dev_alloc(g, &D.pos, n_loc * 3));
+      D.pos_stride = 3;
+    }
+    PGO_TRY(dev_alloc(g, &D.x, n_loc * 6));
+    PGO_TRY(dev_alloc(g, &D.y, n_loc * 6));
+    CUDA_TRY(cudaMemsetAsync(D.x, 0, std::max<size_t>(n_loc * 6, 1) * sizeof(double), g->stream));
+    CUDA_TRY(cudaMemsetAsync(D.y, 0, std::max<size_t>(n_loc * 6, 1) * sizeof(double), g->stream));
+    if (l + 1 < nl) {
+      PGO_TRY(amg_upload(g, &D.agg, H.agg));
+      PGO_TRY(amg_upload(g, &D.mem_ptr, H.mem_ptr));
+      PGO_TRY(amg_upload(g, &D.mem_idx, H.mem_idx));
+      PGO_TRY(amg_upload(g, &D.gal_ptr, H.gal_ptr));
+      PGO_TRY(amg_upload(g, &D.gal_row, H.gal_row));
+      PGO_TRY(amg_upload(g, &D.gal_slot, H.gal_slot));
+      D.c_row0 = H.c_row0; D.c_row1 = H.c_row1;
+      D.c_slot0 = Lh[l + 1].row_ptr[H.c_row0];
+      D.n_cblk = (int)H.gal_ptr.size() - 1;
+    }
+    D.nbr = H.nbr; D.send_ptr = H.send_ptr; D.recv_ptr = H.recv_ptr;
+    D.gather_off = H.gather_off; D.gather_slot_off = H.gather_slot_off;
+    if (l == 0) D.send_idx = g->send_idx;
+    else if (!H.send_idx.empty()) PGO_TRY(amg_upload(g, &D.send_idx, H.send_idx));
+    if (l > 0) max_send = std::max(max_send, H.send_idx.size());
+    M->blocks_all_levels += (long long)H.n_own + (l == 0 ? g->nnz_off : (long long)H.col_idx.size());
+  }
+  // the graph's send buffer (level-0 boundary x 8 doubles) serves every level: a coarse boundary node holds at least one
+  // fine boundary node, so the lists only shrink -- checked, not assumed
+  if (max_send > g->send_idx_h.size()) return set_error(PGO_ERR_NUMERICAL, "amg: a coarse level sends more nodes than level 0");
+  const AmgLevelDev& last = M->lv[nl - 1];
+  if (nl > 1 && (g->world == 1 || last.replicated) && last.n_own <= kAmgDenseMaxNodes)
+    PGO_TRY(dev_alloc(g, &M->dense_inv, (size_t)36 * last.n_own * last.n_own));
+  PGO_TRY(dev_alloc(g, &M->state, 1));
+  CUDA_TRY(pool_pinned(g->device, reinterpret_cast<void**>(&M->state_h)));
+  static_assert(2 * sizeof(PcgMultiState) <= kPinnedBytes, "pinned PCG state slots");
+  CUDA_TRY(pool_event(g->device, &M->ev[0]));
+  CUDA_TRY(pool_event(g->device, &M->ev[1]));
+  M->part_cap = 3 * std::max(8 * g->num_sms, 1);
+  PGO_TRY(dev_alloc(g, &M->part, (size_t)M->part_cap));
+  PGO_TRY(dev_alloc(g, &M->red, 8));
+  // communication per PCG iteration (payload sent by this rank): exchanges of the V-cycle + the SpMV + gathers + scalars
+  if (g->world > 1) {
+    long long bytes = 16; int calls = 1;
+    for (int l = 0; l < nl; ++l) {
+      const AmgLevelDev& D = M->lv[l];
+      if (!D.nbr.empty()) {
+        const int per_cycle = (l + 1 < nl ? 2 * M->nu : M->coarse_sweeps - 1) + (l == 0 ? 1 : 0);
+        bytes += (long long)per_cycle * D.send_ptr.back() * 48; calls += per_cycle;
+      }
+      if (!D.gather_off.empty()) { bytes += (long long)(D.gather_off[g->rank + 1] - D.gather_off[g->rank]) * 48; calls += 1; }
+    }
+    M->comm_bytes_per_iteration = bytes; M->comm_calls_per_iteration = calls;
+  }
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (getenv("PGO_PROFILE_HOST")) {
+    fprintf(stderr, "[pgo amg] rank %d: hierarchy %.1f ms, upload %.1f ms, levels:", g->rank, 1e3 * (t1 - t0), 1e3 * (wall_s() - t1));
+    for (int l = 0; l < nl; ++l) fprintf(stderr, " %d%s(+%d halo, %lld blk)", M->lv[l].n_own, M->lv[l].replicated ? "R" : "", M->lv[l].n_halo, M->lv[l].nnz);
+    fprintf(stderr, "%s\n", M->dense_inv ? " dense coarsest" : " smoothed coarsest");
+  }
+  return PGO_OK;
+}
+
+static pgo::BsrView amg_view(const pgo::AmgLevelDev& D) {
+  pgo::BsrView A;
+  A.n = D.n_own; A.Hdiag = D.Adiag; A.Hoff = D.Aoff; A.row_ptr = D.row_ptr; A.col_idx = D.col_idx;
+  return A;
+}
+
+// Numeric setup for the current H, D and poses: centroids, Galerkin operators, block inverses, coarsest inverse.
+static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
+  using namespace pgo;
+  const int nl = M->num_levels;
+  AmgLevelDev& L0 = M->lv[0];
+  L0.Adiag = g->Hdiag; L0.Aoff = g->Hoff; L0.Dinv = g->Minv; L0.pos = g->poses; L0.r = g->vr;
+  for (int l = 0; l + 1 < nl; ++l) {
+    AmgLevelDev& F = M->lv[l];
+    AmgLevelDev& C = M->lv[l + 1];
+    const int ncomp = F.c_row1 - F.c_row0;
+    if (ncomp > 0) {
+      amg_centroid_kernel<<<(ncomp + 255) / 256, 256, 0, g->stream>>>(ncomp, F.c_row0, F.mem_ptr, F.mem_idx, F.pos, F.pos_stride, C.pos);
+      g->launches++;
+    }
+    if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.pos, C.gather_off, 3));
+    else PGO_TRY(amg_exchange(g, M, C, C.pos, 3, 3, nullptr));
+    if (F.n_cblk > 0) {
+      GalerkinParams P;
+      P.n_cblk = F.n_cblk; P.ncomp = ncomp; P.c_row0 = F.c_row0; P.c_slot0 = F.c_slot0;
+      P.gal_ptr = F.gal_ptr; P.gal_row = F.gal_row; P.gal_slot = F.gal_slot;
+      P.Adiag = F.Adiag; P.Aoff = F.Aoff; P.col_idx = F.col_idx;
+      P.dlm = l == 0 ? g->dlm : nullptr; P.scale = l == 0 ? g->scale : nullptr;
+      P.agg = F.agg; P.pos = F.pos; P.pos_stride = F.pos_stride; P.cpos = C.pos;
+      P.Cdiag = C.Adiag; P.Coff = C.Aoff;
+      amg_galerkin_kernel<<<(F.n_cblk + 7) / 8, 288, 0, g->stream>>>(P);
+      g->launches++;
+    }
+    if (!C.gather_off.empty()) {
+      PGO_TRY(amg_gather(g, C.Adiag, C.gather_off, 36));
+      PGO_TRY(amg_gather(g, C.Aoff, C.gather_slot_off, 36));
+    }
+    if (l + 2 == nl && M->dense_inv) {
+      const int m = 6 * C.n_own;
+      const int smem = m * m * (int)sizeof(double);
+      int have = 0;
+      if (!pool_cache_get(g->device, kCacheAmgDenseAttr, &have)) {
+        CUDA_TRY(cudaFuncSetAttribute(amg_dense_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      36 * kAmgDenseMaxNodes * kAmgDenseMaxNodes * (int)sizeof(double)));
+        pool_cache_set(g->device, kCacheAmgDenseAttr, 1);
+      }
+      amg_dense_inverse_kernel<<<1, kAmgThreads, smem, g->stream>>>(C.n_own, C.Adiag, C.Aoff, C.row_ptr, C.col_idx, M->dense_inv);
+    } else {
+      amg_block_inverse_kernel<<<(C.n_own + 127) / 128, 128, 0, g->stream>>>(C.n_own, C.Adiag, C.Dinv);
+    }
+    g->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PGO_OK;
+}
+
+// One smoothing sweep y = x + omega Dinv (r - A x) on level l (halo of x exchanged first).
+static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, const int* skip) {
+  using namespace pgo;
+  const AmgLevelDev& D = M->lv[l];
+  PGO_TRY(amg_exchange(g, M, D, x, 6, 6, skip));
+  amg_smooth_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  g->launches++;
+  return PGO_OK;
+}
+
+// u = M^-1 r: V(nu, nu) cycle.  Level 0: r = the CG residual (g->vr) and lv[0].x already holds omega Minv r.
+// The result is a level-0 vector (owned rows valid); *out points at it.
+static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
+  using namespace pgo;
+  const int nl = M->num_levels;
+  const int* skip = &M->state->done;
+  std::vector<double*> cur(nl), oth(nl);
+  for (int l = 0; l < nl; ++l) { cur[l] = M->lv[l].x; oth[l] = M->lv[l].y; }
+  for (int l = 0; l + 1 < nl; ++l) {
+    const AmgLevelDev& D = M->lv[l];
+    const AmgLevelDev& C = M->lv[l + 1];
+    if (l > 0) {
+      amg_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, D.r, M->omega, cur[l], skip);
+      g->launches++;
+    }
+    for (int s = 1; s < M->nu; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
+    PGO_TRY(amg_exchange(g, M, D, cur[l], 6, 6, skip));
+    const int ncomp = D.c_row1 - D.c_row0;
+    if (ncomp > 0) {
+      amg_residual_restrict_kernel<<<amg_rows_grid(ncomp), kAmgThreads, 0, g->stream>>>(
+          amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
+          l == 0 ? g->scale : nullptr, C.r, skip);
+      g->launches++;
+    }
+    if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.r, C.gather_off, 6));
+  }
+  {
+    const int l = nl - 1;
+    const AmgLevelDev& D = M->lv[l];
+    if (nl > 1 && M->dense_inv) {
+      amg_dense_solve_kernel<<<1, kAmgThreads, 0, g->stream>>>(6 * D.n_own, M->dense_inv, D.r, cur[l], skip);
+      g->launches++;
+    } else if (nl > 1) {
+      amg_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, D.r, M->omega, cur[l], skip);
+      g->launches++;
+      for (int s = 1; s < M->coarse_sweeps; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
+    }
+    // nl == 1: plain block-Jacobi, lv[0].x = omega Minv r is the result (omega only rescales the preconditioner)
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    const AmgLevelDev& D = M->lv[l];
+    const AmgLevelDev& C = M->lv[l + 1];
+    amg_prolong_kernel<<<(D.n_own * 6 + 255) / 256, 256, 0, g->stream>>>(D.n_own, D.agg, D.pos, D.pos_stride, C.pos, l == 0 ? g->scale : nullptr,
+                                                                         cur[l + 1], cur[l], skip);
+    g->launches++;
+    for (int s = 0; s < M->nu; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
+  }
+  *out = cur[0];
+  return PGO_OK;
+}
+
+// (H + diag(dlm)) x = b by AMG-preconditioned CG.  x -> g->vx; statistics -> g->scalars.  Stream-ordered; the host polls
+// the `done` flag one batch behind the GPU (kernels after convergence are no-ops), and every rank takes the same exit
+// decision because the flag derives from all-reduced, bit-identical scalars.
+static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double* b) {
+  using namespace pgo;
+  Amg* M = g->amg;
+  const int n = M->lv[0].n_own, n6 = 6 * n;
+  PGO_TRY(amg_setup_numeric(g, M));
+  PcgMultiState* st = M->state;
+  const int rows_grid = amg_rows_grid(n);
+  const int sp_ctas = std::max(1, std::min(rows_grid, std::min(8 * g->num_sms, M->part_cap / 3)));
+  const int dot_ctas = std::max(1, std::min((n6 + kAmgThreads - 1) / kAmgThreads, std::min(4 * g->num_sms, M->part_cap / 3)));
+  AmgLevelDev& L0 = M->lv[0];
+  CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
+  amg_pcg_init_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, g->Minv, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
+  g->launches++;
+  const int batch = n >= 100000 ? 4 : 8;
+  int enqueued = 0;          // batches
+  const int max_batches = (o->pcg_max_iterations + batch - 1) / batch + 2;
+  bool finished = false;
+  while (!finished) {
+    for (int k = 0; k < batch; ++k) {
+      double* u = nullptr;
+      PGO_TRY(amg_vcycle(g, M, &u));
+      PGO_TRY(amg_exchange(g, M, L0, u, 6, 6, &st->done));
+      amg_spmv_dots_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
+      amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
+      PGO_TRY(amg_allreduce(g, M->red, 2));
+      amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
+      amg_pcg_update_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
+      g->launches += 4;
+    }
+    const int slot = enqueued & 1;
+    CUDA_TRY(cudaMemcpyAsync(M->state_h + slot, st, sizeof(PcgMultiState), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaEventRecord(M->ev[slot], g->stream));
+    ++enqueued;
+    if (enqueued >= 2) {
+      const int prev = (enqueued - 2) & 1;
+      CUDA_TRY(cudaEventSynchronize(M->ev[prev]));
+      if (M->state_h[prev].done) finished = true;
+    }
+    if (enqueued >= max_batches) finished = true;
+  }
+  // epilogue: w = A x for the model cost change
+  PGO_TRY(amg_exchange(g, M, L0, g->vx, 6, 6, nullptr));
+  spmv_kernel<false><<<sp_ctas, 256, 0, g->stream>>>(amg_view(L0), g->vx, g->dlm, g->vw, true);
+  amg_final_kernel<<<dot_ctas, kAmgThreads, 0, g->stream>>>(n6, g->vx, b, g->vw, g->dlm, M->part);
+  amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, dot_ctas, 3, M->red);
+  PGO_TRY(amg_allreduce(g, M->red, 3));
+  amg_final_store_kernel<<<1, 32, 0, g->stream>>>(M->red, st, g->scalars);
+  g->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return PGO_OK;
+}

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,9 @@
 
 #include "pgo_kernels.cuh"
 #include "pgo_pool.cuh"
+#include "pgo_amg_host.hpp"
+
+namespace pgo { struct PcgMultiState; struct Amg; }
 
 using namespace pgo;
 
@@ -56,17 +60,32 @@ static int set_error(int code, const char* fmt, ...) {
 #include "pgo_level_chol.cuh"
 #include "pgo_candidates.cuh"
 
+static void amg_destroy(pgo::Amg* M, int device);
 static double wall_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-
-namespace pgo { struct PcgMultiState; }
 
 struct pgo_graph {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
-  int N = 0, E = 0, T = 0;
+  int N = 0, E = 0, T = 0;          // LOCAL poses (owned + halo copies), local edges, edge tiles
+  int n_own = 0;                    // block rows / variables stored here (== N on one GPU); local ids [n_own, N) are halo poses
+  int N_global = 0, E_global = 0;   // the whole problem (== N, E on one GPU)
+  int g0 = 0;                       // global id of local pose 0
+  std::vector<int> part_off;        // [world + 1] contiguous pose ranges per rank
+  std::vector<int> halo_gid;        // [N - n_own] global ids of the halo poses, ascending
+  // level-0 halo exchange plan (multi-GPU): neighbours, what they need from here, where their values land
+  std::vector<int> nbr, send_ptr, recv_ptr, send_idx_h;
+  int* send_idx = nullptr;
+  double* halo_sendbuf = nullptr;
+  double* gather_buf = nullptr;     // [N_global][8] pose all-gather staging (multi-GPU get_poses)
+  // global structure kept for the multilevel hierarchy (host): pattern, variable flags, setup-time positions
+  std::vector<int> grow_ptr_h, gcol_idx_h;
+  std::vector<unsigned char> gactive_h;
+  std::vector<double> pos0_h;       // [N_global][3]
+  pgo::Amg* amg = nullptr;
+  long long comm_calls = 0, comm_bytes = 0;   // NCCL calls / payload bytes sent by this rank (multi-GPU)
   bool identity_info = true;
   bool has_dup_blocks = false;
   long long nnz_off = 0;
@@ -117,32 +136,40 @@ struct HostPattern {
   std::vector<int> half_slot;             // [2E]: slot of block (a,b) at 2e, of (b,a) at 2e+1; -1 = none; <= -2: -(slot)-2, shared by several edges
   bool has_dup = false;
 };
-static void build_pattern(int N, int E, const int* edge_ids, const unsigned char* pose_const, HostPattern* out) {
+static void build_pattern(int N, int E, const int* edge_ids, const unsigned char* pose_const, HostPattern* out, int n_own = -1) {
+  // n_own < N (multi-GPU slice): rows exist only for the owned poses [0, n_own); poses >= n_own are halo columns
+  if (n_own < 0) n_own = N;
   out->active.assign(N, 0);
   for (int e = 0; e < E; ++e) { out->active[edge_ids[2 * e]] = 1; out->active[edge_ids[2 * e + 1]] = 1; }
   if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) out->active[i] = 0;
   // bucket the half-edges (row -> col) by row with a counting sort, then order each (short) row by column
   struct Half { int col; int idx; };
-  std::vector<int> start(N + 1, 0);
+  std::vector<int> start(n_own + 1, 0);
   size_t n_half = 0;
   for (int e = 0; e < E; ++e) {
     const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-    if (out->active[a] && out->active[b]) { start[a + 1]++; start[b + 1]++; n_half += 2; }
+    if (out->active[a] && out->active[b]) {
+      if (a < n_own) { start[a + 1]++; ++n_half; }
+      if (b < n_own) { start[b + 1]++; ++n_half; }
+    }
   }
-  for (int i = 0; i < N; ++i) start[i + 1] += start[i];
+  for (int i = 0; i < n_own; ++i) start[i + 1] += start[i];
   std::vector<Half> halves(n_half);
   {
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int e = 0; e < E; ++e) {
       const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
-      if (out->active[a] && out->active[b]) { halves[fill[a]++] = {b, 2 * e}; halves[fill[b]++] = {a, 2 * e + 1}; }
+      if (out->active[a] && out->active[b]) {
+        if (a < n_own) halves[fill[a]++] = {b, 2 * e};
+        if (b < n_own) halves[fill[b]++] = {a, 2 * e + 1};
+      }
     }
   }
   out->half_slot.assign(2 * (size_t)E, -1);
-  out->row_ptr.assign(N + 1, 0);
+  out->row_ptr.assign(n_own + 1, 0);
   out->col_idx.clear();
   out->col_idx.reserve(n_half);
-  for (int i = 0; i < N; ++i) {
+  for (int i = 0; i < n_own; ++i) {
     Half* hb = halves.data() + start[i];
     Half* he = halves.data() + start[i + 1];
     if (he - hb > 1) std::sort(hb, he, [](const Half& x, const Half& y) { return x.col < y.col || (x.col == y.col && x.idx < y.idx); });
@@ -158,7 +185,7 @@ static void build_pattern(int N, int E, const int* edge_ids, const unsigned char
       k = k2;
     }
   }
-  for (int i = 0; i < N; ++i) out->row_ptr[i + 1] += out->row_ptr[i];
+  for (int i = 0; i < n_own; ++i) out->row_ptr[i + 1] += out->row_ptr[i];
 }
 
 static int check_edges(int n_poses, int n_edges, const int* edge_ids) {
@@ -256,6 +283,7 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->own_stream && g->own_stream != g->stream) cudaStreamSynchronize(g->own_stream);
   if (g->comm) ncclCommDestroy(g->comm);
   if (g->chol) level_chol_destroy(g->chol, g->device);
+  if (g->amg) amg_destroy(g->amg, g->device);
   for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
   pool_pinned_release(g->device, g->scalars_h);
   pool_pinned_release(g->device, g->pcgm_state_h);
@@ -272,49 +300,47 @@ extern "C" void pgo_release_cached_memory(int device) { pool_release(device); }
 static thread_local int g_symbolic_hint = -1;   // set by pgo_solve_pose_graph around its pgo_graph_create call
 static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S);
 
-extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
-                                const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
-                                const unsigned char* pose_const) {
-  if (!out || n_poses <= 0 || n_edges < 0 || !poses || (n_edges > 0 && (!edge_ids || !edge_meas)))
-    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_create: null or empty input");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return set_error(PGO_ERR_NO_DEVICE, "pgo_graph_create: no CUDA device available (this library has no CPU path)");
-  }
-  if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
-  PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
+// What one rank holds.  One GPU: the whole problem (n_own == n_loc, no halo).  Multi-GPU: the block rows of its own
+// poses; edges that touch them; copies ("halo") of the other endpoint of every cut edge.
+struct LocalProblem {
+  int n_loc = 0, n_own = 0, n_edges = 0;
+  const double* poses = nullptr;             // [n_loc][7]
+  const int* edge_ids = nullptr;             // [n_edges][2] LOCAL ids
+  const double* edge_meas = nullptr;
+  const double* edge_sqrt_info = nullptr;
+  const unsigned char* pose_const = nullptr; // [n_loc]
+};
+
+static int halo_exchange(pgo_graph* g, const std::vector<int>& nbr, const std::vector<int>& send_ptr, const std::vector<int>& recv_ptr,
+                         const int* send_idx, int n_own, double* v, int width, const int* skip);
+
+static int graph_create_local(pgo_graph* g, const LocalProblem& in) {
+  const int device = g->device;
   const double t0 = wall_s();
   static const bool prof = getenv("PGO_PROFILE_HOST") != nullptr;
   double tp = t0;
   auto lap = [&](const char* what) { if (prof) { const double t = wall_s(); fprintf(stderr, "[pgo create] %-28s %8.1f us\n", what, 1e6 * (t - tp)); tp = t; } };
-  CUDA_TRY(cudaSetDevice(device));
-  pgo_graph* g = new pgo_graph();
-  g->device = device;
-  g->N = n_poses; g->E = n_edges; g->T = (n_edges + kTile - 1) / kTile;
-  const int N = g->N, E = g->E, T = g->T;
-  auto fail = [&](int rc) { pgo_graph_destroy(g); return rc; };
-#define G_TRY(expr) do { int _rc = (expr); if (_rc != PGO_OK) return fail(_rc); } while (0)
-#define GC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(set_error(PGO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); } while (0)
-  GC_TRY(pool_stream(device, &g->own_stream));
+  g->N = in.n_loc; g->n_own = in.n_own; g->E = in.n_edges; g->T = (in.n_edges + kTile - 1) / kTile;
+  const int N = g->N, E = g->E, T = g->T, n_own = g->n_own;
+  CUDA_TRY(pool_stream(device, &g->own_stream));
   g->stream = g->own_stream;
-  GC_TRY(pool_event(device, &g->ev0));
-  GC_TRY(pool_event(device, &g->ev1));
-  GC_TRY(pool_event(device, &g->ev2));
-  GC_TRY(pool_event(device, &g->ev3));
+  CUDA_TRY(pool_event(device, &g->ev0));
+  CUDA_TRY(pool_event(device, &g->ev1));
+  CUDA_TRY(pool_event(device, &g->ev2));
+  CUDA_TRY(pool_event(device, &g->ev3));
   g->num_sms = pool_num_sms(device);
 
   // ---- which poses are variables, block-CSR pattern of the off-diagonal part ----
   lap("stream/events");
   HostPattern pat;
-  build_pattern(N, E, edge_ids, pose_const, &pat);
+  build_pattern(N, E, in.edge_ids, in.pose_const, &pat, n_own);
   lap("block-CSR pattern");
   g->active_h.swap(pat.active);
   g->row_ptr_h.swap(pat.row_ptr);
   g->col_idx_h.swap(pat.col_idx);
   g->nnz_off = (long long)g->col_idx_h.size();
   g->has_dup_blocks = pat.has_dup;
-  if (g_symbolic_hint == PGO_LINEAR_AUTO || g_symbolic_hint == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
+  if (g->world == 1 && (g_symbolic_hint == PGO_LINEAR_AUTO || g_symbolic_hint == PGO_LINEAR_PCG_LEVEL_CHOLESKY)) {
     // the pattern is final: analyse the elimination order on a helper thread while this thread packs and uploads
     g->sym.reset(new LevelCholSymbolic());
     g->sym_solver_type = g_symbolic_hint;
@@ -325,13 +351,23 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
 
   // ---- identity information? (after the helper thread is off: the symbolic analysis is the longer leg) ----
   g->identity_info = true;
-  if (edge_sqrt_info) {
+  if (in.edge_sqrt_info) {
     static const double eye[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
     for (int e = 0; e < E && g->identity_info; ++e)
-      if (std::memcmp(edge_sqrt_info + 36 * (size_t)e, eye, sizeof eye) != 0) {
+      if (std::memcmp(in.edge_sqrt_info + 36 * (size_t)e, eye, sizeof eye) != 0) {
         // memcmp also flags -0.0; confirm numerically
-        for (int k = 0; k < 36; ++k) if (edge_sqrt_info[36 * (size_t)e + k] != eye[k]) { g->identity_info = false; break; }
+        for (int k = 0; k < 36; ++k) if (in.edge_sqrt_info[36 * (size_t)e + k] != eye[k]) { g->identity_info = false; break; }
       }
+  }
+  if (g->world > 1) {
+    // every rank must compile the same kernel variant: information is identity only if it is on all ranks
+    int flag = g->identity_info ? 1 : 0, *flag_d = nullptr;
+    PGO_TRY(dev_alloc(g, &flag_d, 1));
+    CUDA_TRY(cudaMemcpyAsync(flag_d, &flag, sizeof(int), cudaMemcpyHostToDevice, g->stream));
+    NCCL_TRY(ncclAllReduce(flag_d, flag_d, 1, ncclInt, ncclMin, g->comm, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(&flag, flag_d, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->identity_info = flag != 0;
   }
   lap("identity scan");
   // ---- edge tiles (field-major, one warp per tile) ----
@@ -339,74 +375,438 @@ extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_
   std::memset(core_h.data(), 0, core_h.size() * sizeof(EdgeCoreTile));
   std::vector<EdgeInfoTile> info_h;
   if (!g->identity_info) { info_h.resize(std::max(T, 1)); std::memset(info_h.data(), 0, info_h.size() * sizeof(EdgeInfoTile)); }
+  static const double eye_row[6][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}, {0, 0, 0, 1, 0, 0}, {0, 0, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 1}};
   for (int e = 0; e < E; ++e) {
     EdgeCoreTile& t = core_h[e / kTile];
     const int l = e % kTile;
-    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    const int a = in.edge_ids[2 * e], b = in.edge_ids[2 * e + 1];
     t.a[l] = a; t.b[l] = b;
     t.slot_ab[l] = pat.half_slot[2 * (size_t)e];
     t.slot_ba[l] = pat.half_slot[2 * (size_t)e + 1];
-    for (int k = 0; k < 7; ++k) t.meas[k][l] = edge_meas[7 * (size_t)e + k];
-    if (!g->identity_info) for (int k = 0; k < 36; ++k) info_h[e / kTile].S[k][l] = edge_sqrt_info[36 * (size_t)e + k];
+    for (int k = 0; k < 7; ++k) t.meas[k][l] = in.edge_meas[7 * (size_t)e + k];
+    if (!g->identity_info)
+      for (int k = 0; k < 36; ++k) info_h[e / kTile].S[k][l] = in.edge_sqrt_info ? in.edge_sqrt_info[36 * (size_t)e + k] : eye_row[k / 6][k % 6];
   }
   for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
 
   lap("edge tiles");
   // ---- device allocations + uploads ----
-  G_TRY(dev_alloc(g, &g->poses, (size_t)N * 8));
-  G_TRY(dev_alloc(g, &g->poses_cand, (size_t)N * 8));
-  G_TRY(dev_alloc(g, &g->poses_snap, (size_t)N * 8));
-  G_TRY(dev_alloc(g, &g->scale, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->scale_eval, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->core, (size_t)std::max(T, 1)));
-  if (!g->identity_info) G_TRY(dev_alloc(g, &g->info, (size_t)std::max(T, 1)));
-  G_TRY(dev_alloc(g, &g->Hdiag, (size_t)N * 36));
-  G_TRY(dev_alloc(g, &g->Hoff, (size_t)g->nnz_off * 36));
-  G_TRY(dev_alloc(g, &g->row_ptr, (size_t)N + 1));
-  G_TRY(dev_alloc(g, &g->col_idx, (size_t)g->nnz_off));
-  G_TRY(dev_alloc(g, &g->grad, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->grad_unscaled, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->diagonal, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->dlm, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->Minv, (size_t)N * 36));
-  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb}) G_TRY(dev_alloc(g, v, (size_t)N * 6));
-  G_TRY(dev_alloc(g, &g->active, (size_t)N));
-  G_TRY(dev_alloc(g, &g->scalars, 1));
+  PGO_TRY(dev_alloc(g, &g->poses, (size_t)N * 8));
+  PGO_TRY(dev_alloc(g, &g->poses_cand, (size_t)N * 8));
+  PGO_TRY(dev_alloc(g, &g->poses_snap, (size_t)N * 8));
+  PGO_TRY(dev_alloc(g, &g->scale, (size_t)N * 6));
+  PGO_TRY(dev_alloc(g, &g->scale_eval, (size_t)N * 6));
+  PGO_TRY(dev_alloc(g, &g->core, (size_t)std::max(T, 1)));
+  if (!g->identity_info) PGO_TRY(dev_alloc(g, &g->info, (size_t)std::max(T, 1)));
+  PGO_TRY(dev_alloc(g, &g->Hdiag, (size_t)n_own * 36));
+  PGO_TRY(dev_alloc(g, &g->Hoff, (size_t)g->nnz_off * 36));
+  PGO_TRY(dev_alloc(g, &g->row_ptr, (size_t)n_own + 1));
+  PGO_TRY(dev_alloc(g, &g->col_idx, (size_t)g->nnz_off));
+  PGO_TRY(dev_alloc(g, &g->grad, (size_t)n_own * 6));
+  PGO_TRY(dev_alloc(g, &g->grad_unscaled, (size_t)n_own * 6));
+  PGO_TRY(dev_alloc(g, &g->diagonal, (size_t)n_own * 6));
+  PGO_TRY(dev_alloc(g, &g->dlm, (size_t)n_own * 6));
+  PGO_TRY(dev_alloc(g, &g->Minv, (size_t)n_own * 36));
+  // vectors that an SpMV gathers from carry the halo tail
+  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb}) PGO_TRY(dev_alloc(g, v, (size_t)N * 6));
+  PGO_TRY(dev_alloc(g, &g->active, (size_t)N));
+  PGO_TRY(dev_alloc(g, &g->scalars, 1));
   static_assert(sizeof(DeviceScalars) <= kPinnedBytes, "pinned scalars");
-  GC_TRY(pool_pinned(device, reinterpret_cast<void**>(&g->scalars_h)));
-  G_TRY(dev_alloc(g, &g->barrier, 4));
+  CUDA_TRY(pool_pinned(device, reinterpret_cast<void**>(&g->scalars_h)));
+  PGO_TRY(dev_alloc(g, &g->barrier, 4));
 
   lap("device allocations");
-  GC_TRY(cudaMemcpyAsync(g->core, core_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
-  if (!g->identity_info) GC_TRY(cudaMemcpyAsync(g->info, info_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
-  GC_TRY(cudaMemcpyAsync(g->row_ptr, g->row_ptr_h.data(), ((size_t)N + 1) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
-  if (g->nnz_off) GC_TRY(cudaMemcpyAsync(g->col_idx, g->col_idx_h.data(), (size_t)g->nnz_off * sizeof(int), cudaMemcpyHostToDevice, g->stream));
-  GC_TRY(cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)N, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->core, core_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
+  if (!g->identity_info) CUDA_TRY(cudaMemcpyAsync(g->info, info_h.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->row_ptr, g->row_ptr_h.data(), ((size_t)n_own + 1) * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+  if (g->nnz_off) CUDA_TRY(cudaMemcpyAsync(g->col_idx, g->col_idx_h.data(), (size_t)g->nnz_off * sizeof(int), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)N, cudaMemcpyHostToDevice, g->stream));
   {
     std::vector<double> se((size_t)N * 6);
     for (int i = 0; i < N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
-    GC_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-    GC_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
   }
   // (pageable sources: cudaMemcpyAsync returns once they are staged, so the host vectors may go; the stream orders the rest)
-  GC_TRY(cudaMemsetAsync(g->Hoff, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
+  CUDA_TRY(cudaMemsetAsync(g->Hoff, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
+  for (double** v : {&g->vx, &g->vr, &g->vu, &g->vw, &g->vp, &g->vs, &g->vb})
+    CUDA_TRY(cudaMemsetAsync(*v, 0, std::max<size_t>((size_t)N * 6, 1) * sizeof(double), g->stream));
 
   lap("uploads + memset");
   // persistent PCG grid: all CTAs must be co-resident (cooperative launch)
-  static int per_sm = 0;
-  if (per_sm == 0) GC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, kPcgThreads, 0));
+  int per_sm = 0;
+  if (!pool_cache_get(device, kCachePcgPerSm, &per_sm)) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, kPcgThreads, 0));
+    pool_cache_set(device, kCachePcgPerSm, per_sm);
+  }
   g->pcg_max_ctas = std::max(1, std::min(per_sm, 4) * g->num_sms);
-  G_TRY(dev_alloc(g, &g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
+  PGO_TRY(dev_alloc(g, &g->partials, (size_t)2 * 3 * g->pcg_max_ctas));
 
-  *out = g;
-  int rc = pgo_graph_set_poses(g, poses);
-  if (rc != PGO_OK) { *out = nullptr; return fail(rc); }
+  // [n_loc][7] host -> [n_loc][8] device
+  g->pose_stage.resize((size_t)N * 8);
+  for (int i = 0; i < N; ++i) {
+    std::memcpy(&g->pose_stage[8 * (size_t)i], in.poses + 7 * (size_t)i, 7 * sizeof(double));
+    g->pose_stage[8 * (size_t)i + 7] = 0.0;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->poses, g->pose_stage.data(), (size_t)N * 8 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
   lap("poses");
   g->setup_s = wall_s() - t0;
   return PGO_OK;
-#undef G_TRY
-#undef GC_TRY
 }
+
+static int check_create_args(int device, int n_poses, int n_edges, const double* poses, const int* edge_ids, const double* edge_meas) {
+  if (n_poses <= 0 || n_edges < 0 || !poses || (n_edges > 0 && (!edge_ids || !edge_meas)))
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_create: null or empty input");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(PGO_ERR_NO_DEVICE, "pgo_graph_create: no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return set_error(PGO_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  return check_edges(n_poses, n_edges, edge_ids);
+}
+
+extern "C" int pgo_graph_create(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
+                                const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
+                                const unsigned char* pose_const) {
+  if (!out) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_create: null output");
+  PGO_TRY(check_create_args(device, n_poses, n_edges, poses, edge_ids, edge_meas));
+  CUDA_TRY(cudaSetDevice(device));
+  pgo_graph* g = new pgo_graph();
+  g->device = device;
+  g->N_global = n_poses; g->E_global = n_edges; g->g0 = 0;
+  g->part_off = {0, n_poses};
+  LocalProblem in;
+  in.n_loc = in.n_own = n_poses; in.n_edges = n_edges; in.poses = poses; in.edge_ids = edge_ids; in.edge_meas = edge_meas;
+  in.edge_sqrt_info = edge_sqrt_info; in.pose_const = pose_const;
+  const int rc = graph_create_local(g, in);
+  if (rc != PGO_OK) { pgo_graph_destroy(g); return rc; }
+  // setup-time positions: the strength measure of the multilevel hierarchy (built on first use)
+  g->pos0_h.resize(3 * (size_t)n_poses);
+  for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) g->pos0_h[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
+  *out = g;
+  return PGO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: owner-computes row partition.  Every rank passes the SAME global graph; rank r keeps the block rows of
+// the poses [off[r], off[r+1]) (contiguous index ranges: pose graphs are trajectory-ordered, so index locality is
+// spatial locality), every edge that touches one of them, and halo copies of the other endpoints of cut edges.
+// ------------------------------------------------------------------------------------------------
+struct HostPartition {
+  std::vector<int> off;                      // [world + 1]
+  int n_own = 0, g0 = 0;
+  std::vector<int> halo_gid;                 // ascending
+  std::vector<int> edge_sel;                 // global edge ids kept here, ascending
+  std::vector<int> local_ids;                // [2 * kept]
+  std::vector<int> nbr, send_ptr, send_idx, recv_ptr;
+};
+
+static void partition_ranges(int n_poses, int world, std::vector<int>* off) {
+  off->resize(world + 1);
+  for (int r = 0; r <= world; ++r) (*off)[r] = (int)(((long long)n_poses * r) / world);
+}
+
+static void build_partition(int n_poses, int n_edges, const int* edge_ids, int rank, int world, HostPartition* P) {
+  partition_ranges(n_poses, world, &P->off);
+  const int lo = P->off[rank], hi = P->off[rank + 1];
+  P->g0 = lo; P->n_own = hi - lo;
+  P->edge_sel.clear(); P->halo_gid.clear();
+  for (int e = 0; e < n_edges; ++e) {
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    const bool oa = a >= lo && a < hi, ob = b >= lo && b < hi;
+    if (!oa && !ob) continue;
+    P->edge_sel.push_back(e);
+    if (!oa) P->halo_gid.push_back(a);
+    if (!ob) P->halo_gid.push_back(b);
+  }
+  std::sort(P->halo_gid.begin(), P->halo_gid.end());
+  P->halo_gid.erase(std::unique(P->halo_gid.begin(), P->halo_gid.end()), P->halo_gid.end());
+  auto local_of = [&](int gid) -> int {
+    if (gid >= lo && gid < hi) return gid - lo;
+    return P->n_own + (int)(std::lower_bound(P->halo_gid.begin(), P->halo_gid.end(), gid) - P->halo_gid.begin());
+  };
+  P->local_ids.resize(2 * P->edge_sel.size());
+  for (size_t k = 0; k < P->edge_sel.size(); ++k) {
+    const int e = P->edge_sel[k];
+    P->local_ids[2 * k] = local_of(edge_ids[2 * e]);
+    P->local_ids[2 * k + 1] = local_of(edge_ids[2 * e + 1]);
+  }
+  // exchange plan from the cut edges (symmetric by construction: a cut edge puts each endpoint into the other owner's halo)
+  P->nbr.clear(); P->recv_ptr.clear();
+  for (size_t k = 0; k < P->halo_gid.size(); ++k) {
+    const int o = amg_owner_of(P->off, P->halo_gid[k]);
+    if (P->nbr.empty() || P->nbr.back() != o) { P->nbr.push_back(o); P->recv_ptr.push_back((int)k); }
+  }
+  P->recv_ptr.push_back((int)P->halo_gid.size());
+  std::vector<std::vector<int>> need(P->nbr.size());
+  for (size_t k = 0; k < P->edge_sel.size(); ++k) {
+    const int e = P->edge_sel[k];
+    const int a = edge_ids[2 * e], b = edge_ids[2 * e + 1];
+    const bool oa = a >= lo && a < hi, ob = b >= lo && b < hi;
+    if (oa == ob) continue;
+    const int mine = oa ? a : b, other = oa ? b : a;
+    const int o = amg_owner_of(P->off, other);
+    const int q = (int)(std::lower_bound(P->nbr.begin(), P->nbr.end(), o) - P->nbr.begin());
+    need[q].push_back(mine - lo);
+  }
+  P->send_ptr.assign(1, 0);
+  P->send_idx.clear();
+  for (size_t q = 0; q < P->nbr.size(); ++q) {
+    std::sort(need[q].begin(), need[q].end());
+    need[q].erase(std::unique(need[q].begin(), need[q].end()), need[q].end());
+    P->send_idx.insert(P->send_idx.end(), need[q].begin(), need[q].end());
+    P->send_ptr.push_back((int)P->send_idx.size());
+  }
+}
+
+extern "C" int pgo_nccl_unique_id(unsigned char unique_id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  std::memcpy(unique_id, &id, 128);
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_create_partitioned(pgo_graph** out, int device, int n_poses, int n_edges, const double* poses,
+                                            const int* edge_ids, const double* edge_meas, const double* edge_sqrt_info,
+                                            const unsigned char* pose_const, const unsigned char unique_id[128], int rank,
+                                            int world_size) {
+  if (!out || !unique_id || world_size < 1 || rank < 0 || rank >= world_size)
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_create_partitioned: bad arguments");
+  if (world_size == 1) return pgo_graph_create(out, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const);
+  PGO_TRY(check_create_args(device, n_poses, n_edges, poses, edge_ids, edge_meas));
+  if (n_poses < world_size) return set_error(PGO_ERR_INVALID_ARGUMENT, "fewer poses (%d) than ranks (%d)", n_poses, world_size);
+  CUDA_TRY(cudaSetDevice(device));
+  pgo_graph* g = new pgo_graph();
+  g->device = device;
+  g->rank = rank; g->world = world_size;
+  g->N_global = n_poses; g->E_global = n_edges;
+  auto fail = [&](int rc) { pgo_graph_destroy(g); return rc; };
+  {
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, 128);
+    const ncclResult_t e = ncclCommInitRank(&g->comm, world_size, id, rank);
+    if (e != ncclSuccess) return fail(set_error(PGO_ERR_NCCL, "ncclCommInitRank failed: %s", ncclGetErrorString(e)));
+  }
+  HostPartition P;
+  build_partition(n_poses, n_edges, edge_ids, rank, world_size, &P);
+  g->part_off = P.off; g->g0 = P.g0; g->halo_gid = P.halo_gid;
+  g->nbr = P.nbr; g->send_ptr = P.send_ptr; g->recv_ptr = P.recv_ptr; g->send_idx_h = P.send_idx;
+  // local slice of the inputs
+  const int n_loc = P.n_own + (int)P.halo_gid.size(), ne = (int)P.edge_sel.size();
+  std::vector<double> lposes((size_t)n_loc * 7), lmeas((size_t)ne * 7), linfo;
+  std::vector<unsigned char> lconst((size_t)n_loc, 0);
+  auto gid_of = [&](int i) { return i < P.n_own ? P.g0 + i : P.halo_gid[i - P.n_own]; };
+  for (int i = 0; i < n_loc; ++i) {
+    const int gi = gid_of(i);
+    std::memcpy(&lposes[7 * (size_t)i], poses + 7 * (size_t)gi, 7 * sizeof(double));
+    if (pose_const) lconst[i] = pose_const[gi];
+  }
+  if (edge_sqrt_info) linfo.resize((size_t)ne * 36);
+  for (int k = 0; k < ne; ++k) {
+    const int e = P.edge_sel[k];
+    std::memcpy(&lmeas[7 * (size_t)k], edge_meas + 7 * (size_t)e, 7 * sizeof(double));
+    if (edge_sqrt_info) std::memcpy(&linfo[36 * (size_t)k], edge_sqrt_info + 36 * (size_t)e, 36 * sizeof(double));
+  }
+  LocalProblem in;
+  in.n_loc = n_loc; in.n_own = P.n_own; in.n_edges = ne; in.poses = lposes.data(); in.edge_ids = P.local_ids.data();
+  in.edge_meas = lmeas.data(); in.edge_sqrt_info = edge_sqrt_info ? linfo.data() : nullptr; in.pose_const = lconst.data();
+  int rc = graph_create_local(g, in);
+  if (rc != PGO_OK) return fail(rc);
+  // global structure for the hierarchy: pattern and variable flags of the WHOLE graph (every rank, deterministic)
+  {
+    HostPattern gp;
+    build_pattern(n_poses, n_edges, edge_ids, pose_const, &gp);
+    g->gactive_h.swap(gp.active);
+    g->grow_ptr_h.swap(gp.row_ptr);
+    g->gcol_idx_h.swap(gp.col_idx);
+    g->pos0_h.resize(3 * (size_t)n_poses);
+    for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) g->pos0_h[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
+  }
+  size_t max_send = P.send_idx.size();
+  if (!P.send_idx.empty()) {
+    rc = dev_alloc(g, &g->send_idx, P.send_idx.size());
+    if (rc != PGO_OK) return fail(rc);
+    if (cudaMemcpyAsync(g->send_idx, P.send_idx.data(), P.send_idx.size() * sizeof(int), cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess)
+      return fail(set_error(PGO_ERR_CUDA, "uploading the halo plan failed"));
+  }
+  rc = dev_alloc(g, &g->halo_sendbuf, std::max<size_t>(max_send, 1) * 8);
+  if (rc != PGO_OK) return fail(rc);
+  // a pose that is constant / unused on its owner must be inactive in every halo copy as well: owners are authoritative
+  {
+    std::vector<double> act((size_t)n_loc * 6, 0.0);
+    for (int i = 0; i < P.n_own; ++i) if (g->gactive_h[P.g0 + i]) for (int k = 0; k < 6; ++k) act[6 * (size_t)i + k] = 1.0;
+    for (int i = P.n_own; i < n_loc; ++i) if (g->gactive_h[gid_of(i)]) for (int k = 0; k < 6; ++k) act[6 * (size_t)i + k] = 1.0;
+    for (int i = 0; i < n_loc; ++i) g->active_h[i] = act[6 * (size_t)i] != 0.0;
+    if (cudaMemcpyAsync(g->scale_eval, act.data(), act.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->scale, act.data(), act.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)n_loc, cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
+        cudaStreamSynchronize(g->stream) != cudaSuccess)
+      return fail(set_error(PGO_ERR_CUDA, "uploading the variable flags failed"));
+  }
+  *out = g;
+  return PGO_OK;
+}
+
+static unsigned long long mix64(unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (unsigned long long v : {a, b, c, d}) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 31; }
+  return h;
+}
+
+// One rank's complete host-side setup from the global inputs (shared by pgo_analyze_partition; mirrors what
+// pgo_graph_create_partitioned + the first multilevel solve build).
+struct HostRankSetup {
+  HostPartition part;
+  HostPattern local_pat;
+  std::vector<AmgLocalLevel> levels;
+};
+static void host_rank_setup(int n_poses, int n_edges, const double* poses, const int* edge_ids, const unsigned char* pose_const,
+                            int rank, int world, const std::vector<AmgGlobalLevel>& G, HostRankSetup* out) {
+  (void)poses;
+  build_partition(n_poses, n_edges, edge_ids, rank, world, &out->part);
+  const HostPartition& P = out->part;
+  const int n_loc = P.n_own + (int)P.halo_gid.size();
+  std::vector<unsigned char> lconst((size_t)n_loc, 0);
+  for (int i = 0; i < n_loc; ++i) {
+    const int gi = i < P.n_own ? P.g0 + i : P.halo_gid[i - P.n_own];
+    if (pose_const) lconst[i] = pose_const[gi];
+  }
+  build_pattern(n_loc, (int)P.edge_sel.size(), P.local_ids.data(), lconst.data(), &out->local_pat, P.n_own);
+  AmgLocalLevel l0;
+  l0.row_ptr = out->local_pat.row_ptr; l0.col_idx = out->local_pat.col_idx; l0.halo_gid = P.halo_gid;
+  l0.nbr = P.nbr; l0.send_ptr = P.send_ptr; l0.send_idx = P.send_idx; l0.recv_ptr = P.recv_ptr;
+  amg_localize(G, rank, world, l0, &out->levels);
+}
+
+extern "C" int pgo_analyze_partition(int n_poses, int n_edges, const double* poses, const int* edge_ids,
+                                     const unsigned char* pose_const, int rank, int world_size, pgo_partition_info* info) {
+  if (!info || !poses || n_poses <= 0 || n_edges < 0 || (n_edges > 0 && !edge_ids) || world_size < 1 || world_size > 64 || rank < 0 ||
+      rank >= world_size || n_poses < world_size)
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_analyze_partition: bad arguments");
+  PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
+  std::memset(info, 0, sizeof *info);
+  // global structure + hierarchy (what every rank computes redundantly)
+  HostPattern gp;
+  build_pattern(n_poses, n_edges, edge_ids, pose_const, &gp);
+  std::vector<double> pos0(3 * (size_t)n_poses);
+  for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) pos0[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
+  std::vector<int> off;
+  partition_ranges(n_poses, world_size, &off);
+  AmgHostParams prm;
+  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
+  if (const char* e = getenv("PGO_AMG_REPLICATE_MAX")) prm.replicate_max = atoi(e);
+  std::vector<AmgGlobalLevel> G;
+  amg_build_global(n_poses, world_size, off, gp.active.data(), gp.row_ptr.data(), gp.col_idx.data(), pos0.data(), prm, &G);
+  HostRankSetup me;
+  host_rank_setup(n_poses, n_edges, poses, edge_ids, pose_const, rank, world_size, G, &me);
+  const HostPartition& P = me.part;
+  info->n_own = P.n_own; info->n_halo = (int)P.halo_gid.size(); info->n_local_edges = (int)P.edge_sel.size();
+  for (size_t k = 0; k < P.edge_sel.size(); ++k)
+    if ((P.local_ids[2 * k] >= P.n_own) != (P.local_ids[2 * k + 1] >= P.n_own)) info->n_cut_edges++;
+  info->n_neighbours = (int)P.nbr.size();
+  info->send_total = (int)P.send_idx.size(); info->recv_total = (int)P.halo_gid.size();
+  for (size_t q = 0; q < P.nbr.size(); ++q) {
+    info->send_to[P.nbr[q]] = P.send_ptr[q + 1] - P.send_ptr[q];
+    info->recv_from[P.nbr[q]] = P.recv_ptr[q + 1] - P.recv_ptr[q];
+  }
+  const int nl = (int)me.levels.size();
+  info->amg_levels = nl;
+  bool ok = true;
+  unsigned long long hs = 0, hr = 0;
+  for (int l = 0; l < nl && l < 16; ++l) {
+    const AmgLocalLevel& L = me.levels[l];
+    info->level_nodes[l] = G[l].n; info->level_own[l] = L.n_own; info->level_halo[l] = L.n_halo;
+    info->level_replicated[l] = L.replicated ? 1 : 0;
+    info->level_blocks[l] = (long long)L.n_own + (long long)L.col_idx.size();
+    info->level_send[l] = (int)L.send_idx.size(); info->level_recv[l] = L.replicated ? 0 : L.n_halo;
+    for (size_t q = 0; q < L.nbr.size(); ++q) {
+      for (int k = L.send_ptr[q]; k < L.send_ptr[q + 1]; ++k) hs += mix64(rank, L.nbr[q], (unsigned long long)l << 32 | (unsigned)(L.g0 + L.send_idx[k]), k - L.send_ptr[q]);
+      for (int k = L.recv_ptr[q]; k < L.recv_ptr[q + 1]; ++k) hr += mix64(L.nbr[q], rank, (unsigned long long)l << 32 | (unsigned)L.halo_gid[k], k - L.recv_ptr[q]);
+    }
+    // ---- invariants ----
+    const int n_loc = L.n_own + L.n_halo;
+    for (size_t p = 0; p < L.col_idx.size(); ++p) if (L.col_idx[p] < 0 || L.col_idx[p] >= n_loc) ok = false;
+    if (l + 1 < nl) {
+      const AmgLocalLevel& C = me.levels[l + 1];
+      if ((int)L.agg.size() != n_loc) ok = false;
+      // aggregates never cross a rank boundary: the owner of a node owns its aggregate
+      const AmgGlobalLevel& g = G[l];
+      const AmgGlobalLevel& gc = G[l + 1];
+      for (int i = 0; i < g.n && ok; ++i)
+        if (g.agg[i] >= 0 && amg_owner_of(g.off, i) != amg_owner_of(gc.off, g.agg[i])) ok = false;
+      // every stored fine block lands in exactly one gather list; member lists cover the stored variable rows
+      long long want = 0, members = 0;
+      for (int i = 0; i < L.n_own; ++i) {
+        if (L.agg[i] < 0) continue;
+        ++members; ++want;
+        for (int p = L.row_ptr[i]; p < L.row_ptr[i + 1]; ++p) if (L.agg[L.col_idx[p]] >= 0) ++want;
+      }
+      if (want != (long long)L.gal_row.size() || members != (long long)L.mem_idx.size()) ok = false;
+      if ((int)L.gal_ptr.size() - 1 != (L.c_row1 - L.c_row0) + (C.row_ptr[L.c_row1] - C.row_ptr[L.c_row0])) ok = false;
+      for (int a : L.agg) if (a >= C.n_own + C.n_halo) ok = false;
+    }
+  }
+  // ---- cross-rank: what I send to q is exactly what q expects from me, in the same order, on every distributed level ----
+  if (world_size > 1 && world_size <= 16) {
+    for (int q = 0; q < world_size; ++q) {
+      if (q == rank) continue;
+      HostRankSetup peer;
+      host_rank_setup(n_poses, n_edges, poses, edge_ids, pose_const, q, world_size, G, &peer);
+      for (int l = 0; l < nl; ++l) {
+        const AmgLocalLevel& A = me.levels[l];
+        const AmgLocalLevel& B = peer.levels[l];
+        if (A.replicated) continue;
+        std::vector<int> sent, expected;
+        for (size_t k = 0; k < A.nbr.size(); ++k)
+          if (A.nbr[k] == q) for (int t = A.send_ptr[k]; t < A.send_ptr[k + 1]; ++t) sent.push_back(A.g0 + A.send_idx[t]);
+        for (size_t k = 0; k < B.nbr.size(); ++k)
+          if (B.nbr[k] == rank) for (int t = B.recv_ptr[k]; t < B.recv_ptr[k + 1]; ++t) expected.push_back(B.halo_gid[t]);
+        if (sent != expected) ok = false;
+      }
+    }
+  }
+  info->plan_checksum = hs; info->recv_checksum = hr;
+  info->consistent = ok ? 1 : 0;
+  return PGO_OK;
+}
+
+// Host-only: the aggregate of every node on every level of the global hierarchy (tests / design tools).
+// agg_out: concatenation over the levels 0..L-2 of agg[level_nodes[l]]; returns the number of levels in *n_levels.
+extern "C" int pgo_amg_aggregates(int n_poses, int n_edges, const double* poses, const int* edge_ids, const unsigned char* pose_const,
+                                  int world_size, int* n_levels, int* level_nodes /* [16] */, int* agg_out, long long agg_capacity) {
+  if (!poses || !n_levels || !level_nodes || n_poses <= 0 || n_edges < 0 || (n_edges > 0 && !edge_ids) || world_size < 1)
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_amg_aggregates: bad arguments");
+  PGO_TRY(check_edges(n_poses, n_edges, edge_ids));
+  HostPattern gp;
+  build_pattern(n_poses, n_edges, edge_ids, pose_const, &gp);
+  std::vector<double> pos0(3 * (size_t)n_poses);
+  for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) pos0[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
+  std::vector<int> off;
+  partition_ranges(n_poses, world_size, &off);
+  AmgHostParams prm;
+  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
+  std::vector<AmgGlobalLevel> G;
+  amg_build_global(n_poses, world_size, off, gp.active.data(), gp.row_ptr.data(), gp.col_idx.data(), pos0.data(), prm, &G);
+  *n_levels = (int)G.size();
+  long long need = 0;
+  for (size_t l = 0; l < G.size() && l < 16; ++l) { level_nodes[l] = G[l].n; if (l + 1 < G.size()) need += G[l].n; }
+  if (agg_out) {
+    if (agg_capacity < need) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_amg_aggregates: capacity %lld < %lld", agg_capacity, need);
+    long long k = 0;
+    for (size_t l = 0; l + 1 < G.size(); ++l) for (int i = 0; i < G[l].n; ++i) agg_out[k++] = G[l].agg[i];
+  }
+  return PGO_OK;
+}
+
+extern "C" int pgo_graph_rank(const pgo_graph* g) { return g ? g->rank : 0; }
+extern "C" int pgo_graph_world_size(const pgo_graph* g) { return g ? g->world : 0; }
+extern "C" int pgo_graph_num_local_poses(const pgo_graph* g) { return g ? g->n_own : 0; }
+extern "C" int pgo_graph_num_halo_poses(const pgo_graph* g) { return g ? g->N - g->n_own : 0; }
+extern "C" int pgo_graph_num_local_edges(const pgo_graph* g) { return g ? g->E : 0; }
 
 extern "C" int pgo_graph_set_stream(pgo_graph* g, void* cuda_stream) {
   if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
@@ -416,16 +816,18 @@ extern "C" int pgo_graph_set_stream(pgo_graph* g, void* cuda_stream) {
   return PGO_OK;
 }
 
-extern "C" int pgo_graph_num_poses(const pgo_graph* g) { return g ? g->N : 0; }
-extern "C" int pgo_graph_num_edges(const pgo_graph* g) { return g ? g->E : 0; }
+extern "C" int pgo_graph_num_poses(const pgo_graph* g) { return g ? g->N_global : 0; }
+extern "C" int pgo_graph_num_edges(const pgo_graph* g) { return g ? g->E_global : 0; }
 
+// poses: the GLOBAL [n_poses][7] array on every rank
 extern "C" int pgo_graph_set_poses(pgo_graph* g, const double* poses) {
   if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_set_poses: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
   // [N][7] host -> [N][8] device: pad on the host, one contiguous copy (row-pitched DMA of 56-byte rows is slow)
   g->pose_stage.resize((size_t)g->N * 8);
   for (int i = 0; i < g->N; ++i) {
-    std::memcpy(&g->pose_stage[8 * (size_t)i], poses + 7 * (size_t)i, 7 * sizeof(double));
+    const int gi = i < g->n_own ? g->g0 + i : g->halo_gid[i - g->n_own];
+    std::memcpy(&g->pose_stage[8 * (size_t)i], poses + 7 * (size_t)gi, 7 * sizeof(double));
     g->pose_stage[8 * (size_t)i + 7] = 0.0;
   }
   CUDA_TRY(cudaMemcpyAsync(g->poses, g->pose_stage.data(), (size_t)g->N * 8 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
@@ -433,13 +835,28 @@ extern "C" int pgo_graph_set_poses(pgo_graph* g, const double* poses) {
   return PGO_OK;
 }
 
+// poses: the GLOBAL [n_poses][7] array; multi-GPU: collective (all-gather of the owned slices), every rank gets all poses
 extern "C" int pgo_graph_get_poses(pgo_graph* g, double* poses) {
   if (!g || !poses) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_get_poses: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
-  g->pose_stage.resize((size_t)g->N * 8);
-  CUDA_TRY(cudaMemcpyAsync(g->pose_stage.data(), g->poses, (size_t)g->N * 8 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  const int Ng = g->N_global;
+  g->pose_stage.resize((size_t)Ng * 8);
+  const double* src = g->poses;
+  if (g->world > 1) {
+    if (!g->gather_buf) PGO_TRY(dev_alloc(g, &g->gather_buf, (size_t)Ng * 8));
+    CUDA_TRY(cudaMemcpyAsync(g->gather_buf + 8 * (size_t)g->g0, g->poses, (size_t)g->n_own * 8 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+    NCCL_TRY(ncclGroupStart());
+    for (int r = 0; r < g->world; ++r) {
+      const size_t cnt = (size_t)(g->part_off[r + 1] - g->part_off[r]) * 8;
+      double* p = g->gather_buf + 8 * (size_t)g->part_off[r];
+      if (cnt) NCCL_TRY(ncclBroadcast(p, p, cnt, ncclDouble, r, g->comm, g->stream));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    src = g->gather_buf;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->pose_stage.data(), src, (size_t)Ng * 8 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
-  for (int i = 0; i < g->N; ++i) std::memcpy(poses + 7 * (size_t)i, &g->pose_stage[8 * (size_t)i], 7 * sizeof(double));
+  for (int i = 0; i < Ng; ++i) std::memcpy(poses + 7 * (size_t)i, &g->pose_stage[8 * (size_t)i], 7 * sizeof(double));
   return PGO_OK;
 }
 
@@ -459,42 +876,86 @@ extern "C" int pgo_graph_restore_poses(pgo_graph* g) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// NCCL plumbing: edges sharded across ranks, poses replicated.
+// halo exchange (multi-GPU): pack the owned boundary entries, NCCL send / receive straight into the halo tail
 // ------------------------------------------------------------------------------------------------
-extern "C" int pgo_nccl_unique_id(unsigned char unique_id[128]) {
-  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
-  ncclUniqueId id;
-  NCCL_TRY(ncclGetUniqueId(&id));
-  std::memcpy(unique_id, &id, 128);
+namespace pgo {
+__global__ void halo_pack_kernel(int n_send, int width, const int* __restrict__ send_idx, const double* __restrict__ v,
+                                 double* __restrict__ buf, const int* skip) {
+  if (skip && *skip) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = t / width, c = t - k * width;
+  if (k >= n_send) return;
+  buf[(size_t)k * width + c] = v[(size_t)send_idx[k] * width + c];
+}
+}  // namespace pgo
+
+static int halo_exchange(pgo_graph* g, const std::vector<int>& nbr, const std::vector<int>& send_ptr, const std::vector<int>& recv_ptr,
+                         const int* send_idx, int n_own, double* v, int width, const int* skip) {
+  if (g->world <= 1 || nbr.empty()) return PGO_OK;
+  const int n_send = send_ptr.back();
+  if (n_send > 0) {
+    const int items = n_send * width;
+    halo_pack_kernel<<<(items + 255) / 256, 256, 0, g->stream>>>(n_send, width, send_idx, v, g->halo_sendbuf, skip);
+    g->launches++;
+  }
+  NCCL_TRY(ncclGroupStart());
+  for (size_t k = 0; k < nbr.size(); ++k) {
+    const int ns = send_ptr[k + 1] - send_ptr[k], nr = recv_ptr[k + 1] - recv_ptr[k];
+    if (ns > 0) NCCL_TRY(ncclSend(g->halo_sendbuf + (size_t)send_ptr[k] * width, (size_t)ns * width, ncclDouble, nbr[k], g->comm, g->stream));
+    if (nr > 0) NCCL_TRY(ncclRecv(v + ((size_t)n_own + recv_ptr[k]) * width, (size_t)nr * width, ncclDouble, nbr[k], g->comm, g->stream));
+  }
+  NCCL_TRY(ncclGroupEnd());
+  g->comm_calls++;
+  g->comm_bytes += (long long)n_send * width * 8;
   return PGO_OK;
 }
-
-extern "C" int pgo_graph_init_comm(pgo_graph* g, const unsigned char unique_id[128], int rank, int world_size) {
-  if (!g || !unique_id || world_size < 1 || rank < 0 || rank >= world_size)
-    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_init_comm: bad arguments");
-  CUDA_TRY(cudaSetDevice(g->device));
-  if (world_size == 1) { g->rank = 0; g->world = 1; return PGO_OK; }
-  ncclUniqueId id;
-  std::memcpy(&id, unique_id, 128);
-  NCCL_TRY(ncclCommInitRank(&g->comm, world_size, id, rank));
-  g->rank = rank; g->world = world_size;
-  // A pose is a variable when ANY rank's shard uses it: make the active set (and the unit scaling derived from it) global.
-  NCCL_TRY(ncclAllReduce(g->active, g->active, (size_t)g->N, ncclUint8, ncclMax, g->comm, g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->active_h.data(), g->active, (size_t)g->N, cudaMemcpyDeviceToHost, g->stream));
-  CUDA_TRY(cudaStreamSynchronize(g->stream));
-  {
-    std::vector<double> se((size_t)g->N * 6);
-    for (int i = 0; i < g->N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
-    CUDA_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-    CUDA_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-    CUDA_TRY(cudaStreamSynchronize(g->stream));
-  }
-  return PGO_OK;
+// level-0 vectors / poses / scales
+static int halo_exchange0(pgo_graph* g, double* v, int width, const int* skip = nullptr) {
+  return halo_exchange(g, g->nbr, g->send_ptr, g->recv_ptr, g->send_idx, g->n_own, v, width, skip);
 }
 
 static int allreduce_sum(pgo_graph* g, double* buf, size_t count) {
   if (g->world <= 1) return PGO_OK;
   NCCL_TRY(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, g->comm, g->stream));
+  g->comm_calls++;
+  g->comm_bytes += (long long)count * 8;
+  return PGO_OK;
+}
+
+// host [N_global][width] -> device local layout (owned rows, then the halo copies)
+static int upload_global(pgo_graph* g, const double* src, int width, double* dst_dev, bool with_halo) {
+  if (g->world <= 1) {
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src, (size_t)g->N * width * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    return PGO_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(dst_dev, src + (size_t)g->g0 * width, (size_t)g->n_own * width * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  if (with_halo && g->N > g->n_own) {
+    std::vector<double> h((size_t)(g->N - g->n_own) * width);
+    for (int k = 0; k < g->N - g->n_own; ++k) std::memcpy(&h[(size_t)k * width], src + (size_t)g->halo_gid[k] * width, width * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(dst_dev + (size_t)g->n_own * width, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));   // `h` is pageable and goes out of scope
+  }
+  return PGO_OK;
+}
+// device owned rows [n_own][width] -> host [N_global][width] on every rank (collective when world > 1)
+static int download_global(pgo_graph* g, const double* src_dev, int width, double* dst) {
+  if (g->world <= 1) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src_dev, (size_t)g->N * width * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    return PGO_OK;
+  }
+  if (width > 8) return set_error(PGO_ERR_INVALID_ARGUMENT, "download_global: width");
+  if (!g->gather_buf) PGO_TRY(dev_alloc(g, &g->gather_buf, (size_t)g->N_global * 8));
+  CUDA_TRY(cudaMemcpyAsync(g->gather_buf + (size_t)width * g->g0, src_dev, (size_t)g->n_own * width * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
+  NCCL_TRY(ncclGroupStart());
+  for (int r = 0; r < g->world; ++r) {
+    const size_t cnt = (size_t)(g->part_off[r + 1] - g->part_off[r]) * width;
+    double* p = g->gather_buf + (size_t)width * g->part_off[r];
+    if (cnt) NCCL_TRY(ncclBroadcast(p, p, cnt, ncclDouble, r, g->comm, g->stream));
+  }
+  NCCL_TRY(ncclGroupEnd());
+  CUDA_TRY(cudaMemcpyAsync(dst, g->gather_buf, (size_t)g->N_global * width * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PGO_OK;
 }
 
@@ -505,8 +966,13 @@ template <bool kIdent, int kMode, int kMinBlocks>
 static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
   constexpr int smem = lin_smem_bytes<kIdent>();
   auto kern = linearize_kernel<kIdent, kMode, kMinBlocks>;
-  static bool attr_set = false;
-  if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; }
+  // the attribute belongs to the device that was current when it was set: remember it per device, not per process
+  constexpr int key = kCacheLinAttrBase + (kIdent ? 0 : 8) + (kMode == kLinFull ? 0 : (kMode == kLinCost ? 2 : 4)) + (kMinBlocks >= 3 ? 1 : 0);
+  int have = 0;
+  if (!pool_cache_get(g->device, key, &have)) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pool_cache_set(g->device, key, 1);
+  }
   const int ctas = std::max(1, std::min((g->T + kLinWarps - 1) / kLinWarps, kMinBlocks * g->num_sms));
   kern<<<ctas, kLinWarps * 32, smem, g->stream>>>(p);
   g->launches++;
@@ -517,7 +983,7 @@ static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
 static int launch_linearize(pgo_graph* g, int mode, const double* poses, const double* scale, int loss_type,
                             double loss_a, double* res_out = nullptr, double* jac_out = nullptr) {
   LinParams p;
-  p.n_edges = g->E; p.n_tiles = g->T; p.core = g->core; p.info = g->info; p.poses = poses; p.scale = scale;
+  p.n_edges = g->E; p.n_tiles = g->T; p.n_own = g->n_own; p.core = g->core; p.info = g->info; p.poses = poses; p.scale = scale;
   p.Hdiag = g->Hdiag; p.Hoff = g->Hoff; p.grad = g->grad; p.scalars = g->scalars;
   p.loss_type = loss_type; p.loss_a = loss_a; p.res_out = res_out; p.jac_out = jac_out;
   if (g->E == 0) return PGO_OK;
@@ -532,10 +998,10 @@ static int launch_linearize(pgo_graph* g, int mode, const double* poses, const d
 
 static int zero_system(pgo_graph* g, bool hessian) {
   if (hessian) {
-    CUDA_TRY(cudaMemsetAsync(g->Hdiag, 0, (size_t)g->N * 36 * sizeof(double), g->stream));
+    CUDA_TRY(cudaMemsetAsync(g->Hdiag, 0, (size_t)g->n_own * 36 * sizeof(double), g->stream));
     if (g->has_dup_blocks && g->nnz_off) CUDA_TRY(cudaMemsetAsync(g->Hoff, 0, (size_t)g->nnz_off * 36 * sizeof(double), g->stream));
   }
-  CUDA_TRY(cudaMemsetAsync(g->grad, 0, (size_t)g->N * 6 * sizeof(double), g->stream));
+  CUDA_TRY(cudaMemsetAsync(g->grad, 0, (size_t)g->n_own * 6 * sizeof(double), g->stream));
   return PGO_OK;
 }
 
@@ -544,22 +1010,25 @@ static int zero_scalars(pgo_graph* g) {
   return PGO_OK;
 }
 static int fetch_scalars(pgo_graph* g) {
-  // every rank must take the same LM decisions: rank 0's scalars are authoritative
-  if (g->world > 1) NCCL_TRY(ncclBroadcast(g->scalars, g->scalars, sizeof(DeviceScalars), ncclUint8, 0, g->comm, g->stream));
+  // multi-GPU: every rank reduced over its own rows / edges; the all-reduced values are bit-identical on every rank, so
+  // all ranks take the same LM decisions.  (The PCG statistics already are global.)
+  if (g->world > 1) {
+    static_assert(offsetof(DeviceScalars, step_norm2) == 8 && offsetof(DeviceScalars, x_norm2) == 16, "cost, step_norm2, x_norm2 are contiguous");
+    NCCL_TRY(ncclAllReduce(&g->scalars->cost, &g->scalars->cost, 3, ncclDouble, ncclSum, g->comm, g->stream));
+    NCCL_TRY(ncclAllReduce(&g->scalars->gnorm2, &g->scalars->gnorm2, 1, ncclDouble, ncclSum, g->comm, g->stream));
+    NCCL_TRY(ncclAllReduce(&g->scalars->gmax_bits, &g->scalars->gmax_bits, 1, ncclUint64, ncclMax, g->comm, g->stream));
+    g->comm_calls += 3; g->comm_bytes += 40;
+  }
   CUDA_TRY(cudaMemcpyAsync(g->scalars_h, g->scalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PGO_OK;
 }
 
-// full linearization at `poses` with column scaling `scale`: H, g (all-reduced across ranks)
+// full linearization at `poses` with column scaling `scale`: H, g of the owned block rows (multi-GPU: cut edges are
+// evaluated by both owners, each keeping its own rows -- no exchange; the halo tails of poses and scale must be current)
 static int linearize_full(pgo_graph* g, const double* poses, const double* scale, int loss_type, double loss_a) {
   PGO_TRY(zero_system(g, true));
   PGO_TRY(launch_linearize(g, kLinFull, poses, scale, loss_type, loss_a));
-  if (g->world > 1) {
-    PGO_TRY(allreduce_sum(g, g->Hdiag, (size_t)g->N * 36));
-    PGO_TRY(allreduce_sum(g, g->grad, (size_t)g->N * 6));
-    PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
-  }
   return PGO_OK;
 }
 
@@ -573,11 +1042,12 @@ static void swap_system(pgo_graph* g) {
 
 static BsrView bsr_view(const pgo_graph* g) {
   BsrView A;
-  A.n = g->N; A.Hdiag = g->Hdiag; A.Hoff = g->Hoff; A.row_ptr = g->row_ptr; A.col_idx = g->col_idx;
+  A.n = g->n_own; A.Hdiag = g->Hdiag; A.Hoff = g->Hoff; A.row_ptr = g->row_ptr; A.col_idx = g->col_idx;
   return A;
 }
 
 constexpr int kStreamPcgMinPoses = 200000;
+constexpr int kAmgMinPoses = 512;          // PGO_LINEAR_AUTO: below this a mesh-like graph stays with block-Jacobi PCG
 constexpr int kClusterPcgMaxPoses = 400;   // measured: at 2500 poses the 16-SM cluster is already 2.5x slower than the full grid
 
 static int pcg_grid(const pgo_graph* g, const pgo_solver_options* o) {
@@ -596,8 +1066,8 @@ static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b
   P.max_iterations = o->pcg_max_iterations; P.tolerance = o->pcg_tolerance;
   CUDA_TRY(cudaMemsetAsync(g->barrier, 0, 4 * sizeof(unsigned int), g->stream));
   // small graphs: one 16-CTA cluster, hardware barrier (an iteration is a few microseconds, the barrier dominates)
-  static int cluster_ctas = -1;
-  if (cluster_ctas < 0) {
+  int cluster_ctas = 0;
+  if (!pool_cache_get(g->device, kCachePcgCluster, &cluster_ctas)) {
     cluster_ctas = 0;
     cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
@@ -612,6 +1082,7 @@ static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b
       if (cudaOccupancyMaxActiveClusters(&ncl, pcg_kernel<true>, &cfg) == cudaSuccess && ncl >= 1) { cluster_ctas = cs; break; }
       cudaGetLastError();
     }
+    pool_cache_set(g->device, kCachePcgCluster, cluster_ctas);
   }
   if (cluster_ctas > 0 && g->N <= kClusterPcgMaxPoses && o->pcg_num_ctas <= 0) {
     cudaLaunchConfig_t cfg = {};
@@ -632,6 +1103,25 @@ static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b
 
 #include "pgo_pcg_multi.cuh"
 
+// The multilevel hierarchy of this graph: global aggregation (every rank computes the same one), then this rank's slice.
+static int graph_amg_hierarchy(pgo_graph* g, const AmgHostParams& prm, std::vector<AmgGlobalLevel>* G, std::vector<AmgLocalLevel>* L) {
+  AmgLocalLevel l0;
+  l0.row_ptr = g->row_ptr_h; l0.col_idx = g->col_idx_h; l0.halo_gid = g->halo_gid;
+  l0.nbr = g->nbr; l0.send_ptr = g->send_ptr; l0.send_idx = g->send_idx_h; l0.recv_ptr = g->recv_ptr;
+  if ((size_t)g->N_global * 3 != g->pos0_h.size()) return set_error(PGO_ERR_NUMERICAL, "amg: setup-time positions are missing");
+  if (g->world == 1) {
+    amg_build_global(g->N, 1, g->part_off, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(), g->pos0_h.data(), prm, G);
+  } else {
+    amg_build_global(g->N_global, g->world, g->part_off, g->gactive_h.data(), g->grow_ptr_h.data(), g->gcol_idx_h.data(),
+                     g->pos0_h.data(), prm, G);
+    std::vector<int>().swap(g->grow_ptr_h);
+    std::vector<int>().swap(g->gcol_idx_h);
+  }
+  amg_localize(*G, g->rank, g->world, l0, L);
+  return PGO_OK;
+}
+#include "pgo_amg.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI: evaluate / linearize / hessian / spmv / linear solve
 // ------------------------------------------------------------------------------------------------
@@ -639,26 +1129,30 @@ extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, do
                                   double* gradient, double* jacobians) {
   if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
   CUDA_TRY(cudaSetDevice(g->device));
+  if (g->world > 1 && (residuals || jacobians))
+    return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_evaluate: per-edge outputs are not available on a partitioned graph (cost and gradient are)");
   double *res_d = nullptr, *jac_d = nullptr;
   const size_t res_bytes = std::max<size_t>((size_t)g->E * 6, 1) * sizeof(double), jac_bytes = std::max<size_t>((size_t)g->E * 72, 1) * sizeof(double);
   CUDA_TRY(pool_alloc(g->device, reinterpret_cast<void**>(&res_d), res_bytes));
-  CUDA_TRY(pool_alloc(g->device, reinterpret_cast<void**>(&jac_d), jac_bytes));
+  {
+    const cudaError_t e2 = pool_alloc(g->device, reinterpret_cast<void**>(&jac_d), jac_bytes);
+    if (e2 != cudaSuccess) {
+      pool_free(g->device, res_d, res_bytes);
+      return set_error(PGO_ERR_CUDA, "pgo_graph_evaluate: allocating %zu bytes failed: %s", jac_bytes, cudaGetErrorString(e2));
+    }
+  }
   int rc = PGO_OK;
   do {
     if ((rc = zero_system(g, false)) != PGO_OK) break;
     if ((rc = zero_scalars(g)) != PGO_OK) break;
     if ((rc = launch_linearize(g, kLinEval, g->poses, g->scale_eval, loss_type, loss_a, res_d, jac_d)) != PGO_OK) break;
-    if (g->world > 1) {
-      if ((rc = allreduce_sum(g, g->grad, (size_t)g->N * 6)) != PGO_OK) break;
-      if ((rc = allreduce_sum(g, &g->scalars->cost, 1)) != PGO_OK) break;
-    }
     if ((rc = fetch_scalars(g)) != PGO_OK) break;
     if (cost) *cost = g->scalars_h->cost;
     cudaError_t ce = cudaSuccess;
     if (residuals && g->E) ce = cudaMemcpy(residuals, res_d, (size_t)g->E * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess && jacobians && g->E) ce = cudaMemcpy(jacobians, jac_d, (size_t)g->E * 72 * sizeof(double), cudaMemcpyDeviceToHost);
-    if (ce == cudaSuccess && gradient) ce = cudaMemcpy(gradient, g->grad, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) rc = set_error(PGO_ERR_CUDA, "evaluate copy-back failed: %s", cudaGetErrorString(ce));
+    if (rc == PGO_OK && gradient) rc = download_global(g, g->grad, 6, gradient);
   } while (0);
   cudaStreamSynchronize(g->stream);
   pool_free(g->device, res_d, res_bytes); pool_free(g->device, jac_d, jac_bytes);
@@ -669,18 +1163,13 @@ extern "C" int pgo_graph_linearize(pgo_graph* g, int loss_type, double loss_a, c
                                    float* elapsed_ms) {
   if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
   CUDA_TRY(cudaSetDevice(g->device));
-  if (scale) CUDA_TRY(cudaMemcpyAsync(g->scale, scale, (size_t)g->N * 6 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  if (scale) PGO_TRY(upload_global(g, scale, 6, g->scale, true));
   else CUDA_TRY(cudaMemcpyAsync(g->scale, g->scale_eval, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
   PGO_TRY(zero_system(g, true));
   PGO_TRY(zero_scalars(g));
   CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
   PGO_TRY(launch_linearize(g, kLinFull, g->poses, g->scale, loss_type, loss_a));
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-  if (g->world > 1) {
-    PGO_TRY(allreduce_sum(g, g->Hdiag, (size_t)g->N * 36));
-    PGO_TRY(allreduce_sum(g, g->grad, (size_t)g->N * 6));
-    PGO_TRY(allreduce_sum(g, &g->scalars->cost, 1));
-  }
   PGO_TRY(fetch_scalars(g));
   if (cost) *cost = g->scalars_h->cost;
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
@@ -691,6 +1180,7 @@ extern "C" int pgo_graph_get_hessian(pgo_graph* g, long long* nnzb, int* row_ptr
                                      double* gradient) {
   if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
   CUDA_TRY(cudaSetDevice(g->device));
+  if (g->world > 1) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_get_hessian: not available on a partitioned graph");
   const long long total = g->nnz_off + g->N;
   if (nnzb) *nnzb = total;
   if (gradient) CUDA_TRY(cudaMemcpy(gradient, g->grad, (size_t)g->N * 6 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -718,21 +1208,20 @@ extern "C" int pgo_graph_get_hessian(pgo_graph* g, long long* nnzb, int* row_ptr
 extern "C" int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, double* y, int repeats, float* elapsed_ms) {
   if (!g || !x || !y) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_spmv: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
-  const size_t nv = (size_t)g->N * 6 * sizeof(double);
-  CUDA_TRY(cudaMemcpyAsync(g->vu, x, nv, cudaMemcpyHostToDevice, g->stream));
-  if (d) CUDA_TRY(cudaMemcpyAsync(g->dlm, d, nv, cudaMemcpyHostToDevice, g->stream));
-  const int warps = (g->N + kRowsPerWarp - 1) / kRowsPerWarp;
+  // x, d, y are GLOBAL arrays; multi-GPU: the owned slice of x goes up and the halo tail arrives by the exchange
+  PGO_TRY(upload_global(g, x, 6, g->vu, false));
+  if (d) PGO_TRY(upload_global(g, d, 6, g->dlm, false));
+  const int warps = (g->n_own + kRowsPerWarp - 1) / kRowsPerWarp;
   const int ctas = std::max(1, std::min((warps + 7) / 8, 8 * g->num_sms));
   CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
   for (int k = 0; k < std::max(repeats, 1); ++k) {
-    spmv_kernel<false><<<ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, d ? g->dlm : nullptr, g->vw, g->rank == 0);
+    PGO_TRY(halo_exchange0(g, g->vu, 6));
+    spmv_kernel<false><<<ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, d ? g->dlm : nullptr, g->vw, true);
     g->launches++;
   }
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
   CUDA_TRY(cudaGetLastError());
-  if (g->world > 1) PGO_TRY(allreduce_sum(g, g->vw, (size_t)g->N * 6));
-  CUDA_TRY(cudaMemcpyAsync(y, g->vw, nv, cudaMemcpyDeviceToHost, g->stream));
-  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  PGO_TRY(download_global(g, g->vw, 6, y));
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
   return PGO_OK;
 }
@@ -747,7 +1236,15 @@ static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S) {
 
 static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
   int t = o->linear_solver_type;
-  if (g->world > 1) return PGO_LINEAR_PCG_BLOCK_JACOBI;  // the factor is not distributed
+  auto want_amg = [&]() -> int {
+    if (!g->amg) {
+      const int rc = amg_create(g, &g->amg);
+      if (rc != PGO_OK) { amg_destroy(g->amg, g->device); g->amg = nullptr; return rc; }
+    }
+    return PGO_LINEAR_PCG_AMG;
+  };
+  if (g->world > 1) return want_amg();        // the one solver that follows the row partition (the factor is not distributed)
+  if (t == PGO_LINEAR_PCG_AMG) return want_amg();
   if (t == PGO_LINEAR_AUTO || t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     if (!g->chol) {
       LevelChol* c = nullptr;
@@ -766,6 +1263,8 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
     }
     if (g->chol && g->chol->usable) return PGO_LINEAR_PCG_LEVEL_CHOLESKY;
     if (t == PGO_LINEAR_PCG_LEVEL_CHOLESKY) return set_error(PGO_ERR_NUMERICAL, "level Cholesky analysis failed");
+    // mesh-like graph (no cheap exact factor): the multilevel preconditioner; tiny graphs stay with block-Jacobi
+    if (g->n_own >= kAmgMinPoses) return want_amg();
     return PGO_LINEAR_PCG_BLOCK_JACOBI;
   }
   return PGO_LINEAR_PCG_BLOCK_JACOBI;
@@ -782,13 +1281,14 @@ static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int so
                             g->stream, &g->launches);
   }
   const int tpb = 128;
-  lm_prepare_kernel<<<(g->N + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->N, g->Hdiag, g->active, lm.mode, lm.min_diag, lm.max_diag,
-                                                                   lm.radius, lm.diagonal, lm.dlm, g->Minv);
+  lm_prepare_kernel<<<(g->n_own + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->n_own, g->Hdiag, g->active, lm.mode, lm.min_diag, lm.max_diag,
+                                                                       lm.radius, lm.diagonal, lm.dlm, g->Minv);
   g->launches++;
-  static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;   // tests: multi-GPU code path on one GPU
+  if (solver == PGO_LINEAR_PCG_AMG) return amg_pcg_solve(g, o, b);
+  static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;   // tests: the stream-ordered form on a small graph
   // large graphs: separate launches at full occupancy beat the persistent kernel (whose grid barriers only pay when an
   // iteration is a few microseconds long)
-  if (g->world > 1 || force_stream_pcg || g->N >= kStreamPcgMinPoses) return pcg_multi(g, o, b);
+  if (force_stream_pcg || g->N >= kStreamPcgMinPoses) return pcg_multi(g, o, b);
   return launch_pcg(g, o, b);
 }
 
@@ -797,18 +1297,18 @@ extern "C" int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* op
                                       float* elapsed_ms) {
   if (!g || !options || !d || !b || !y) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_linear_solve: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
-  const size_t nv = (size_t)g->N * 6 * sizeof(double);
   const int solver = resolve_linear_solver(g, options);
   if (solver < 0) return solver;
-  CUDA_TRY(cudaMemcpyAsync(g->dlm, d, nv, cudaMemcpyHostToDevice, g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->vb, b, nv, cudaMemcpyHostToDevice, g->stream));
+  PGO_TRY(upload_global(g, d, 6, g->dlm, false));
+  PGO_TRY(upload_global(g, b, 6, g->vb, false));
   PGO_TRY(zero_scalars(g));
   CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
   const LmDiagonal lm = {2, 0.0, 0.0, 1.0, g->diagonal, g->dlm};
   PGO_TRY(linear_solve_device(g, options, solver, g->vb, lm));
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-  PGO_TRY(fetch_scalars(g));
-  CUDA_TRY(cudaMemcpy(y, g->vx, nv, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpyAsync(g->scalars_h, g->scalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  PGO_TRY(download_global(g, g->vx, 6, y));
   if (iterations) *iterations = g->scalars_h->pcg_iterations;
   if (relative_residual) *relative_residual = g->scalars_h->pcg_gamma0 > 0 ? std::sqrt(g->scalars_h->pcg_gamma / g->scalars_h->pcg_gamma0) : 0.0;
   if (elapsed_ms) CUDA_TRY(cudaEventElapsedTime(elapsed_ms, g->ev0, g->ev1));
@@ -827,9 +1327,11 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   const double t_begin = wall_s();
   std::memset(summary, 0, sizeof *summary);
   const long long launches0 = g->launches;
-  const int N = g->N;
-  const int tpb = 128, nblk = (N + tpb - 1) / tpb;
+  const int N = g->N;            // local poses incl. halo copies (pose / scale arrays)
+  const int R = g->n_own;        // block rows = variables stored here
+  const int tpb = 128, nblk = (R + tpb - 1) / tpb;
   float ms = 0.f;
+  const long long comm_calls0 = g->comm_calls, comm_bytes0 = g->comm_bytes;
   auto push_log = [&](const pgo_iteration_summary& it) {
     if (log && summary->num_iterations < log_cap) log[summary->num_iterations] = it;
     summary->num_iterations++;
@@ -838,11 +1340,13 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   if (solver < 0) return solver;
   summary->linear_solver_used = solver;
   if (!g->Hdiag_alt) {
-    PGO_TRY(dev_alloc(g, &g->Hdiag_alt, (size_t)N * 36));
+    PGO_TRY(dev_alloc(g, &g->Hdiag_alt, (size_t)R * 36));
     PGO_TRY(dev_alloc(g, &g->Hoff_alt, (size_t)g->nnz_off * 36));
-    PGO_TRY(dev_alloc(g, &g->grad_alt, (size_t)N * 6));
+    PGO_TRY(dev_alloc(g, &g->grad_alt, (size_t)R * 6));
+    CUDA_TRY(cudaMemsetAsync(g->Hoff_alt, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
   }
-  summary->hessian_blocks = g->nnz_off + g->N;
+  summary->hessian_blocks = g->nnz_off + R;
+  if (solver == PGO_LINEAR_PCG_AMG) { summary->amg_levels = g->amg->num_levels; summary->amg_blocks = g->amg->blocks_all_levels; }
   if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) { summary->factor_blocks = g->chol->factor_blocks; summary->factor_levels = g->chol->num_levels; }
   summary->time_setup_s = g->setup_s;
 
@@ -853,15 +1357,16 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
   summary->num_linearizations++;
   if (opt->jacobi_scaling) {
-    jacobi_scale_kernel<<<nblk, tpb, 0, g->stream>>>(N, g->Hdiag, g->active, 1, g->scale);
+    jacobi_scale_kernel<<<nblk, tpb, 0, g->stream>>>(R, g->Hdiag, g->active, 1, g->scale);
     g->launches++;
+    PGO_TRY(halo_exchange0(g, g->scale, 6));   // the off-diagonal blocks of a cut edge need the other owner's column scaling
     PGO_TRY(zero_scalars(g));
     PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
     summary->num_linearizations++;
   }
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-  xnorm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->active, g->scalars);
-  gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
+  xnorm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->active, g->scalars);
+  gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
   g->launches += 2;
   PGO_TRY(fetch_scalars(g));
   CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
@@ -905,14 +1410,15 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     reuse_diagonal = true;
     // ---- candidate = Plus(x, -y .* scale), |step|, |x_cand|, and -- speculatively -- the full linearisation at the
     //      candidate (cost, H, g, gradient norms) into the alternate system: everything the decision needs in one sync
-    plus_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
+    plus_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
     g->launches++;
+    PGO_TRY(halo_exchange0(g, g->poses_cand, 8));   // candidate poses of the cut edges' other endpoints
     swap_system(g);
     CUDA_TRY(cudaEventRecord(g->ev2, g->stream));
     PGO_TRY(linearize_full(g, g->poses_cand, g->scale, opt->loss_type, opt->loss_a));
     CUDA_TRY(cudaEventRecord(g->ev3, g->stream));
     summary->num_linearizations++;
-    gradient_norm_kernel<<<(N + 255) / 256, 256, 0, g->stream>>>(N, g->poses_cand, g->grad, g->scale, g->active, nullptr, g->scalars);
+    gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses_cand, g->grad, g->scale, g->active, nullptr, g->scalars);
     g->launches++;
     PGO_TRY(fetch_scalars(g));
     const double th2 = wall_s();
@@ -995,6 +1501,9 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     push_log(it);
   }
   summary->final_cost = x_cost;
+  summary->comm_calls = g->comm_calls - comm_calls0;
+  summary->comm_bytes = g->comm_bytes - comm_bytes0;
+  if (g->amg) { summary->comm_bytes_per_pcg_iteration = g->amg->comm_bytes_per_iteration; summary->comm_calls_per_pcg_iteration = g->amg->comm_calls_per_iteration; }
   summary->kernel_launches = g->launches - launches0;
   summary->time_total_s = wall_s() - t_begin;
   return PGO_OK;

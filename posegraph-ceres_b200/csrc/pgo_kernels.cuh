@@ -23,6 +23,8 @@ enum LinMode { kLinFull = 0, kLinCost = 1, kLinEval = 2 };
 struct LinParams {
   int n_edges;
   int n_tiles;
+  int n_own;                    // block rows stored here: poses >= n_own are halo copies owned by another rank (multi-GPU);
+                                // their diagonal blocks / gradient are that rank's, and an edge's cost is its id_begin owner's
   const EdgeCoreTile* core;
   const EdgeInfoTile* info;     // nullptr when identity
   const double* poses;          // [N][8]
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
       for (int i = 0; i < 6; ++i) sq = fma(r[i], r[i], sq);
       double rho1;
       const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
-      if (valid) cost_acc += 0.5 * rho;
+      if (valid && a < p.n_own) cost_acc += 0.5 * rho;
       __syncwarp();
       stage = stage1;
       if (stage == 0) ++round;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
     for (int i = 0; i < 6; ++i) sq = fma(L.r[i], L.r[i], sq);
     double rho1;
     const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
-    if (valid) cost_acc += 0.5 * rho;
+    if (valid && a < p.n_own) cost_acc += 0.5 * rho;
     if (!valid) rho1 = 0.0;   // padded lanes contribute exact zeros
 
     double sa[6], sb[6];
@@ -226,8 +228,8 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
           for (int i = 0; i < 6; ++i) { s1 = fma(L.B1[i][k], L.r[i], s1); s2 = fma(L.B2[i][k], L.r[i], s2); sc = fma(L.C[i][k], L.r[i], sc); }
           g1[k] = rho1 * s1; g2[k] = rho1 * s2; gc[k] = rho1 * sc;
         }
-        sidx[lane] = valid ? a : -1;
-        sidx[32 + lane] = valid ? b : -1;
+        sidx[lane] = (valid && a < p.n_own) ? a : -1;
+        sidx[32 + lane] = (valid && b < p.n_own) ? b : -1;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           stg[lane * 6 + k] = -sa[k] * g1[k];        stg[lane * 6 + 3 + k] = sa[3 + k] * gc[k];
@@ -292,8 +294,8 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
           }
           __syncwarp();
         };
-        emit([&](int r, int c) { return rho1 * sa[r] * sa[c] * Haa(r, c); }, valid ? a : -1, p.Hdiag, true);
-        emit([&](int r, int c) { return rho1 * sb[r] * sb[c] * Hbb(r, c); }, valid ? b : -1, p.Hdiag, true);
+        emit([&](int r, int c) { return rho1 * sa[r] * sa[c] * Haa(r, c); }, (valid && a < p.n_own) ? a : -1, p.Hdiag, true);
+        emit([&](int r, int c) { return rho1 * sb[r] * sb[c] * Hbb(r, c); }, (valid && b < p.n_own) ? b : -1, p.Hdiag, true);
         // off-diagonal blocks: (a,b) = H_ab, (b,a) = H_ab^T; slot >= 0: sole producer (store), <= -2: shared slot (RED)
         emit([&](int r, int c) { return rho1 * sa[r] * sb[c] * Hab(r, c); }, valid ? ct->slot_ab[lane] : -1, p.Hoff, false);
         emit([&](int r, int c) { return rho1 * sb[r] * sa[c] * Hab(c, r); }, valid ? ct->slot_ba[lane] : -1, p.Hoff, false);

@@ -1,6 +1,6 @@
-// pgo_pcg_multi.cuh -- stream-ordered block-Jacobi PCG for the multi-GPU path: every rank holds an
-// edge shard (a partial off-diagonal Hessian) and replicas of all vectors; the one exchange per
-// iteration is an NCCL all-reduce of the SpMV product over NVLink.  Included by pgo_b200.cu.
+// pgo_pcg_multi.cuh -- stream-ordered block-Jacobi PCG (one GPU): separate launches at full occupancy for graphs of
+// >= 200 k poses, where the grid barriers of the persistent kernel no longer pay.  (Multi-GPU solves use the
+// row-partitioned multilevel PCG of pgo_amg.cuh.)  Included by pgo_b200.cu.
 #pragma once
 
 namespace pgo {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kPcgmThreads) pcgm_final_reduce_kernel(const d
 
 }  // namespace pgo
 
-// (H + diag(dlm)) x = b across g->world ranks. Stream-ordered; the host polls `done` every
+// (H + diag(dlm)) x = b. Stream-ordered; the host polls `done` every
 // kCheckEvery iterations (kernels after convergence are no-ops).
 static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b) {
   using namespace pgo;
@@ -184,7 +184,7 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
   PcgMultiState* st = g->pcgm_state;
   PcgMultiState* st_h = g->pcgm_state_h;
   double *part0 = g->pcgm_part0, *part1 = g->pcgm_part1;
-  const bool with_diag = (g->rank == 0);
+  const bool with_diag = true;
   CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
   pcgm_init_kernel<<<nb, kPcgmThreads, 0, g->stream>>>(N, b, g->Minv, g->vx, g->vr, g->vu, g->vp, g->vs, part0);
   pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 0, o->pcg_max_iterations, o->pcg_tolerance, part0, nb);
@@ -193,32 +193,20 @@ static int pcg_multi(pgo_graph* g, const pgo_solver_options* o, const double* b)
   int launched = 0;
   for (;;) {
     for (int k = 0; k < kCheckEvery; ++k) {
-      if (g->world > 1) {
-        // the SpMV product is a sum over ranks: all-reduce it, then w . u on the summed vector
-        spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
-        PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
-        pcgm_dot_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vw, g->vu, st, part1);
-        pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, dot_ctas);
-        g->launches += 1;
-      } else {
-        // one GPU: w . u rides on the SpMV (per-CTA partials in a fixed order)
-        spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
-        pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, sp_ctas);
-      }
+      // w . u rides on the SpMV (per-CTA partials in a fixed order)
+      spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vu, g->dlm, g->vw, with_diag, part1, &st->done);
+      pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 1, o->pcg_max_iterations, o->pcg_tolerance, part1, sp_ctas);
       pcgm_update_kernel<<<nbu, kPcgmThreads, 0, g->stream>>>(N, g->Minv, g->vw, g->vx, g->vr, g->vu, g->vp, g->vs, st, part0);
       pcgm_scalar_kernel<<<1, kPcgmThreads, 0, g->stream>>>(st, 2, o->pcg_max_iterations, o->pcg_tolerance, part0, nbu);
       g->launches += 4;
       ++launched;
     }
-    // the exit decision must be the same on every rank: rank 0's state is authoritative
-    if (g->world > 1) NCCL_TRY(ncclBroadcast(st, st, sizeof(PcgMultiState), ncclUint8, 0, g->comm, g->stream));
     CUDA_TRY(cudaMemcpyAsync(st_h, st, sizeof(PcgMultiState), cudaMemcpyDeviceToHost, g->stream));
     CUDA_TRY(cudaStreamSynchronize(g->stream));
     if (st_h->done || launched >= o->pcg_max_iterations + kCheckEvery) break;
   }
-  // epilogue: w = A x (all-reduced) for the model cost change
+  // epilogue: w = A x for the model cost change
   spmv_kernel<false><<<sp_ctas, 256, 0, g->stream>>>(bsr_view(g), g->vx, g->dlm, g->vw, with_diag);
-  PGO_TRY(allreduce_sum(g, g->vw, (size_t)n6));
   pcgm_final_kernel<<<dot_ctas, kPcgmThreads, 0, g->stream>>>(n6, g->vx, b, g->vw, g->dlm, part1);
   pcgm_final_reduce_kernel<<<1, kPcgmThreads, 0, g->stream>>>(part1, dot_ctas, st, g->scalars);
   g->launches += 3;

@@ -16,11 +16,21 @@ namespace pgo {
 struct DevicePool {
   std::mutex mu;
   std::multimap<size_t, void*> free_blocks;     // size -> device pointer
+  std::map<void*, size_t> alloc_size;           // true (rounded) size of every block this pool ever handed out
   size_t cached_bytes = 0;
   std::vector<cudaStream_t> streams;
   std::vector<cudaEvent_t> events;
   std::vector<void*> pinned;                    // kPinnedBytes each
   int num_sms = 0;
+  // per-device facts about kernels: occupancy results and "function attribute already set on THIS device" flags
+  // (cudaFuncSetAttribute applies to the current device only, so a process-wide static would be wrong)
+  int cache_val[64] = {};
+  bool cache_has[64] = {};
+};
+
+enum PoolCacheKey {
+  kCachePcgPerSm = 0, kCachePcgCluster = 1, kCacheCholPerSm = 2, kCacheCholCluster = 3, kCacheAmgDenseAttr = 4,
+  kCacheLinAttrBase = 8   // + variant index (< 16)
 };
 
 constexpr size_t kPinnedBytes = 4096;
@@ -29,6 +39,19 @@ constexpr int kMaxDevices = 64;
 inline DevicePool& device_pool(int device) {
   static DevicePool pools[kMaxDevices];
   return pools[device < 0 || device >= kMaxDevices ? 0 : device];
+}
+
+inline bool pool_cache_get(int device, int key, int* v) {
+  DevicePool& P = device_pool(device);
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (!P.cache_has[key]) return false;
+  *v = P.cache_val[key];
+  return true;
+}
+inline void pool_cache_set(int device, int key, int v) {
+  DevicePool& P = device_pool(device);
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.cache_val[key] = v; P.cache_has[key] = true;
 }
 
 inline size_t pool_round(size_t bytes) {
@@ -44,7 +67,7 @@ inline cudaError_t pool_alloc(int device, void** out, size_t bytes) {
     std::lock_guard<std::mutex> lk(P.mu);
     auto it = P.free_blocks.lower_bound(want);
     if (it != P.free_blocks.end() && it->first <= want + want / 4) {
-      *out = it->second;
+      *out = it->second;   // (its true size stays registered in alloc_size)
       P.cached_bytes -= it->first;
       P.free_blocks.erase(it);
       return cudaSuccess;
@@ -56,12 +79,16 @@ inline cudaError_t pool_alloc(int device, void** out, size_t bytes) {
     std::vector<void*> drop;
     {
       std::lock_guard<std::mutex> lk(P.mu);
-      for (auto& kv : P.free_blocks) drop.push_back(kv.second);
+      for (auto& kv : P.free_blocks) { drop.push_back(kv.second); P.alloc_size.erase(kv.second); }
       P.free_blocks.clear();
       P.cached_bytes = 0;
     }
     for (void* p : drop) cudaFree(p);
     e = cudaMalloc(out, want);
+  }
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.alloc_size[*out] = want;
   }
   return e;
 }
@@ -70,12 +97,16 @@ inline cudaError_t pool_alloc(int device, void** out, size_t bytes) {
 inline void pool_free(int device, void* p, size_t bytes) {
   if (!p) return;
   DevicePool& P = device_pool(device);
-  const size_t sz = pool_round(bytes);
+  size_t sz = pool_round(bytes);
   bool keep = true;
   {
     std::lock_guard<std::mutex> lk(P.mu);
+    // a reused block may be larger than what its last user asked for: file it under its TRUE size
+    auto it = P.alloc_size.find(p);
+    if (it != P.alloc_size.end()) sz = it->second;
     if (P.cached_bytes + sz > ((size_t)8 << 30)) keep = false;   // never sit on more than 8 GiB
     if (keep) { P.free_blocks.emplace(sz, p); P.cached_bytes += sz; }
+    else P.alloc_size.erase(p);
   }
   if (!keep) cudaFree(p);
 }
@@ -142,7 +173,7 @@ inline void pool_release(int device) {
     std::vector<cudaEvent_t> ev;
     {
       std::lock_guard<std::mutex> lk(P.mu);
-      for (auto& kv : P.free_blocks) blocks.push_back(kv.second);
+      for (auto& kv : P.free_blocks) { blocks.push_back(kv.second); P.alloc_size.erase(kv.second); }
       P.free_blocks.clear(); P.cached_bytes = 0;
       st.swap(P.streams); ev.swap(P.events); pins.swap(P.pinned);
     }

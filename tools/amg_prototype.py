@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""CPU prototype (numpy/scipy + the oracle's Jacobians) of the aggregation-AMG preconditioner for the damped normal
+equations of a pose graph.  Design evidence only: it answers "how many PCG iterations does a rigid-body-mode
+aggregation V-cycle need on sphere / grid / torus" before the CUDA version is written.  Not part of the product."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle_py as O  # noqa: E402
+import posegraph_ceres_b200.datasets as D  # noqa: E402
+
+
+def assemble(g, jac):
+    E, N = g.n_edges, g.n_poses
+    Ja = jac[:, 0].reshape(E, 6, 6)
+    Jb = jac[:, 1].reshape(E, 6, 6)
+    a, b = g.edge_ids[:, 0], g.edge_ids[:, 1]
+    rows = np.concatenate([a, b, a, b])
+    cols = np.concatenate([a, b, b, a])
+    blk = np.concatenate([np.einsum("eki,ekj->eij", Ja, Ja), np.einsum("eki,ekj->eij", Jb, Jb),
+                          np.einsum("eki,ekj->eij", Ja, Jb), np.einsum("eki,ekj->eij", Jb, Ja)])
+    # expand to COO scalars
+    r = (rows[:, None, None] * 6 + np.arange(6)[None, :, None]) + np.zeros((1, 1, 6), int)
+    c = (cols[:, None, None] * 6 + np.arange(6)[None, None, :]) + np.zeros((1, 6, 1), int)
+    H = sp.coo_matrix((blk.ravel(), (r.ravel(), c.ravel())), shape=(6 * N, 6 * N)).tocsr()
+    return H
+
+
+def aggregate(adj, n, target=None, rng=None):
+    """Greedy aggregation: pass 1 roots with all-unaggregated neighbourhoods, pass 2 attach leftovers to a neighbour
+    aggregate, pass 3 leftovers form their own."""
+    agg = -np.ones(n, int)
+    indptr, indices = adj.indptr, adj.indices
+    na = 0
+    for i in range(n):
+        if agg[i] >= 0:
+            continue
+        nb = indices[indptr[i]:indptr[i + 1]]
+        if np.all(agg[nb] < 0):
+            agg[i] = na
+            agg[nb] = na
+            na += 1
+    for i in range(n):
+        if agg[i] >= 0:
+            continue
+        nb = indices[indptr[i]:indptr[i + 1]]
+        cand = agg[nb]
+        cand = cand[cand >= 0]
+        if len(cand):
+            agg[i] = -2 - cand[0]
+    m = agg <= -2
+    agg[m] = -agg[m] - 2
+    for i in range(n):
+        if agg[i] < 0:
+            agg[i] = na
+            na += 1
+    return agg, na
+
+
+def pairwise_aggregate(adj_w, n, passes=2):
+    """Notay-style pairwise matching by strongest connection, repeated `passes` times (aggregates of <= 2^passes)."""
+    agg = np.arange(n)
+    na = n
+    A = adj_w
+    for _ in range(passes):
+        A = A.tocsr()
+        m = A.shape[0]
+        match = -np.ones(m, int)
+        new = -np.ones(m, int)
+        k = 0
+        deg = np.diff(A.indptr)
+        for i in np.argsort(deg, kind="stable"):
+            if new[i] >= 0:
+                continue
+            nb = A.indices[A.indptr[i]:A.indptr[i + 1]]
+            w = A.data[A.indptr[i]:A.indptr[i + 1]]
+            best, bw = -1, 0.0
+            for j, ww in zip(nb, w):
+                if j != i and new[j] < 0 and ww > bw:
+                    best, bw = j, ww
+            new[i] = k
+            if best >= 0:
+                new[best] = k
+            k += 1
+        agg = new[agg]
+        P = sp.coo_matrix((np.ones(m), (np.arange(m), new)), shape=(m, k)).tocsr()
+        A = (P.T @ A @ P).tocsr()
+        A.setdiag(0)
+        A.eliminate_zeros()
+        na = k
+    return agg, na
+
+
+def block_diag_inv(A, n):
+    """inverse of the 6x6 diagonal blocks -> BSR"""
+    Ab = A.tobsr(blocksize=(6, 6))
+    Dinv = np.zeros((n, 6, 6))
+    for i in range(n):
+        for p in range(Ab.indptr[i], Ab.indptr[i + 1]):
+            if Ab.indices[p] == i:
+                Dinv[i] = np.linalg.inv(Ab.data[p])
+    return sp.bsr_matrix((Dinv, np.arange(n), np.arange(n + 1)), shape=(6 * n, 6 * n)).tocsr()
+
+
+class Level:
+    pass
+
+
+def build_hierarchy(A, pos, n, scale_inv, args, active):
+    """A: (6n x 6n) csr incl. LM diagonal, in SCALED coordinates; pos: (n,3) positions; scale_inv (n,6): 1/scale
+    (the rigid-body modes of the unscaled problem are B_i = [[I, -2[p_i - c]x],[0, I]]; scaled: S^-1 B)."""
+    levels = []
+    cur_A, cur_pos, cur_n = A, pos, n
+    cur_Sinv = scale_inv
+    cur_active = active
+    while True:
+        L = Level()
+        L.A = cur_A
+        L.n = cur_n
+        L.Dinv = block_diag_inv(cur_A, cur_n) if cur_n > 0 else None
+        levels.append(L)
+        if cur_n <= args.coarsest and not (args.agg == "cxx" and len(levels) - 1 < len(args.cxx_aggs)):
+            L.dense = np.linalg.pinv(cur_A.toarray())
+            break
+        Ab = cur_A.tobsr(blocksize=(6, 6))
+        w = np.linalg.norm(Ab.data.reshape(-1, 36), axis=1)
+        adj = sp.csr_matrix((w, Ab.indices, Ab.indptr), shape=(cur_n, cur_n))
+        adj.setdiag(0)
+        adj.eliminate_zeros()
+        if args.theta > 0:
+            # geometric strength: 1 / |p_i - p_j|^2, keep neighbours within theta of the row maximum
+            coo = adj.tocoo()
+            d2 = np.sum((cur_pos[coo.row] - cur_pos[coo.col]) ** 2, axis=1) + 1e-12
+            wgt = 1.0 / d2
+            W = sp.csr_matrix((wgt, (coo.row, coo.col)), shape=adj.shape)
+            rmax = W.max(axis=1).toarray().ravel()
+            keep = wgt >= args.theta * np.maximum(rmax[coo.row], rmax[coo.col])
+            adj = sp.csr_matrix((wgt[keep], (coo.row[keep], coo.col[keep])), shape=adj.shape)
+        if args.agg == "cxx":
+            agg = args.cxx_aggs[len(levels) - 1].astype(int).copy()
+            na = int(agg.max()) + 1
+            if len(agg) < cur_n:       # the parking node of the inactive poses (below) rides along
+                agg = np.concatenate([agg, -np.ones(cur_n - len(agg), int)])
+            if (agg < 0).any():        # inactive nodes: park them in an extra (empty-operator) aggregate
+                agg[agg < 0] = na
+                na += 1
+        elif args.agg == "greedy":
+            agg, na = aggregate(adj, cur_n)
+        else:
+            agg, na = pairwise_aggregate(adj, cur_n, args.passes)
+        cnt = np.bincount(agg, minlength=na).astype(float)
+        cpos = np.stack([np.bincount(agg, weights=cur_pos[:, k], minlength=na) / cnt for k in range(3)], axis=1)
+        # tentative prolongator blocks P_i = Sinv_i * [[I, -2 [p_i - c_I]x], [0, I]]
+        d = cur_pos - cpos[agg]
+        Pb = np.zeros((cur_n, 6, 6))
+        Pb[:, np.arange(6), np.arange(6)] = 1.0
+        if args.modes == 6:
+            # dp = omega x d with omega = 2 delta  ->  dp = -2 [d]x delta
+            Pb[:, 0, 4] = 2 * d[:, 2]; Pb[:, 0, 5] = -2 * d[:, 1]
+            Pb[:, 1, 3] = -2 * d[:, 2]; Pb[:, 1, 5] = 2 * d[:, 0]
+            Pb[:, 2, 3] = 2 * d[:, 1]; Pb[:, 2, 4] = -2 * d[:, 0]
+        Pb = Pb * cur_Sinv[:, :, None]
+        Pb = Pb * cur_active[:, None, None]
+        P = sp.bsr_matrix((Pb, agg, np.arange(cur_n + 1)), shape=(6 * cur_n, 6 * na)).tocsr()
+        if args.smooth_p > 0:
+            P = P - args.smooth_p * (L.Dinv @ (cur_A @ P))
+        L.P = P
+        cur_A = (P.T @ cur_A @ P).tocsr()
+        cur_pos, cur_n = cpos, na
+        cur_Sinv = np.ones((na, 6))
+        cur_active = np.ones(na)
+    return levels
+
+
+def vcycle(levels, k, r, args):
+    L = levels[k]
+    if k == len(levels) - 1:
+        return L.dense @ r
+    om = args.omega
+    x = om * (L.Dinv @ r)
+    for _ in range(args.nu - 1):
+        x = x + om * (L.Dinv @ (r - L.A @ x))
+    rc = L.P.T @ (r - L.A @ x)
+    ec = vcycle(levels, k + 1, rc, args)
+    if args.gamma == 2 and k + 1 < len(levels) - 1:
+        # W-cycle-ish second visit
+        rc2 = rc - levels[k + 1].A @ ec
+        ec = ec + vcycle(levels, k + 1, rc2, args)
+    x = x + args.over * (L.P @ ec)
+    for _ in range(args.nu):
+        x = x + om * (L.Dinv @ (r - L.A @ x))
+    return x
+
+
+def pcg(A, b, M, tol, maxit):
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = M(r)
+    p = z.copy()
+    rz = r @ z
+    rz0 = rz
+    for it in range(1, maxit + 1):
+        Ap = A @ p
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        z = M(r)
+        rz_new = r @ z
+        if rz_new <= tol * tol * rz0:
+            return x, it
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, maxit
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--graph", default="sphere")
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--radius", type=float, nargs="+", default=[1e4, 1e6, 1e8])
+    ap.add_argument("--agg", default="greedy")
+    ap.add_argument("--passes", type=int, default=2)
+    ap.add_argument("--modes", type=int, default=6)
+    ap.add_argument("--omega", type=float, default=0.7)
+    ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--over", type=float, default=1.0)
+    ap.add_argument("--gamma", type=int, default=1)
+    ap.add_argument("--smooth-p", type=float, default=0.0)
+    ap.add_argument("--coarsest", type=int, default=8)
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--theta", type=float, default=0.0)
+    ap.add_argument("--loops", type=int, default=-1)
+    ap.add_argument("--world", type=int, default=1)
+    ap.add_argument("--at-truth", action="store_true")
+    args = ap.parse_args()
+    if args.graph == "sphere":
+        g = D.sphere()
+    elif args.graph == "grid":
+        s = args.n or 100
+        g = D.manhattan_grid(s, s, max(1, s * s // 20) if args.loops < 0 else args.loops)
+    elif args.graph == "torus":
+        g = D.torus(args.n or 10000)
+    elif args.graph == "kitti":
+        g = D.kitti00()
+    poses = g.truth if args.at_truth and g.truth is not None else g.poses
+    if args.agg == "cxx":
+        import posegraph_ceres_b200 as P
+        sizes, args.cxx_aggs = P.amg_aggregates(g, args.world)
+        args.coarsest = sizes[-1] + 1
+        print("cxx hierarchy", sizes)
+    t0 = time.time()
+    cost, res, grad, jac = O.evaluate(g, poses=poses)
+    H = assemble(g, jac)
+    N = g.n_poses
+    active = (1 - g.pose_const).astype(float)
+    diag = H.diagonal().reshape(N, 6)
+    scale = active[:, None] / (1.0 + np.sqrt(diag))
+    S = sp.diags(scale.ravel())
+    Hs = (S @ H @ S).tocsr()
+    gs = (scale * grad).ravel()
+    print(f"{g.name}: N={N} E={g.n_edges} assemble {time.time() - t0:.1f}s cost {cost:.3f}")
+    dsc = np.clip(Hs.diagonal(), 1e-6, 1e32)
+    scale_inv = np.where(scale > 0, 1.0 / np.maximum(scale, 1e-300), 0.0)
+    for radius in args.radius:
+        A = (Hs + sp.diags(dsc / radius)).tocsr()
+        # constant pose rows: identity-ish (diag = d only) -- fine
+        Dinv = block_diag_inv(A, N)
+        t0 = time.time()
+        _, it_j = pcg(A, gs, lambda r: Dinv @ r, args.tol, 20000)
+        tj = time.time() - t0
+        t0 = time.time()
+        levels = build_hierarchy(A, poses[:, :3], N, scale_inv, args, active)
+        tb = time.time() - t0
+        sizes = [L.n for L in levels]
+        nnz = [L.A.nnz // 36 for L in levels]
+        t0 = time.time()
+        x, it_a = pcg(A, gs, lambda r: vcycle(levels, 0, r, args), args.tol, 2000)
+        ta = time.time() - t0
+        rel = np.linalg.norm(A @ x - gs) / np.linalg.norm(gs)
+        print(f"  radius {radius:.0e}: block-Jacobi PCG {it_j} it ({tj:.1f}s) | AMG-PCG {it_a} it ({ta:.1f}s, build {tb:.1f}s) "
+              f"levels {sizes} blocks {nnz} opcx {sum(nnz) / nnz[0]:.2f} true rel res {rel:.1e}")
+
+
+if __name__ == "__main__":
+    main()
