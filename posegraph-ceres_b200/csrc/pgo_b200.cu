@@ -736,7 +736,8 @@ extern "C" int pgo_analyze_partition(int n_poses, int n_edges, const double* pos
       // aggregates never cross a rank boundary: the owner of a node owns its aggregate
       const AmgGlobalLevel& g = G[l];
       const AmgGlobalLevel& gc = G[l + 1];
-      for (int i = 0; i < g.n && ok; ++i)
+      // (a replicated level lives whole on every rank: its aggregates are free to span the former ranges)
+      for (int i = 0; i < g.n && ok && !g.replicated; ++i)
         if (g.agg[i] >= 0 && amg_owner_of(g.off, i) != amg_owner_of(gc.off, g.agg[i])) ok = false;
       // every stored fine block lands in exactly one gather list; member lists cover the stored variable rows
       long long want = 0, members = 0;

@@ -340,6 +340,43 @@ def shard_edges(g: PoseGraph, rank: int, world: int) -> PoseGraph:
                      g.edge_sqrt_info[lo:hi], g.pose_const, g.truth)
 
 
+@dataclass
+class RowPartition:
+    """One rank's slice under the owner-computes row partition of the multi-GPU path (host-side mirror of
+    build_partition in csrc/pgo_b200.cu): the block rows of poses [lo, hi), every edge touching one of them, and halo
+    copies of the other endpoints of cut edges.  Local ids: owned poses first (global id - lo), then the halo in
+    ascending global id."""
+    lo: int
+    hi: int
+    halo_gid: np.ndarray       # (n_halo,) global ids, ascending
+    edge_sel: np.ndarray       # global ids of the local edges, ascending
+    local: PoseGraph           # poses = owned + halo, edge_ids in LOCAL ids
+    cost_edges: np.ndarray     # bool per local edge: its cost is accounted here (id_begin is owned)
+
+    @property
+    def n_own(self) -> int:
+        return self.hi - self.lo
+
+
+def partition_rows(g: PoseGraph, rank: int, world: int) -> RowPartition:
+    n = g.n_poses
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    a, b = g.edge_ids[:, 0], g.edge_ids[:, 1]
+    oa, ob = (a >= lo) & (a < hi), (b >= lo) & (b < hi)
+    sel = np.nonzero(oa | ob)[0]
+    halo = np.unique(np.concatenate([a[sel][~oa[sel]], b[sel][~ob[sel]]])).astype(np.int64)
+
+    def local_of(gid):
+        own = (gid >= lo) & (gid < hi)
+        return np.where(own, gid - lo, (hi - lo) + np.searchsorted(halo, gid))
+
+    ids = np.stack([local_of(a[sel]), local_of(b[sel])], axis=1).astype(np.int32)
+    gids = np.concatenate([np.arange(lo, hi), halo])
+    loc = PoseGraph(f"{g.name}[rows {rank}/{world}]", g.poses[gids].copy(), ids, g.edge_meas[sel].copy(),
+                    g.edge_sqrt_info[sel].copy(), g.pose_const[gids].copy(), None if g.truth is None else g.truth[gids].copy())
+    return RowPartition(lo, hi, halo, sel, loc, oa[sel])
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # config/Edge_Candidates_index.txt: "cur cand cand ..." per line for frames 1..n-1, written by
 # REF/src/POSE_GRAPH_CERES_PLUS/test/generate_edges_from_trajectory_origion.cpp:36-52 and read back by

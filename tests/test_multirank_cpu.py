@@ -1,5 +1,7 @@
-"""world_size-2 gloo test of the multi-rank host logic: contiguous edge shards + all-reduce(sum) of
-the per-shard J^T r / cost reproduce the single-rank quantities (what the NCCL path does on GPUs)."""
+"""world_size-2 gloo test of the multi-rank host logic: under the owner-computes row partition every rank evaluates the
+edges that touch its own poses (cut edges on both sides), keeps its own rows of J^T r and accounts the cost of the edges
+whose id_begin it owns; gathering the owned rows and summing the costs reproduces the single-rank quantities (what the
+row-partitioned CUDA path does with NCCL).  The halo plan of the C++ host code is cross-checked between the ranks."""
 import os
 import sys
 
@@ -15,22 +17,43 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import oracle_py as O
-    import posegraph_ceres_b200.datasets as D
+    import posegraph_ceres_b200 as P
+    D = P.datasets
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = D.sphere(6, 10, None)
-    shard = D.shard_edges(g, rank, world)
-    cost, _, grad, _ = O.evaluate(shard)
-    t = torch.from_numpy(np.concatenate([[cost], grad.ravel()]))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    part = D.partition_rows(g, rank, world)
+    loc = part.local
+    # owned rows of the gradient from ALL local edges; cost from the edges whose id_begin is owned
+    _, _, grad, _ = O.evaluate(loc)
+    import dataclasses
+    mine = dataclasses.replace(loc, edge_ids=loc.edge_ids[part.cost_edges], edge_meas=loc.edge_meas[part.cost_edges],
+                               edge_sqrt_info=loc.edge_sqrt_info[part.cost_edges])
+    cost = O.evaluate(mine)[0] if mine.n_edges else 0.0
+    full = torch.zeros(g.n_poses, 6, dtype=torch.float64)
+    full[part.lo:part.hi] = torch.from_numpy(grad[:part.n_own])
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)          # disjoint slices: the sum is the all-gather
+    c = torch.tensor([cost], dtype=torch.float64)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    # halo plan of the C++ host code: counts all-gathered and compared pairwise
+    info = P.analyze_partition(g, rank, world)
+    plan = torch.tensor([list(info.send_to[:world]), list(info.recv_from[:world])], dtype=torch.int64)
+    plans = [torch.zeros_like(plan) for _ in range(world)]
+    dist.all_gather(plans, plan)
+    sums = torch.tensor([info.plan_checksum % 2 ** 62, info.recv_checksum % 2 ** 62, info.plan_checksum >> 62, info.recv_checksum >> 62], dtype=torch.int64)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     if rank == 0:
         full_cost, _, full_grad, _ = O.evaluate(g)
-        out.put((abs(t[0].item() - full_cost), float(np.abs(t[1:].numpy() - full_grad.ravel()).max()), shard.n_edges, g.n_edges))
+        sym = all(int(plans[a][0][b]) == int(plans[b][1][a]) for a in range(world) for b in range(world))
+        send_sum = (int(sums[0]) + (int(sums[2]) << 62)) % 2 ** 64
+        recv_sum = (int(sums[1]) + (int(sums[3]) << 62)) % 2 ** 64
+        out.put((abs(c.item() - full_cost), float(np.abs(full.numpy() - full_grad).max()), sym, send_sum == recv_sum,
+                 info.consistent, info.n_own, len(part.halo_gid), info.n_halo))
     dist.destroy_process_group()
 
 
-def test_edge_sharding_allreduce_world2():
+def test_row_partition_owner_computes_world2():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = 29500 + os.getpid() % 2000
@@ -38,7 +61,9 @@ def test_edge_sharding_allreduce_world2():
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
+        p.join(180)
         assert p.exitcode == 0
-    dc, dg, ne, total = out.get(timeout=10)
-    assert dc < 1e-9 and dg < 1e-9 and ne == total // 2
+    dc, dg, sym, sums_ok, consistent, n_own, n_halo_py, n_halo_c = out.get(timeout=10)
+    assert dc < 1e-9 and dg < 1e-9
+    assert sym and sums_ok and consistent == 1
+    assert n_own == 30 and n_halo_py == n_halo_c and n_halo_c > 0
