@@ -196,7 +196,7 @@ struct Solver {
     // device-specific knobs (not in Ceres)
     int device = 0;
     int device_linear_solver = PGO_LINEAR_AUTO;   // pgo_linear_solver_type
-    double pcg_tolerance = 1e-10;
+    double pcg_tolerance = 1e-8;
     int pcg_max_iterations = 20000;
     double direct_residual_accept = 1e-8;
   };

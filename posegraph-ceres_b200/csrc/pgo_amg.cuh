@@ -56,7 +56,10 @@ struct Amg {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   double* part = nullptr;                  // per-CTA partial sums
   int part_cap = 0;
+  bool warp_spmv = false;
   double* red = nullptr;                   // [8] reduced scalars (all-reduced across ranks)
+  struct IterGraph { const void* key[4]; int max_it; double tol; cudaGraphExec_t exec; int kernels; };
+  std::vector<IterGraph> graphs;           // captured PCG iteration per (H, poses) buffer pair (the LM loop alternates two)
   long long blocks_all_levels = 0;
   long long comm_bytes_per_iteration = 0;  // payload this rank sends per PCG iteration (halo + gathers + scalars)
   int comm_calls_per_iteration = 0;
@@ -265,10 +268,12 @@ __global__ void __launch_bounds__(kAmgThreads) amg_dense_solve_kernel(int m, con
   __shared__ double rs[6 * kAmgDenseMaxNodes];
   for (int k = threadIdx.x; k < m; k += blockDim.x) rs[k] = r[k];
   __syncthreads();
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x >> 5; i < m; i += kAmgThreads / 32) {     // one warp per row: three independent loads per lane
     double s = 0.0;
-    for (int k = 0; k < m; ++k) s = fma(inv[i * m + k], rs[k], s);
-    x[i] = s;
+    for (int k = lane; k < m; k += 32) s = fma(inv[i * m + k], rs[k], s);
+    s = warp_sum(s);
+    if (lane == 0) x[i] = s;
   }
 }
 
@@ -328,7 +333,8 @@ __global__ void __launch_bounds__(kAmgThreads) amg_residual_restrict_kernel(cons
                                                                             const int* __restrict__ mem_idx, const double* __restrict__ pos,
                                                                             int pos_stride, const double* __restrict__ cpos,
                                                                             const double* __restrict__ scale, double* __restrict__ rc,
-                                                                            const int* skip) {
+                                                                            const double* __restrict__ Dinv_c, double omega,
+                                                                            double* __restrict__ xc, const int* skip) {
   if (skip && *skip) return;
   const RowLane L = amg_row_lane(ncomp);      // L.i = computed coarse row (relative)
   const unsigned full = 0xffffffffu;
@@ -363,6 +369,12 @@ __global__ void __launch_bounds__(kAmgThreads) amg_residual_restrict_kernel(cons
     }
   }
   if (L.on) rc[6 * (size_t)I + L.c] = acc;
+  // the coarse level's first smoothing sweep x_c = omega Dinv_c r_c rides along (Dinv_c == nullptr: done by the caller,
+  // e.g. after an all-gather of r_c, or the coarsest level is solved densely)
+  if (Dinv_c != nullptr) {
+    const double z = amg_block_row_dot(L.on ? Dinv_c + 36 * (size_t)I : nullptr, L.c, L.g0, L.on ? acc : 0.0);
+    if (L.on) xc[6 * (size_t)I + L.c] = omega * z;
+  }
 }
 
 // x_i += P_i e_{agg(i)} over the stored rows
@@ -389,6 +401,115 @@ __global__ void __launch_bounds__(kAmgThreads) amg_prolong_kernel(int n, const i
   }
   if (scale) { const double sv = scale[6 * (size_t)i + c]; v = sv > 0.0 ? v / sv : 0.0; }
   x[6 * (size_t)i + c] += v;
+}
+
+// ---- whole-warp-per-row forms for the levels that cannot fill the machine (<= kAmgWarpRowMax rows): there the cost of a
+// sweep is the length of the longest dependent chain, and coarse Galerkin rows hold up to a few hundred blocks.  Five
+// 6-lane groups stride through the row's blocks; a shuffle tree adds the five partial rows.  Result on lanes 0..5.
+constexpr int kAmgWarpRowMax = 32768;
+__device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag, const double* __restrict__ Hoff,
+                                                const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                                const double* __restrict__ x, const double* __restrict__ d, int i, int lane) {
+  const int grp = lane / 6, r = lane - grp * 6;
+  double acc = 0.0;
+  if (grp < 5) {
+    if (grp == 0) {
+      const double2* hd = reinterpret_cast<const double2*>(Hdiag + 36 * (size_t)i) + r;
+      const double2 h0 = __ldg(hd), h1 = __ldg(hd + 6), h2 = __ldg(hd + 12);
+      const double* xi = x + 6 * (size_t)i;
+      const double2 x0 = __ldg(reinterpret_cast<const double2*>(xi)), x1 = __ldg(reinterpret_cast<const double2*>(xi + 2)),
+                    x2 = __ldg(reinterpret_cast<const double2*>(xi + 4));
+      acc = h0.x * x0.x;
+      acc = fma(h0.y, x0.y, acc); acc = fma(h1.x, x1.x, acc); acc = fma(h1.y, x1.y, acc);
+      acc = fma(h2.x, x2.x, acc); acc = fma(h2.y, x2.y, acc);
+      if (d != nullptr) {
+        const double xr = (r == 0) ? x0.x : (r == 1) ? x0.y : (r == 2) ? x1.x : (r == 3) ? x1.y : (r == 4) ? x2.x : x2.y;
+        acc = fma(__ldg(d + 6 * (size_t)i + r), xr, acc);
+      }
+    }
+    const int p0 = __ldg(row_ptr + i), p1 = __ldg(row_ptr + i + 1);
+    for (int p = p0 + grp; p < p1; p += 5) {
+      const int j = __ldg(col_idx + p);
+      const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
+      const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
+      const double* xa = x + 6 * (size_t)j;
+      const double2 u0 = __ldg(reinterpret_cast<const double2*>(xa)), u1 = __ldg(reinterpret_cast<const double2*>(xa + 2)),
+                    u2 = __ldg(reinterpret_cast<const double2*>(xa + 4));
+      acc = fma(a0.x, u0.x, acc); acc = fma(a0.y, u0.y, acc); acc = fma(a1.x, u1.x, acc);
+      acc = fma(a1.y, u1.y, acc); acc = fma(a2.x, u2.x, acc); acc = fma(a2.y, u2.y, acc);
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const double a = acc + __shfl_down_sync(full, acc, 12);     // lane c: g0 + g2, lane c + 6: g1 + g3
+  const double b = a + __shfl_down_sync(full, a, 6);          // lane c: g0 + g2 + g1 + g3
+  return b + __shfl_down_sync(full, acc, 24);                 // + g4
+}
+
+// y = x + omega Dinv (r - A x), one warp per row; kResidualOnly: y = r - A x
+template <bool kResidualOnly>
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth_warp_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ Dinv,
+                                                                      const double* __restrict__ r, const double* __restrict__ x, double omega,
+                                                                      double* __restrict__ y, const int* skip) {
+  if (skip && *skip) return;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
+  if (i >= A.n) return;                         // warp-uniform
+  const double ax = bsr6_row_warp(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, lane);
+  const bool on = lane < 6;
+  const size_t q = 6 * (size_t)i + (on ? lane : 0);
+  const double t = on ? r[q] - ax : 0.0;
+  if (kResidualOnly) { if (on) y[q] = t; return; }
+  const double z = amg_block_row_dot(on ? Dinv + 36 * (size_t)i : nullptr, on ? lane : 0, 0, t);
+  if (on) y[q] = x[q] + omega * z;
+}
+
+// rc_I = sum_{i in I} P_i^T t_i from a stored residual t (the split form of amg_residual_restrict_kernel): one warp per
+// coarse row, five 6-lane groups stride through the members, shuffle tree, then the fused first sweep of the coarse level
+__global__ void __launch_bounds__(kAmgThreads) amg_restrict_kernel(const double* __restrict__ t, int ncomp, int c_row0,
+                                                                   const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx,
+                                                                   const double* __restrict__ pos, int pos_stride,
+                                                                   const double* __restrict__ cpos, const double* __restrict__ scale,
+                                                                   double* __restrict__ rc, const double* __restrict__ Dinv_c, double omega,
+                                                                   double* __restrict__ xc, const int* skip) {
+  if (skip && *skip) return;
+  const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6;
+  const int k = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
+  if (k >= ncomp) return;                       // warp-uniform
+  const int I = c_row0 + k;
+  double acc = 0.0;
+  if (grp < 5) {
+    const int m0 = __ldg(mem_ptr + k), m1 = __ldg(mem_ptr + k + 1);
+    for (int m = m0 + grp; m < m1; m += 5) {
+      const int i = __ldg(mem_idx + m);
+      const double* ti = t + 6 * (size_t)i;
+      double s = 1.0, s0 = 1.0, s1 = 1.0, s2 = 1.0;
+      if (scale) {
+        const double* sc = scale + 6 * (size_t)i;
+        s = sc[c] > 0.0 ? 1.0 / sc[c] : 0.0;
+        s0 = sc[0] > 0.0 ? 1.0 / sc[0] : 0.0; s1 = sc[1] > 0.0 ? 1.0 / sc[1] : 0.0; s2 = sc[2] > 0.0 ? 1.0 / sc[2] : 0.0;
+      }
+      double v = s * ti[c];
+      if (c >= 3) {
+        double dd[3];
+        amg_delta(pos, pos_stride, i, cpos, I, dd);
+        const double u0 = s0 * ti[0], u1 = s1 * ti[1], u2 = s2 * ti[2];
+        if (c == 3) v += 2.0 * (dd[1] * u2 - dd[2] * u1);
+        else if (c == 4) v += 2.0 * (dd[2] * u0 - dd[0] * u2);
+        else v += 2.0 * (dd[0] * u1 - dd[1] * u0);
+      }
+      acc += v;
+    }
+  }
+  const unsigned full = 0xffffffffu;
+  const double a = acc + __shfl_down_sync(full, acc, 12);
+  const double b2 = a + __shfl_down_sync(full, a, 6);
+  const double tot = b2 + __shfl_down_sync(full, acc, 24);
+  const bool on = lane < 6;
+  if (on) rc[6 * (size_t)I + lane] = tot;
+  if (Dinv_c != nullptr) {
+    const double z = amg_block_row_dot(on ? Dinv_c + 36 * (size_t)I : nullptr, on ? lane : 0, 0, on ? tot : 0.0);
+    if (on) xc[6 * (size_t)I + lane] = omega * z;
+  }
 }
 
 // ---- PCG pieces (Chronopoulos-Gear with a general preconditioner) ----
@@ -437,6 +558,37 @@ __global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_kernel(const BsrVie
   }
 }
 
+// the same with a whole warp per row (small level 0: the sweep is latency bound)
+__global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_warp_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ u,
+                                                                         const double* __restrict__ r, double* __restrict__ w,
+                                                                         double* __restrict__ part /* [2][gridDim.x] */, const int* skip) {
+  __shared__ double red0[kAmgThreads / 32], red1[kAmgThreads / 32];
+  const bool idle = skip && *skip;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
+  double a0 = 0.0, a1 = 0.0;
+  if (!idle && i < A.n) {
+    const double v = bsr6_row_warp(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, u, d, i, lane);
+    if (lane < 6) {
+      const size_t q = 6 * (size_t)i + lane;
+      w[q] = v;
+      const double uv = __ldg(u + q);
+      a0 = v * uv;
+      a1 = __ldg(r + q) * uv;
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if (lane == 0) { red0[threadIdx.x >> 5] = a0; red1[threadIdx.x >> 5] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAmgThreads / 32; ++k) { t0 += red0[k]; t1 += red1[k]; }
+    part[blockIdx.x] = t0;
+    part[gridDim.x + blockIdx.x] = t1;
+  }
+}
+
 // sums nq quantities of per-CTA partials (part[q * nparts + k]) into out[q] in a fixed order (one CTA)
 __global__ void __launch_bounds__(kAmgThreads) amg_reduce_kernel(const double* __restrict__ part, int nparts, int nq, double* __restrict__ out) {
   __shared__ double red[kAmgThreads / 32];
@@ -456,10 +608,9 @@ __global__ void __launch_bounds__(kAmgThreads) amg_reduce_kernel(const double* _
   }
 }
 
-// scalar step: red[0] = w.u (delta), red[1] = r.u (gamma)
-__global__ void amg_pcg_scalar_kernel(PcgMultiState* st, const double* __restrict__ red, int max_iterations, double tol) {
-  if (threadIdx.x != 0 || st->done) return;
-  const double delta = red[0], gamma = red[1];
+// scalar step: delta = w.u, gamma = r.u
+__device__ __forceinline__ void amg_pcg_scalar_step(PcgMultiState* st, double delta, double gamma, int max_iterations, double tol) {
+  if (st->done) return;
   if (st->iter == 0) { st->gamma0 = gamma; st->gamma = gamma; }
   else { st->gamma_old = st->gamma; st->gamma = gamma; }
   if (!(st->gamma0 > 0.0)) { st->flag = 0; st->done = 1; return; }
@@ -470,6 +621,27 @@ __global__ void amg_pcg_scalar_kernel(PcgMultiState* st, const double* __restric
   else { st->beta = gamma / st->gamma_old; st->alpha = gamma / (delta - st->beta * gamma / st->alpha); }
   if (!(st->alpha > 0.0) || !isfinite(st->alpha)) { st->flag = 2; st->done = 1; return; }
   st->iter++;
+}
+// multi-GPU: red[0], red[1] were all-reduced
+__global__ void amg_pcg_scalar_kernel(PcgMultiState* st, const double* __restrict__ red, int max_iterations, double tol) {
+  if (threadIdx.x == 0) amg_pcg_scalar_step(st, red[0], red[1], max_iterations, tol);
+}
+// one GPU: sum the per-CTA partials (fixed order) and take the scalar step in the same one-CTA kernel
+__global__ void __launch_bounds__(kAmgThreads) amg_pcg_reduce_scalar_kernel(PcgMultiState* st, const double* __restrict__ part, int nparts,
+                                                                            int max_iterations, double tol) {
+  __shared__ double red[2][kAmgThreads / 32];
+  if (st->done) return;
+  double t0 = 0.0, t1 = 0.0;
+  for (int k = threadIdx.x; k < nparts; k += kAmgThreads) { t0 += part[k]; t1 += part[nparts + k]; }
+  t0 = warp_sum(t0); t1 = warp_sum(t1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = t0; red[1][threadIdx.x >> 5] = t1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAmgThreads / 32; ++k) { s0 += red[0][k]; s1 += red[1][k]; }
+    amg_pcg_scalar_step(st, s0, s1, max_iterations, tol);
+  }
 }
 
 // p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, x0 = omega Minv r
@@ -529,6 +701,7 @@ static void amg_destroy(pgo::Amg* M, int device) {
   pgo::pool_pinned_release(device, M->state_h);
   pgo::pool_event_release(device, M->ev[0]);
   pgo::pool_event_release(device, M->ev[1]);
+  for (auto& e : M->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
   delete M;   // device blocks were borrowed through dev_alloc and go back with the graph's
 }
 
@@ -726,7 +899,10 @@ static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, con
   using namespace pgo;
   const AmgLevelDev& D = M->lv[l];
   PGO_TRY(amg_exchange(g, M, D, x, 6, 6, skip));
-  amg_smooth_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  if (D.n_own <= kAmgWarpRowMax)
+    amg_smooth_warp_kernel<false><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  else
+    amg_smooth_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
   g->launches++;
   return PGO_OK;
 }
@@ -742,17 +918,29 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
   for (int l = 0; l + 1 < nl; ++l) {
     const AmgLevelDev& D = M->lv[l];
     const AmgLevelDev& C = M->lv[l + 1];
-    if (l > 0) {
+    // (x_l = omega Dinv r_l arrives with r_l: from the PCG update on level 0, from the restriction below otherwise)
+    if (l > 0 && !M->lv[l].gather_off.empty()) {
       amg_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, D.r, M->omega, cur[l], skip);
       g->launches++;
     }
     for (int s = 1; s < M->nu; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
     PGO_TRY(amg_exchange(g, M, D, cur[l], 6, 6, skip));
     const int ncomp = D.c_row1 - D.c_row0;
-    if (ncomp > 0) {
+    // the next level's first sweep is fused unless its residual still has to be gathered or it is solved densely
+    const bool coarsest_next = l + 2 == nl;
+    const bool fuse_next = C.gather_off.empty() && !(coarsest_next && M->dense_inv);
+    if (ncomp > 0 && D.n_own <= kAmgWarpRowMax) {
+      // small level: residual with a whole warp per row into the spare buffer, then the restriction
+      amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, nullptr, D.r, cur[l],
+                                                                                      0.0, oth[l], skip);
+      amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
+                                                                               l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
+                                                                               M->omega, cur[l + 1], skip);
+      g->launches += 2;
+    } else if (ncomp > 0) {
       amg_residual_restrict_kernel<<<amg_rows_grid(ncomp), kAmgThreads, 0, g->stream>>>(
           amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
-          l == 0 ? g->scale : nullptr, C.r, skip);
+          l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr, M->omega, cur[l + 1], skip);
       g->launches++;
     }
     if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.r, C.gather_off, 6));
@@ -764,8 +952,10 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
       amg_dense_solve_kernel<<<1, kAmgThreads, 0, g->stream>>>(6 * D.n_own, M->dense_inv, D.r, cur[l], skip);
       g->launches++;
     } else if (nl > 1) {
-      amg_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, D.r, M->omega, cur[l], skip);
-      g->launches++;
+      if (!D.gather_off.empty()) {
+        amg_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, D.r, M->omega, cur[l], skip);
+        g->launches++;
+      }
       for (int s = 1; s < M->coarse_sweeps; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
     }
     // nl == 1: plain block-Jacobi, lv[0].x = omega Minv r is the result (omega only rescales the preconditioner)
@@ -782,9 +972,35 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
   return PGO_OK;
 }
 
+// One PCG iteration, enqueued on g->stream: V-cycle, halo of u, SpMV + partial dots, (all-)reduce, scalar step, update.
+static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_options* o, int sp_ctas, int rows_grid) {
+  using namespace pgo;
+  AmgLevelDev& L0 = M->lv[0];
+  PcgMultiState* st = M->state;
+  const int n = L0.n_own;
+  double* u = nullptr;
+  PGO_TRY(amg_vcycle(g, M, &u));
+  PGO_TRY(amg_exchange(g, M, L0, u, 6, 6, &st->done));
+  if (M->warp_spmv) amg_spmv_dots_warp_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
+  else amg_spmv_dots_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
+  if (g->world > 1) {
+    amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
+    PGO_TRY(amg_allreduce(g, M->red, 2));
+    amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
+    g->launches++;
+  } else {
+    amg_pcg_reduce_scalar_kernel<<<1, kAmgThreads, 0, g->stream>>>(st, M->part, sp_ctas, o->pcg_max_iterations, o->pcg_tolerance);
+  }
+  amg_pcg_update_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
+  g->launches += 3;
+  return PGO_OK;
+}
+
 // (H + diag(dlm)) x = b by AMG-preconditioned CG.  x -> g->vx; statistics -> g->scalars.  Stream-ordered; the host polls
 // the `done` flag one batch behind the GPU (kernels after convergence are no-ops), and every rank takes the same exit
-// decision because the flag derives from all-reduced, bit-identical scalars.
+// decision because the flag derives from all-reduced, bit-identical scalars.  One GPU: the iteration is captured once
+// per (H, poses) buffer pair into a CUDA graph and replayed -- a small graph's iteration is two dozen dependent
+// few-microsecond kernels, i.e. launch bound.
 static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double* b) {
   using namespace pgo;
   Amg* M = g->amg;
@@ -792,27 +1008,49 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
   PGO_TRY(amg_setup_numeric(g, M));
   PcgMultiState* st = M->state;
   const int rows_grid = amg_rows_grid(n);
-  const int sp_ctas = std::max(1, std::min(rows_grid, std::min(8 * g->num_sms, M->part_cap / 3)));
+  // small level 0: one warp per row (its grid is exact, 8 rows per CTA), else the grid-stride 6-lanes-per-row form
+  M->warp_spmv = (n + 7) / 8 <= M->part_cap / 3;
+  const int sp_ctas = M->warp_spmv ? std::max(1, (n + 7) / 8) : std::max(1, std::min(rows_grid, std::min(8 * g->num_sms, M->part_cap / 3)));
   const int dot_ctas = std::max(1, std::min((n6 + kAmgThreads - 1) / kAmgThreads, std::min(4 * g->num_sms, M->part_cap / 3)));
   AmgLevelDev& L0 = M->lv[0];
   CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
   amg_pcg_init_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, g->Minv, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
   g->launches++;
+  static const int graph_env = getenv("PGO_AMG_GRAPH") ? atoi(getenv("PGO_AMG_GRAPH")) : -1;
+  const bool use_graph = graph_env >= 0 ? graph_env != 0 : g->world == 1;
+  Amg::IterGraph* ig = nullptr;
+  if (use_graph) {
+    const void* key[4] = {g->Hdiag, g->Hoff, g->poses, g->scale};
+    for (auto& e : M->graphs)
+      if (!std::memcmp(e.key, key, sizeof key) && e.max_it == o->pcg_max_iterations && e.tol == o->pcg_tolerance) ig = &e;
+    if (!ig) {
+      if (M->graphs.size() >= 8) { for (auto& e : M->graphs) cudaGraphExecDestroy(e.exec); M->graphs.clear(); }
+      const long long l0 = g->launches;
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = amg_enqueue_iteration(g, M, o, sp_ctas, rows_grid);
+      const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
+      if (rc != PGO_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return set_error(PGO_ERR_CUDA, "capturing the PCG iteration failed: %s", cudaGetErrorString(ce));
+      Amg::IterGraph e;
+      std::memcpy(e.key, key, sizeof key);
+      e.max_it = o->pcg_max_iterations; e.tol = o->pcg_tolerance; e.kernels = (int)(g->launches - l0); e.exec = nullptr;
+      g->launches = l0;
+      const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) return set_error(PGO_ERR_CUDA, "instantiating the PCG iteration graph failed: %s", cudaGetErrorString(ie));
+      M->graphs.push_back(e);
+      ig = &M->graphs.back();
+    }
+  }
   const int batch = n >= 100000 ? 4 : 8;
   int enqueued = 0;          // batches
   const int max_batches = (o->pcg_max_iterations + batch - 1) / batch + 2;
   bool finished = false;
   while (!finished) {
     for (int k = 0; k < batch; ++k) {
-      double* u = nullptr;
-      PGO_TRY(amg_vcycle(g, M, &u));
-      PGO_TRY(amg_exchange(g, M, L0, u, 6, 6, &st->done));
-      amg_spmv_dots_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
-      amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
-      PGO_TRY(amg_allreduce(g, M->red, 2));
-      amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
-      amg_pcg_update_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
-      g->launches += 4;
+      if (ig) { CUDA_TRY(cudaGraphLaunch(ig->exec, g->stream)); g->launches += ig->kernels; }
+      else PGO_TRY(amg_enqueue_iteration(g, M, o, sp_ctas, rows_grid));
     }
     const int slot = enqueued & 1;
     CUDA_TRY(cudaMemcpyAsync(M->state_h + slot, st, sizeof(PcgMultiState), cudaMemcpyDeviceToHost, g->stream));

@@ -261,7 +261,7 @@ extern "C" void pgo_default_options(pgo_solver_options* o) {
   o->loss_a = 1.0;
   o->linear_solver_type = PGO_LINEAR_AUTO;
   o->pcg_max_iterations = 20000;
-  o->pcg_tolerance = 1e-10;
+  o->pcg_tolerance = 1e-8;      // in the M^-1 norm; a direct factorisation of these systems is no more accurate (kappa ~ 1e6..1e9)
   o->pcg_num_ctas = 0;
   o->direct_residual_accept = 1e-8;
   o->verbose = 0;
