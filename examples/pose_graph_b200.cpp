@@ -24,7 +24,7 @@
 namespace ceres = ceres_b200;
 
 namespace POSE_GRAPH {
-typedef ceres::Pose3d Pose3d;                         // REF/include/types.h:15-20
+typedef ceres::pgo::PosePod Pose3d;                   // REF/include/types.h:15-20 (Eigen-free: p[3], q[4] = x y z w)
 typedef std::map<int, Pose3d> MapOfPoses;             // REF/include/types.h:22-24
 struct Matrix6d {                                     // stand-in for Eigen::Matrix<double, 6, 6>
   double m[6][6];
@@ -95,7 +95,8 @@ static void BuildOptimizationProblem(const VectorOfEdges& Edges, MapOfPoses* pos
     }
     Matrix6d sqrt_information;
     if (!edge.information.lltMatrixL(&sqrt_information)) { std::cerr << "information matrix is not positive definite\n"; std::exit(2); }
-    ceres::CostFunction* cost_function = ceres::PoseGraph3dErrorTerm::Create(edge.t_be, sqrt_information);
+    const double t_be[7] = {edge.t_be.p[0], edge.t_be.p[1], edge.t_be.p[2], edge.t_be.q[0], edge.t_be.q[1], edge.t_be.q[2], edge.t_be.q[3]};
+    ceres::CostFunction* cost_function = ceres::pgo::MakePoseGraph3dCost(t_be, &sqrt_information.m[0][0]);
     problem->AddResidualBlock(cost_function, loss_function, pose_begin_iter->second.p, pose_begin_iter->second.q,
                               pose_end_iter->second.p, pose_end_iter->second.q);
     problem->SetParameterization(pose_begin_iter->second.q, quaternion_local_parameterization);

@@ -7,7 +7,7 @@
 //   Problem::SetParameterization(q, EigenQuaternionParameterization)            :496-497,519-522
 //   Problem::SetParameterBlockConstant(p) / (q)                                 :526-527
 //   ceres::HuberLoss(1.0)                                                       :495
-//   PoseGraph3dErrorTerm::Create(t_ab_measured, sqrt_information)               REF/include/PoseGraph3dError.h:56-61
+//   ceres::AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>            REF/include/PoseGraph3dError.h:56-61
 //   ceres::Solver::Options {max_num_iterations, linear_solver_type}             :534-536
 //   ceres::Solve(options, problem, &summary), Summary::FullReport(), IsSolutionUsable()   :538-543
 //
@@ -22,8 +22,10 @@
 // Ownership follows Ceres: the Problem takes ownership of cost functions, loss functions and local
 // parameterizations passed by pointer (each distinct pointer is deleted once).
 //
-// Usage in the reference: include this header instead of <ceres/ceres.h>, add
-// `namespace ceres = ceres_b200;` (or compile with -DCERES_B200_AS_CERES), and link -lpgo_b200.
+// Usage in the reference: NO source change -- put include/ceres_b200/compat first on the include
+// path (its ceres/ceres.h and ceres/autodiff_cost_function.h are this header with `namespace ceres = ceres_b200`) and link
+// -lpgo_b200.  The reference's own PoseGraph3dError.h / types.h stay as they are: its functor is accepted by
+// AutoDiffCostFunction below.  Helper types that Ceres does not have live in ceres_b200::pgo.
 #ifndef CERES_B200_CERES_H_
 #define CERES_B200_CERES_H_
 
@@ -114,13 +116,7 @@ class EigenQuaternionParameterization : public LocalParameterization {
   bool is_eigen_quaternion() const override { return true; }
 };
 
-// ---- the one cost function of the path ----
-// Eigen-free stand-in for POSE_GRAPH::Pose3d (REF/include/types.h:15-20): p = x y z, q = coeffs() x y z w.
-struct Pose3d {
-  double p[3];
-  double q[4];
-};
-
+// ---- cost functions (ceres/cost_function.h, ceres/autodiff_cost_function.h) ----
 class CostFunction {
  public:
   virtual ~CostFunction() {}
@@ -128,11 +124,22 @@ class CostFunction {
   virtual const std::vector<int>& parameter_block_sizes() const = 0;
 };
 
-// AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4> (REF/include/PoseGraph3dError.h:56-61): holds the
-// measurement t_ab and the square-root information; evaluated on the device by the fused linearize kernel.
-class PoseGraph3dCostFunction : public CostFunction {
+// Helper types that real Ceres does NOT have live in ceres_b200::pgo, so that `using namespace ceres;` next to the
+// reference's own `using namespace POSE_GRAPH;` (REF/test/pose_graph_ceres_plus_finial.cpp:20-22) stays unambiguous.
+namespace pgo {
+
+// Eigen-free pose: p = x y z, q = coeffs() x y z w  (layout of POSE_GRAPH::Pose3d, REF/include/types.h:15-20)
+struct PosePod {
+  double p[3];
+  double q[4];
+};
+
+// The one cost function of the path -- the SE(3) relative-pose residual of REF/include/PoseGraph3dError.h:21-54 --
+// as data: the measurement t_ab and the square-root information.  It is evaluated on the device by the fused
+// linearize kernel; this object only carries its constants.
+class PoseGraph3dCost : public CostFunction {
  public:
-  PoseGraph3dCostFunction(const double t_ab[7], const double sqrt_information_row_major[36]) : sizes_{3, 4, 3, 4} {
+  PoseGraph3dCost(const double t_ab[7], const double sqrt_information_row_major[36]) : sizes_{3, 4, 3, 4} {
     std::memcpy(t_ab_, t_ab, sizeof t_ab_);
     std::memcpy(sqrt_info_, sqrt_information_row_major, sizeof sqrt_info_);
   }
@@ -140,38 +147,170 @@ class PoseGraph3dCostFunction : public CostFunction {
   const std::vector<int>& parameter_block_sizes() const override { return sizes_; }
   const double* t_ab() const { return t_ab_; }
   const double* sqrt_information() const { return sqrt_info_; }
- private:
+ protected:
+  PoseGraph3dCost() : sizes_{3, 4, 3, 4} {}
   std::vector<int> sizes_;
   double t_ab_[7];
   double sqrt_info_[36];
 };
 
-class PoseGraph3dErrorTerm {
+// plain-array form: t_ab = x y z qx qy qz qw, sqrt_information ROW-major 6x6 (nullptr = identity)
+inline CostFunction* MakePoseGraph3dCost(const double t_ab[7], const double* sqrt_information_row_major) {
+  double s[36];
+  if (sqrt_information_row_major) std::memcpy(s, sqrt_information_row_major, sizeof s);
+  else for (int k = 0; k < 36; ++k) s[k] = (k / 6 == k % 6) ? 1.0 : 0.0;
+  return new PoseGraph3dCost(t_ab, s);
+}
+// Eigen-style form: t.p is indexable as p(i), t.q has x() y() z() w(); Matrix6 is indexable as m(i, j)
+template <typename PoseT, typename Matrix6,
+          typename = typename std::enable_if<std::is_class<PoseT>::value && std::is_class<Matrix6>::value>::type>
+inline CostFunction* MakePoseGraph3dCost(const PoseT& t, const Matrix6& sqrt_information) {
+  double a[7] = {t.p(0), t.p(1), t.p(2), t.q.x(), t.q.y(), t.q.z(), t.q.w()}, s[36];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) s[i * 6 + j] = sqrt_information(i, j);
+  return new PoseGraph3dCost(a, s);
+}
+
+// ---- small dense helpers for the functor probe below ----
+inline double det3(const double a[3], const double b[3], const double c[3]) {
+  return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+// closed form of the residual with q_m unit: r = S [R(q_a)^T (p_b - p_a) - p_m ; 2 vec(q_m * conj(conj(q_a) * q_b))]
+inline void pose_graph_residual(const double t_ab[7], const double S[36], const double* pa, const double* qa, const double* pb,
+                                const double* qb, double r[6]) {
+  auto qmul = [](const double* a, const double* b, double* o) {   // x y z w
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  };
+  const double qi[4] = {-qa[0], -qa[1], -qa[2], qa[3]};
+  const double d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+  // Eigen's quaternion * vector: v + w t + u x t with t = 2 u x v
+  const double tx = 2 * (qi[1] * d[2] - qi[2] * d[1]), ty = 2 * (qi[2] * d[0] - qi[0] * d[2]), tz = 2 * (qi[0] * d[1] - qi[1] * d[0]);
+  double e[6];
+  e[0] = d[0] + qi[3] * tx + (qi[1] * tz - qi[2] * ty) - t_ab[0];
+  e[1] = d[1] + qi[3] * ty + (qi[2] * tx - qi[0] * tz) - t_ab[1];
+  e[2] = d[2] + qi[3] * tz + (qi[0] * ty - qi[1] * tx) - t_ab[2];
+  double qab[4], dq[4];
+  qmul(qi, qb, qab);
+  const double qabc[4] = {-qab[0], -qab[1], -qab[2], qab[3]};
+  qmul(t_ab + 3, qabc, dq);
+  e[3] = 2 * dq[0]; e[4] = 2 * dq[1]; e[5] = 2 * dq[2];
+  for (int i = 0; i < 6; ++i) { double s = 0; for (int k = 0; k < 6; ++k) s += S[i * 6 + k] * e[k]; r[i] = s; }
+}
+
+}  // namespace pgo
+
+// ceres::AutoDiffCostFunction<Functor, 6, 3, 4, 3, 4>(new Functor(...)) -- what PoseGraph3dErrorTerm::Create builds
+// (REF/include/PoseGraph3dError.h:56-61).  The device path does not differentiate a functor: it evaluates the SE(3)
+// relative-pose residual in closed form.  So the functor is PROBED once, on the host, at construction: with p_a = 0 and
+// q_a = identity the functor is f(p_b, q_b) = S_p (p_b - p_m) + 2 S_r L(q_m) q_b with L = [-w_m I - [v_m]x | v_m]
+// (quaternion products are bilinear and the functor never normalises), so nine evaluations give S_p (columns of
+// f(e_k, 0) - f(0, 0)), G = 2 S_r L (columns f(0, e_b) - f(0, 0)), q_m as the null vector of G (L q_m = 0, L L^T = I),
+// S_r = G L^T / 2 and p_m from S_p p_m = -f(0, 0).  The recovered constants are then checked against the functor at
+// random poses; a functor that is not this residual is rejected with std::invalid_argument.  (Problem setup, not a CPU
+// fallback: no residual or Jacobian of the solve is ever evaluated on the host.)
+template <typename CostFunctor, int kNumResiduals, int N0 = 0, int N1 = 0, int N2 = 0, int N3 = 0, int N4 = 0, int N5 = 0,
+          int N6 = 0, int N7 = 0, int N8 = 0, int N9 = 0>
+class AutoDiffCostFunction : public pgo::PoseGraph3dCost {
+  static_assert(kNumResiduals == 6 && N0 == 3 && N1 == 4 && N2 == 3 && N3 == 4 && N4 == 0,
+                "ceres_b200: only the SE(3) relative-pose residual <6, 3, 4, 3, 4> runs on the device path");
  public:
-  // Matrix6 is anything indexable as m(i, j) -- e.g. the Eigen::Matrix<double, 6, 6> the reference passes.
-  template <typename PoseT, typename Matrix6,
-            typename = typename std::enable_if<std::is_class<PoseT>::value && std::is_class<Matrix6>::value>::type>
-  static CostFunction* Create(const PoseT& t_ab_measured, const Matrix6& sqrt_information) {
-    double t[7], s[36];
-    pose_to_array(t_ab_measured, t);
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) s[i * 6 + j] = sqrt_information(i, j);
-    return new PoseGraph3dCostFunction(t, s);
+  explicit AutoDiffCostFunction(CostFunctor* functor) : functor_(functor) {
+    if (!functor) throw std::invalid_argument("ceres_b200::AutoDiffCostFunction: null functor");
+    probe();
   }
-  // plain-array form: t_ab = x y z qx qy qz qw, sqrt_information ROW-major 6x6 (nullptr = identity)
-  static CostFunction* Create(const double t_ab[7], const double* sqrt_information_row_major) {
-    double s[36];
-    if (sqrt_information_row_major) std::memcpy(s, sqrt_information_row_major, sizeof s);
-    else for (int k = 0; k < 36; ++k) s[k] = (k / 6 == k % 6) ? 1.0 : 0.0;
-    return new PoseGraph3dCostFunction(t_ab, s);
-  }
+  ~AutoDiffCostFunction() override { delete functor_; }
+  AutoDiffCostFunction(const AutoDiffCostFunction&) = delete;
+  AutoDiffCostFunction& operator=(const AutoDiffCostFunction&) = delete;
+
  private:
-  static void pose_to_array(const Pose3d& t, double* out) { std::memcpy(out, t.p, 24); std::memcpy(out + 3, t.q, 32); }
-  // Eigen-style pose: .p is a Vector3d, .q a Quaterniond
-  template <typename PoseT>
-  static void pose_to_array(const PoseT& t, double* out) {
-    out[0] = t.p(0); out[1] = t.p(1); out[2] = t.p(2);
-    out[3] = t.q.x(); out[4] = t.q.y(); out[5] = t.q.z(); out[6] = t.q.w();
+  void eval(const double* pa, const double* qa, const double* pb, const double* qb, double* r) const {
+    if (!(*functor_)(pa, qa, pb, qb, r)) throw std::invalid_argument("ceres_b200::AutoDiffCostFunction: the functor returned false");
   }
+  void probe() {
+    const double zero3[3] = {0, 0, 0}, ident[4] = {0, 0, 0, 1}, zero4[4] = {0, 0, 0, 0};
+    double c0[6], f[6], Sp[6][3], G[6][4];
+    eval(zero3, ident, zero3, zero4, c0);
+    for (int k = 0; k < 3; ++k) {
+      double e[3] = {0, 0, 0};
+      e[k] = 1.0;
+      eval(zero3, ident, e, zero4, f);
+      for (int i = 0; i < 6; ++i) Sp[i][k] = f[i] - c0[i];
+    }
+    for (int b = 0; b < 4; ++b) {
+      double e[4] = {0, 0, 0, 0};
+      e[b] = 1.0;
+      eval(zero3, ident, zero3, e, f);
+      for (int i = 0; i < 6; ++i) G[i][b] = f[i] - c0[i];
+    }
+    // q_m: null vector of G = the 4-D cross product of three independent rows; take the best-conditioned triple
+    double qm[4] = {0, 0, 0, 1}, best = -1.0;
+    for (int i = 0; i < 6; ++i) for (int j = i + 1; j < 6; ++j) for (int k = j + 1; k < 6; ++k) {
+      double n[4];
+      for (int c = 0; c < 4; ++c) {
+        double ra[3], rb[3], rc[3];
+        for (int t = 0, u = 0; t < 4; ++t) if (t != c) { ra[u] = G[i][t]; rb[u] = G[j][t]; rc[u] = G[k][t]; ++u; }
+        n[c] = ((c & 1) ? -1.0 : 1.0) * pgo::det3(ra, rb, rc);
+      }
+      const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2] + n[3] * n[3];
+      if (nn > best) { best = nn; std::memcpy(qm, n, sizeof qm); }
+    }
+    if (!(best > 0.0)) throw std::invalid_argument("ceres_b200::AutoDiffCostFunction: rank-deficient orientation information, cannot recover the measurement");
+    {
+      const double inv = 1.0 / std::sqrt(best) * (qm[3] < 0 ? -1.0 : 1.0);
+      for (double& v : qm) v *= inv;
+    }
+    // S_r = G L^T / 2 with L = [-w I - [v]x | v]
+    const double vx = qm[0], vy = qm[1], vz = qm[2], w = qm[3];
+    const double L[3][4] = {{-w, vz, -vy, vx}, {-vz, -w, vx, vy}, {vy, -vx, -w, vz}};
+    double S[36];
+    for (int i = 0; i < 6; ++i) {
+      for (int k = 0; k < 3; ++k) S[i * 6 + k] = Sp[i][k];
+      for (int k = 0; k < 3; ++k) { double s = 0; for (int b = 0; b < 4; ++b) s += G[i][b] * L[k][b]; S[i * 6 + 3 + k] = 0.5 * s; }
+    }
+    // p_m from the normal equations of S_p p_m = -c0
+    double A[3][3], rhs[3];
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3; ++b) { double s = 0; for (int i = 0; i < 6; ++i) s += Sp[i][a] * Sp[i][b]; A[a][b] = s; }
+      double s = 0;
+      for (int i = 0; i < 6; ++i) s -= Sp[i][a] * c0[i];
+      rhs[a] = s;
+    }
+    const double det = pgo::det3(A[0], A[1], A[2]);
+    if (!(std::fabs(det) > 0.0)) throw std::invalid_argument("ceres_b200::AutoDiffCostFunction: rank-deficient position information, cannot recover the measurement");
+    double pm[3];
+    for (int c = 0; c < 3; ++c) {
+      double M[3][3];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) M[a][b] = (b == c) ? rhs[a] : A[a][b];
+      pm[c] = pgo::det3(M[0], M[1], M[2]) / det;
+    }
+    // one step of refinement of p_m against the rounding of the normal equations
+    {
+      double res[3] = {0, 0, 0};
+      for (int a = 0; a < 3; ++a) { double s = rhs[a]; for (int b = 0; b < 3; ++b) s -= A[a][b] * pm[b]; res[a] = s; }
+      for (int c = 0; c < 3; ++c) {
+        double M[3][3];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) M[a][b] = (b == c) ? res[a] : A[a][b];
+        pm[c] += pgo::det3(M[0], M[1], M[2]) / det;
+      }
+    }
+    t_ab_[0] = pm[0]; t_ab_[1] = pm[1]; t_ab_[2] = pm[2];
+    std::memcpy(t_ab_ + 3, qm, sizeof qm);
+    std::memcpy(sqrt_info_, S, sizeof S);
+    // the functor must BE this residual: compare at poses that exercise every term
+    const double pa[3] = {0.3, -1.1, 0.7}, pb[3] = {-0.4, 0.9, 1.6};
+    const double qa[4] = {0.18257418583505536, -0.3651483716701107, 0.5477225575051661, 0.7302967433402214};
+    const double qb[4] = {-0.4, 0.2, 0.1, 0.8888194417315589};
+    double want[6], got[6], scale = 0.0, err = 0.0;
+    eval(pa, qa, pb, qb, got);
+    pgo::pose_graph_residual(t_ab_, sqrt_info_, pa, qa, pb, qb, want);
+    for (int i = 0; i < 6; ++i) { scale = std::max(scale, std::fabs(want[i])); err = std::max(err, std::fabs(want[i] - got[i])); }
+    if (!(err <= 1e-9 * std::max(scale, 1.0)))
+      throw std::invalid_argument("ceres_b200::AutoDiffCostFunction: the functor is not the SE(3) relative-pose residual of "
+                                  "PoseGraph3dError.h (the only cost function the device path evaluates)");
+  }
+  CostFunctor* functor_;
 };
 
 class Problem;
@@ -283,8 +422,8 @@ class Problem {
   // problem->AddResidualBlock(cost_function, loss_function, p_a, q_a, p_b, q_b)   (REF ...plus_finial.cpp:513-517)
   ResidualBlockId AddResidualBlock(CostFunction* cost_function, LossFunction* loss_function, double* p_a, double* q_a,
                                    double* p_b, double* q_b) {
-    PoseGraph3dCostFunction* c = dynamic_cast<PoseGraph3dCostFunction*>(cost_function);
-    if (!c) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: only PoseGraph3dErrorTerm cost functions run on the device path");
+    pgo::PoseGraph3dCost* c = dynamic_cast<pgo::PoseGraph3dCost*>(cost_function);
+    if (!c) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: only SE(3) relative-pose cost functions (AutoDiffCostFunction<F, 6, 3, 4, 3, 4> / pgo::MakePoseGraph3dCost) run on the device path");
     if (!p_a || !q_a || !p_b || !q_b) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: null parameter block");
     const int a = pose_of(p_a, q_a), b = pose_of(p_b, q_b);
     if (a == b) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: duplicate parameter blocks in one residual block");
@@ -292,6 +431,11 @@ class Problem {
     owned_costs_.insert(cost_function);
     if (loss_function) owned_losses_.insert(loss_function);
     return (int)edges_.size() - 1;
+  }
+
+  ResidualBlockId AddResidualBlock(CostFunction* cost_function, LossFunction* loss_function, const std::vector<double*>& blocks) {
+    if (blocks.size() != 4) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: the pose-graph residual takes 4 parameter blocks");
+    return AddResidualBlock(cost_function, loss_function, blocks[0], blocks[1], blocks[2], blocks[3]);
   }
 
   void AddParameterBlock(double* values, int size) { block_of(values, size); }
@@ -339,7 +483,7 @@ class Problem {
  private:
   friend void Solve(const Solver::Options&, Problem*, Solver::Summary*);
   struct Block { int size = 0; LocalParameterization* param = nullptr; bool constant = false; int pose = -1; };
-  struct Edge { int a, b; PoseGraph3dCostFunction* cost; LossFunction* loss; };
+  struct Edge { int a, b; pgo::PoseGraph3dCost* cost; LossFunction* loss; };
   struct PoseRef { double* p; double* q; };
   struct Packed {
     int n_poses = 0, n_edges = 0, loss_type = PGO_LOSS_TRIVIAL;

@@ -64,12 +64,12 @@ int main() {
     ok &= throws([&] { pr.SetParameterBlockConstant(p0); });
     ok &= throws([&] { pr.SetParameterization(q0, new ceres::EigenQuaternionParameterization); }); }
   { ceres::Problem pr;   // p paired with two different q blocks
-    pr.AddResidualBlock(ceres::PoseGraph3dErrorTerm::Create(t, nullptr), nullptr, p0, q0, p1, q1);
-    ok &= throws([&] { pr.AddResidualBlock(ceres::PoseGraph3dErrorTerm::Create(t, nullptr), nullptr, p0, q2, p1, q1); });
-    ok &= throws([&] { pr.AddResidualBlock(ceres::PoseGraph3dErrorTerm::Create(t, nullptr), nullptr, p0, q0, p0, q0); });
+    pr.AddResidualBlock(ceres::pgo::MakePoseGraph3dCost(t, nullptr), nullptr, p0, q0, p1, q1);
+    ok &= throws([&] { pr.AddResidualBlock(ceres::pgo::MakePoseGraph3dCost(t, nullptr), nullptr, p0, q2, p1, q1); });
+    ok &= throws([&] { pr.AddResidualBlock(ceres::pgo::MakePoseGraph3dCost(t, nullptr), nullptr, p0, q0, p0, q0); });
     ok &= (pr.NumResidualBlocks() == 1 && pr.NumParameterBlocks() == 5 && pr.NumResiduals() == 6); }
   { ceres::Problem pr;   // q without EigenQuaternionParameterization / half-constant pose / mixed losses -> Solve rejects
-    pr.AddResidualBlock(ceres::PoseGraph3dErrorTerm::Create(t, nullptr), new ceres::HuberLoss(1.0), p0, q0, p1, q1);
+    pr.AddResidualBlock(ceres::pgo::MakePoseGraph3dCost(t, nullptr), new ceres::HuberLoss(1.0), p0, q0, p1, q1);
     ceres::Solver::Options o; ceres::Solver::Summary s;
     ok &= throws([&] { ceres::Solve(o, &pr, &s); });
     ceres::LocalParameterization* lp = new ceres::EigenQuaternionParameterization;
@@ -77,7 +77,7 @@ int main() {
     pr.SetParameterBlockConstant(p0);
     ok &= throws([&] { ceres::Solve(o, &pr, &s); });
     pr.SetParameterBlockConstant(q0);
-    pr.AddResidualBlock(ceres::PoseGraph3dErrorTerm::Create(t, nullptr), new ceres::CauchyLoss(1.0), p1, q1, p0, q0);
+    pr.AddResidualBlock(ceres::pgo::MakePoseGraph3dCost(t, nullptr), new ceres::CauchyLoss(1.0), p1, q1, p0, q0);
     ok &= throws([&] { ceres::Solve(o, &pr, &s); });
     ok &= pr.IsParameterBlockConstant(p0) && !pr.IsParameterBlockConstant(p1); }
   { double rho[3]; ceres::HuberLoss h(1.0); h.Evaluate(4.0, rho); ok &= (rho[0] == 3.0 && rho[1] == 0.5 && rho[2] == -0.0625); }
@@ -101,6 +101,178 @@ int main() {
     env["LD_LIBRARY_PATH"] = ":".join(extra + [env.get("LD_LIBRARY_PATH", "")])
     r = subprocess.run([exe], capture_output=True, text=True, env=env)
     assert r.returncode == 0 and "CONTRACTS_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_mirror_compiles_in_a_reference_shaped_translation_unit_and_recovers_the_functor(tmp_path, pgo):
+    """The reference TU has `using namespace ceres; using namespace POSE_GRAPH;` (REF test/pose_graph_ceres_plus_finial.cpp:20-22)
+    and its own POSE_GRAPH::Pose3d / PoseGraph3dErrorTerm: the mirror must not export colliding names, and
+    ceres::AutoDiffCostFunction<Functor, 6, 3, 4, 3, 4> must recover (t_ab, sqrt_information) from ANY functor that is the
+    SE(3) relative-pose residual -- here a restatement on plain arrays with random full sqrt-information -- and reject
+    everything else.  Host-only: no GPU needed."""
+    src = tmp_path / "ref_shaped.cpp"
+    src.write_text(r"""
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <ceres/ceres.h>          // resolves to include/ceres_b200/compat/ceres/ceres.h
+namespace POSE_GRAPH {
+struct Pose3d { double p[3]; double q[4]; };
+// the residual of PoseGraph3dError.h:21-54 on plain arrays (templated like the reference's functor)
+class PoseGraph3dErrorTerm {
+ public:
+  PoseGraph3dErrorTerm(const Pose3d& t, const double* S, double bias = 0.0) : t_(t), bias_(bias) { for (int k = 0; k < 36; ++k) S_[k] = S[k]; }
+  template <typename T> static void qmul(const T* a, const T* b, T* o) {
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  }
+  template <typename T>
+  bool operator()(const T* const pa, const T* const qa, const T* const pb, const T* const qb, T* r) const {
+    const T qi[4] = {-qa[0], -qa[1], -qa[2], qa[3]};
+    const T d[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+    const T tx = T(2.0) * (qi[1] * d[2] - qi[2] * d[1]), ty = T(2.0) * (qi[2] * d[0] - qi[0] * d[2]), tz = T(2.0) * (qi[0] * d[1] - qi[1] * d[0]);
+    T e[6];
+    e[0] = d[0] + qi[3] * tx + (qi[1] * tz - qi[2] * ty) - T(t_.p[0]);
+    e[1] = d[1] + qi[3] * ty + (qi[2] * tx - qi[0] * tz) - T(t_.p[1]);
+    e[2] = d[2] + qi[3] * tz + (qi[0] * ty - qi[1] * tx) - T(t_.p[2]);
+    T qab[4], dq[4];
+    qmul(qi, qb, qab);
+    const T qabc[4] = {-qab[0], -qab[1], -qab[2], qab[3]};
+    const T qm[4] = {T(t_.q[0]), T(t_.q[1]), T(t_.q[2]), T(t_.q[3])};
+    qmul(qm, qabc, dq);
+    e[3] = T(2.0) * dq[0]; e[4] = T(2.0) * dq[1]; e[5] = T(2.0) * dq[2];
+    for (int i = 0; i < 6; ++i) { T s = T(bias_); for (int k = 0; k < 6; ++k) s = s + T(S_[i * 6 + k]) * e[k]; r[i] = s; }
+    return true;
+  }
+  static ceres::CostFunction* Create(const Pose3d& t, const double* S) {
+    return new ceres::AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>(new PoseGraph3dErrorTerm(t, S));
+  }
+ private:
+  Pose3d t_; double S_[36]; double bias_;
+};
+}  // namespace POSE_GRAPH
+using namespace std;
+using namespace ceres;
+using namespace POSE_GRAPH;       // Pose3d / PoseGraph3dErrorTerm must stay unambiguous
+int main() {
+  std::mt19937_64 rng(7);
+  std::normal_distribution<double> nrm;
+  double worst = 0.0;
+  for (int trial = 0; trial < 200; ++trial) {
+    Pose3d t;
+    double S[36], n = 0.0;
+    for (double& v : t.p) v = 3.0 * nrm(rng);
+    for (double& v : t.q) { v = nrm(rng); n += v * v; }
+    for (double& v : t.q) v /= std::sqrt(n);
+    for (int k = 0; k < 36; ++k) S[k] = (k / 6 == k % 6 ? 5.0 : 0.0) + nrm(rng) * (trial % 2 ? 1.0 : 0.2);
+    if (trial % 3 == 0) for (int i = 0; i < 6; ++i) for (int j = i + 1; j < 6; ++j) S[i * 6 + j] = 0.0;   // llt().matrixL()
+    CostFunction* c = PoseGraph3dErrorTerm::Create(t, S);
+    ceres::pgo::PoseGraph3dCost* pc = dynamic_cast<ceres::pgo::PoseGraph3dCost*>(c);
+    if (!pc || pc->num_residuals() != 6 || pc->parameter_block_sizes().size() != 4) { std::printf("BAD_TYPE\n"); return 1; }
+    PoseGraph3dErrorTerm f(t, S);
+    for (int k = 0; k < 8; ++k) {
+      double pa[3], qa[4], pb[3], qb[4], na = 0, nb = 0, want[6], got[6];
+      for (double& v : pa) v = nrm(rng);
+      for (double& v : pb) v = nrm(rng);
+      for (double& v : qa) { v = nrm(rng); na += v * v; }
+      for (double& v : qb) { v = nrm(rng); nb += v * v; }
+      for (double& v : qa) v /= std::sqrt(na);
+      for (double& v : qb) v /= std::sqrt(nb);
+      f(pa, qa, pb, qb, want);
+      ceres::pgo::pose_graph_residual(pc->t_ab(), pc->sqrt_information(), pa, qa, pb, qb, got);
+      double sc = 1.0;
+      for (int i = 0; i < 6; ++i) sc = std::max(sc, std::fabs(want[i]));
+      for (int i = 0; i < 6; ++i) worst = std::max(worst, std::fabs(want[i] - got[i]) / sc);
+    }
+    delete c;
+  }
+  int rejected = 0;
+  { Pose3d t = {{1, 2, 3}, {0, 0, 0, 1}}; double S[36]; for (int k = 0; k < 36; ++k) S[k] = k / 6 == k % 6;
+    try { delete new ceres::AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>(new PoseGraph3dErrorTerm(t, S, 0.25)); }
+    catch (const std::invalid_argument&) { rejected = 1; } }
+  std::printf("worst %.3e rejected %d\n", worst, rejected);
+  std::printf("%s\n", worst <= 1e-12 && rejected ? "PROBE_OK" : "PROBE_BROKEN");
+  return worst <= 1e-12 && rejected ? 0 : 1;
+}
+""")
+    exe = str(tmp_path / "ref_shaped")
+    libdir = os.path.join(ROOT, "posegraph-ceres_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include", "ceres_b200", "compat"), "-o", exe, str(src),
+                           "-L", libdir, "-lpgo_b200", f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"])
+    r = subprocess.run([exe], capture_output=True, text=True, env=_loader_env())
+    assert r.returncode == 0 and "PROBE_OK" in r.stdout, r.stdout + r.stderr
+
+
+def _loader_env():
+    env = dict(os.environ)
+    import torch  # noqa: F401  (its bundled libnccl / libcudart directories are on the loader path below)
+    extra = []
+    for mod in ("nvidia.nccl", "nvidia.cuda_runtime"):
+        try:
+            m = __import__(mod, fromlist=["x"])
+            extra.append(os.path.join(list(m.__path__)[0], "lib"))
+        except Exception:
+            pass
+    env["LD_LIBRARY_PATH"] = ":".join(extra + [env.get("LD_LIBRARY_PATH", "")])
+    return env
+
+
+def _write_drop_in_graph(g, path):
+    """graph file of oracle/ref_drop_in.cpp: poses, then edges with the 6x6 information = S S^T (row-major)"""
+    with open(path, "w") as f:
+        f.write(f"{g.n_poses} {g.n_edges}\n")
+        for i in range(g.n_poses):
+            f.write(f"{i} " + " ".join(repr(float(v)) for v in g.poses[i]) + "\n")
+        for e in range(g.n_edges):
+            S = g.edge_sqrt_info[e].reshape(6, 6)
+            info = S @ S.T
+            f.write(f"{g.edge_ids[e, 0]} {g.edge_ids[e, 1]} " + " ".join(repr(float(v)) for v in g.edge_meas[e]) + " "
+                    + " ".join(repr(float(v)) for v in info.ravel()) + "\n")
+
+
+REF_DROP_IN = os.path.join(ROOT, "oracle", "_ref", "ref_drop_in")
+
+
+def _need_drop_in(oracle):
+    oracle.ref_functor()          # runs `make -C oracle ref` when /root/reference is present
+    if not os.path.exists(REF_DROP_IN):
+        pytest.skip("oracle/_ref/ref_drop_in not built (needs /root/reference at build time)")
+
+
+def test_reference_text_drop_in_fails_loudly_without_gpu(pgo, oracle, D, tmp_path):
+    """The reference's own BuildOptimizationProblem / SolveOptimizationProblem / OutputPoses text (REF :491-567, extracted
+    at build time) compiled against the mirror: builds, runs its problem setup on the host, and -- without a GPU --
+    reports FAILURE instead of falling back to anything."""
+    _need_drop_in(oracle)
+    if pgo.device_count() > 0:
+        pytest.skip("GPU present")
+    path = str(tmp_path / "g.txt")
+    _write_drop_in_graph(D.manhattan_loop(), path)
+    r = subprocess.run([REF_DROP_IN, path, str(tmp_path / "out.txt")], capture_output=True, text=True, env=_loader_env())
+    assert r.returncode == 1, r.stdout + r.stderr
+    assert "Number of poses: 100" in r.stdout and "no CUDA device" in r.stdout and "May be some problems!" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["kitti00", "sphere"])
+def test_reference_text_drop_in_matches_oracle(pgo, oracle, D, tmp_path, name):
+    """The reference's own optimisation-stage text + its unmodified PoseGraph3dError.h, linked against libpgo_b200.so
+    (oracle/ref_drop_in.cpp): the poses it writes with its own OutputPoses equal the CPU oracle's."""
+    if not os.path.exists(REF_DROP_IN):
+        pytest.skip("oracle/_ref/ref_drop_in not built (needs /root/reference at build time)")
+    g = D.kitti00() if name == "kitti00" else D.sphere(10, 20, None)
+    path, out = str(tmp_path / "g.txt"), str(tmp_path / "out.txt")
+    _write_drop_in_graph(g, path)
+    r = subprocess.run([REF_DROP_IN, path, out], capture_output=True, text=True, env=_loader_env())
+    assert r.returncode == 0 and "Optimizing Suscessfully!" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    got = np.loadtxt(out)
+    assert np.array_equal(got[:, 0], np.arange(g.n_poses))
+    ref, rs, _ = oracle.solve(g)
+    # OutputPoses prints 6 significant digits (the stream's default precision): that is the reference's own text
+    assert np.abs(got[:, 1:4] - ref[:, :3]).max() <= 1e-4 + 1e-5 * np.abs(ref[:, :3]).max()
+    from helpers import rot_angle_between
+    assert rot_angle_between(got[:, 4:8], ref[:, 3:]).max() <= 1e-4 + 2e-5
 
 
 @pytest.mark.gpu
