@@ -85,6 +85,12 @@ struct pgo_graph {
   std::vector<unsigned char> gactive_h;
   std::vector<double> pos0_h;       // [N_global][3]
   pgo::Amg* amg = nullptr;
+  // device-resident LM loop (pgo_lm.cuh)
+  pgo::LmState* lm_state = nullptr;
+  pgo::LmState* lm_ring = nullptr;          // pinned: 3 look-behind slots + 1
+  cudaEvent_t lm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  pgo_iteration_summary* lm_log = nullptr;
+  int lm_log_cap = 0;
   long long comm_calls = 0, comm_bytes = 0;   // NCCL calls / payload bytes sent by this rank (multi-GPU)
   bool identity_info = true;
   bool has_dup_blocks = false;
@@ -287,6 +293,8 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
   pool_pinned_release(g->device, g->scalars_h);
   pool_pinned_release(g->device, g->pcgm_state_h);
+  pool_pinned_release(g->device, g->lm_ring);
+  for (int k = 0; k < 4; ++k) pool_event_release(g->device, g->lm_ev[k]);
   pool_event_release(g->device, g->ev0);
   pool_event_release(g->device, g->ev1);
   pool_event_release(g->device, g->ev2);
@@ -981,11 +989,14 @@ static int launch_linearize_t(pgo_graph* g, const LinParams& p) {
   return PGO_OK;
 }
 
+struct LinTarget { double* Hdiag; double* Hoff; double* grad; };   // the system a linearisation accumulates into
 static int launch_linearize(pgo_graph* g, int mode, const double* poses, const double* scale, int loss_type,
-                            double loss_a, double* res_out = nullptr, double* jac_out = nullptr) {
+                            double loss_a, double* res_out = nullptr, double* jac_out = nullptr, const LinTarget* target = nullptr,
+                            const LmState* lm = nullptr) {
   LinParams p;
   p.n_edges = g->E; p.n_tiles = g->T; p.n_own = g->n_own; p.core = g->core; p.info = g->info; p.poses = poses; p.scale = scale;
-  p.Hdiag = g->Hdiag; p.Hoff = g->Hoff; p.grad = g->grad; p.scalars = g->scalars;
+  p.Hdiag = target ? target->Hdiag : g->Hdiag; p.Hoff = target ? target->Hoff : g->Hoff; p.grad = target ? target->grad : g->grad;
+  p.scalars = g->scalars; p.lm = lm;
   p.loss_type = loss_type; p.loss_a = loss_a; p.res_out = res_out; p.jac_out = jac_out;
   if (g->E == 0) return PGO_OK;
   static const int occ = getenv("PGO_LIN_OCC") ? atoi(getenv("PGO_LIN_OCC")) : 2;   // CTAs per SM of the full kernel (tuning knob)
@@ -1010,9 +1021,9 @@ static int zero_scalars(pgo_graph* g) {
   CUDA_TRY(cudaMemsetAsync(g->scalars, 0, sizeof(DeviceScalars), g->stream));
   return PGO_OK;
 }
-static int fetch_scalars(pgo_graph* g) {
-  // multi-GPU: every rank reduced over its own rows / edges; the all-reduced values are bit-identical on every rank, so
-  // all ranks take the same LM decisions.  (The PCG statistics already are global.)
+// multi-GPU: every rank reduced over its own rows / edges; the all-reduced values are bit-identical on every rank, so all
+// ranks take the same LM decisions.  (The PCG statistics already are global.)
+static int reduce_scalars(pgo_graph* g) {
   if (g->world > 1) {
     static_assert(offsetof(DeviceScalars, step_norm2) == 8 && offsetof(DeviceScalars, x_norm2) == 16, "cost, step_norm2, x_norm2 are contiguous");
     NCCL_TRY(ncclAllReduce(&g->scalars->cost, &g->scalars->cost, 3, ncclDouble, ncclSum, g->comm, g->stream));
@@ -1020,6 +1031,10 @@ static int fetch_scalars(pgo_graph* g) {
     NCCL_TRY(ncclAllReduce(&g->scalars->gmax_bits, &g->scalars->gmax_bits, 1, ncclUint64, ncclMax, g->comm, g->stream));
     g->comm_calls += 3; g->comm_bytes += 40;
   }
+  return PGO_OK;
+}
+static int fetch_scalars(pgo_graph* g) {
+  PGO_TRY(reduce_scalars(g));
   CUDA_TRY(cudaMemcpyAsync(g->scalars_h, g->scalars, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PGO_OK;
@@ -1031,14 +1046,6 @@ static int linearize_full(pgo_graph* g, const double* poses, const double* scale
   PGO_TRY(zero_system(g, true));
   PGO_TRY(launch_linearize(g, kLinFull, poses, scale, loss_type, loss_a));
   return PGO_OK;
-}
-
-// The LM loop linearises speculatively at every candidate point into the alternate system (H, g) while the current one
-// stays intact: an accepted step keeps the swap, a rejected one swaps back.  One stream synchronisation per iteration.
-static void swap_system(pgo_graph* g) {
-  std::swap(g->Hdiag, g->Hdiag_alt);
-  std::swap(g->Hoff, g->Hoff_alt);
-  std::swap(g->grad, g->grad_alt);
 }
 
 static BsrView bsr_view(const pgo_graph* g) {
@@ -1058,8 +1065,9 @@ static int pcg_grid(const pgo_graph* g, const pgo_solver_options* o) {
 }
 
 // Single-GPU persistent PCG: (H + diag(dlm)) x = b, x in g->vx. Results land in g->scalars.
-static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b) {
+static int launch_pcg(pgo_graph* g, const pgo_solver_options* o, const double* b, const LmState* lm = nullptr) {
   PcgParams P;
+  P.lm = lm;
   P.A = bsr_view(g);
   P.d = g->dlm; P.Minv = g->Minv; P.b = b;
   P.x = g->vx; P.r = g->vr; P.u = g->vu; P.w = g->vw; P.p = g->vp; P.s = g->vs;
@@ -1273,24 +1281,33 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
 
 // LevenbergMarquardtStrategy::ComputeStep: D = diagonal / radius (new, reused or given), then solve
 // (H + D) x = b with the chosen solver; x -> g->vx, stats -> g->scalars (after fetch).
-static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b, const LmDiagonal& lm) {
+// lm_state != nullptr: inside the device-resident LM loop -- radius and diagonal reuse are read from it on the device.
+static int linear_solve_device(pgo_graph* g, const pgo_solver_options* o, int solver, const double* b, const LmDiagonal& lm,
+                               const LmState* lm_state = nullptr) {
   if (g->world == 1 && solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) {
     // the LM diagonal is formed inside the factor kernel
-    return level_chol_solve(g->chol, bsr_view(g), lm, g->active, b, g->vx, g->vr, g->vu, g->vw, g->vp, g->vs,
+    return level_chol_solve(g->chol, bsr_view(g), lm, lm_state, g->active, b, g->vx, g->vr, g->vu, g->vw, g->vp, g->vs,
                             std::min(o->pcg_max_iterations, 200), o->pcg_tolerance, std::max(o->pcg_tolerance, o->direct_residual_accept),
                             o->pcg_num_ctas, g->scalars,
                             g->stream, &g->launches);
   }
   const int tpb = 128;
   lm_prepare_kernel<<<(g->n_own + tpb - 1) / tpb, tpb, 0, g->stream>>>(g->n_own, g->Hdiag, g->active, lm.mode, lm.min_diag, lm.max_diag,
-                                                                       lm.radius, lm.diagonal, lm.dlm, g->Minv);
+                                                                       lm.radius, lm.diagonal, lm.dlm, g->Minv, lm_state);
   g->launches++;
   if (solver == PGO_LINEAR_PCG_AMG) return amg_pcg_solve(g, o, b);
   static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;   // tests: the stream-ordered form on a small graph
   // large graphs: separate launches at full occupancy beat the persistent kernel (whose grid barriers only pay when an
   // iteration is a few microseconds long)
   if (force_stream_pcg || g->N >= kStreamPcgMinPoses) return pcg_multi(g, o, b);
-  return launch_pcg(g, o, b);
+  return launch_pcg(g, o, b, lm_state);
+}
+// does the solver poll the device from the host (its own convergence loop)?  Then the LM loop cannot run ahead of it.
+static bool solver_is_host_polled(const pgo_graph* g, int solver) {
+  static const bool force_stream_pcg = getenv("PGO_FORCE_STREAM_PCG") != nullptr;
+  if (solver == PGO_LINEAR_PCG_AMG) return true;
+  if (solver == PGO_LINEAR_PCG_BLOCK_JACOBI && (force_stream_pcg || g->N >= kStreamPcgMinPoses)) return true;
+  return false;
 }
 
 extern "C" int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* options, const double* d,
@@ -1317,10 +1334,27 @@ extern "C" int pgo_graph_linear_solve(pgo_graph* g, const pgo_solver_options* op
 }
 
 // ------------------------------------------------------------------------------------------------
-// ceres::Solve: TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy (ceres 1.13 flow),
-// the same sequence of decisions as oracle/pgo_oracle.c:oracle_solve, driven from the host with
-// two stream synchronisations per iteration.
+// ceres::Solve: TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy (ceres 1.13 flow), the same sequence of
+// decisions as oracle/pgo_oracle.c:oracle_solve -- taken ON THE DEVICE (pgo_lm.cuh).  One iteration is: linear solve,
+// candidate = Plus(x, -y .* scale), speculative linearisation at the candidate into the alternate system (cost, H, g and
+// the gradient norms arrive with the step statistics), decision kernel, commit kernel.  The host enqueues iterations
+// ahead of the GPU and watches the `done` flag two iterations behind, so no iteration waits for a host round trip;
+// iterations enqueued past the end return at once.  (Linear solvers with a host-polled inner loop -- the multilevel and
+// the stream-ordered PCG of large graphs -- keep the LM loop in step with the host: there an iteration is milliseconds.)
 // ------------------------------------------------------------------------------------------------
+static void lm_message(const LmState& st, const pgo_solver_options* opt, char* out, size_t cap) {
+  switch (st.reason) {
+    case kLmMaxIterations: snprintf(out, cap, "Maximum number of iterations reached. Number of iterations: %d.", (int)st.reason_value); break;
+    case kLmGradientTolerance: snprintf(out, cap, "Gradient tolerance reached. Gradient max norm: %e <= %e", st.reason_value, opt->gradient_tolerance); break;
+    case kLmMinRadius: snprintf(out, cap, "Minimum trust region radius reached."); break;
+    case kLmInvalidSteps: snprintf(out, cap, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", opt->max_num_consecutive_invalid_steps); break;
+    case kLmParameterTolerance: snprintf(out, cap, "Parameter tolerance reached. Relative step_norm: %e <= %e.", st.reason_value, opt->parameter_tolerance); break;
+    case kLmFunctionTolerance: snprintf(out, cap, "Function tolerance reached. |cost_change|/cost: %e <= %e", st.reason_value, opt->function_tolerance); break;
+    case kLmInitialCostNotFinite: snprintf(out, cap, "Initial cost is not finite."); break;
+    default: snprintf(out, cap, "The minimizer did not terminate."); break;
+  }
+}
+
 extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_solver_summary* summary,
                                pgo_iteration_summary* log, int log_cap) {
   if (!g || !opt || !summary) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_solve: null argument");
@@ -1331,12 +1365,7 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   const int N = g->N;            // local poses incl. halo copies (pose / scale arrays)
   const int R = g->n_own;        // block rows = variables stored here
   const int tpb = 128, nblk = (R + tpb - 1) / tpb;
-  float ms = 0.f;
   const long long comm_calls0 = g->comm_calls, comm_bytes0 = g->comm_bytes;
-  auto push_log = [&](const pgo_iteration_summary& it) {
-    if (log && summary->num_iterations < log_cap) log[summary->num_iterations] = it;
-    summary->num_iterations++;
-  };
   const int solver = resolve_linear_solver(g, opt);
   if (solver < 0) return solver;
   summary->linear_solver_used = solver;
@@ -1346,10 +1375,29 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     PGO_TRY(dev_alloc(g, &g->grad_alt, (size_t)R * 6));
     CUDA_TRY(cudaMemsetAsync(g->Hoff_alt, 0, std::max<size_t>((size_t)g->nnz_off * 36, 1) * sizeof(double), g->stream));
   }
+  // device-resident LM state, the iteration log, and a pinned ring the host reads the state from
+  const int dev_log_cap = std::max(2, std::min(opt->max_num_iterations + 2, 1 << 16));
+  if (!g->lm_state) {
+    PGO_TRY(dev_alloc(g, &g->lm_state, 1));
+    CUDA_TRY(pool_pinned(g->device, reinterpret_cast<void**>(&g->lm_ring)));
+    static_assert(4 * sizeof(LmState) <= kPinnedBytes, "pinned LM state ring");
+    for (int k = 0; k < 4; ++k) CUDA_TRY(pool_event(g->device, &g->lm_ev[k]));
+  }
+  if (g->lm_log_cap < dev_log_cap) {
+    PGO_TRY(dev_alloc(g, &g->lm_log, (size_t)dev_log_cap));
+    g->lm_log_cap = dev_log_cap;
+  }
+  LmState* st = g->lm_state;
   summary->hessian_blocks = g->nnz_off + R;
   if (solver == PGO_LINEAR_PCG_AMG) { summary->amg_levels = g->amg->num_levels; summary->amg_blocks = g->amg->blocks_all_levels; }
   if (solver == PGO_LINEAR_PCG_LEVEL_CHOLESKY) { summary->factor_blocks = g->chol->factor_blocks; summary->factor_levels = g->chol->num_levels; }
   summary->time_setup_s = g->setup_s;
+  LmOptions lo;
+  lo.max_num_iterations = opt->max_num_iterations;
+  lo.function_tolerance = opt->function_tolerance; lo.gradient_tolerance = opt->gradient_tolerance; lo.parameter_tolerance = opt->parameter_tolerance;
+  lo.initial_radius = opt->initial_trust_region_radius; lo.max_radius = opt->max_trust_region_radius; lo.min_radius = opt->min_trust_region_radius;
+  lo.min_relative_decrease = opt->min_relative_decrease; lo.max_consecutive_invalid = opt->max_num_consecutive_invalid_steps;
+  lo.verbose = opt->verbose;
 
   // ---- IterationZero: evaluate, Jacobi scaling from the unscaled diagonal, re-linearize scaled ----
   CUDA_TRY(cudaMemcpyAsync(g->scale, g->scale_eval, (size_t)N * 6 * sizeof(double), cudaMemcpyDeviceToDevice, g->stream));
@@ -1368,140 +1416,97 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
   xnorm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->active, g->scalars);
   gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
-  g->launches += 2;
-  PGO_TRY(fetch_scalars(g));
-  CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
-  summary->time_linearize_ms += ms;
+  PGO_TRY(reduce_scalars(g));
+  lm_init_kernel<<<1, 32, 0, g->stream>>>(st, g->scalars, lo, g->lm_log, g->lm_log_cap);
+  g->launches += 3;
 
-  double x_cost = g->scalars_h->cost;
-  double x_norm = std::sqrt(g->scalars_h->x_norm2);
-  double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
-  bool reuse_diagonal = false;
-  int num_consecutive_invalid = 0, iter = 0;
-  pgo_iteration_summary it;
-  std::memset(&it, 0, sizeof it);
-  it.cost = x_cost; it.trust_region_radius = radius;
-  { long long bits = (long long)g->scalars_h->gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
-  it.gradient_norm = std::sqrt(g->scalars_h->gnorm2);
-  summary->initial_cost = x_cost;
-  push_log(it);
-  if (!std::isfinite(x_cost)) {
-    summary->termination_type = PGO_FAILURE;
-    snprintf(summary->message, sizeof summary->message, "Initial cost is not finite.");
-    summary->final_cost = x_cost;
-    summary->time_total_s = wall_s() - t_begin;
+  // ---- the loop ----
+  const LinTarget alt = {g->Hdiag_alt, g->Hoff_alt, g->grad_alt};
+  const LmDiagonal lmd = {0, opt->min_lm_diagonal, opt->max_lm_diagonal, opt->initial_trust_region_radius, g->diagonal, g->dlm};
+  const int commit_ctas = std::max(1, std::min((int)(((long long)R * 36 + g->nnz_off * 36 + 511) / 512), 4 * g->num_sms));
+  auto enqueue_iteration = [&]() -> int {
+    // LevenbergMarquardtStrategy::ComputeStep: D = diag / radius, solve (H + D) y = g, step = -y
+    PGO_TRY(linear_solve_device(g, opt, solver, g->grad, lmd, st));
+    // candidate = Plus(x, -y .* scale), |step|, |x_cand|; the alternate system is zeroed on the way
+    plus_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars, st,
+                                                        g->Hdiag_alt, g->grad_alt);
+    g->launches++;
+    if (g->has_dup_blocks && g->nnz_off) CUDA_TRY(cudaMemsetAsync(g->Hoff_alt, 0, (size_t)g->nnz_off * 36 * sizeof(double), g->stream));
+    PGO_TRY(halo_exchange0(g, g->poses_cand, 8, &st->done));   // candidate poses of the cut edges' other endpoints
+    PGO_TRY(launch_linearize(g, kLinFull, g->poses_cand, g->scale, opt->loss_type, opt->loss_a, nullptr, nullptr, &alt, st));
+    gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses_cand, g->grad_alt, g->scale, g->active, nullptr, g->scalars, st);
+    PGO_TRY(reduce_scalars(g));
+    lm_decide_kernel<<<1, 32, 0, g->stream>>>(st, g->scalars, lo, g->lm_log, g->lm_log_cap);
+    lm_commit_kernel<<<commit_ctas, 256, 0, g->stream>>>(st, g->scalars, (long long)N * 8, g->poses_cand, g->poses, (long long)R * 36, g->Hdiag_alt,
+                                                         g->Hdiag, g->nnz_off * 36, g->Hoff_alt, g->Hoff, (long long)R * 6, g->grad_alt, g->grad);
+    g->launches += 3;
     return PGO_OK;
-  }
-
-  for (;;) {
-    if (iter >= opt->max_num_iterations) { summary->termination_type = PGO_NO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Maximum number of iterations reached. Number of iterations: %d.", iter); break; }
-    if (it.gradient_max_norm <= opt->gradient_tolerance) { summary->termination_type = PGO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Gradient tolerance reached. Gradient max norm: %e <= %e", it.gradient_max_norm, opt->gradient_tolerance); break; }
-    if (radius < opt->min_trust_region_radius) { summary->termination_type = PGO_CONVERGENCE; snprintf(summary->message, sizeof summary->message, "Minimum trust region radius reached."); break; }
-    ++iter;
-    { const double gm = it.gradient_max_norm, gn = it.gradient_norm; std::memset(&it, 0, sizeof it); it.iteration = iter; it.gradient_max_norm = gm; it.gradient_norm = gn; }
-
-    // ---- LevenbergMarquardtStrategy::ComputeStep: D = diag / radius, solve (H + D) y = g, step = -y ----
-    PGO_TRY(zero_scalars(g));
-    CUDA_TRY(cudaEventRecord(g->ev0, g->stream));
-    const LmDiagonal lm = {reuse_diagonal ? 1 : 0, opt->min_lm_diagonal, opt->max_lm_diagonal, radius, g->diagonal, g->dlm};
-    const double th0 = wall_s();
-    PGO_TRY(linear_solve_device(g, opt, solver, g->grad, lm));
-    CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-    const double th1 = wall_s();
-    reuse_diagonal = true;
-    // ---- candidate = Plus(x, -y .* scale), |step|, |x_cand|, and -- speculatively -- the full linearisation at the
-    //      candidate (cost, H, g, gradient norms) into the alternate system: everything the decision needs in one sync
-    plus_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->vx, g->scale, g->active, -1.0, g->poses_cand, g->scalars);
-    g->launches++;
-    PGO_TRY(halo_exchange0(g, g->poses_cand, 8));   // candidate poses of the cut edges' other endpoints
-    swap_system(g);
-    CUDA_TRY(cudaEventRecord(g->ev2, g->stream));
-    PGO_TRY(linearize_full(g, g->poses_cand, g->scale, opt->loss_type, opt->loss_a));
-    CUDA_TRY(cudaEventRecord(g->ev3, g->stream));
-    summary->num_linearizations++;
-    gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses_cand, g->grad, g->scale, g->active, nullptr, g->scalars);
-    g->launches++;
-    PGO_TRY(fetch_scalars(g));
-    const double th2 = wall_s();
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
-    summary->time_linear_solver_ms += ms;
-    { float ms2 = 0.f; CUDA_TRY(cudaEventElapsedTime(&ms2, g->ev2, g->ev3)); summary->time_linearize_ms += ms2; }
-    if (opt->verbose >= 2)
-      fprintf(stderr, "[pgo host] it %d: enqueue solver %.1f us, enqueue plus+linearize + wait %.1f us, solver on GPU %.1f us\n", iter,
-              1e6 * (th1 - th0), 1e6 * (th2 - th1), 1e3 * ms);
-    const DeviceScalars sc = *g->scalars_h;
-    summary->total_pcg_iterations += sc.pcg_iterations;
-    it.linear_solver_iterations = sc.pcg_iterations;
-    it.pcg_relative_residual = sc.pcg_gamma0 > 0 ? std::sqrt(std::fabs(sc.pcg_gamma) / sc.pcg_gamma0) : 0.0;
-    it.trust_region_radius = radius;
-
-    // model_cost_change = -(J step)^T (r + J step / 2) = y^T g - y^T H y / 2
-    const double model_cost_change = sc.xtb - 0.5 * (sc.xtAx - sc.xtDx);
-    bool step_valid = sc.pcg_flag < 2 && std::isfinite(model_cost_change) && model_cost_change > 0.0;   // 2: CG breakdown, 3: pivot failure
-    if (opt->verbose)
-      fprintf(stderr, "[pgo] it %d radius %.3e pcg %d (flag %d, rel %.2e) model %.6e\n", iter, radius, sc.pcg_iterations,
-              sc.pcg_flag, it.pcg_relative_residual, model_cost_change);
-    if (!step_valid) {
-      swap_system(g);   // discard the speculative system
-      it.step_is_valid = 0; it.cost = x_cost;
-      if (++num_consecutive_invalid >= opt->max_num_consecutive_invalid_steps) {
-        summary->termination_type = PGO_FAILURE;
-        snprintf(summary->message, sizeof summary->message, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", opt->max_num_consecutive_invalid_steps);
-        push_log(it);
-        break;
+  };
+  const int depth = solver_is_host_polled(g, solver) ? 0 : 2;   // iterations the host may run ahead of what it has seen
+  LmState final_state;
+  {
+    // state after iteration zero (a non-finite initial cost or a zero gradient ends the solve before the loop)
+    int k = 0;
+    bool finished = false;
+    auto publish = [&](int slot) -> int {
+      CUDA_TRY(cudaMemcpyAsync(g->lm_ring + slot, st, sizeof(LmState), cudaMemcpyDeviceToHost, g->stream));
+      CUDA_TRY(cudaEventRecord(g->lm_ev[slot], g->stream));
+      return PGO_OK;
+    };
+    PGO_TRY(publish(3));
+    if (depth == 0) {
+      CUDA_TRY(cudaEventSynchronize(g->lm_ev[3]));
+      finished = g->lm_ring[3].done != 0;
+    }
+    const int hard_cap = opt->max_num_iterations + 8;
+    while (!finished && k < hard_cap) {
+      PGO_TRY(enqueue_iteration());
+      summary->num_linearizations++;
+      const int slot = k % 3;
+      PGO_TRY(publish(slot));
+      if (depth == 0) {
+        CUDA_TRY(cudaEventSynchronize(g->lm_ev[slot]));
+        finished = g->lm_ring[slot].done != 0;
+      } else if (k == 0) {
+        CUDA_TRY(cudaEventSynchronize(g->lm_ev[3]));          // the state after iteration zero
+        finished = g->lm_ring[3].done != 0;
+      } else if (k >= depth - 1) {
+        const int seen = (k - (depth - 1)) % 3;               // the iteration `depth - 1` before this one
+        CUDA_TRY(cudaEventSynchronize(g->lm_ev[seen]));
+        finished = g->lm_ring[seen].done != 0;
       }
-      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-      summary->num_unsuccessful_steps++;
-      push_log(it);
-      continue;
+      ++k;
     }
-    num_consecutive_invalid = 0;
-    it.step_is_valid = 1;
-    double cand_cost = sc.cost;
-    if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
-    const double step_norm = std::sqrt(sc.step_norm2);
-    it.step_norm = step_norm;
-    if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
-      summary->termination_type = PGO_CONVERGENCE;
-      snprintf(summary->message, sizeof summary->message, "Parameter tolerance reached. Relative step_norm: %e <= %e.", step_norm / (x_norm + opt->parameter_tolerance), opt->parameter_tolerance);
-      swap_system(g);
-      it.cost = x_cost; push_log(it);
-      break;
-    }
-    const double cost_change = x_cost - cand_cost;
-    it.cost_change = cost_change;
-    if (std::fabs(cost_change) <= opt->function_tolerance * x_cost) {
-      summary->termination_type = PGO_CONVERGENCE;
-      snprintf(summary->message, sizeof summary->message, "Function tolerance reached. |cost_change|/cost: %e <= %e", std::fabs(cost_change) / x_cost, opt->function_tolerance);
-      swap_system(g);
-      it.cost = x_cost; push_log(it);
-      break;
-    }
-    const double relative_decrease = cost_change / model_cost_change;
-    it.relative_decrease = relative_decrease;
-    if (relative_decrease > opt->min_relative_decrease) {
-      // HandleSuccessfulStep: x = candidate; its linearisation is already the current system
-      std::swap(g->poses, g->poses_cand);
-      x_norm = std::sqrt(sc.x_norm2);
-      x_cost = sc.cost;
-      { long long bits = (long long)sc.gmax_bits; double gm; std::memcpy(&gm, &bits, 8); it.gradient_max_norm = gm; }
-      it.gradient_norm = std::sqrt(sc.gnorm2);
-      it.step_is_successful = 1; it.cost = x_cost;
-      summary->num_successful_steps++;
-      double t = 2.0 * relative_decrease - 1.0;
-      t = 1.0 - t * t * t;
-      if (t < 1.0 / 3.0) t = 1.0 / 3.0;
-      radius = std::min(radius / t, opt->max_trust_region_radius);
-      decrease_factor = 2.0; reuse_diagonal = false;
-    } else {
-      swap_system(g);   // HandleUnsuccessfulStep: discard the speculative system
-      it.step_is_successful = 0; it.cost = x_cost;
-      summary->num_unsuccessful_steps++;
-      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
-    }
-    push_log(it);
+    CUDA_TRY(cudaMemcpyAsync(g->lm_ring + 3, st, sizeof(LmState), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    final_state = g->lm_ring[3];
+    // linearisations that actually ran (iterations enqueued past the end returned at once)
+    summary->num_linearizations = (opt->jacobi_scaling ? 2 : 1) + std::max(final_state.num_rows - 1, 0);
   }
-  summary->final_cost = x_cost;
+  CUDA_TRY(cudaGetLastError());
+  {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+    summary->time_linearize_ms = ms + final_state.linearize_ns * 1e-6;
+    summary->time_linear_solver_ms = final_state.solver_ns * 1e-6;
+  }
+  const int rows = std::min(final_state.num_rows, g->lm_log_cap);
+  std::vector<pgo_iteration_summary> rows_h((size_t)std::max(rows, 1));
+  if (rows > 0) CUDA_TRY(cudaMemcpy(rows_h.data(), g->lm_log, (size_t)rows * sizeof(pgo_iteration_summary), cudaMemcpyDeviceToHost));
+  if (log) for (int k = 0; k < rows && k < log_cap; ++k) log[k] = rows_h[k];
+  if (opt->verbose)
+    for (int k = 1; k < rows; ++k)
+      fprintf(stderr, "[pgo] it %d radius %.3e pcg %d (rel %.2e) cost %.6e %s\n", rows_h[k].iteration, rows_h[k].trust_region_radius,
+              rows_h[k].linear_solver_iterations, rows_h[k].pcg_relative_residual, rows_h[k].cost,
+              rows_h[k].step_is_successful ? "accepted" : (rows_h[k].step_is_valid ? "rejected" : "invalid"));
+  summary->num_iterations = final_state.num_rows;
+  summary->initial_cost = final_state.initial_cost;
+  summary->final_cost = final_state.x_cost;
+  summary->num_successful_steps = final_state.num_successful;
+  summary->num_unsuccessful_steps = final_state.num_unsuccessful;
+  summary->termination_type = final_state.done ? final_state.termination_type : PGO_NO_CONVERGENCE;
+  summary->total_pcg_iterations = final_state.total_pcg_iterations;
+  lm_message(final_state, opt, summary->message, sizeof summary->message);
   summary->comm_calls = g->comm_calls - comm_calls0;
   summary->comm_bytes = g->comm_bytes - comm_bytes0;
   if (g->amg) { summary->comm_bytes_per_pcg_iteration = g->amg->comm_bytes_per_iteration; summary->comm_calls_per_pcg_iteration = g->amg->comm_calls_per_iteration; }

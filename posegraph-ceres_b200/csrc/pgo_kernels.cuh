@@ -15,6 +15,7 @@
 
 #include "pgo_common.cuh"
 #include "pgo_edge_math.cuh"
+#include "pgo_lm.cuh"
 
 namespace pgo {
 
@@ -38,6 +39,7 @@ struct LinParams {
   // kLinEval outputs
   double* res_out;              // [E][6]
   double* jac_out;              // [E][2][36] row-major
+  const LmState* lm;            // device-resident LM loop: return at once when lm->done (else nullptr)
 };
 
 __device__ __forceinline__ void load_pose(const double* poses, int i, double* p) {
@@ -81,6 +83,7 @@ constexpr int lin_smem_bytes() {
 template <bool kIdentityInfo, int kMode, int kMinBlocks>
 __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(const LinParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (p.lm && p.lm->done) return;
   // per warp: core ring, then the info ring; the output staging tile [32][36] aliases the CURRENT info stage (its
   // sqrt-information is dead once the Jacobians are in registers) or, without information tiles, a dedicated buffer
   constexpr int kWarpBytes = kLinStages * kCoreTileBytes + (kIdentityInfo ? kInfoTileBytes : kLinInfoStages * kInfoTileBytes);
@@ -441,6 +444,7 @@ struct PcgParams {
   DeviceScalars* scalars;
   int max_iterations;
   double tolerance;
+  const LmState* lm;      // device-resident LM loop (done flag), or nullptr
 };
 
 __device__ __forceinline__ double cta_sum(double v, double* red) {
@@ -482,6 +486,7 @@ template <bool kCluster>
 __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
   __shared__ double red[kPcgThreads / 32];
   __shared__ double bcast;
+  if (P.lm && P.lm->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane / 6, r = lane - grp * 6;
   const bool lane_on = grp < kRowsPerWarp;
@@ -626,9 +631,14 @@ __global__ void jacobi_scale_kernel(int n, const double* __restrict__ Hdiag, con
 __global__ void lm_prepare_kernel(int n, const double* __restrict__ Hdiag, const unsigned char* __restrict__ active,
                                   int mode /*0: new diagonal, 1: reuse diagonal, 2: dlm given*/, double min_diag,
                                   double max_diag, double radius, double* __restrict__ diagonal,
-                                  double* __restrict__ dlm, double* __restrict__ Minv) {
+                                  double* __restrict__ dlm, double* __restrict__ Minv, const LmState* lm = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (lm) {                       // device-resident LM loop: the radius and the reuse decision live on the device
+    if (lm->done) return;
+    mode = lm->reuse_diagonal ? 1 : 0;
+    radius = lm->radius;
+  }
   double A[6][6];
   double dd[6];
 #pragma unroll
@@ -699,10 +709,27 @@ __global__ void lm_prepare_kernel(int n, const double* __restrict__ Hdiag, const
 // x_cand = Plus(x, sign * y .* scale) for active poses; accumulates |x - x_cand|^2 and |x_cand|^2.
 __global__ void __launch_bounds__(256) plus_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
                                                    const double* __restrict__ scale, const unsigned char* __restrict__ active,
-                                                   double sign, double* __restrict__ out, DeviceScalars* scalars) {
+                                                   double sign, double* __restrict__ out, DeviceScalars* scalars,
+                                                   LmState* lm = nullptr, double* __restrict__ zero_hdiag = nullptr,
+                                                   double* __restrict__ zero_grad = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm) {
+    if (lm->done) return;
+    if (i == 0) lm->t_solved = lm_globaltimer();      // the linear solve ends where this kernel starts
+  }
   double sn = 0.0, xn = 0.0;
   if (i < n) {
+    // the system the speculative linearisation is about to accumulate into starts from zero (folded memsets)
+    if (zero_hdiag) {
+      double2* z = reinterpret_cast<double2*>(zero_hdiag + 36 * (size_t)i);
+#pragma unroll
+      for (int k = 0; k < 18; ++k) z[k] = make_double2(0.0, 0.0);
+    }
+    if (zero_grad) {
+      double2* z = reinterpret_cast<double2*>(zero_grad + 6 * (size_t)i);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) z[k] = make_double2(0.0, 0.0);
+    }
     double xi[7], d[6], o[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) xi[k] = x[8 * (size_t)i + k];
@@ -727,8 +754,10 @@ __global__ void __launch_bounds__(256) plus_kernel(int n, const double* __restri
 // gradient norms as Ceres reports them: |x - Plus(x, -g)| with g = unscaled gradient = g_s / scale.
 __global__ void __launch_bounds__(256) gradient_norm_kernel(int n, const double* __restrict__ x, const double* __restrict__ gs,
                                                             const double* __restrict__ scale, const unsigned char* __restrict__ active,
-                                                            double* __restrict__ g_unscaled, DeviceScalars* scalars) {
+                                                            double* __restrict__ g_unscaled, DeviceScalars* scalars,
+                                                            const LmState* lm = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm && lm->done) return;
   double mx = 0.0, l2 = 0.0;
   if (i < n) {
     double g[6];

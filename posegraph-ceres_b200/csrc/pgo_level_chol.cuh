@@ -87,6 +87,7 @@ struct CholParams {
   BsrView A;
   // LM diagonal: mode 0 = new diagonal from H, 1 = reuse `diagonal`, 2 = dlm given
   int lm_mode; double min_diag, max_diag, radius;
+  const LmState* lm;              // device-resident LM loop: radius / reuse-diagonal / done come from here (else nullptr)
   double* diagonal; double* dlm;
   const unsigned char* active;
   const double* b;
@@ -504,16 +505,18 @@ __device__ __forceinline__ double cta_sum_n(double v, double* red) {
 // S phase: LM diagonal D = clamp(diag H) / radius, factor storage <- A + D, working rhs t = b, PCG vectors.
 __device__ __forceinline__ void chol_setup_phase(const CholParams& P, int gtid, int gthreads) {
   const int n6 = 6 * P.A.n;
+  const int lm_mode = P.lm ? (P.lm->reuse_diagonal ? 1 : 0) : P.lm_mode;
+  const double radius = P.lm ? P.lm->radius : P.radius;
   for (int k = gtid; k < n6; k += gthreads) {
     const int i = k / 6, c = k - 6 * i;
     double dd;
-    if (P.lm_mode == 2) {
+    if (lm_mode == 2) {
       dd = P.dlm[k];
     } else {
       double dg;
-      if (P.lm_mode == 1) dg = P.diagonal[k];
+      if (lm_mode == 1) dg = P.diagonal[k];
       else { dg = fmin(fmax(P.A.Hdiag[36 * (size_t)i + pidx(c, c)], P.min_diag), P.max_diag); P.diagonal[k] = dg; }
-      dd = dg / P.radius;
+      dd = dg / radius;
       P.dlm[k] = dd;
     }
     P.vt[k] = P.b[k];
@@ -563,6 +566,7 @@ __device__ __forceinline__ void chol_setup_phase(const CholParams& P, int gtid, 
 // phase 1 = factor the nodes [k0, k1) of one level in `mode` (8 / 16 / 32 lanes per node).
 __global__ void __launch_bounds__(kCholThreads, 1) chol_wide_kernel(const CholParams P, int phase, int mode, int k0, int k1) {
   extern __shared__ __align__(16) unsigned char chol_smem[];
+  if (P.lm && P.lm->done) return;   // the LM loop has terminated: iterations enqueued ahead of the host's check are no-ops
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * (kCholThreads / 32) + warp, nw = gridDim.x * (kCholThreads / 32);
   if (phase == 0) { chol_setup_phase(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); return; }
@@ -579,6 +583,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) level_chol_pcg_kernel(const C
   __shared__ double red[kCholThreads / 32];
   __shared__ double bcast;
   extern __shared__ __align__(16) unsigned char chol_smem[];
+  if (P.lm && P.lm->done) return;   // uniform over the whole launch (nobody writes `done` while a solver kernel runs)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpStash& stash = reinterpret_cast<WarpStash*>(chol_smem)[warp];
   const int warps_per_cta = kCholThreads / 32;
@@ -1058,22 +1063,23 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCho
   PGO_TRY(chol_alloc(C, device, &C->Ldiag, (size_t)N * 36));
   PGO_TRY(chol_alloc(C, device, &C->vt, (size_t)N * 6));
   PGO_TRY(chol_alloc(C, device, &C->barrier, 4));
-  static int per_sm = -1, cluster_max = -1;   // launch-shape queries are per kernel, not per graph
+  // function attributes and occupancy are facts about (kernel, DEVICE): cached per device (pgo_pool.cuh), not per process
+  int per_sm = -1, cluster_max = -1;
   const int sms = pool_num_sms(device);
-  if (per_sm < 0) {
+  if (!pool_cache_get(device, kCacheCholPerSm, &per_sm)) {
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeGrid>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(chol_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmemBytes));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, level_chol_pcg_kernel<kShapeGrid>, kCholThreads, kCholSmemBytes));
+    pool_cache_set(device, kCacheCholPerSm, per_sm);
   }
   C->max_ctas = std::max(1, std::min(per_sm, 1) * sms);
   // cluster shape: the largest cluster (16, then 8) the device can co-schedule
   C->cluster_ctas = 0;
   // the cluster shape only pays when the whole factorisation is tiny (latency bound); otherwise all SMs are needed
   const bool want_cluster = S.n_nodes <= kCholClusterMaxNodes && (long long)S.tasks.size() <= kCholClusterMaxTasks;
-  if (want_cluster && cluster_max >= 0) C->cluster_ctas = cluster_max;
-  if (want_cluster && cluster_max < 0) {
+  if (want_cluster && !pool_cache_get(device, kCacheCholCluster, &cluster_max)) {
     cluster_max = 0;
     cudaFuncSetAttribute(level_chol_pcg_kernel<kShapeCluster>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaGetLastError();
@@ -1086,12 +1092,14 @@ static int level_chol_analyze(LevelChol** out, int device, int N, const LevelCho
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
       if (cudaOccupancyMaxActiveClusters(&nclusters, level_chol_pcg_kernel<kShapeCluster>, &cfg) == cudaSuccess && nclusters >= 1) {
-        C->cluster_ctas = cluster_max = cs;
+        cluster_max = cs;
         break;
       }
       cudaGetLastError();
     }
+    pool_cache_set(device, kCacheCholCluster, cluster_max);
   }
+  if (want_cluster) C->cluster_ctas = std::max(cluster_max, 0);
   PGO_TRY(chol_alloc(C, device, &C->partials, (size_t)8 * 4 * std::max(C->max_ctas, 16)));
   CUDA_TRY(cudaStreamSynchronize(stream));
   C->usable = true;
@@ -1105,11 +1113,12 @@ struct LmDiagonal {           // LevenbergMarquardtStrategy::ComputeStep's D = s
 };
 
 // Factor (H + D) and solve (H + D) x = b by PCG preconditioned with the factor, one launch.
-static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const unsigned char* active, const double* b,
+static int level_chol_solve(LevelChol* C, BsrView A, const LmDiagonal& lm, const LmState* lm_state, const unsigned char* active, const double* b,
                             double* x, double* r, double* z, double* q, double* p, double* ax, int max_iterations,
                             double tolerance, double accept, int num_ctas, DeviceScalars* scalars, cudaStream_t stream,
                             long long* launches) {
   CholParams P;
+  P.lm = lm_state;
   P.A = A; P.lm_mode = lm.mode; P.min_diag = lm.min_diag; P.max_diag = lm.max_diag; P.radius = lm.radius;
   P.diagonal = lm.diagonal; P.dlm = lm.dlm; P.active = active;
   P.b = b; P.x = x; P.r = r; P.z = z; P.q = q; P.p = p; P.ax = ax;
