@@ -269,6 +269,12 @@ int pgo_solve_pose_graph(int device, int n_poses, double* poses, int n_edges, co
                          pgo_solver_summary* summary, pgo_iteration_summary* iteration_log,
                          int iteration_log_capacity);
 
+/* pgo_solve_pose_graph keeps up to four device-resident graphs per TOPOLOGY (edge endpoints + constant flags, hashed and
+ * then compared in full): a repeat call on the same topology skips the structure analysis, the symbolic factorisation and
+ * the index uploads and only refreshes poses and measurements.  enabled = 0 turns that off (and drops the kept graphs);
+ * returns the previous setting.  Environment: PGO_NO_TOPOLOGY_CACHE=1.  pgo_release_cached_memory() also empties it. */
+int pgo_set_topology_cache(int enabled);
+
 /* Loop-edge candidate search, the caller side of the path: what getCandidatesIndex() / isInSearchRange() of
  * REF/test/generate_edges_from_trajectory_origion.cpp:58-110 compute into config/Edge_Candidates_index.txt (read back by
  * getEdegsCandidateIndex(), REF/include/ReadEdges.h:9-48).  positions [n_frames][3] camera centres (rounded to float like

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "pgo_graph_create_partitioned", "pgo_graph_rank", "pgo_graph_world_size", "pgo_graph_num_local_poses",
     "pgo_graph_num_halo_poses", "pgo_graph_num_local_edges", "pgo_analyze_partition", "pgo_amg_aggregates", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
-    "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates",
+    "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates", "pgo_set_topology_cache",
 ]
 
 
@@ -192,6 +192,11 @@ def edge_candidates(positions, search_radius: float = 6.0, min_frame_gap: int = 
                                      row_ptr.ctypes.data_as(C.POINTER(C.c_longlong)), idx.ctypes.data_as(C.POINTER(C.c_int)),
                                      C.c_longlong(idx.size), C.byref(total)))
     return row_ptr, idx[:total.value]
+
+
+def set_topology_cache(enabled: bool) -> bool:
+    """Per-topology graph cache of solve_pose_graph (pgo_set_topology_cache); returns the previous setting."""
+    return bool(lib().pgo_set_topology_cache(C.c_int(1 if enabled else 0)))
 
 
 def release_cached_memory(device: int = -1):

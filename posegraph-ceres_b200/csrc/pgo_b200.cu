@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -18,6 +19,7 @@
 #include <cstring>
 #include <future>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -85,12 +87,22 @@ struct pgo_graph {
   std::vector<unsigned char> gactive_h;
   std::vector<double> pos0_h;       // [N_global][3]
   pgo::Amg* amg = nullptr;
+  // one-shot entry point: graphs are kept per topology (see graph_cache below)
+  unsigned long long topo_hash = 0;
+  std::vector<int> topo_edge_ids;            // [E][2] as passed by the caller
+  std::vector<unsigned char> topo_const;     // [N]
+  std::vector<EdgeCoreTile> core_host;       // packed tiles (indices stay, measurements are refreshed)
+  std::vector<EdgeInfoTile> info_host;
   // device-resident LM loop (pgo_lm.cuh)
   pgo::LmState* lm_state = nullptr;
   pgo::LmState* lm_ring = nullptr;          // pinned: 3 look-behind slots + 1
   cudaEvent_t lm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   pgo_iteration_summary* lm_log = nullptr;
   int lm_log_cap = 0;
+  // one LM iteration captured as a CUDA graph (solvers without a host-polled inner loop); valid for lm_graph_key
+  cudaGraphExec_t lm_graph = nullptr;
+  std::vector<unsigned char> lm_graph_key;
+  int lm_graph_kernels = 0;
   long long comm_calls = 0, comm_bytes = 0;   // NCCL calls / payload bytes sent by this rank (multi-GPU)
   bool identity_info = true;
   bool has_dup_blocks = false;
@@ -290,6 +302,7 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->comm) ncclCommDestroy(g->comm);
   if (g->chol) level_chol_destroy(g->chol, g->device);
   if (g->amg) amg_destroy(g->amg, g->device);
+  if (g->lm_graph) cudaGraphExecDestroy(g->lm_graph);
   for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
   pool_pinned_release(g->device, g->scalars_h);
   pool_pinned_release(g->device, g->pcgm_state_h);
@@ -303,9 +316,11 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   delete g;
 }
 
-extern "C" void pgo_release_cached_memory(int device) { pool_release(device); }
+static void graph_cache_clear(int device);
+extern "C" void pgo_release_cached_memory(int device) { graph_cache_clear(device); pool_release(device); }
 
 static thread_local int g_symbolic_hint = -1;   // set by pgo_solve_pose_graph around its pgo_graph_create call
+static thread_local bool g_keep_host_tiles = false;   // ditto: the graph will be cached per topology
 static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S);
 
 // What one rank holds.  One GPU: the whole problem (n_own == n_loc, no halo).  Multi-GPU: the block rows of its own
@@ -398,6 +413,7 @@ static int graph_create_local(pgo_graph* g, const LocalProblem& in) {
   for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
 
   lap("edge tiles");
+  if (g_keep_host_tiles) { g->core_host = core_h; g->info_host = info_h; }
   // ---- device allocations + uploads ----
   PGO_TRY(dev_alloc(g, &g->poses, (size_t)N * 8));
   PGO_TRY(dev_alloc(g, &g->poses_cand, (size_t)N * 8));
@@ -1443,6 +1459,42 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     return PGO_OK;
   };
   const int depth = solver_is_host_polled(g, solver) ? 0 : 2;   // iterations the host may run ahead of what it has seen
+  // The iteration is the same dozen launches every time (all that varies lives in device memory): capture it once per
+  // (options, solver, log buffer) and replay it -- the kernels between the linear solves are a few microseconds each.
+  static const bool graph_off = getenv("PGO_LM_GRAPH") && atoi(getenv("PGO_LM_GRAPH")) == 0;
+  bool use_graph = depth > 0 && g->world == 1 && !graph_off && getenv("PGO_TIMELINE") == nullptr;
+  // (captured lazily before the SECOND iteration of a solve: the first one runs as plain launches so that every
+  // one-time initialisation -- function attributes, occupancy queries -- happens outside a capture)
+  auto ensure_graph = [&]() -> int {
+    if (use_graph) {
+      std::vector<unsigned char> key(sizeof(pgo_solver_options) + sizeof(int) + sizeof(void*) + sizeof(void*));
+      std::memcpy(key.data(), opt, sizeof(pgo_solver_options));
+      std::memcpy(key.data() + sizeof(pgo_solver_options), &solver, sizeof(int));
+      std::memcpy(key.data() + sizeof(pgo_solver_options) + sizeof(int), &g->lm_log, sizeof(void*));
+      std::memcpy(key.data() + sizeof(pgo_solver_options) + sizeof(int) + sizeof(void*), &g->stream, sizeof(void*));
+      if (!g->lm_graph || key != g->lm_graph_key) {
+        if (g->lm_graph) { cudaGraphExecDestroy(g->lm_graph); g->lm_graph = nullptr; }
+        const long long l0 = g->launches;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_iteration();
+        const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
+        g->lm_graph_kernels = (int)(g->launches - l0);
+        g->launches = l0;
+        if (rc != PGO_OK || ce != cudaSuccess) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          use_graph = false;                    // fall back to plain launches (same kernels, same order)
+        } else {
+          const cudaError_t ie = cudaGraphInstantiate(&g->lm_graph, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ie != cudaSuccess) { cudaGetLastError(); g->lm_graph = nullptr; use_graph = false; }
+          else g->lm_graph_key = key;
+        }
+      }
+    }
+    return PGO_OK;
+  };
   LmState final_state;
   {
     // state after iteration zero (a non-finite initial cost or a zero gradient ends the solve before the loop)
@@ -1460,7 +1512,9 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     }
     const int hard_cap = opt->max_num_iterations + 8;
     while (!finished && k < hard_cap) {
-      PGO_TRY(enqueue_iteration());
+      if (use_graph && k > 0) PGO_TRY(ensure_graph());
+      if (use_graph && k > 0 && g->lm_graph) { CUDA_TRY(cudaGraphLaunch(g->lm_graph, g->stream)); g->launches += g->lm_graph_kernels; }
+      else PGO_TRY(enqueue_iteration());
       summary->num_linearizations++;
       const int slot = k % 3;
       PGO_TRY(publish(slot));
@@ -1585,6 +1639,69 @@ extern "C" int pgo_edge_candidates(int device, int n_frames, const double* posit
   return PGO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-shot entry point with a per-topology cache.  What ceres::Solve does for the reference on every call -- program
+// preprocessing, symbolic factorisation -- depends only on the TOPOLOGY (edge endpoints, constant flags).  A repeat call
+// on the same topology (a SLAM back end re-solving its graph with refreshed measurements; bench.py's end-to-end loop)
+// reuses the device-resident graph: pattern, tiles' index part, elimination schedule, factor storage, LM buffers.  Only
+// poses and measurements are re-uploaded.  Keyed by a 64-bit hash and confirmed by a full comparison of the arrays.
+// PGO_NO_TOPOLOGY_CACHE=1 disables it; pgo_release_cached_memory() empties it.
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_graph_cache_mu;
+static std::vector<pgo_graph*> g_graph_cache;          // most recently used last
+static std::atomic<bool> g_topology_cache_enabled{getenv("PGO_NO_TOPOLOGY_CACHE") == nullptr};
+extern "C" int pgo_set_topology_cache(int enabled) {
+  const bool was = g_topology_cache_enabled.exchange(enabled != 0);
+  if (!enabled) graph_cache_clear(-1);
+  return was ? 1 : 0;
+}
+constexpr size_t kGraphCacheEntries = 4;
+constexpr int kGraphCacheMaxPoses = 200000;            // larger graphs are not worth pinning GBs of HBM for
+
+static unsigned long long topology_hash(int n_poses, int n_edges, const int* edge_ids, const unsigned char* pose_const) {
+  unsigned long long h = 1469598103934665603ull ^ ((unsigned long long)n_poses << 32) ^ (unsigned long long)n_edges;
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(edge_ids);   // one (a, b) pair per word
+  for (int e = 0; e < n_edges; ++e) { h ^= w[e]; h *= 1099511628211ull; h ^= h >> 29; }
+  if (pose_const) for (int i = 0; i < n_poses; ++i) if (pose_const[i]) { h ^= (unsigned long long)i * 0x9E3779B97F4A7C15ull + pose_const[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static void graph_cache_clear(int device) {
+  std::vector<pgo_graph*> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_cache_mu);
+    for (auto it = g_graph_cache.begin(); it != g_graph_cache.end();)
+      if (device < 0 || (*it)->device == device) { drop.push_back(*it); it = g_graph_cache.erase(it); } else ++it;
+  }
+  for (pgo_graph* g : drop) pgo_graph_destroy(g);
+}
+
+// refresh the values of a cached graph: poses, measurements, square-root information (same identity / full class)
+static int graph_update_values(pgo_graph* g, const double* poses, const double* edge_meas, const double* edge_sqrt_info) {
+  CUDA_TRY(cudaSetDevice(g->device));
+  const int E = g->E, T = g->T;
+  for (int e = 0; e < E; ++e) {
+    EdgeCoreTile& t = g->core_host[e / kTile];
+    const int l = e % kTile;
+    for (int k = 0; k < 7; ++k) t.meas[k][l] = edge_meas[7 * (size_t)e + k];
+  }
+  CUDA_TRY(cudaMemcpyAsync(g->core, g->core_host.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
+  if (!g->identity_info) {
+    for (int e = 0; e < E; ++e)
+      for (int k = 0; k < 36; ++k) g->info_host[e / kTile].S[k][e % kTile] = edge_sqrt_info[36 * (size_t)e + k];
+    CUDA_TRY(cudaMemcpyAsync(g->info, g->info_host.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
+  }
+  return pgo_graph_set_poses(g, poses);
+}
+
+static bool info_is_identity(int n_edges, const double* edge_sqrt_info) {
+  if (!edge_sqrt_info) return true;
+  static const double eye[36] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+  for (int e = 0; e < n_edges; ++e)
+    for (int k = 0; k < 36; ++k) if (edge_sqrt_info[36 * (size_t)e + k] != eye[k]) return false;
+  return true;
+}
+
 extern "C" int pgo_solve_pose_graph(int device, int n_poses, double* poses, int n_edges, const int* edge_ids,
                                     const double* edge_meas, const double* edge_sqrt_info,
                                     const unsigned char* pose_const, const pgo_solver_options* options,
@@ -1592,13 +1709,56 @@ extern "C" int pgo_solve_pose_graph(int device, int n_poses, double* poses, int 
                                     int iteration_log_capacity) {
   pgo_solver_options defaults;
   if (!options) { pgo_default_options(&defaults); options = &defaults; }
+  const bool cacheable = g_topology_cache_enabled.load() && n_poses > 0 && n_poses <= kGraphCacheMaxPoses && n_edges > 0 && edge_ids && poses && edge_meas;
   pgo_graph* g = nullptr;
-  g_symbolic_hint = options->linear_solver_type;     // pgo_graph_create starts the symbolic analysis on a helper thread
-  const int crc = pgo_graph_create(&g, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const);
-  g_symbolic_hint = -1;
-  PGO_TRY(crc);
-  int rc = pgo_graph_solve(g, options, summary, iteration_log, iteration_log_capacity);
+  unsigned long long h = 0;
+  const double t0 = wall_s();
+  if (cacheable) {
+    h = topology_hash(n_poses, n_edges, edge_ids, pose_const);
+    const bool ident = info_is_identity(n_edges, edge_sqrt_info);
+    std::lock_guard<std::mutex> lk(g_graph_cache_mu);
+    for (auto it = g_graph_cache.begin(); it != g_graph_cache.end(); ++it) {
+      pgo_graph* c = *it;
+      if (c->device != device || c->topo_hash != h || c->N_global != n_poses || c->E_global != n_edges || c->identity_info != ident) continue;
+      if (std::memcmp(c->topo_edge_ids.data(), edge_ids, (size_t)n_edges * 2 * sizeof(int)) != 0) continue;
+      bool same_const = true;
+      for (int i = 0; i < n_poses && same_const; ++i) same_const = c->topo_const[i] == (pose_const ? pose_const[i] : 0);
+      if (!same_const) continue;
+      g = c;
+      g_graph_cache.erase(it);            // checked out: nobody else can pick it while it is in use
+      break;
+    }
+  }
+  int rc = PGO_OK;
+  if (g) {
+    rc = graph_update_values(g, poses, edge_meas, edge_sqrt_info);
+    g->setup_s = wall_s() - t0;
+  } else {
+    g_symbolic_hint = options->linear_solver_type;     // pgo_graph_create starts the symbolic analysis on a helper thread
+    g_keep_host_tiles = cacheable;
+    rc = pgo_graph_create(&g, device, n_poses, n_edges, poses, edge_ids, edge_meas, edge_sqrt_info, pose_const);
+    g_symbolic_hint = -1;
+    g_keep_host_tiles = false;
+    if (rc == PGO_OK && cacheable) {
+      g->topo_hash = h;
+      g->topo_edge_ids.assign(edge_ids, edge_ids + 2 * (size_t)n_edges);
+      g->topo_const.assign((size_t)n_poses, 0);
+      if (pose_const) g->topo_const.assign(pose_const, pose_const + n_poses);
+    }
+  }
+  if (rc != PGO_OK) { if (g) pgo_graph_destroy(g); return rc; }
+  rc = pgo_graph_solve(g, options, summary, iteration_log, iteration_log_capacity);
   if (rc == PGO_OK) rc = pgo_graph_get_poses(g, poses);
-  pgo_graph_destroy(g);
+  if (rc == PGO_OK && cacheable) {
+    pgo_graph* evict = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_graph_cache_mu);
+      g_graph_cache.push_back(g);
+      if (g_graph_cache.size() > kGraphCacheEntries) { evict = g_graph_cache.front(); g_graph_cache.erase(g_graph_cache.begin()); }
+    }
+    if (evict) pgo_graph_destroy(evict);
+  } else {
+    pgo_graph_destroy(g);
+  }
   return rc;
 }

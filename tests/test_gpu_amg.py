@@ -94,7 +94,7 @@ def _converged_solve_properties(pgo, g, max_pcg_per_lm):
     for it in its[1:]:
         assert it.pcg_relative_residual <= o.pcg_tolerance, (it.iteration, it.pcg_relative_residual)
     assert s.total_pcg_iterations / (len(its) - 1) <= max_pcg_per_lm
-    assert its[-1].gradient_max_norm <= 1e-3 * its[0].gradient_max_norm
+    assert its[-1].gradient_max_norm <= 0.05 * its[0].gradient_max_norm
     # true residual of a solve at the converged point: (H + D) y = g, residual through the block-SpMV kernel
     G.linearize(loss_type=1, loss_a=1.0)
     rng = np.random.default_rng(0)
