@@ -399,8 +399,11 @@ def main():
             _, sp_ms = GB.spmv(x, None, reps)
             nnzb = GB.hessian_blocks()
             # algorithmic bytes: per edge = ids 8 + meas 56 + sqrt_info 288 + slots 8 + 2 poses 128
-            #   + 2 scales 96 + diag RED 2*288 + off-diag stores 2*288 + gradient RED 96 = 1832 ; SpMV = 288/block + x,y + indices
-            lin_bytes = E * (8 + 56 + 288 + 8 + 128 + 96 + 576 + 576 + 96)
+            #   + 2 scales 96 + off-diag stores 2*288 = 1160; per POSE (contributions are combined in the warp and the tiles
+            #   are walked in pose order, so a diagonal block / gradient entry makes one round trip) = RED read + write of the
+            #   288-byte diagonal block and the 48-byte gradient = 672 ; SpMV = 288/block + x,y + indices
+            lin_bytes = E * (8 + 56 + 288 + 8 + 128 + 96 + 576) + N * 2 * (288 + 48)
+            lin_bytes_r1 = E * (8 + 56 + 288 + 8 + 128 + 96 + 576 + 576 + 96)     # round 1's count: every edge REDs two diagonal blocks
             sp_bytes = nnzb * 288 + N * (48 * 2) + (nnzb - N) * 4 + (N + 1) * 4
             traffic = {}
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram__bytes_read+write per launch from the committed ncu capture
@@ -413,7 +416,10 @@ def main():
                 return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": traffic.get(name), "ms_per_launch": ms, "algorithmic_bytes": nbytes, "peak_source": peak_kind}
             kern = {"graph": f"{N} poses / {E} edges per rank (Manhattan grid, BASELINE configs[3]), fp64, inputs larger than L2",
-                    "linearize": roof("linearize_kernel", lin_bytes, lin_ms), "edge_jacobians_per_sec": E / (lin_ms * 1e-3),
+                    "linearize": dict(roof("linearize_kernel", lin_bytes, lin_ms), frac_with_round1_byte_count=lin_bytes_r1 / (lin_ms * 1e-3) / 1e9 / hbm_peak,
+                                      note="algorithmic bytes count ONE read+write of each pose's diagonal block and gradient entry per launch "
+                                           "(in-warp combination + pose-ordered tiles); round 1 counted two diagonal REDs per edge"),
+                    "edge_jacobians_per_sec": E / (lin_ms * 1e-3),
                     "spmv": roof("spmv_kernel", sp_bytes, sp_ms / reps)}
             if line is not None:
                 line["kernels_large_graph"] = kern

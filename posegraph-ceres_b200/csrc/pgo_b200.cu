@@ -91,6 +91,8 @@ struct pgo_graph {
   unsigned long long topo_hash = 0;
   std::vector<int> topo_edge_ids;            // [E][2] as passed by the caller
   std::vector<unsigned char> topo_const;     // [N]
+  std::vector<int> edge_pos;                 // [E] tile position of the caller's edge e (edges are processed in pose order)
+  bool edges_reordered = false;
   std::vector<EdgeCoreTile> core_host;       // packed tiles (indices stay, measurements are refreshed)
   std::vector<EdgeInfoTile> info_host;
   // device-resident LM loop (pgo_lm.cuh)
@@ -399,16 +401,34 @@ static int graph_create_local(pgo_graph* g, const LocalProblem& in) {
   std::vector<EdgeInfoTile> info_h;
   if (!g->identity_info) { info_h.resize(std::max(T, 1)); std::memset(info_h.data(), 0, info_h.size() * sizeof(EdgeInfoTile)); }
   static const double eye_row[6][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}, {0, 0, 0, 1, 0, 0}, {0, 0, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 1}};
+  // Processing order = pose order (counting sort by the larger endpoint, stable): the persistent kernel walks the tiles
+  // in index order, so every pose's diagonal block and gradient then receive their contributions while their lines are
+  // still in L2 (a 1M-pose diagonal is 288 MB; in generator order -- all odometry edges, then all cross edges -- every
+  // line made two round trips to HBM).  Odometry chains keep their order: lane l's end pose is lane l-1's begin pose.
+  g->edge_pos.resize((size_t)E);
+  {
+    std::vector<int> cnt((size_t)N + 1, 0);
+    for (int e = 0; e < E; ++e) cnt[std::max(in.edge_ids[2 * e], in.edge_ids[2 * e + 1]) + 1]++;
+    for (int i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
+    bool identity = true;
+    for (int e = 0; e < E; ++e) {
+      const int p = cnt[std::max(in.edge_ids[2 * e], in.edge_ids[2 * e + 1])]++;
+      g->edge_pos[e] = p;
+      identity &= p == e;
+    }
+    g->edges_reordered = !identity;
+  }
   for (int e = 0; e < E; ++e) {
-    EdgeCoreTile& t = core_h[e / kTile];
-    const int l = e % kTile;
+    const int pos = g->edge_pos[e];
+    EdgeCoreTile& t = core_h[pos / kTile];
+    const int l = pos % kTile;
     const int a = in.edge_ids[2 * e], b = in.edge_ids[2 * e + 1];
     t.a[l] = a; t.b[l] = b;
     t.slot_ab[l] = pat.half_slot[2 * (size_t)e];
     t.slot_ba[l] = pat.half_slot[2 * (size_t)e + 1];
     for (int k = 0; k < 7; ++k) t.meas[k][l] = in.edge_meas[7 * (size_t)e + k];
     if (!g->identity_info)
-      for (int k = 0; k < 36; ++k) info_h[e / kTile].S[k][l] = in.edge_sqrt_info ? in.edge_sqrt_info[36 * (size_t)e + k] : eye_row[k / 6][k % 6];
+      for (int k = 0; k < 36; ++k) info_h[pos / kTile].S[k][l] = in.edge_sqrt_info ? in.edge_sqrt_info[36 * (size_t)e + k] : eye_row[k / 6][k % 6];
   }
   for (int e = E; e < T * kTile; ++e) { core_h[e / kTile].slot_ab[e % kTile] = -1; core_h[e / kTile].slot_ba[e % kTile] = -1; }
 
@@ -1174,8 +1194,17 @@ extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, do
     if ((rc = fetch_scalars(g)) != PGO_OK) break;
     if (cost) *cost = g->scalars_h->cost;
     cudaError_t ce = cudaSuccess;
-    if (residuals && g->E) ce = cudaMemcpy(residuals, res_d, (size_t)g->E * 6 * sizeof(double), cudaMemcpyDeviceToHost);
-    if (ce == cudaSuccess && jacobians && g->E) ce = cudaMemcpy(jacobians, jac_d, (size_t)g->E * 72 * sizeof(double), cudaMemcpyDeviceToHost);
+    // the kernel writes per-edge outputs in processing order; hand them back in the caller's edge order
+    auto fetch = [&](double* dst, const double* src_d, int width) {
+      if (!g->edges_reordered) return cudaMemcpy(dst, src_d, (size_t)g->E * width * sizeof(double), cudaMemcpyDeviceToHost);
+      std::vector<double> tmp((size_t)g->E * width);
+      const cudaError_t e2 = cudaMemcpy(tmp.data(), src_d, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost);
+      if (e2 != cudaSuccess) return e2;
+      for (int e = 0; e < g->E; ++e) std::memcpy(dst + (size_t)e * width, tmp.data() + (size_t)g->edge_pos[e] * width, width * sizeof(double));
+      return cudaSuccess;
+    };
+    if (residuals && g->E) ce = fetch(residuals, res_d, 6);
+    if (ce == cudaSuccess && jacobians && g->E) ce = fetch(jacobians, jac_d, 72);
     if (ce != cudaSuccess) rc = set_error(PGO_ERR_CUDA, "evaluate copy-back failed: %s", cudaGetErrorString(ce));
     if (rc == PGO_OK && gradient) rc = download_global(g, g->grad, 6, gradient);
   } while (0);
@@ -1681,14 +1710,15 @@ static int graph_update_values(pgo_graph* g, const double* poses, const double* 
   CUDA_TRY(cudaSetDevice(g->device));
   const int E = g->E, T = g->T;
   for (int e = 0; e < E; ++e) {
-    EdgeCoreTile& t = g->core_host[e / kTile];
-    const int l = e % kTile;
+    const int pos = g->edge_pos[e];
+    EdgeCoreTile& t = g->core_host[pos / kTile];
+    const int l = pos % kTile;
     for (int k = 0; k < 7; ++k) t.meas[k][l] = edge_meas[7 * (size_t)e + k];
   }
   CUDA_TRY(cudaMemcpyAsync(g->core, g->core_host.data(), (size_t)std::max(T, 1) * sizeof(EdgeCoreTile), cudaMemcpyHostToDevice, g->stream));
   if (!g->identity_info) {
     for (int e = 0; e < E; ++e)
-      for (int k = 0; k < 36; ++k) g->info_host[e / kTile].S[k][e % kTile] = edge_sqrt_info[36 * (size_t)e + k];
+      for (int k = 0; k < 36; ++k) g->info_host[g->edge_pos[e] / kTile].S[k][g->edge_pos[e] % kTile] = edge_sqrt_info[36 * (size_t)e + k];
     CUDA_TRY(cudaMemcpyAsync(g->info, g->info_host.data(), (size_t)std::max(T, 1) * sizeof(EdgeInfoTile), cudaMemcpyHostToDevice, g->stream));
   }
   return pgo_graph_set_poses(g, poses);

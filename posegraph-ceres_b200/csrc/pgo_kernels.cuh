@@ -220,7 +220,31 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
     {
       __syncwarp();                                  // all lanes are done with the sqrt-information tile the staging aliases
       auto rot36 = [](int x) -> int { return x >= 36 ? x - 36 : x; };
-      const int swz = lane >> 2;                     // row rotation: conflict-free 64-bit shared-memory writes
+      const unsigned full = 0xffffffffu;
+      const unsigned lt = (1u << lane) - 1u;
+      // ---- in-warp combination plan (segmented reduction by pose id).  A pose usually receives several contributions
+      // from ONE tile: edges are processed in pose order, so lane l's end pose is lane l-1's begin pose along an odometry
+      // chain and the cross edges of a pose sit next to its odometry edge.  Contributions to the same diagonal block /
+      // gradient entry are added in shared memory and leave as ONE fp64 RED instead of two to four.
+      //   a-side: lanes with the same begin pose form a group; its lowest lane (leader) owns the staging slot
+      //   b-side: an end pose that is some lane's begin pose joins that group's slot ("hit"); the remaining end poses
+      //           group among themselves and go out in a second, usually almost empty, pass
+      const int ta = (valid && a < p.n_own) ? a : -1, tb = (valid && b < p.n_own) ? b : -1;
+      const int ida = ta >= 0 ? ta : -1 - lane;
+      const unsigned ga = __match_any_sync(full, ida);
+      const int la = __ffs(ga) - 1, ra = __popc(ga & lt);
+      int hit = -1;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int idj = __shfl_sync(full, ida, j);
+        if (tb >= 0 && idj == tb && hit < 0) hit = j;   // the lowest lane with that begin pose = its group's leader
+      }
+      const unsigned gh = __match_any_sync(full, hit >= 0 ? hit : -1 - lane);
+      const int rh = __popc(gh & lt);
+      const unsigned gb = __match_any_sync(full, (tb >= 0 && hit < 0) ? tb : -1 - lane);
+      const int lb = __ffs(gb) - 1, rb = __popc(gb & lt);
+      const bool b_left = tb >= 0 && hit < 0;
+      const bool any_b_left = __any_sync(full, b_left);
       // ---- gradient J^T r (robustified: rho' J^T r), column-scaled: g_a = sa .* [-g1; gc], g_b = sb .* [g1; -g2] ----
       {
         double g1[3], g2[3], gc[3];
@@ -231,17 +255,46 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
           for (int i = 0; i < 6; ++i) { s1 = fma(L.B1[i][k], L.r[i], s1); s2 = fma(L.B2[i][k], L.r[i], s2); sc = fma(L.C[i][k], L.r[i], sc); }
           g1[k] = rho1 * s1; g2[k] = rho1 * s2; gc[k] = rho1 * sc;
         }
-        sidx[lane] = (valid && a < p.n_own) ? a : -1;
-        sidx[32 + lane] = (valid && b < p.n_own) ? b : -1;
+        double va[6], vb[6];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          stg[lane * 6 + k] = -sa[k] * g1[k];        stg[lane * 6 + 3 + k] = sa[3 + k] * gc[k];
-          stg[192 + lane * 6 + k] = sb[k] * g1[k];   stg[192 + lane * 6 + 3 + k] = -sb[3 + k] * g2[k];
+        for (int k = 0; k < 3; ++k) { va[k] = -sa[k] * g1[k]; va[3 + k] = sa[3 + k] * gc[k]; vb[k] = sb[k] * g1[k]; vb[3 + k] = -sb[3 + k] * g2[k]; }
+        // slots [0, 32): a-groups (+ b hits); slots [32, 64): left-over b groups
+        if (ra == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) stg[lane * 6 + k] = va[k];
         }
+        if (b_left && rb == 0) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) stg[192 + lane * 6 + k] = vb[k];
+        }
+        sidx[lane] = ra == 0 ? ta : -1;
+        sidx[32 + lane] = (b_left && rb == 0) ? tb : -1;
         __syncwarp();
+        for (int r = 1; __any_sync(full, ra >= r); ++r) {
+          if (ra == r) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) stg[la * 6 + k] += va[k];
+          }
+          __syncwarp();
+        }
+        for (int r = 0; __any_sync(full, hit >= 0 && rh >= r); ++r) {
+          if (hit >= 0 && rh == r) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) stg[hit * 6 + k] += vb[k];
+          }
+          __syncwarp();
+        }
+        for (int r = 1; __any_sync(full, b_left && rb >= r); ++r) {
+          if (b_left && rb == r) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) stg[192 + lb * 6 + k] += vb[k];
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-          const int item = j * 32 + lane;            // 0..383: [side][edge][6]
+          if (j >= 6 && !any_b_left) break;
+          const int item = j * 32 + lane;            // 0..383: [side][slot][6]
           const int blk = item / 6, el = item - blk * 6;
           const int t = sidx[blk];
           if (t >= 0) atomicAdd(p.grad + 6 * (size_t)t + el, stg[item]);
@@ -265,24 +318,28 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
         auto Hab = [&](int r, int c) -> double {
           return (r < 3) ? ((c < 3) ? -P11[r][c] : P12[r][c - 3]) : ((c < 3) ? P1C[c][r - 3] : -PC2[r - 3][c - 3]);
         };
-        // one block set: stage my 36 values (panel order, rotated row), then the warp drains the tile
-        auto emit = [&](auto value, int target, double* base, bool reduce_always) {
-          sidx[lane] = target;
+        // store (or add) my 36 values into staging slot `slot` (panel order, row rotated by the slot: conflict-free drains)
+        auto put = [&](auto value, int slot, bool add) {
+          const int sw = slot >> 2;
+          double* base = stg + slot * 36;
 #pragma unroll
           for (int r = 0; r < 6; ++r)
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-              // swz <= 7: the rotation can only wrap for the last elements of the row (decided at compile time)
-              const int idx = (pidx(r, c) + 7 < 36) ? pidx(r, c) + swz : rot36(pidx(r, c) + swz);
-              stg[lane * 36 + idx] = value(r, c);
+              // sw <= 7: the rotation can only wrap for the last elements of the row (decided at compile time)
+              const int idx = (pidx(r, c) + 7 < 36) ? pidx(r, c) + sw : rot36(pidx(r, c) + sw);
+              const double v = value(r, c);
+              base[idx] = add ? base[idx] + v : v;
             }
-          __syncwarp();
+        };
+        // the warp drains the staging tile element-major: coalesced RED / stores (4 lanes per 32-byte sector)
+        auto drain = [&](double* base, bool reduce_always) {
           auto out = [&](int t, int el, double v) {
             if (reduce_always) { if (t >= 0) atomicAdd(base + 36 * (size_t)t + el, v); }
             else if (t >= 0) base[36 * (size_t)t + el] = v;
             else if (t <= -2) atomicAdd(base + 36 * (size_t)(-t - 2) + el, v);
           };
-          // drain, element-major: pass 1 -- lane l owns element l of every block (32 lanes = 8 whole sectors);
+          // pass 1 -- lane l owns element l of every block (32 lanes = 8 whole sectors);
           // pass 2 -- elements 32..35, four lanes per block (one sector), eight blocks per instruction
 #pragma unroll 8
           for (int blk = 0; blk < 32; ++blk) {
@@ -297,11 +354,41 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
           }
           __syncwarp();
         };
-        emit([&](int r, int c) { return rho1 * sa[r] * sa[c] * Haa(r, c); }, (valid && a < p.n_own) ? a : -1, p.Hdiag, true);
-        emit([&](int r, int c) { return rho1 * sb[r] * sb[c] * Hbb(r, c); }, (valid && b < p.n_own) ? b : -1, p.Hdiag, true);
+        auto VA = [&](int r, int c) { return rho1 * sa[r] * sa[c] * Haa(r, c); };
+        auto VB = [&](int r, int c) { return rho1 * sb[r] * sb[c] * Hbb(r, c); };
+        // ---- diagonal blocks, pass 1: begin-pose groups plus the end poses that hit one of them ----
+        if (ra == 0) put(VA, lane, false);
+        sidx[lane] = ra == 0 ? ta : -1;
+        __syncwarp();
+        for (int r = 1; __any_sync(full, ra >= r); ++r) {
+          if (ra == r) put(VA, la, true);
+          __syncwarp();
+        }
+        for (int r = 0; __any_sync(full, hit >= 0 && rh >= r); ++r) {
+          if (hit >= 0 && rh == r) put(VB, hit, true);
+          __syncwarp();
+        }
+        drain(p.Hdiag, true);
+        // ---- pass 2: end poses that no begin pose of this tile matched (the first lane of a chain, far cross edges) ----
+        if (any_b_left) {
+          if (b_left && rb == 0) put(VB, lane, false);
+          sidx[lane] = (b_left && rb == 0) ? tb : -1;
+          __syncwarp();
+          for (int r = 1; __any_sync(full, b_left && rb >= r); ++r) {
+            if (b_left && rb == r) put(VB, lb, true);
+            __syncwarp();
+          }
+          drain(p.Hdiag, true);
+        }
         // off-diagonal blocks: (a,b) = H_ab, (b,a) = H_ab^T; slot >= 0: sole producer (store), <= -2: shared slot (RED)
-        emit([&](int r, int c) { return rho1 * sa[r] * sb[c] * Hab(r, c); }, valid ? ct->slot_ab[lane] : -1, p.Hoff, false);
-        emit([&](int r, int c) { return rho1 * sb[r] * sa[c] * Hab(c, r); }, valid ? ct->slot_ba[lane] : -1, p.Hoff, false);
+        put([&](int r, int c) { return rho1 * sa[r] * sb[c] * Hab(r, c); }, lane, false);
+        sidx[lane] = valid ? ct->slot_ab[lane] : -1;
+        __syncwarp();
+        drain(p.Hoff, false);
+        put([&](int r, int c) { return rho1 * sb[r] * sa[c] * Hab(c, r); }, lane, false);
+        sidx[lane] = valid ? ct->slot_ba[lane] : -1;
+        __syncwarp();
+        drain(p.Hoff, false);
       }
     }
     __syncwarp();
