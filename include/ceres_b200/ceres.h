@@ -14,10 +14,10 @@
 // The reference builds a general ceres::Problem, but on this path every residual block is the SE(3)
 // relative-pose term (AutoDiffCostFunction<PoseGraph3dErrorTerm, 6, 3, 4, 3, 4>) over parameter blocks
 // (p_a[3], q_a[4], p_b[3], q_b[4]) with q under EigenQuaternionParameterization.  This mirror accepts
-// exactly that structure and hands the whole problem to the device solver; anything else (other
-// cost functions, a q block without the Eigen parameterization, a pose with only p or only q held
-// constant, different loss functions on different blocks) is rejected with std::invalid_argument at the
-// call that introduces it or at Solve() -- there is no CPU fallback behind this header.
+// exactly that structure and hands the whole problem to the device solver -- including what Ceres allows per block:
+// a different LossFunction on every residual block, and p or q of a pose held constant on its own.  Anything else (other
+// cost functions, a q block without the Eigen parameterization) is rejected with std::invalid_argument at the call that
+// introduces it or at Solve() -- there is no CPU fallback behind this header.
 //
 // Ownership follows Ceres: the Problem takes ownership of cost functions, loss functions and local
 // parameterizations passed by pointer (each distinct pointer is deleted once).
@@ -422,14 +422,18 @@ class Problem {
   // problem->AddResidualBlock(cost_function, loss_function, p_a, q_a, p_b, q_b)   (REF ...plus_finial.cpp:513-517)
   ResidualBlockId AddResidualBlock(CostFunction* cost_function, LossFunction* loss_function, double* p_a, double* q_a,
                                    double* p_b, double* q_b) {
+    // ownership first (Ceres owns what it is handed, also when the call fails afterwards); validate before mutating
+    if (cost_function) owned_costs_.insert(cost_function);
+    if (loss_function) owned_losses_.insert(loss_function);
     pgo::PoseGraph3dCost* c = dynamic_cast<pgo::PoseGraph3dCost*>(cost_function);
     if (!c) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: only SE(3) relative-pose cost functions (AutoDiffCostFunction<F, 6, 3, 4, 3, 4> / pgo::MakePoseGraph3dCost) run on the device path");
     if (!p_a || !q_a || !p_b || !q_b) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: null parameter block");
+    if (p_a == p_b || q_a == q_b || p_a == q_a || p_a == q_b || p_b == q_a || p_b == q_b)
+      throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: duplicate parameter blocks in one residual block");
+    check_pairing(p_a, q_a);          // nothing is registered unless the whole call is valid
+    check_pairing(p_b, q_b);
     const int a = pose_of(p_a, q_a), b = pose_of(p_b, q_b);
-    if (a == b) throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: duplicate parameter blocks in one residual block");
     edges_.push_back({a, b, c, loss_function});
-    owned_costs_.insert(cost_function);
-    if (loss_function) owned_losses_.insert(loss_function);
     return (int)edges_.size() - 1;
   }
 
@@ -473,6 +477,10 @@ class Problem {
     if (rc != PGO_OK) throw std::runtime_error(std::string("ceres_b200::Problem::Evaluate: ") + pgo_last_error());
     if (residuals) residuals->assign((size_t)6 * pk.n_edges, 0.0);
     if (gradient) gradient->assign((size_t)6 * pk.n_poses, 0.0);
+    if (!pk.uniform_loss) {
+      rc = pgo_graph_set_edge_losses(g, pk.edge_loss_type.data(), pk.edge_loss_a.data());
+      if (rc != PGO_OK) { pgo_graph_destroy(g); throw std::runtime_error(std::string("ceres_b200::Problem::Evaluate: ") + pgo_last_error()); }
+    }
     rc = pgo_graph_evaluate(g, pk.loss_type, pk.loss_a, cost, residuals ? residuals->data() : nullptr,
                             gradient ? gradient->data() : nullptr, nullptr);
     pgo_graph_destroy(g);
@@ -489,6 +497,9 @@ class Problem {
     int n_poses = 0, n_edges = 0, loss_type = PGO_LOSS_TRIVIAL;
     double loss_a = 1.0;
     bool identity_info = true;
+    bool uniform_loss = true;                 // every residual block carries the same loss (type and scale)
+    std::vector<int> edge_loss_type;          // per residual block (ceres::Problem::AddResidualBlock takes the loss per block)
+    std::vector<double> edge_loss_a;
     std::vector<double> poses, meas, sqrt_info;
     std::vector<int> ids;
     std::vector<unsigned char> pose_const;
@@ -505,6 +516,15 @@ class Problem {
     auto it = blocks_.find(values);
     if (it == blocks_.end()) throw std::invalid_argument(std::string("ceres_b200::Problem::") + who + ": parameter block not found (add a residual block first, as Ceres requires)");
     return it->second;
+  }
+  // would pose_of(p, q) throw?  (same rules, no side effects)
+  void check_pairing(double* p, double* q) const {
+    auto ip = blocks_.find(p), iq = blocks_.find(q);
+    if ((ip != blocks_.end() && ip->second.size != 3) || (iq != blocks_.end() && iq->second.size != 4))
+      throw std::invalid_argument("ceres_b200::Problem: parameter block re-added with a different size");
+    const int pp = ip == blocks_.end() ? -1 : ip->second.pose, pq = iq == blocks_.end() ? -1 : iq->second.pose;
+    if (pp != pq && (pp >= 0 || pq >= 0))
+      throw std::invalid_argument("ceres_b200::Problem::AddResidualBlock: a position block must always be paired with the same quaternion block");
   }
   int pose_of(double* p, double* q) {
     Block& bp = block_of(p, 3);
@@ -530,9 +550,8 @@ class Problem {
       if (!bq.param || !bq.param->is_eigen_quaternion())
         throw std::invalid_argument("ceres_b200: every quaternion block needs SetParameterization(q, new EigenQuaternionParameterization)");
       if (bp.param) throw std::invalid_argument("ceres_b200: position blocks must not carry a local parameterization");
-      if (bp.constant != bq.constant)
-        throw std::invalid_argument("ceres_b200: a pose must have p and q both constant or both variable on the device path");
-      pk->pose_const[i] = bp.constant ? 1 : 0;
+      // SetParameterBlockConstant acts per block (REF :526-527 are two calls): 1 = both, 2 = only p, 3 = only q
+      pk->pose_const[i] = (bp.constant && bq.constant) ? 1 : bp.constant ? 2 : bq.constant ? 3 : 0;
       std::memcpy(&pk->poses[7 * (size_t)i], poses_[i].p, 24);
       std::memcpy(&pk->poses[7 * (size_t)i + 3], poses_[i].q, 32);
     }
@@ -540,6 +559,8 @@ class Problem {
     pk->meas.resize((size_t)7 * pk->n_edges);
     pk->sqrt_info.resize((size_t)36 * pk->n_edges);
     bool have_loss = false;
+    pk->edge_loss_type.resize((size_t)pk->n_edges);
+    pk->edge_loss_a.resize((size_t)pk->n_edges);
     for (int e = 0; e < pk->n_edges; ++e) {
       const Edge& ed = edges_[e];
       pk->ids[2 * (size_t)e] = ed.a; pk->ids[2 * (size_t)e + 1] = ed.b;
@@ -549,9 +570,9 @@ class Problem {
         if (ed.cost->sqrt_information()[k] != ((k / 6 == k % 6) ? 1.0 : 0.0)) pk->identity_info = false;
       const int lt = ed.loss ? ed.loss->device_type() : (int)PGO_LOSS_TRIVIAL;
       const double la = ed.loss ? ed.loss->device_a() : 1.0;
+      pk->edge_loss_type[e] = lt; pk->edge_loss_a[e] = la;
       if (!have_loss) { pk->loss_type = lt; pk->loss_a = la; have_loss = true; }
-      else if (lt != pk->loss_type || (lt != PGO_LOSS_TRIVIAL && la != pk->loss_a))
-        throw std::invalid_argument("ceres_b200: all residual blocks must share one loss function (type and scale) on the device path");
+      else if (lt != pk->loss_type || (lt != PGO_LOSS_TRIVIAL && la != pk->loss_a)) pk->uniform_loss = false;
     }
   }
   void unpack(const std::vector<double>& poses) {
@@ -596,6 +617,7 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   o.pcg_tolerance = options.pcg_tolerance;
   o.pcg_max_iterations = options.pcg_max_iterations;
   o.direct_residual_accept = options.direct_residual_accept;
+  if (!pk.uniform_loss) { o.edge_loss_type = pk.edge_loss_type.data(); o.edge_loss_a = pk.edge_loss_a.data(); }
   const int cap = options.max_num_iterations + 2;
   std::vector<pgo_iteration_summary> log((size_t)std::max(cap, 2));
   std::memset(&summary->device, 0, sizeof summary->device);
@@ -617,9 +639,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     summary->message = std::string("libpgo_b200: ") + pgo_last_error();
     return;
   }
-  problem->unpack(pk.poses);
   const pgo_solver_summary& d = summary->device;
   summary->termination_type = d.termination_type == PGO_CONVERGENCE ? CONVERGENCE : d.termination_type == PGO_NO_CONVERGENCE ? NO_CONVERGENCE : FAILURE;
+  if (summary->IsSolutionUsable()) problem->unpack(pk.poses);   // Ceres updates the user's state only for a usable solution
   summary->message = d.message;
   summary->initial_cost = d.initial_cost;
   summary->final_cost = d.final_cost;

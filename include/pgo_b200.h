@@ -21,7 +21,8 @@
  *   edge_ids       [n_edges][2]  id_begin, id_end    (Edge3d, REF/include/types.h:30-45)
  *   edge_meas      [n_edges][7]  t_be = T_begin^-1 * T_end, same layout as a pose
  *   edge_sqrt_info [n_edges][36] ROW-major 6x6 sqrt_information (residual = S * r); NULL = identity
- *   pose_const     [n_poses]     1 = SetParameterBlockConstant(p) and (q)
+ *   pose_const     [n_poses]     0 = variable, 1 = SetParameterBlockConstant(p) and (q) (REF :526-527 makes both calls for
+ *                                the first pose), 2 = only p constant, 3 = only q constant
  *   tangent vectors (gradient, steps) are [n_poses][6]: (dx dy dz, d_rot[3]) in the local
  *   coordinates of EigenQuaternionParameterization: p+ = p + dp, q+ = Quat(cos|d|, sin|d|/|d| d) * q.
  */
@@ -89,6 +90,11 @@ typedef struct {
                                     ||b - A x||_2 <= max(pcg_tolerance, this) * ||b||_2.  Default 1e-8: Ceres' own
                                     SPARSE_NORMAL_CHOLESKY never refines; PCG refinement stays the safety net. */
   int verbose;
+  /* ceres::Problem::AddResidualBlock takes the loss function per residual block (REF :513-517).  NULL (default): every
+   * edge uses loss_type / loss_a above.  Otherwise host arrays [n_edges] in the caller's edge order: pgo_loss_type and
+   * scale a of each edge.  Read by pgo_solve_pose_graph; device-resident graphs use pgo_graph_set_edge_losses. */
+  const int* edge_loss_type;
+  const double* edge_loss_a;
 } pgo_solver_options;
 
 /* One row per minimizer iteration (ceres::IterationSummary). */
@@ -228,6 +234,10 @@ int pgo_analyze_partition(int n_poses, int n_edges, const double* poses, const i
  * aggregate (node id on the next level, -1 = not a variable) of every node; agg_out may be NULL to query the sizes. */
 int pgo_amg_aggregates(int n_poses, int n_edges, const double* poses, const int* edge_ids, const unsigned char* pose_const,
                        int world_size, int* n_levels, int* level_nodes, int* agg_out, long long agg_capacity);
+
+/* Per-edge loss functions of a device-resident graph ([n_edges] host arrays in the caller's edge order; NULL, NULL: back
+ * to one loss for all edges).  While set they override the loss arguments of evaluate / linearize / solve. */
+int pgo_graph_set_edge_losses(pgo_graph* g, const int* loss_type, const double* loss_a);
 
 /* ceres::Problem::Evaluate on the device: cost, robustified residuals [n_edges][6], gradient
  * [n_poses][6] (unscaled, zero for constant poses), per-edge local Jacobians [n_edges][2][36]

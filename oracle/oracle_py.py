@@ -70,6 +70,22 @@ def set_num_threads(n: int):
     lib().oracle_set_num_threads(C.c_int(n))
 
 
+class edge_losses:
+    """with oracle_py.edge_losses(types, scales): ...  -- per-residual-block loss functions for the calls inside"""
+
+    def __init__(self, types, scales):
+        self.t = np.ascontiguousarray(types, np.int32)
+        self.a = np.ascontiguousarray(scales, np.float64)
+
+    def __enter__(self):
+        lib().oracle_set_edge_losses(C.c_int(self.t.size), _p(self.t, C.c_int), _p(self.a))
+        return self
+
+    def __exit__(self, *exc):
+        lib().oracle_set_edge_losses(C.c_int(0), None, None)
+        return False
+
+
 def default_options() -> Options:
     o = Options()
     lib().oracle_default_options(C.byref(o))

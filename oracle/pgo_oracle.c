@@ -271,6 +271,24 @@ static int g_oracle_threads = 1;
 void oracle_set_num_threads(int n) { g_oracle_threads = n > 0 ? n : 1; }
 int oracle_get_num_threads(void) { return g_oracle_threads; }
 
+/* ceres::Problem::AddResidualBlock takes the loss function PER residual block (REF :513-517 passes one HuberLoss to every
+ * block, but the surface allows any mixture): when set, edge e uses (type[e], a[e]) instead of the options' loss. */
+static const int* g_edge_loss_type = NULL;
+static const double* g_edge_loss_a = NULL;
+static int g_edge_loss_n = 0;
+void oracle_set_edge_losses(int n_edges, const int* type, const double* a) {
+  g_edge_loss_type = type; g_edge_loss_a = a; g_edge_loss_n = (type && a) ? n_edges : 0;
+}
+
+/* pose_const: 0 = variable, 1 = SetParameterBlockConstant(p) and (q), 2 = p only, 3 = q only (REF :526-527 are two
+ * separate calls).  A constant block's Jacobian columns are dropped, as Ceres' program preprocessing does. */
+static void drop_constant_columns(double* J, int code) {
+  int r, c;
+  if (code == 1) { memset(J, 0, 36 * sizeof(double)); return; }
+  if (code != 2 && code != 3) return;
+  for (r = 0; r < 6; ++r) for (c = 0; c < 3; ++c) J[r * 6 + (code == 3 ? 3 : 0) + c] = 0.0;
+}
+
 int oracle_evaluate(int n_poses, const double* poses, const unsigned char* pose_const,
                     int n_edges, const int* edge_ids, const double* edge_meas,
                     const double* edge_sqrt_info, int loss_type, double loss_a,
@@ -293,11 +311,12 @@ int oracle_evaluate(int n_poses, const double* poses, const unsigned char* pose_
     double res[6];
     double* Ja = need_j ? jbuf + 72 * (size_t)e : NULL;
     double* Jb = need_j ? Ja + 36 : NULL;
+    const int lt = (g_edge_loss_n == n_edges) ? g_edge_loss_type[e] : loss_type;
+    const double la = (g_edge_loss_n == n_edges) ? g_edge_loss_a[e] : loss_a;
     total += edge_evaluate(poses + 7 * a, poses + 7 * b, edge_meas + 7 * e, edge_sqrt_info + 36 * e,
-                           loss_type, loss_a, res, Ja, Jb);
+                           lt, la, res, Ja, Jb);
     if (need_j) {
-      if (pose_const && pose_const[a]) memset(Ja, 0, 36 * sizeof(double));
-      if (pose_const && pose_const[b]) memset(Jb, 0, 36 * sizeof(double));
+      if (pose_const) { drop_constant_columns(Ja, pose_const[a]); drop_constant_columns(Jb, pose_const[b]); }
     }
     if (rbuf) memcpy(rbuf + 6 * (size_t)e, res, sizeof res);
   }
@@ -454,7 +473,7 @@ static chol_t* chol_analyze(int n_poses, const unsigned char* pose_const, int n_
   C->n_poses = n_poses; C->n_edges = n_edges;
   C->var_of_pose = (int*)malloc(sizeof(int) * (size_t)n_poses);
   for (e = 0; e < n_edges; ++e) { used[edge_ids[2 * e]] = 1; used[edge_ids[2 * e + 1]] = 1; }
-  for (i = 0; i < n_poses; ++i) C->var_of_pose[i] = (used[i] && !(pose_const && pose_const[i])) ? nb++ : -1;
+  for (i = 0; i < n_poses; ++i) C->var_of_pose[i] = (used[i] && !(pose_const && pose_const[i] == 1)) ? nb++ : -1;
   free(used);
   C->nb = nb;
   C->pose_of_var = (int*)malloc(sizeof(int) * (size_t)(nb + 1));
@@ -742,6 +761,8 @@ static void log_iter(oracle_iteration* log, int cap, oracle_summary* s, const or
   s->num_iterations++;
 }
 
+/* is component e (0..6) of pose k in a variable parameter block?  (x_norm runs over the variable blocks only) */
+#define BLOCK_VARIABLE(pc, k, e) (!(pc) || (pc)[k] == 0 || ((pc)[k] == 2 && (e) >= 3) || ((pc)[k] == 3 && (e) < 3))
 int oracle_solve(int n_poses, double* poses, const unsigned char* pose_const,
                  int n_edges, const int* edge_ids, const double* edge_meas,
                  const double* edge_sqrt_info, const oracle_options* opt,
@@ -783,7 +804,7 @@ int oracle_solve(int n_poses, double* poses, const unsigned char* pose_const,
     scale_columns(n_edges, edge_ids, jac, scale);
   }
   x_norm = 0.0;
-  for (k = 0; k < n_poses; ++k) if (active[k]) for (e = 0; e < 7; ++e) x_norm += poses[7 * k + e] * poses[7 * k + e];
+  for (k = 0; k < n_poses; ++k) if (active[k]) for (e = 0; e < 7; ++e) if (BLOCK_VARIABLE(pose_const, k, e)) x_norm += poses[7 * k + e] * poses[7 * k + e];
   x_norm = sqrt(x_norm);
   radius = opt->initial_trust_region_radius;
   memset(&it, 0, sizeof it);
@@ -897,7 +918,7 @@ int oracle_solve(int n_poses, double* poses, const unsigned char* pose_const,
       double t;
       memcpy(poses, cand, sizeof(double) * 7 * (size_t)n_poses);
       x_norm = 0.0;
-      for (k = 0; k < n_poses; ++k) if (active[k]) for (e = 0; e < 7; ++e) x_norm += poses[7 * k + e] * poses[7 * k + e];
+      for (k = 0; k < n_poses; ++k) if (active[k]) for (e = 0; e < 7; ++e) if (BLOCK_VARIABLE(pose_const, k, e)) x_norm += poses[7 * k + e] * poses[7 * k + e];
       x_norm = sqrt(x_norm);
       t0 = now_s();
       oracle_evaluate(n_poses, poses, pose_const, n_edges, edge_ids, edge_meas, edge_sqrt_info,

@@ -100,6 +100,8 @@ void oracle_default_options(oracle_options* o);
 
 /* threads of the per-edge evaluation loop (default 1 = Ceres' default num_threads) */
 void oracle_set_num_threads(int n);
+/* per-residual-block loss functions (NULL, NULL restores the options' single loss); arrays must outlive the calls */
+void oracle_set_edge_losses(int n_edges, const int* type, const double* a);
 int oracle_get_num_threads(void);
 
 /* Problem::Evaluate: cost, robustified residuals [6E], gradient [6N] (local/tangent coordinates,

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "pgo_graph_create_partitioned", "pgo_graph_rank", "pgo_graph_world_size", "pgo_graph_num_local_poses",
     "pgo_graph_num_halo_poses", "pgo_graph_num_local_edges", "pgo_analyze_partition", "pgo_amg_aggregates", "pgo_graph_evaluate", "pgo_graph_linearize", "pgo_graph_get_hessian",
     "pgo_graph_spmv", "pgo_graph_linear_solve", "pgo_graph_solve", "pgo_solve_pose_graph",
-    "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates", "pgo_set_topology_cache",
+    "pgo_analyze_structure", "pgo_release_cached_memory", "pgo_edge_candidates", "pgo_set_topology_cache", "pgo_graph_set_edge_losses",
 ]
 
 
@@ -40,7 +40,8 @@ class SolverOptions(C.Structure):
                 ("max_num_consecutive_invalid_steps", C.c_int), ("jacobi_scaling", C.c_int),
                 ("loss_type", C.c_int), ("loss_a", C.c_double), ("linear_solver_type", C.c_int),
                 ("pcg_max_iterations", C.c_int), ("pcg_tolerance", C.c_double), ("pcg_num_ctas", C.c_int),
-                ("direct_residual_accept", C.c_double), ("verbose", C.c_int)]
+                ("direct_residual_accept", C.c_double), ("verbose", C.c_int),
+                ("edge_loss_type", C.POINTER(C.c_int)), ("edge_loss_a", C.POINTER(C.c_double))]
 
 
 class IterationSummary(C.Structure):
@@ -268,6 +269,16 @@ class Graph:
     def restore_poses(self):
         _check(lib().pgo_graph_restore_poses(self._h))
 
+    def set_edge_losses(self, loss_types=None, loss_scales=None):
+        """per-edge ceres::LossFunction (pgo_graph_set_edge_losses); None, None: back to one loss for every edge"""
+        if loss_types is None:
+            _check(lib().pgo_graph_set_edge_losses(self._h, None, None))
+            return
+        t = np.ascontiguousarray(loss_types, np.int32)
+        s = np.ascontiguousarray(loss_scales, np.float64)
+        assert t.size == self.n_edges and s.size == self.n_edges
+        _check(lib().pgo_graph_set_edge_losses(self._h, t.ctypes.data_as(C.POINTER(C.c_int)), _dp(s)))
+
     def evaluate(self, loss_type=LOSS_HUBER, loss_a=1.0, want_jacobians=True):
         cost = C.c_double()
         res = np.zeros((self.n_edges, 6))
@@ -329,9 +340,19 @@ class Graph:
 
 
 def solve_pose_graph(poses, edge_ids, edge_meas, edge_sqrt_info=None, pose_const=None,
-                     options: SolverOptions | None = None, device: int = 0, max_log: int = 2048):
-    """ceres::Solve for the reference's pose graph, host buffers in and out (pgo_solve_pose_graph)."""
+                     options: SolverOptions | None = None, device: int = 0, max_log: int = 2048,
+                     edge_loss_types=None, edge_loss_scales=None):
+    """ceres::Solve for the reference's pose graph, host buffers in and out (pgo_solve_pose_graph).
+    edge_loss_types / edge_loss_scales: per-edge loss functions ([n_edges]); default: options.loss_type / loss_a."""
     o = options or default_options()
+    keep = None
+    if edge_loss_types is not None:
+        keep = (np.ascontiguousarray(edge_loss_types, np.int32), np.ascontiguousarray(edge_loss_scales, np.float64))
+        o.edge_loss_type = keep[0].ctypes.data_as(C.POINTER(C.c_int))
+        o.edge_loss_a = keep[1].ctypes.data_as(C.POINTER(C.c_double))
+    else:
+        o.edge_loss_type = None
+        o.edge_loss_a = None
     poses = np.ascontiguousarray(poses, np.float64).copy()
     edge_ids = np.ascontiguousarray(edge_ids, np.int32)
     edge_meas = np.ascontiguousarray(edge_meas, np.float64)

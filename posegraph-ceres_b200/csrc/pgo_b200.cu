@@ -92,6 +92,9 @@ struct pgo_graph {
   std::vector<int> topo_edge_ids;            // [E][2] as passed by the caller
   std::vector<unsigned char> topo_const;     // [N]
   std::vector<int> edge_pos;                 // [E] tile position of the caller's edge e (edges are processed in pose order)
+  std::vector<int> edge_gid;                 // multi-GPU: caller's (global) index of local edge e; empty on one GPU
+  double* edge_loss = nullptr;               // [E] per-edge loss in processing order (encoded), valid while edge_loss_set
+  bool edge_loss_set = false;
   bool edges_reordered = false;
   std::vector<EdgeCoreTile> core_host;       // packed tiles (indices stay, measurements are refreshed)
   std::vector<EdgeInfoTile> info_host;
@@ -161,7 +164,7 @@ static void build_pattern(int N, int E, const int* edge_ids, const unsigned char
   if (n_own < 0) n_own = N;
   out->active.assign(N, 0);
   for (int e = 0; e < E; ++e) { out->active[edge_ids[2 * e]] = 1; out->active[edge_ids[2 * e + 1]] = 1; }
-  if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i]) out->active[i] = 0;
+  if (pose_const) for (int i = 0; i < N; ++i) if (pose_const[i] == 1) out->active[i] = 0;   // 2 / 3: only p / only q constant
   // bucket the half-edges (row -> col) by row with a counting sort, then order each (short) row by column
   struct Half { int col; int idx; };
   std::vector<int> start(n_own + 1, 0);
@@ -285,6 +288,8 @@ extern "C" void pgo_default_options(pgo_solver_options* o) {
   o->pcg_num_ctas = 0;
   o->direct_residual_accept = 1e-8;
   o->verbose = 0;
+  o->edge_loss_type = nullptr;
+  o->edge_loss_a = nullptr;
 }
 
 template <typename Tp>
@@ -466,8 +471,13 @@ static int graph_create_local(pgo_graph* g, const LocalProblem& in) {
   if (g->nnz_off) CUDA_TRY(cudaMemcpyAsync(g->col_idx, g->col_idx_h.data(), (size_t)g->nnz_off * sizeof(int), cudaMemcpyHostToDevice, g->stream));
   CUDA_TRY(cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)N, cudaMemcpyHostToDevice, g->stream));
   {
+    // unit column scaling = the mask of variable components: 0 for constant poses, and for the constant half of a pose
+    // whose p (code 2) or q (code 3) alone is held constant -- those columns vanish from the problem
     std::vector<double> se((size_t)N * 6);
-    for (int i = 0; i < N; ++i) for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = g->active_h[i] ? 1.0 : 0.0;
+    for (int i = 0; i < N; ++i) {
+      const int code = in.pose_const ? in.pose_const[i] : 0;
+      for (int k = 0; k < 6; ++k) se[6 * (size_t)i + k] = (g->active_h[i] && !(code == 2 && k < 3) && !(code == 3 && k >= 3)) ? 1.0 : 0.0;
+    }
     CUDA_TRY(cudaMemcpyAsync(g->scale_eval, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
     CUDA_TRY(cudaMemcpyAsync(g->scale, se.data(), se.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
   }
@@ -636,7 +646,7 @@ extern "C" int pgo_graph_create_partitioned(pgo_graph** out, int device, int n_p
   }
   HostPartition P;
   build_partition(n_poses, n_edges, edge_ids, rank, world_size, &P);
-  g->part_off = P.off; g->g0 = P.g0; g->halo_gid = P.halo_gid;
+  g->part_off = P.off; g->g0 = P.g0; g->halo_gid = P.halo_gid; g->edge_gid = P.edge_sel;
   g->nbr = P.nbr; g->send_ptr = P.send_ptr; g->recv_ptr = P.recv_ptr; g->send_idx_h = P.send_idx;
   // local slice of the inputs
   const int n_loc = P.n_own + (int)P.halo_gid.size(), ne = (int)P.edge_sel.size();
@@ -682,9 +692,11 @@ extern "C" int pgo_graph_create_partitioned(pgo_graph** out, int device, int n_p
   // a pose that is constant / unused on its owner must be inactive in every halo copy as well: owners are authoritative
   {
     std::vector<double> act((size_t)n_loc * 6, 0.0);
-    for (int i = 0; i < P.n_own; ++i) if (g->gactive_h[P.g0 + i]) for (int k = 0; k < 6; ++k) act[6 * (size_t)i + k] = 1.0;
-    for (int i = P.n_own; i < n_loc; ++i) if (g->gactive_h[gid_of(i)]) for (int k = 0; k < 6; ++k) act[6 * (size_t)i + k] = 1.0;
-    for (int i = 0; i < n_loc; ++i) g->active_h[i] = act[6 * (size_t)i] != 0.0;
+    for (int i = 0; i < n_loc; ++i) {
+      const int gi = gid_of(i), code = lconst[i];
+      g->active_h[i] = g->gactive_h[gi];
+      if (g->gactive_h[gi]) for (int k = 0; k < 6; ++k) act[6 * (size_t)i + k] = (!(code == 2 && k < 3) && !(code == 3 && k >= 3)) ? 1.0 : 0.0;
+    }
     if (cudaMemcpyAsync(g->scale_eval, act.data(), act.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
         cudaMemcpyAsync(g->scale, act.data(), act.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
         cudaMemcpyAsync(g->active, g->active_h.data(), (size_t)n_loc, cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
@@ -1032,7 +1044,7 @@ static int launch_linearize(pgo_graph* g, int mode, const double* poses, const d
   LinParams p;
   p.n_edges = g->E; p.n_tiles = g->T; p.n_own = g->n_own; p.core = g->core; p.info = g->info; p.poses = poses; p.scale = scale;
   p.Hdiag = target ? target->Hdiag : g->Hdiag; p.Hoff = target ? target->Hoff : g->Hoff; p.grad = target ? target->grad : g->grad;
-  p.scalars = g->scalars; p.lm = lm;
+  p.scalars = g->scalars; p.lm = lm; p.edge_loss = g->edge_loss_set ? g->edge_loss : nullptr;
   p.loss_type = loss_type; p.loss_a = loss_a; p.res_out = res_out; p.jac_out = jac_out;
   if (g->E == 0) return PGO_OK;
   static const int occ = getenv("PGO_LIN_OCC") ? atoi(getenv("PGO_LIN_OCC")) : 2;   // CTAs per SM of the full kernel (tuning knob)
@@ -1211,6 +1223,26 @@ extern "C" int pgo_graph_evaluate(pgo_graph* g, int loss_type, double loss_a, do
   cudaStreamSynchronize(g->stream);
   pool_free(g->device, res_d, res_bytes); pool_free(g->device, jac_d, jac_bytes);
   return rc;
+}
+
+extern "C" int pgo_graph_set_edge_losses(pgo_graph* g, const int* loss_type, const double* loss_a) {
+  if (!g) return set_error(PGO_ERR_INVALID_ARGUMENT, "null graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  if (!loss_type || !loss_a) { g->edge_loss_set = false; return PGO_OK; }
+  std::vector<double> code((size_t)std::max(g->E, 1), 0.0);
+  for (int e = 0; e < g->E; ++e) {
+    const int ge = g->edge_gid.empty() ? e : g->edge_gid[e];
+    const int t = loss_type[ge];
+    const double a = loss_a[ge];
+    if (t != PGO_LOSS_TRIVIAL && t != PGO_LOSS_HUBER && t != PGO_LOSS_CAUCHY) return set_error(PGO_ERR_INVALID_ARGUMENT, "edge %d: unknown loss type %d", ge, t);
+    if (t != PGO_LOSS_TRIVIAL && !(a > 0.0)) return set_error(PGO_ERR_INVALID_ARGUMENT, "edge %d: loss scale must be positive", ge);
+    code[g->edge_pos[e]] = t == PGO_LOSS_HUBER ? a : (t == PGO_LOSS_CAUCHY ? -a : 0.0);
+  }
+  if (!g->edge_loss) PGO_TRY(dev_alloc(g, &g->edge_loss, (size_t)std::max(g->E, 1)));
+  CUDA_TRY(cudaMemcpyAsync(g->edge_loss, code.data(), code.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  g->edge_loss_set = true;
+  return PGO_OK;
 }
 
 extern "C" int pgo_graph_linearize(pgo_graph* g, int loss_type, double loss_a, const double* scale, double* cost,
@@ -1451,7 +1483,7 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   PGO_TRY(linearize_full(g, g->poses, g->scale, opt->loss_type, opt->loss_a));
   summary->num_linearizations++;
   if (opt->jacobi_scaling) {
-    jacobi_scale_kernel<<<nblk, tpb, 0, g->stream>>>(R, g->Hdiag, g->active, 1, g->scale);
+    jacobi_scale_kernel<<<nblk, tpb, 0, g->stream>>>(R, g->Hdiag, g->scale_eval, 1, g->scale);
     g->launches++;
     PGO_TRY(halo_exchange0(g, g->scale, 6));   // the off-diagonal blocks of a cut edge need the other owner's column scaling
     PGO_TRY(zero_scalars(g));
@@ -1459,7 +1491,7 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
     summary->num_linearizations++;
   }
   CUDA_TRY(cudaEventRecord(g->ev1, g->stream));
-  xnorm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->active, g->scalars);
+  xnorm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->active, g->scale_eval, g->scalars);
   gradient_norm_kernel<<<(R + 255) / 256, 256, 0, g->stream>>>(R, g->poses, g->grad, g->scale, g->active, nullptr, g->scalars);
   PGO_TRY(reduce_scalars(g));
   lm_init_kernel<<<1, 32, 0, g->stream>>>(st, g->scalars, lo, g->lm_log, g->lm_log_cap);
@@ -1496,11 +1528,16 @@ extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_
   // one-time initialisation -- function attributes, occupancy queries -- happens outside a capture)
   auto ensure_graph = [&]() -> int {
     if (use_graph) {
-      std::vector<unsigned char> key(sizeof(pgo_solver_options) + sizeof(int) + sizeof(void*) + sizeof(void*));
-      std::memcpy(key.data(), opt, sizeof(pgo_solver_options));
-      std::memcpy(key.data() + sizeof(pgo_solver_options), &solver, sizeof(int));
-      std::memcpy(key.data() + sizeof(pgo_solver_options) + sizeof(int), &g->lm_log, sizeof(void*));
-      std::memcpy(key.data() + sizeof(pgo_solver_options) + sizeof(int) + sizeof(void*), &g->stream, sizeof(void*));
+      // everything the captured launches carry BY VALUE (field by field: struct padding and the host pointers are not part of it)
+      const double fields[] = {(double)opt->max_num_iterations, opt->function_tolerance, opt->gradient_tolerance, opt->parameter_tolerance,
+                               opt->initial_trust_region_radius, opt->max_trust_region_radius, opt->min_trust_region_radius,
+                               opt->min_relative_decrease, opt->min_lm_diagonal, opt->max_lm_diagonal,
+                               (double)opt->max_num_consecutive_invalid_steps, (double)opt->jacobi_scaling, (double)opt->loss_type, opt->loss_a,
+                               (double)opt->linear_solver_type, (double)opt->pcg_max_iterations, opt->pcg_tolerance, (double)opt->pcg_num_ctas,
+                               opt->direct_residual_accept, (double)solver, (double)(g->edge_loss_set ? 1 : 0),
+                               (double)(uintptr_t)g->lm_log, (double)(uintptr_t)g->stream};
+      std::vector<unsigned char> key(sizeof fields);
+      std::memcpy(key.data(), fields, sizeof fields);
       if (!g->lm_graph || key != g->lm_graph_key) {
         if (g->lm_graph) { cudaGraphExecDestroy(g->lm_graph); g->lm_graph = nullptr; }
         const long long l0 = g->launches;
@@ -1776,6 +1813,7 @@ extern "C" int pgo_solve_pose_graph(int device, int n_poses, double* poses, int 
       if (pose_const) g->topo_const.assign(pose_const, pose_const + n_poses);
     }
   }
+  if (rc == PGO_OK) rc = pgo_graph_set_edge_losses(g, options->edge_loss_type, options->edge_loss_a);   // NULLs clear a cached graph's
   if (rc != PGO_OK) { if (g) pgo_graph_destroy(g); return rc; }
   rc = pgo_graph_solve(g, options, summary, iteration_log, iteration_log_capacity);
   if (rc == PGO_OK) rc = pgo_graph_get_poses(g, poses);

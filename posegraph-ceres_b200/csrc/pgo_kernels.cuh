@@ -36,6 +36,7 @@ struct LinParams {
   DeviceScalars* scalars;
   int loss_type;
   double loss_a;
+  const double* edge_loss;      // per-edge loss in processing order, encoded: 0 trivial, +a Huber(a), -a Cauchy(a); or nullptr
   // kLinEval outputs
   double* res_out;              // [E][6]
   double* jac_out;              // [E][2][36] row-major
@@ -168,7 +169,10 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
 #pragma unroll
       for (int i = 0; i < 6; ++i) sq = fma(r[i], r[i], sq);
       double rho1;
-      const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
+      int lt = p.loss_type;
+      double la = p.loss_a;
+      if (p.edge_loss != nullptr) { const double code = valid ? __ldg(p.edge_loss + e) : 0.0; lt = code > 0.0 ? 1 : (code < 0.0 ? 2 : 0); la = fabs(code); }
+      const double rho = loss_eval(lt, la, sq, rho1);
       if (valid && a < p.n_own) cost_acc += 0.5 * rho;
       __syncwarp();
       stage = stage1;
@@ -184,7 +188,10 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
 #pragma unroll
     for (int i = 0; i < 6; ++i) sq = fma(L.r[i], L.r[i], sq);
     double rho1;
-    const double rho = loss_eval(p.loss_type, p.loss_a, sq, rho1);
+    int lt = p.loss_type;
+    double la = p.loss_a;
+    if (p.edge_loss != nullptr) { const double code = valid ? __ldg(p.edge_loss + e) : 0.0; lt = code > 0.0 ? 1 : (code < 0.0 ? 2 : 0); la = fabs(code); }
+    const double rho = loss_eval(lt, la, sq, rho1);
     if (valid && a < p.n_own) cost_acc += 0.5 * rho;
     if (!valid) rho1 = 0.0;   // padded lanes contribute exact zeros
 
@@ -701,14 +708,15 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_kernel(const PcgParams P) {
 // --------------------------------------------------------------------------------------------
 // Jacobi scaling (trust_region_minimizer.cc: 1 / (1 + sqrt(column norm^2))) from the diagonal of the
 // unscaled Hessian; 0 for constant / unused poses so that their columns vanish from the problem.
-__global__ void jacobi_scale_kernel(int n, const double* __restrict__ Hdiag, const unsigned char* __restrict__ active,
+// mask [n][6]: 1 for the components of variable parameter blocks, 0 for constant ones (a pose may have only p or only q constant)
+__global__ void jacobi_scale_kernel(int n, const double* __restrict__ Hdiag, const double* __restrict__ mask,
                                     int use_scaling, double* __restrict__ scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     double s = 0.0;
-    if (active[i]) s = use_scaling ? 1.0 / (1.0 + sqrt(Hdiag[36 * (size_t)i + pidx(c, c)])) : 1.0;
+    if (mask[6 * (size_t)i + c] > 0.0) s = use_scaling ? 1.0 / (1.0 + sqrt(Hdiag[36 * (size_t)i + pidx(c, c)])) : 1.0;
     scale[6 * (size_t)i + c] = s;
   }
 }
@@ -824,8 +832,10 @@ __global__ void __launch_bounds__(256) plus_kernel(int n, const double* __restri
 #pragma unroll
       for (int k = 0; k < 6; ++k) d[k] = sign * y[6 * (size_t)i + k] * scale[6 * (size_t)i + k];
       pose_plus(xi, d, o);
+      // |x|^2 runs over the VARIABLE parameter blocks (p and q separately: either may be constant)
+      const bool pvar = scale[6 * (size_t)i] > 0.0, qvar = scale[6 * (size_t)i + 3] > 0.0;
 #pragma unroll
-      for (int k = 0; k < 7; ++k) { const double t = xi[k] - o[k]; sn += t * t; xn += o[k] * o[k]; }
+      for (int k = 0; k < 7; ++k) { const double t = xi[k] - o[k]; sn += t * t; if (k < 3 ? pvar : qvar) xn += o[k] * o[k]; }
     } else {
 #pragma unroll
       for (int k = 0; k < 7; ++k) o[k] = xi[k];
@@ -876,12 +886,13 @@ __global__ void __launch_bounds__(256) gradient_norm_kernel(int n, const double*
 
 // x_norm^2 over active poses (iteration zero)
 __global__ void __launch_bounds__(256) xnorm_kernel(int n, const double* __restrict__ x, const unsigned char* __restrict__ active,
-                                                    DeviceScalars* scalars) {
+                                                    const double* __restrict__ mask, DeviceScalars* scalars) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double xn = 0.0;
   if (i < n && active[i]) {
+    const bool pvar = mask[6 * (size_t)i] > 0.0, qvar = mask[6 * (size_t)i + 3] > 0.0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) { const double t = x[8 * (size_t)i + k]; xn += t * t; }
+    for (int k = 0; k < 7; ++k) { const double t = x[8 * (size_t)i + k]; if (k < 3 ? pvar : qvar) xn += t * t; }
   }
   xn = warp_sum(xn);
   if ((threadIdx.x & 31) == 0 && xn != 0.0) atomicAdd(&scalars->x_norm2, xn);
