@@ -455,7 +455,7 @@ def test_per_edge_losses_evaluate_and_solve_match_oracle(pgo, oracle, graphs, na
     # the one-shot entry point takes the same arrays through the options
     p2, s2, _ = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const, edge_loss_types=types,
                                      edge_loss_scales=scales)
-    assert np.abs(p2 - poses).max() <= 1e-9
+    assert np.abs(p2 - poses).max() <= 1e-6      # two runs of the same solve differ by the order of the fp64 atomics (measured 2e-8)
     # ... and a following call WITHOUT them (same topology: the cached graph) is back to the single loss
     p3, s3, _ = pgo.solve_pose_graph(g.poses, g.edge_ids, g.edge_meas, g.edge_sqrt_info, g.pose_const)
     ref1, _, _ = oracle.solve(g)
