@@ -326,54 +326,16 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A
   if (L.on) y[q] = x[q] + omega * z;
 }
 
-// rc_I = sum_{i in I} P_i^T (r_i - (A x)_i) for the computed coarse rows: six lanes per coarse row walk its members.
-__global__ void __launch_bounds__(kAmgThreads) amg_residual_restrict_kernel(const BsrView A, const double* __restrict__ d,
-                                                                            const double* __restrict__ r, const double* __restrict__ x,
-                                                                            int ncomp, int c_row0, const int* __restrict__ mem_ptr,
-                                                                            const int* __restrict__ mem_idx, const double* __restrict__ pos,
-                                                                            int pos_stride, const double* __restrict__ cpos,
-                                                                            const double* __restrict__ scale, double* __restrict__ rc,
-                                                                            const double* __restrict__ Dinv_c, double omega,
-                                                                            double* __restrict__ xc, const int* skip) {
+// t = r - A x over the stored rows (six lanes per row): the residual half of residual + restriction on LARGE levels.
+// (A fused kernel -- one six-lane group walking its aggregate's member rows -- was measured at 515 us on the 1M-pose level
+// against 360 us for a whole smoothing sweep: a long dependent chain per group; this is a streaming SpMV.)
+__global__ void __launch_bounds__(kAmgThreads) amg_residual_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ r,
+                                                                   const double* __restrict__ x, double* __restrict__ t, const int* skip) {
   if (skip && *skip) return;
-  const RowLane L = amg_row_lane(ncomp);      // L.i = computed coarse row (relative)
-  const unsigned full = 0xffffffffu;
-  int m0 = 0, m1 = 0;
-  if (L.on) { m0 = mem_ptr[L.i]; m1 = mem_ptr[L.i + 1]; }
-  int cnt = m1 - m0;
-  int maxcnt = cnt;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(full, maxcnt, o));
-  const int I = c_row0 + (L.on ? L.i : 0);
-  double acc = 0.0;
-  for (int k = 0; k < maxcnt; ++k) {
-    const bool on = L.on && k < cnt;
-    double u = 0.0;
-    double dd[3] = {0.0, 0.0, 0.0};
-    if (on) {
-      const int i = mem_idx[m0 + k];
-      const double t = r[6 * (size_t)i + L.c] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, L.c);
-      double s = 1.0;
-      if (scale) { const double sv = scale[6 * (size_t)i + L.c]; s = sv > 0.0 ? 1.0 / sv : 0.0; }
-      u = s * t;
-      amg_delta(pos, pos_stride, i, cpos, I, dd);
-    }
-    const double u0 = __shfl_sync(full, u, L.g0), u1 = __shfl_sync(full, u, L.g0 + 1), u2 = __shfl_sync(full, u, L.g0 + 2);
-    if (on) {
-      // (P^T t)[c] = u_c, plus for the rotation rows X^T u_p = 2 d x u_p
-      double v = u;
-      if (L.c == 3) v += 2.0 * (dd[1] * u2 - dd[2] * u1);
-      else if (L.c == 4) v += 2.0 * (dd[2] * u0 - dd[0] * u2);
-      else if (L.c == 5) v += 2.0 * (dd[0] * u1 - dd[1] * u0);
-      acc += v;
-    }
-  }
-  if (L.on) rc[6 * (size_t)I + L.c] = acc;
-  // the coarse level's first smoothing sweep x_c = omega Dinv_c r_c rides along (Dinv_c == nullptr: done by the caller,
-  // e.g. after an all-gather of r_c, or the coarsest level is solved densely)
-  if (Dinv_c != nullptr) {
-    const double z = amg_block_row_dot(L.on ? Dinv_c + 36 * (size_t)I : nullptr, L.c, L.g0, L.on ? acc : 0.0);
-    if (L.on) xc[6 * (size_t)I + L.c] = omega * z;
+  const RowLane L = amg_row_lane(A.n);
+  if (L.on) {
+    const size_t q = 6 * (size_t)L.i + L.c;
+    t[q] = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, L.i, L.c);
   }
 }
 
@@ -428,7 +390,30 @@ __device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag
       }
     }
     const int p0 = __ldg(row_ptr + i), p1 = __ldg(row_ptr + i + 1);
-    for (int p = p0 + grp; p < p1; p += 5) {
+    // Galerkin rows of the coarse levels hold up to a few hundred blocks: four blocks per trip with all their loads
+    // (column ids first, then blocks and x gathers) in flight together, two accumulators
+    double acc2 = 0.0;
+    int p = p0 + grp;
+    for (; p + 15 < p1; p += 20) {
+      int j[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) j[q] = __ldg(col_idx + p + 5 * q);
+      double2 hb[4][3], xb[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)(p + 5 * q)) + r;
+        hb[q][0] = __ldg(ha); hb[q][1] = __ldg(ha + 6); hb[q][2] = __ldg(ha + 12);
+        const double2* xa = reinterpret_cast<const double2*>(x + 6 * (size_t)j[q]);
+        xb[q][0] = __ldg(xa); xb[q][1] = __ldg(xa + 1); xb[q][2] = __ldg(xa + 2);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double& t = (q & 1) ? acc2 : acc;
+        t = fma(hb[q][0].x, xb[q][0].x, t); t = fma(hb[q][0].y, xb[q][0].y, t); t = fma(hb[q][1].x, xb[q][1].x, t);
+        t = fma(hb[q][1].y, xb[q][1].y, t); t = fma(hb[q][2].x, xb[q][2].x, t); t = fma(hb[q][2].y, xb[q][2].y, t);
+      }
+    }
+    for (; p < p1; p += 5) {
       const int j = __ldg(col_idx + p);
       const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
       const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
@@ -438,6 +423,7 @@ __device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag
       acc = fma(a0.x, u0.x, acc); acc = fma(a0.y, u0.y, acc); acc = fma(a1.x, u1.x, acc);
       acc = fma(a1.y, u1.y, acc); acc = fma(a2.x, u2.x, acc); acc = fma(a2.y, u2.y, acc);
     }
+    acc += acc2;
   }
   const unsigned full = 0xffffffffu;
   const double a = acc + __shfl_down_sync(full, acc, 12);     // lane c: g0 + g2, lane c + 6: g1 + g3
@@ -463,7 +449,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_warp_kernel(const BsrV
   if (on) y[q] = x[q] + omega * z;
 }
 
-// rc_I = sum_{i in I} P_i^T t_i from a stored residual t (the split form of amg_residual_restrict_kernel): one warp per
+// rc_I = sum_{i in I} P_i^T t_i from a stored residual t (the residual is computed by amg_residual_kernel / amg_smooth_warp_kernel<true>): one warp per
 // coarse row, five 6-lane groups stride through the members, shuffle tree, then the fused first sweep of the coarse level
 __global__ void __launch_bounds__(kAmgThreads) amg_restrict_kernel(const double* __restrict__ t, int ncomp, int c_row0,
                                                                    const int* __restrict__ mem_ptr, const int* __restrict__ mem_idx,
@@ -938,10 +924,12 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
                                                                                M->omega, cur[l + 1], skip);
       g->launches += 2;
     } else if (ncomp > 0) {
-      amg_residual_restrict_kernel<<<amg_rows_grid(ncomp), kAmgThreads, 0, g->stream>>>(
-          amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
-          l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr, M->omega, cur[l + 1], skip);
-      g->launches++;
+      // large level: streaming residual into the spare buffer, then the restriction (a warp per coarse row)
+      amg_residual_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
+      amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
+                                                                          l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
+                                                                          M->omega, cur[l + 1], skip);
+      g->launches += 2;
     }
     if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.r, C.gather_off, 6));
   }
