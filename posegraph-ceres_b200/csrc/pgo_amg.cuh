@@ -58,6 +58,11 @@ struct Amg {
   int part_cap = 0;
   bool warp_spmv = false;
   double* red = nullptr;                   // [8] reduced scalars (all-reduced across ranks)
+  // multi-GPU: the replicated tail of the V-cycle as a CUDA graph
+  cudaGraphExec_t tail_graph = nullptr;
+  int tail_graph_kernels = 0, tail_calls = 0;
+  bool tail_graph_failed = false;
+  std::vector<double*> tail_cur;
   struct IterGraph { const void* key[4]; int max_it; double tol; cudaGraphExec_t exec; int kernels; };
   std::vector<IterGraph> graphs;           // captured PCG iteration per (H, poses) buffer pair (the LM loop alternates two)
   long long blocks_all_levels = 0;
@@ -688,6 +693,7 @@ static void amg_destroy(pgo::Amg* M, int device) {
   pgo::pool_event_release(device, M->ev[0]);
   pgo::pool_event_release(device, M->ev[1]);
   for (auto& e : M->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+  if (M->tail_graph) cudaGraphExecDestroy(M->tail_graph);
   delete M;   // device blocks were borrowed through dev_alloc and go back with the graph's
 }
 
@@ -901,7 +907,8 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
   const int* skip = &M->state->done;
   std::vector<double*> cur(nl), oth(nl);
   for (int l = 0; l < nl; ++l) { cur[l] = M->lv[l].x; oth[l] = M->lv[l].y; }
-  for (int l = 0; l + 1 < nl; ++l) {
+  // going down from level l: remaining pre-smoothing sweeps, residual, restriction (+ first sweep of level l + 1)
+  auto down = [&](int l) -> int {
     const AmgLevelDev& D = M->lv[l];
     const AmgLevelDev& C = M->lv[l + 1];
     // (x_l = omega Dinv r_l arrives with r_l: from the PCG update on level 0, from the restriction below otherwise)
@@ -915,25 +922,23 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     // the next level's first sweep is fused unless its residual still has to be gathered or it is solved densely
     const bool coarsest_next = l + 2 == nl;
     const bool fuse_next = C.gather_off.empty() && !(coarsest_next && M->dense_inv);
-    if (ncomp > 0 && D.n_own <= kAmgWarpRowMax) {
-      // small level: residual with a whole warp per row into the spare buffer, then the restriction
-      amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, nullptr, D.r, cur[l],
-                                                                                      0.0, oth[l], skip);
-      amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
-                                                                               l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
-                                                                               M->omega, cur[l + 1], skip);
-      g->launches += 2;
-    } else if (ncomp > 0) {
-      // large level: streaming residual into the spare buffer, then the restriction (a warp per coarse row)
-      amg_residual_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
+    if (ncomp > 0) {
+      // residual into the spare buffer (small level: a whole warp per row; large level: streaming, six lanes per row),
+      // then the restriction (a warp per coarse row)
+      if (D.n_own <= kAmgWarpRowMax)
+        amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, nullptr, D.r, cur[l],
+                                                                                        0.0, oth[l], skip);
+      else
+        amg_residual_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
       amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
                                                                           l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
                                                                           M->omega, cur[l + 1], skip);
       g->launches += 2;
     }
     if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.r, C.gather_off, 6));
-  }
-  {
+    return PGO_OK;
+  };
+  auto coarsest = [&]() -> int {
     const int l = nl - 1;
     const AmgLevelDev& D = M->lv[l];
     if (nl > 1 && M->dense_inv) {
@@ -947,15 +952,66 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
       for (int s = 1; s < M->coarse_sweeps; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
     }
     // nl == 1: plain block-Jacobi, lv[0].x = omega Minv r is the result (omega only rescales the preconditioner)
-  }
-  for (int l = nl - 2; l >= 0; --l) {
+    return PGO_OK;
+  };
+  // coming back up to level l: prolongation, post-smoothing
+  auto up = [&](int l) -> int {
     const AmgLevelDev& D = M->lv[l];
     const AmgLevelDev& C = M->lv[l + 1];
     amg_prolong_kernel<<<(D.n_own * 6 + 255) / 256, 256, 0, g->stream>>>(D.n_own, D.agg, D.pos, D.pos_stride, C.pos, l == 0 ? g->scale : nullptr,
                                                                          cur[l + 1], cur[l], skip);
     g->launches++;
     for (int s = 0; s < M->nu; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
+    return PGO_OK;
+  };
+  // Levels [Lc, nl) are the replicated tail of a multi-GPU hierarchy (one GPU: just the coarsest): no communication in
+  // there, the same launches with the same pointers in every cycle -- and each of them a few microseconds long, i.e.
+  // launch bound.  Multi-GPU runs replay that tail as a CUDA graph (NCCL stays outside of captures; on one GPU the whole
+  // PCG iteration is one graph anyway).
+  int Lr = nl;
+  for (int l = nl - 1; l >= 0; --l) if (g->world > 1 && M->lv[l].replicated) Lr = l;
+  const int Lc = std::min(Lr, nl - 1);
+  auto tail = [&]() -> int {
+    for (int l = Lc; l + 1 < nl; ++l) PGO_TRY(down(l));
+    PGO_TRY(coarsest());
+    for (int l = nl - 2; l >= Lc; --l) PGO_TRY(up(l));
+    return PGO_OK;
+  };
+  for (int l = 0; l < Lc; ++l) PGO_TRY(down(l));
+  static const bool tail_graph_off = getenv("PGO_AMG_TAIL_GRAPH") && atoi(getenv("PGO_AMG_TAIL_GRAPH")) == 0;
+  const bool want_tail_graph = g->world > 1 && Lc < nl - 1 && !tail_graph_off;
+  if (want_tail_graph && M->tail_graph) {
+    CUDA_TRY(cudaGraphLaunch(M->tail_graph, g->stream));
+    g->launches += M->tail_graph_kernels;
+    for (int l = Lc; l < nl; ++l) cur[l] = M->tail_cur[l];
+  } else if (want_tail_graph && M->tail_calls >= 1 && !M->tail_graph_failed) {
+    // (the first cycle ran as plain launches: every lazy initialisation is behind us)
+    const std::vector<double*> cur0 = cur, oth0 = oth;
+    const long long l0 = g->launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = tail();
+    const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
+    M->tail_graph_kernels = (int)(g->launches - l0);
+    g->launches = l0;
+    bool ok = rc == PGO_OK && ce == cudaSuccess && graph != nullptr;
+    if (ok && cudaGraphInstantiate(&M->tail_graph, graph, 0) != cudaSuccess) { M->tail_graph = nullptr; ok = false; }
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      M->tail_graph_failed = true;
+      cur = cur0; oth = oth0;
+      PGO_TRY(tail());
+    } else {
+      M->tail_cur = cur;                       // where the captured tail leaves its results
+      CUDA_TRY(cudaGraphLaunch(M->tail_graph, g->stream));
+      g->launches += M->tail_graph_kernels;
+    }
+  } else {
+    PGO_TRY(tail());
+    M->tail_calls++;
   }
+  for (int l = Lc - 1; l >= 0; --l) PGO_TRY(up(l));
   *out = cur[0];
   return PGO_OK;
 }
