@@ -108,6 +108,7 @@ struct pgo_graph {
   cudaGraphExec_t lm_graph = nullptr;
   std::vector<unsigned char> lm_graph_key;
   int lm_graph_kernels = 0;
+  bool failed = false;                       // a collective call returned an error on this rank
   long long comm_calls = 0, comm_bytes = 0;   // NCCL calls / payload bytes sent by this rank (multi-GPU)
   bool identity_info = true;
   bool has_dup_blocks = false;
@@ -306,7 +307,8 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->sym_future.valid()) g->sym_future.get();
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->own_stream && g->own_stream != g->stream) cudaStreamSynchronize(g->own_stream);
-  if (g->comm) ncclCommDestroy(g->comm);
+  // a rank that failed inside a collective solve must not leave its peers blocked in NCCL: abort instead of a graceful destroy
+  if (g->comm) { if (g->failed) ncclCommAbort(g->comm); else ncclCommDestroy(g->comm); }
   if (g->chol) level_chol_destroy(g->chol, g->device);
   if (g->amg) amg_destroy(g->amg, g->device);
   if (g->lm_graph) cudaGraphExecDestroy(g->lm_graph);
@@ -1316,8 +1318,10 @@ extern "C" int pgo_graph_spmv(pgo_graph* g, const double* x, const double* d, do
 // levels, node degree <= 16, fill <= 8x); mesh-like graphs (sphere, grids, dense random loops) go to block-Jacobi PCG.
 static int run_symbolic(const pgo_graph* g, int t, LevelCholSymbolic* S) {
   const bool autosel = t == PGO_LINEAR_AUTO;
-  return level_chol_symbolic(S, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(), autosel ? 8.0 : 1e30,
-                             autosel ? 64 : 8192, autosel ? 16 : (1 << 30));
+  const int rc = level_chol_symbolic(S, g->N, g->active_h.data(), g->row_ptr_h.data(), g->col_idx_h.data(), autosel ? 8.0 : 1e30,
+                                     autosel ? 64 : 8192, autosel ? 16 : (1 << 30));
+  if (rc != PGO_OK) S->error = g_last_error;     // carried to the thread that asked (this may be the helper thread)
+  return rc;
 }
 
 static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
@@ -1336,7 +1340,8 @@ static int resolve_linear_solver(pgo_graph* g, const pgo_solver_options* o) {
       LevelChol* c = nullptr;
       int rc = PGO_OK;
       if (g->sym_future.valid() && g->sym_solver_type == t) {
-        rc = g->sym_future.get();                      // started by pgo_solve_pose_graph
+        rc = g->sym_future.get();                      // started by pgo_solve_pose_graph (helper thread)
+        if (rc != PGO_OK && g->sym && !g->sym->error.empty()) set_error(rc, "%s", g->sym->error.c_str());
       } else {
         if (g->sym_future.valid()) g->sym_future.get();
         g->sym.reset(new LevelCholSymbolic());
@@ -1432,8 +1437,14 @@ static void lm_message(const LmState& st, const pgo_solver_options* opt, char* o
   }
 }
 
+static int graph_solve_impl(pgo_graph* g, const pgo_solver_options* opt, pgo_solver_summary* summary, pgo_iteration_summary* log, int log_cap);
 extern "C" int pgo_graph_solve(pgo_graph* g, const pgo_solver_options* opt, pgo_solver_summary* summary,
                                pgo_iteration_summary* log, int log_cap) {
+  const int rc = graph_solve_impl(g, opt, summary, log, log_cap);
+  if (rc != PGO_OK && g && g->world > 1) g->failed = true;   // pgo_graph_destroy then aborts the communicator (peers may be inside a collective)
+  return rc;
+}
+static int graph_solve_impl(pgo_graph* g, const pgo_solver_options* opt, pgo_solver_summary* summary, pgo_iteration_summary* log, int log_cap) {
   if (!g || !opt || !summary) return set_error(PGO_ERR_INVALID_ARGUMENT, "pgo_graph_solve: null argument");
   CUDA_TRY(cudaSetDevice(g->device));
   const double t_begin = wall_s();

@@ -811,6 +811,7 @@ static int chol_upload(LevelChol* C, int device, Tp** dst, const std::vector<Tp>
 
 // Pure host part: elimination levels, structure of L, gather map, Schur tasks.
 struct LevelCholSymbolic {
+  std::string error;            // message of a failed analysis (the analysis may run on a helper thread; pgo_last_error() is per thread)
   bool usable = false;
   int n_nodes = 0, num_levels = 0, max_degree = 0;
   long long n_slots = 0;
