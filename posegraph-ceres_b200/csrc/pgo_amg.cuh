@@ -323,12 +323,19 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A
                                                                  const double* __restrict__ r, const double* __restrict__ x, double omega,
                                                                  double* __restrict__ y, const int* skip) {
   if (skip && *skip) return;
-  const RowLane L = amg_row_lane(A.n);
-  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
-  double t = 0.0;
-  if (L.on) t = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, L.i, L.c);
-  const double z = amg_block_row_dot(L.on ? Dinv + 36 * (size_t)L.i : nullptr, L.c, L.g0, t);
-  if (L.on) y[q] = x[q] + omega * z;
+  // grid-stride over groups of five rows per warp, like spmv_kernel (the launch is a fixed 8 CTAs per SM)
+  const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6, g0 = grp * 6;
+  const int wpc = kAmgThreads / 32;
+  const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
+  for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
+    const int i = base + grp;
+    const bool on = grp < kRowsPerWarp && i < A.n;
+    const size_t q = 6 * (size_t)(on ? i : 0) + c;
+    double t = 0.0;
+    if (on) t = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
+    const double z = amg_block_row_dot(on ? Dinv + 36 * (size_t)i : nullptr, c, g0, t);
+    if (on) y[q] = x[q] + omega * z;
+  }
 }
 
 // t = r - A x over the stored rows (six lanes per row): the residual half of residual + restriction on LARGE levels.
@@ -337,10 +344,15 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A
 __global__ void __launch_bounds__(kAmgThreads) amg_residual_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ r,
                                                                    const double* __restrict__ x, double* __restrict__ t, const int* skip) {
   if (skip && *skip) return;
-  const RowLane L = amg_row_lane(A.n);
-  if (L.on) {
-    const size_t q = 6 * (size_t)L.i + L.c;
-    t[q] = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, L.i, L.c);
+  const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6;
+  const int wpc = kAmgThreads / 32;
+  const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
+  for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
+    const int i = base + grp;
+    if (grp < kRowsPerWarp && i < A.n) {
+      const size_t q = 6 * (size_t)i + c;
+      t[q] = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
+    }
   }
 }
 
@@ -577,6 +589,25 @@ __global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_warp_kernel(const B
     for (int k = 0; k < kAmgThreads / 32; ++k) { t0 += red0[k]; t1 += red1[k]; }
     part[blockIdx.x] = t0;
     part[gridDim.x + blockIdx.x] = t1;
+  }
+}
+
+// per-CTA partials of a . b in a fixed order (the r.u of the large-graph path: there the CG product is the plain spmv_kernel
+// with w.u in its epilogue -- 0.27 ms on the 1M-pose level against 0.35 ms for the kernel that carries both sums)
+__global__ void __launch_bounds__(kAmgThreads) amg_dot_kernel(int n6, const double* __restrict__ a, const double* __restrict__ b,
+                                                              double* __restrict__ part, const int* skip) {
+  __shared__ double red[kAmgThreads / 32];
+  double acc = 0.0;
+  if (!(skip && *skip))
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n6; k += gridDim.x * blockDim.x) acc = fma(a[k], b[k], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAmgThreads / 32; ++k) t += red[k];
+    part[blockIdx.x] = t;
   }
 }
 
@@ -894,7 +925,7 @@ static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, con
   if (D.n_own <= kAmgWarpRowMax)
     amg_smooth_warp_kernel<false><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
   else
-    amg_smooth_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+    amg_smooth_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
   g->launches++;
   return PGO_OK;
 }
@@ -929,7 +960,7 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
         amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, nullptr, D.r, cur[l],
                                                                                         0.0, oth[l], skip);
       else
-        amg_residual_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
+        amg_residual_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
       amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
                                                                           l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
                                                                           M->omega, cur[l + 1], skip);
@@ -1025,8 +1056,13 @@ static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_opt
   double* u = nullptr;
   PGO_TRY(amg_vcycle(g, M, &u));
   PGO_TRY(amg_exchange(g, M, L0, u, 6, 6, &st->done));
-  if (M->warp_spmv) amg_spmv_dots_warp_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
-  else amg_spmv_dots_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
+  if (M->warp_spmv) {
+    amg_spmv_dots_warp_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
+  } else {
+    spmv_kernel<true><<<sp_ctas, 256, 0, g->stream>>>(amg_view(L0), u, g->dlm, g->vw, true, M->part, &st->done);
+    amg_dot_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(6 * n, g->vr, u, M->part + sp_ctas, &st->done);
+    g->launches++;
+  }
   if (g->world > 1) {
     amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
     PGO_TRY(amg_allreduce(g, M->red, 2));
