@@ -20,7 +20,10 @@
 namespace pgo {
 
 constexpr int kAmgThreads = 256;
-constexpr int kAmgDenseMaxNodes = 16;      // coarsest level: explicit dense inverse in the shared memory of one CTA
+constexpr int kAmgDenseSmemNodes = 16;     // coarsest level of at most this many nodes: Gauss-Jordan in the shared memory of one CTA
+constexpr int kAmgDenseMaxNodes = 512;     // ... up to this many: block Gauss-Jordan in global memory by a cooperative grid (3072^2 fp64 = 75 MB)
+constexpr int kGjThreads = 1024;
+constexpr int kGjMaxOwnRows = 6 * 8;       // block rows of the dense system a CTA may own (x 6 scalar rows)
 
 struct AmgLevelDev {
   bool replicated = false;
@@ -48,6 +51,8 @@ struct Amg {
   int num_levels = 0;
   std::vector<AmgLevelDev> lv;
   double* dense_inv = nullptr;             // [6 n][6 n] of the coarsest level (n <= kAmgDenseMaxNodes), else nullptr
+  double* gj_rows = nullptr;               // [2][6][6 n] pivot rows of the block Gauss-Jordan (n > kAmgDenseSmemNodes)
+  unsigned int* gj_counter = nullptr;
   double omega = 0.85;                     // damped block-Jacobi smoother (measured on the 1M grid and the 100k torus: 0.6 < 0.7 < 0.85)
   int nu = 1;
   int coarse_sweeps = 4;
@@ -223,7 +228,7 @@ __global__ void amg_block_inverse_kernel(int n, const double* __restrict__ Adiag
   for (int k = 0; k < 36; ++k) Dinv[36 * (size_t)i + k] = ok ? inv[k] : 0.0;
 }
 
-// Dense inverse of the coarsest operator (n <= kAmgDenseMaxNodes nodes) by Gauss-Jordan in shared memory, one CTA.
+// Dense inverse of the coarsest operator (n <= kAmgDenseSmemNodes nodes) by Gauss-Jordan in shared memory, one CTA.
 __global__ void __launch_bounds__(kAmgThreads) amg_dense_inverse_kernel(int n, const double* __restrict__ Adiag, const double* __restrict__ Aoff,
                                                                         const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                                                                         double* __restrict__ inv) {
@@ -266,20 +271,143 @@ __global__ void __launch_bounds__(kAmgThreads) amg_dense_inverse_kernel(int n, c
   for (int k = threadIdx.x; k < m * m; k += blockDim.x) inv[k] = M[k];
 }
 
-// x = inv * r on the coarsest level (one CTA)
+// ---- coarsest levels of up to kAmgDenseMaxNodes nodes: explicit inverse by 6x6-block Gauss-Jordan in global memory ----
+// (an aggregation V-cycle loses a constant factor per level, and the small levels are pure launch latency: solving the
+// first level of <= 512 nodes exactly removes two or three levels from every cycle -- sphere2500 57 -> 26 PCG iterations
+// per LM step in tools/amg_prototype.py --dense-below -- for one inversion per LM step and one dense mat-vec per cycle.)
+// scatter of the block-CSR operator into the zeroed dense matrix, one CTA per block row
+__global__ void __launch_bounds__(kAmgThreads) amg_dense_fill_kernel(int n, const double* __restrict__ Adiag, const double* __restrict__ Aoff,
+                                                                     const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                                                                     double* __restrict__ M) {
+  const int i = blockIdx.x;
+  const size_t m = 6 * (size_t)n;
+  const int p0 = row_ptr[i], p1 = row_ptr[i + 1];
+  for (int t = threadIdx.x; t < (p1 - p0 + 1) * 36; t += blockDim.x) {
+    const int q = t / 36, e = t - q * 36, r = e / 6, c = e - r * 6;
+    if (q == 0) M[(6 * (size_t)i + r) * m + 6 * (size_t)i + c] = Adiag[36 * (size_t)i + pidx(r, c)];
+    else {
+      const int p = p0 + q - 1;
+      M[(6 * (size_t)i + r) * m + 6 * (size_t)col_idx[p] + c] = Aoff[36 * (size_t)p + pidx(r, c)];
+    }
+  }
+}
+
+struct GjParams {
+  int nb;                  // block rows (nodes); the matrix is [6 nb][6 nb], row-major
+  double* M;               // in: the SPD operator, out: its inverse
+  double* R;               // [2][6][6 nb]: the normalised pivot rows of the current / the next step
+  unsigned int* counter;   // grid barrier (zeroed before the launch)
+};
+
+// In-place block Gauss-Jordan without pivoting (the operator is SPD).  Every CTA owns a contiguous range of block rows.
+// Step k, with R = P_k M[K, :] (P_k the inverse of the pivot block, and R[:, K] := P_k):
+//   rows of K:  M[K, :] = R;      other rows i:  M[i, j] = (j in K ? 0 : M[i, j]) - sum_q M_old[i, K_q] R[q, j].
+// The owner of block row k + 1 updates those six rows first, inverts the next pivot and publishes the next R (double
+// buffered) before it turns to its other rows: ONE grid barrier per step.
+__global__ void __launch_bounds__(kGjThreads) amg_dense_gj_kernel(const GjParams P) {
+  __shared__ double Cs[kGjMaxOwnRows][6];
+  __shared__ double Pk[36];
+  const int nb = P.nb;
+  const size_t m = 6 * (size_t)nb;
+  const int per = (nb + gridDim.x - 1) / gridDim.x;
+  const int b0 = min(nb, (int)blockIdx.x * per), b1 = min(nb, b0 + per);
+  const int nrows = 6 * (b1 - b0);
+  double* const M = P.M;
+  unsigned int epoch = 0;
+
+  // R_kn = P M[Kn, :] from the (final) rows of block kn, which this CTA owns
+  auto publish = [&](int kn) {
+    __syncthreads();                                   // the rows of Kn were written by this CTA's threads
+    if (threadIdx.x == 0) {
+      double A[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) A[r][c] = M[(6 * (size_t)kn + r) * m + 6 * (size_t)kn + c];
+      double inv[36];
+      const bool ok = spd6_inverse(A, inv);
+#pragma unroll
+      for (int e = 0; e < 36; ++e) Pk[e] = ok ? inv[e] : 0.0;
+    }
+    __syncthreads();
+    double* Rn = P.R + (size_t)(kn & 1) * 6 * m;
+    const double* rows = M + 6 * (size_t)kn * m;
+    for (int j = threadIdx.x; j < (int)m; j += blockDim.x) {
+      const int c = j - 6 * kn;
+      if (c >= 0 && c < 6) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Rn[q * m + j] = Pk[q * 6 + c];
+      } else {
+        double a[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[r] = rows[r * m + j];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          double t = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) t = fma(Pk[q * 6 + r], a[r], t);
+          Rn[q * m + j] = t;
+        }
+      }
+    }
+  };
+
+  if (b0 <= 0 && 0 < b1) publish(0);
+  grid_barrier(P.counter, epoch);
+  for (int k = 0; k < nb; ++k) {
+    const double* R = P.R + (size_t)(k & 1) * 6 * m;
+    for (int t = threadIdx.x; t < nrows * 6; t += blockDim.x) Cs[t / 6][t % 6] = M[(6 * (size_t)b0 + t / 6) * m + 6 * (size_t)k + t % 6];
+    __syncthreads();
+    auto update = [&](int r_lo, int r_hi) {           // local scalar rows [r_lo, r_hi)
+      for (int j = threadIdx.x; j < (int)m; j += blockDim.x) {
+        double Rq[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Rq[q] = __ldcg(R + q * m + j);
+        const bool in_k = (j / 6) == k;
+        for (int i = r_lo; i < r_hi; ++i) {
+          const int gi = 6 * b0 + i;
+          double* a = M + (size_t)gi * m + j;
+          const int pr = gi - 6 * k;
+          if (pr >= 0 && pr < 6) { *a = Rq[pr]; continue; }
+          double t = in_k ? 0.0 : *a;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) t = fma(-Cs[i][q], Rq[q], t);
+          *a = t;
+        }
+      }
+    };
+    const int kn = k + 1;
+    if (kn < nb && kn >= b0 && kn < b1) {
+      const int lo = 6 * (kn - b0);
+      update(lo, lo + 6);
+      publish(kn);
+      update(0, lo);
+      update(lo + 6, nrows);
+    } else {
+      update(0, nrows);
+    }
+    grid_barrier(P.counter, epoch);
+  }
+}
+
+// x = inv * r on a densely inverted level: one warp per row
 __global__ void __launch_bounds__(kAmgThreads) amg_dense_solve_kernel(int m, const double* __restrict__ inv, const double* __restrict__ r,
                                                                       double* __restrict__ x, const int* skip) {
   if (skip && *skip) return;
-  __shared__ double rs[6 * kAmgDenseMaxNodes];
-  for (int k = threadIdx.x; k < m; k += blockDim.x) rs[k] = r[k];
-  __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x >> 5; i < m; i += kAmgThreads / 32) {     // one warp per row: three independent loads per lane
-    double s = 0.0;
-    for (int k = lane; k < m; k += 32) s = fma(inv[i * m + k], rs[k], s);
-    s = warp_sum(s);
-    if (lane == 0) x[i] = s;
+  const int i = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
+  if (i >= m) return;                           // warp-uniform
+  const double* row = inv + (size_t)i * m;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = lane;
+  for (; k + 96 < m; k += 128) {
+    const double a0 = __ldg(row + k), a1 = __ldg(row + k + 32), a2 = __ldg(row + k + 64), a3 = __ldg(row + k + 96);
+    s0 = fma(a0, __ldg(r + k), s0); s1 = fma(a1, __ldg(r + k + 32), s1);
+    s2 = fma(a2, __ldg(r + k + 64), s2); s3 = fma(a3, __ldg(r + k + 96), s3);
   }
+  for (; k < m; k += 32) s0 = fma(__ldg(row + k), __ldg(r + k), s0);
+  const double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) x[i] = s;
 }
 
 // six lanes per block row, five rows per warp (the lane layout of bsr6_row)
@@ -768,9 +896,7 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   using namespace pgo;
   Amg* M = new Amg();
   *out = M;
-  AmgHostParams prm;
-  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
-  if (const char* e = getenv("PGO_AMG_REPLICATE_MAX")) prm.replicate_max = atoi(e);
+  const AmgHostParams prm = amg_host_params(g->N_global);
   if (const char* e = getenv("PGO_AMG_OMEGA")) M->omega = atof(e);
   if (const char* e = getenv("PGO_AMG_NU")) M->nu = std::max(1, atoi(e));
   if (const char* e = getenv("PGO_AMG_COARSE_SWEEPS")) M->coarse_sweeps = std::max(1, atoi(e));
@@ -829,8 +955,13 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   // fine boundary node, so the lists only shrink -- checked, not assumed
   if (max_send > g->send_idx_h.size()) return set_error(PGO_ERR_NUMERICAL, "amg: a coarse level sends more nodes than level 0");
   const AmgLevelDev& last = M->lv[nl - 1];
-  if (nl > 1 && (g->world == 1 || last.replicated) && last.n_own <= kAmgDenseMaxNodes)
+  if (nl > 1 && (g->world == 1 || last.replicated) && last.n_own <= kAmgDenseMaxNodes) {
     PGO_TRY(dev_alloc(g, &M->dense_inv, (size_t)36 * last.n_own * last.n_own));
+    if (last.n_own > kAmgDenseSmemNodes) {
+      PGO_TRY(dev_alloc(g, &M->gj_rows, (size_t)2 * 36 * last.n_own));
+      PGO_TRY(dev_alloc(g, &M->gj_counter, 1));
+    }
+  }
   PGO_TRY(dev_alloc(g, &M->state, 1));
   CUDA_TRY(pool_pinned(g->device, reinterpret_cast<void**>(&M->state_h)));
   static_assert(2 * sizeof(PcgMultiState) <= kPinnedBytes, "pinned PCG state slots");
@@ -898,13 +1029,26 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
       PGO_TRY(amg_gather(g, C.Adiag, C.gather_off, 36));
       PGO_TRY(amg_gather(g, C.Aoff, C.gather_slot_off, 36));
     }
-    if (l + 2 == nl && M->dense_inv) {
+    if (l + 2 == nl && M->dense_inv && C.n_own > kAmgDenseSmemNodes) {
+      const size_t m = 6 * (size_t)C.n_own;
+      CUDA_TRY(cudaMemsetAsync(M->dense_inv, 0, m * m * sizeof(double), g->stream));
+      CUDA_TRY(cudaMemsetAsync(M->gj_counter, 0, sizeof(unsigned int), g->stream));
+      amg_dense_fill_kernel<<<C.n_own, kAmgThreads, 0, g->stream>>>(C.n_own, C.Adiag, C.Aoff, C.row_ptr, C.col_idx, M->dense_inv);
+      GjParams P;
+      P.nb = C.n_own; P.M = M->dense_inv; P.R = M->gj_rows; P.counter = M->gj_counter;
+      const int per = std::max((C.n_own + g->num_sms - 1) / g->num_sms, 1);
+      if (6 * per > kGjMaxOwnRows) return set_error(PGO_ERR_NUMERICAL, "amg: dense coarsest level of %d nodes on %d SMs", C.n_own, g->num_sms);
+      const int grid = (C.n_own + per - 1) / per;
+      void* args[] = {&P};
+      CUDA_TRY(cudaLaunchCooperativeKernel((void*)amg_dense_gj_kernel, dim3(grid), dim3(kGjThreads), args, 0, g->stream));
+      g->launches++;
+    } else if (l + 2 == nl && M->dense_inv) {
       const int m = 6 * C.n_own;
       const int smem = m * m * (int)sizeof(double);
       int have = 0;
       if (!pool_cache_get(g->device, kCacheAmgDenseAttr, &have)) {
         CUDA_TRY(cudaFuncSetAttribute(amg_dense_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      36 * kAmgDenseMaxNodes * kAmgDenseMaxNodes * (int)sizeof(double)));
+                                      36 * kAmgDenseSmemNodes * kAmgDenseSmemNodes * (int)sizeof(double)));
         pool_cache_set(g->device, kCacheAmgDenseAttr, 1);
       }
       amg_dense_inverse_kernel<<<1, kAmgThreads, smem, g->stream>>>(C.n_own, C.Adiag, C.Aoff, C.row_ptr, C.col_idx, M->dense_inv);
@@ -973,7 +1117,7 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     const int l = nl - 1;
     const AmgLevelDev& D = M->lv[l];
     if (nl > 1 && M->dense_inv) {
-      amg_dense_solve_kernel<<<1, kAmgThreads, 0, g->stream>>>(6 * D.n_own, M->dense_inv, D.r, cur[l], skip);
+      amg_dense_solve_kernel<<<(6 * D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(6 * D.n_own, M->dense_inv, D.r, cur[l], skip);
       g->launches++;
     } else if (nl > 1) {
       if (!D.gather_off.empty()) {

@@ -20,17 +20,30 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 namespace pgo {
 
 struct AmgHostParams {
   double theta = 0.3;        // geometric strength: neighbour j of i is strong when 1/|p_i-p_j|^2 >= theta * max over both rows
-  int coarsest_max = 16;     // stop coarsening at <= this many nodes (the coarsest system is inverted densely: 96 x 96)
+  int coarsest_max = 16;     // stop coarsening at <= this many nodes: that level is inverted densely (amg_host_params sizes it)
   int max_levels = 12;
   int replicate_max = 32768; // multi-GPU: a level with at most this many nodes lives on every rank
   double stall_ratio = 0.85; // give up coarsening when a level keeps more than this share of its nodes
 };
+
+// The parameters every entry point uses for a graph of n_poses poses.  The first level of at most coarsest_max nodes is
+// solved exactly (dense inverse, once per LM step): N/16 keeps that inversion a small share of an LM step on small graphs,
+// 512 nodes (a 3072 x 3072 fp64 inverse, 75 MB) bounds it on large ones.
+inline AmgHostParams amg_host_params(int n_poses) {
+  AmgHostParams prm;
+  prm.coarsest_max = std::min(512, std::max(16, n_poses / 16));
+  if (const char* e = getenv("PGO_AMG_DENSE_MAX")) prm.coarsest_max = std::min(512, std::max(1, atoi(e)));
+  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
+  if (const char* e = getenv("PGO_AMG_REPLICATE_MAX")) prm.replicate_max = atoi(e);
+  return prm;
+}
 
 // One level of the global hierarchy.  Nodes are numbered rank by rank: rank r owns [off[r], off[r+1]).
 struct AmgGlobalLevel {

@@ -754,9 +754,7 @@ extern "C" int pgo_analyze_partition(int n_poses, int n_edges, const double* pos
   for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) pos0[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
   std::vector<int> off;
   partition_ranges(n_poses, world_size, &off);
-  AmgHostParams prm;
-  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
-  if (const char* e = getenv("PGO_AMG_REPLICATE_MAX")) prm.replicate_max = atoi(e);
+  const AmgHostParams prm = amg_host_params(n_poses);
   std::vector<AmgGlobalLevel> G;
   amg_build_global(n_poses, world_size, off, gp.active.data(), gp.row_ptr.data(), gp.col_idx.data(), pos0.data(), prm, &G);
   HostRankSetup me;
@@ -846,8 +844,7 @@ extern "C" int pgo_amg_aggregates(int n_poses, int n_edges, const double* poses,
   for (int i = 0; i < n_poses; ++i) for (int k = 0; k < 3; ++k) pos0[3 * (size_t)i + k] = poses[7 * (size_t)i + k];
   std::vector<int> off;
   partition_ranges(n_poses, world_size, &off);
-  AmgHostParams prm;
-  if (const char* e = getenv("PGO_AMG_THETA")) prm.theta = atof(e);
+  const AmgHostParams prm = amg_host_params(n_poses);
   std::vector<AmgGlobalLevel> G;
   amg_build_global(n_poses, world_size, off, gp.active.data(), gp.row_ptr.data(), gp.col_idx.data(), pos0.data(), prm, &G);
   *n_levels = (int)G.size();

@@ -57,12 +57,13 @@ def test_world_one_is_the_whole_graph(pgo, D):
 
 
 def test_aggregates_are_connected_patches_that_shrink_the_graph(pgo, D):
-    """Every aggregate is a connected set of poses; constant poses stay out; the hierarchy ends in <= 16 nodes."""
+    """Every aggregate is a connected set of poses; constant poses stay out; the hierarchy ends in a level small enough to
+    be inverted densely (<= max(16, N / 16), at most 512 nodes: amg_host_params)."""
     import scipy.sparse as sp
     import scipy.sparse.csgraph as csg
     for g in (D.sphere(), D.manhattan_grid(60, 60, 200), D.torus(5000, winds=50)):
         sizes, aggs = pgo.amg_aggregates(g, 1)
-        assert sizes[0] == g.n_poses and sizes[-1] <= 16 and len(sizes) >= 3
+        assert sizes[0] == g.n_poses and sizes[-1] <= min(512, max(16, g.n_poses // 16)) and len(sizes) >= 3
         assert all(sizes[k + 1] < 0.6 * sizes[k] for k in range(len(sizes) - 1)), sizes
         a0 = aggs[0]
         assert (a0[g.pose_const != 0] == -1).all() and (a0[g.pose_const == 0] >= 0).all()

@@ -127,7 +127,7 @@ def build_hierarchy(A, pos, n, scale_inv, args, active):
         L.n = cur_n
         L.Dinv = block_diag_inv(cur_A, cur_n) if cur_n > 0 else None
         levels.append(L)
-        if cur_n <= args.coarsest and not (args.agg == "cxx" and len(levels) - 1 < len(args.cxx_aggs)):
+        if (cur_n <= args.coarsest and not (args.agg == "cxx" and len(levels) - 1 < len(args.cxx_aggs))) or cur_n <= args.dense_below:
             L.dense = np.linalg.pinv(cur_A.toarray())
             break
         Ab = cur_A.tobsr(blocksize=(6, 6))
@@ -169,7 +169,29 @@ def build_hierarchy(A, pos, n, scale_inv, args, active):
             Pb[:, 2, 3] = 2 * d[:, 1]; Pb[:, 2, 4] = -2 * d[:, 0]
         Pb = Pb * cur_Sinv[:, :, None]
         Pb = Pb * cur_active[:, None, None]
-        P = sp.bsr_matrix((Pb, agg, np.arange(cur_n + 1)), shape=(6 * cur_n, 6 * na)).tocsr()
+        if args.geo_smooth > 0:
+            # scalar partition-of-unity weights from one damped-Jacobi step on the strong-connection graph Laplacian; every
+            # (node, aggregate) weight multiplies the rigid-body transfer block T(p_i - c_J): rigid motions are reproduced exactly
+            Aw = adj.copy().tocsr()
+            if args.geo_unweighted:
+                Aw.data[:] = 1.0
+            deg = np.asarray(Aw.sum(axis=1)).ravel()
+            deg[deg == 0] = 1.0
+            P0 = sp.csr_matrix((np.ones(cur_n), (np.arange(cur_n), agg)), shape=(cur_n, na))
+            Wt = ((1 - args.geo_smooth) * P0 + args.geo_smooth * (sp.diags(1.0 / deg) @ (Aw @ P0))).tocoo()
+            dd = cur_pos[Wt.row] - cpos[Wt.col]
+            nb = len(Wt.row)
+            Pb = np.zeros((nb, 6, 6))
+            Pb[:, np.arange(6), np.arange(6)] = 1.0
+            Pb[:, 0, 4] = 2 * dd[:, 2]; Pb[:, 0, 5] = -2 * dd[:, 1]
+            Pb[:, 1, 3] = -2 * dd[:, 2]; Pb[:, 1, 5] = 2 * dd[:, 0]
+            Pb[:, 2, 3] = 2 * dd[:, 1]; Pb[:, 2, 4] = -2 * dd[:, 0]
+            Pb = Pb * (cur_Sinv[Wt.row][:, :, None]) * (cur_active[Wt.row] * Wt.data)[:, None, None]
+            order = np.lexsort((Wt.col, Wt.row))
+            indptr = np.concatenate([[0], np.cumsum(np.bincount(Wt.row, minlength=cur_n))])
+            P = sp.bsr_matrix((Pb[order], Wt.col[order], indptr), shape=(6 * cur_n, 6 * na)).tocsr()
+        else:
+            P = sp.bsr_matrix((Pb, agg, np.arange(cur_n + 1)), shape=(6 * cur_n, 6 * na)).tocsr()
         if args.smooth_p > 0:
             P = P - args.smooth_p * (L.Dinv @ (cur_A @ P))
         L.P = P
@@ -190,7 +212,7 @@ def vcycle(levels, k, r, args):
         x = x + om * (L.Dinv @ (r - L.A @ x))
     rc = L.P.T @ (r - L.A @ x)
     ec = vcycle(levels, k + 1, rc, args)
-    if args.gamma == 2 and k + 1 < len(levels) - 1:
+    if args.gamma == 2 and k + 1 < len(levels) - 1 and k + 1 <= args.gamma_depth:
         # W-cycle-ish second visit
         rc2 = rc - levels[k + 1].A @ ec
         ec = ec + vcycle(levels, k + 1, rc2, args)
@@ -233,8 +255,12 @@ def main():
     ap.add_argument("--nu", type=int, default=1)
     ap.add_argument("--over", type=float, default=1.0)
     ap.add_argument("--gamma", type=int, default=1)
+    ap.add_argument("--gamma-depth", type=int, default=99, help="levels 1..depth are visited twice (truncated W-cycle)")
     ap.add_argument("--smooth-p", type=float, default=0.0)
+    ap.add_argument("--geo-smooth", type=float, default=0.0, help="topology-only prolongator smoothing weight")
+    ap.add_argument("--geo-unweighted", action="store_true")
     ap.add_argument("--coarsest", type=int, default=8)
+    ap.add_argument("--dense-below", type=int, default=0, help="levels of at most this many nodes are solved exactly")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--theta", type=float, default=0.0)
     ap.add_argument("--loops", type=int, default=-1)
