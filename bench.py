@@ -145,7 +145,9 @@ def run_partitioned(P, torch, dist, g, rank, world, local_rank, barrier):
            "max_rank_slice": {"own_poses": int(smax[0].item()), "halo_poses": int(smax[1].item()), "edges": int(smax[2].item())},
            "nccl_bytes_per_pcg_iteration_per_rank": int(s.comm_bytes_per_pcg_iteration),
            "nccl_calls_per_pcg_iteration": int(s.comm_calls_per_pcg_iteration),
-           "nccl_bytes_per_solve_per_rank": int(s.comm_bytes)}
+           "nccl_bytes_per_solve_per_rank": int(s.comm_bytes),
+           "peer_memory_exchanges_per_pcg_iteration": int(s.peer_exchanges_per_pcg_iteration),
+           "peer_memory_bytes_per_solve_per_rank": int(s.peer_bytes)}
     if world > 1 and rank == 0:
         # agreement with the one-GPU solve of the same graph (rank 0's GPU, outside the timed region)
         G1 = P.Graph.from_dataset(g, device=local_rank)
@@ -153,7 +155,8 @@ def run_partitioned(P, torch, dist, g, rank, world, local_rank, barrier):
         p1 = G1.get_poses()
         G1.close()
         out["vs_one_gpu"] = {"max_abs_pose_diff": float(np.abs(poses - p1).max()), "lm_iterations_one_gpu": s1.num_iterations - 1,
-                             "pcg_iterations_one_gpu": int(s1.total_pcg_iterations), "final_cost_one_gpu": s1.final_cost}
+                             "pcg_iterations_one_gpu": int(s1.total_pcg_iterations), "final_cost_one_gpu": s1.final_cost,
+                             "device_ms_one_gpu_first_solve": s1.time_linear_solver_ms + s1.time_linearize_ms}
     if world > 1:
         dist.barrier()
     return out
@@ -448,8 +451,11 @@ def main():
                 sharded[key] = {"error": str(ex)[:300]}
         if line is not None:
             sharded["how"] = ("every rank passes the same global graph and keeps the block rows of a contiguous pose range; cut edges are "
-                              "evaluated by both owners; per PCG iteration halo slices + one 2-scalar all-reduce move over NCCL; "
-                              "linear solver: PCG preconditioned by the aggregation-multigrid V-cycle; time = CUDA events, max over ranks")
+                              "evaluated by both owners; per PCG iteration halo slices, one residual gather and one 2-scalar all-reduce "
+                              "move over NVLink peer memory (stores into the neighbours' windows + flags, no NCCL call: the iteration is "
+                              "one CUDA graph; NCCL when windows cannot be mapped); linear solver: PCG preconditioned by an "
+                              "aggregation-multigrid cycle (V; W on the first two coarse levels when a rank holds >= 400k poses) with the "
+                              "first level of <= 512 nodes inverted densely; time = CUDA events, max over ranks")
             line["sharded_large_graph"] = sharded
     # ---------------- loop-edge candidate search (the producer of the path's edge topology), rank 0 only ----------------
     if rank == 0 and line is not None:

@@ -140,7 +140,10 @@ typedef struct {
   long long comm_calls;          /* multi-GPU: NCCL calls issued by this rank during the solve */
   long long comm_bytes;          /*            payload bytes this rank sent */
   long long comm_bytes_per_pcg_iteration;   /* halo + gather + scalar payload this rank sends per PCG iteration */
-  int comm_calls_per_pcg_iteration;
+  int comm_calls_per_pcg_iteration;         /* NCCL calls per PCG iteration (0 when the exchanges run over peer memory) */
+  long long peer_exchanges;      /* multi-GPU: exchanges done over NVLink peer memory (pgo_peer.cuh) during the solve ... */
+  long long peer_bytes;          /*            ... and the bytes this rank stored into its peers' windows */
+  int peer_exchanges_per_pcg_iteration;
 } pgo_solver_summary;
 
 /* Result of the host-side structure analysis (no GPU needed). */

@@ -62,7 +62,8 @@ class SolverSummary(C.Structure):
                 ("hessian_blocks", C.c_longlong), ("factor_blocks", C.c_longlong), ("factor_levels", C.c_int),
                 ("amg_levels", C.c_int), ("amg_blocks", C.c_longlong), ("comm_calls", C.c_longlong),
                 ("comm_bytes", C.c_longlong), ("comm_bytes_per_pcg_iteration", C.c_longlong),
-                ("comm_calls_per_pcg_iteration", C.c_int)]
+                ("comm_calls_per_pcg_iteration", C.c_int), ("peer_exchanges", C.c_longlong), ("peer_bytes", C.c_longlong),
+                ("peer_exchanges_per_pcg_iteration", C.c_int)]
 
 
 class StructureInfo(C.Structure):

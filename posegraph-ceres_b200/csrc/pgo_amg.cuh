@@ -15,6 +15,8 @@
 // so P is never stored: restriction and prolongation cost one cross product per node.
 #pragma once
 
+#include <functional>
+
 #include "pgo_amg_host.hpp"
 
 namespace pgo {
@@ -36,6 +38,7 @@ struct AmgLevelDev {
   long long nnz = 0;
   double* Dinv = nullptr;                  // [n_own][36] row-major inverses of the diagonal blocks (level 0: Minv)
   double *r = nullptr, *x = nullptr, *y = nullptr;   // [n_own + n_halo][6]
+  double* z = nullptr;                     // third iterate buffer of the levels a W-cycle visits twice
   double* pos = nullptr;                   // [n_own + n_halo][pos_stride] (level 0: the pose array)
   int pos_stride = 3;
   // coarsening towards the next level
@@ -45,6 +48,11 @@ struct AmgLevelDev {
   // exchange plans (host copies drive the NCCL calls)
   std::vector<int> nbr, send_ptr, recv_ptr, gather_off, gather_slot_off;
   int* send_idx = nullptr;
+  // the same exchanges over peer memory (pgo_peer.cuh): halo of this level, residual gather INTO this level
+  int peer_ch = -1, gather_ch = -1;
+  PeerPushArgs push, gpush;
+  PeerWaitArgs wait, gwait;
+  int push_ctas = 1, wait_ctas = 1, gpush_ctas = 1, gwait_ctas = 1;
 };
 
 struct Amg {
@@ -56,6 +64,8 @@ struct Amg {
   double omega = 0.85;                     // damped block-Jacobi smoother (measured on the 1M grid and the 100k torus: 0.6 < 0.7 < 0.85)
   int nu = 1;
   int coarse_sweeps = 4;
+  int gamma = 1, gamma_depth = 0;          // cycle shape, see amg_vcycle
+  pgo_graph* owner = nullptr;
   PcgMultiState* state = nullptr;
   PcgMultiState* state_h = nullptr;        // pinned, two slots
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -70,6 +80,13 @@ struct Amg {
   std::vector<double*> tail_cur;
   struct IterGraph { const void* key[4]; int max_it; double tol; cudaGraphExec_t exec; int kernels; };
   std::vector<IterGraph> graphs;           // captured PCG iteration per (H, poses) buffer pair (the LM loop alternates two)
+  // multi-GPU: per-iteration exchanges over peer memory instead of NCCL (nullptr: NCCL)
+  PeerCtx* peer = nullptr;
+  PeerPushArgs rpush;                      // the 2-scalar all-reduce
+  PeerWaitArgs rwait;
+  bool whole_iteration_graph = false;      // the PCG iteration is being captured / replayed as ONE graph
+  unsigned long long* prof = nullptr;      // [64] PGO_AMG_PROFILE stage times (ns), [63] = the previous mark
+  int peer_exchanges_per_iteration = 0;
   long long blocks_all_levels = 0;
   long long comm_bytes_per_iteration = 0;  // payload this rank sends per PCG iteration (halo + gathers + scalars)
   int comm_calls_per_iteration = 0;
@@ -446,6 +463,23 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth0_kernel(int n, const d
   if (L.on) x[q] = omega * t;
 }
 
+// second visit of a level: r = t (the new right-hand side), x = omega * Dinv t
+__global__ void __launch_bounds__(kAmgThreads) amg_rhs_smooth0_kernel(int n, const double* __restrict__ Dinv, const double* __restrict__ t,
+                                                                      double omega, double* __restrict__ r, double* __restrict__ x, const int* skip) {
+  if (skip && *skip) return;
+  const RowLane L = amg_row_lane(n);
+  const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
+  const double tv = L.on ? t[q] : 0.0;
+  const double z = amg_block_row_dot(L.on ? Dinv + 36 * (size_t)L.i : nullptr, L.c, L.g0, tv);
+  if (L.on) { r[q] = tv; x[q] = omega * z; }
+}
+// y += x
+__global__ void amg_add_kernel(int n6, const double* __restrict__ x, double* __restrict__ y, const int* skip) {
+  if (skip && *skip) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n6) y[k] += x[k];
+}
+
 // y = x + omega * Dinv (r - A x)
 __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ Dinv,
                                                                  const double* __restrict__ r, const double* __restrict__ x, double omega,
@@ -641,6 +675,14 @@ __global__ void __launch_bounds__(kAmgThreads) amg_restrict_kernel(const double*
     const double z = amg_block_row_dot(on ? Dinv_c + 36 * (size_t)I : nullptr, on ? lane : 0, 0, on ? tot : 0.0);
     if (on) xc[6 * (size_t)I + lane] = omega * z;
   }
+}
+
+// PGO_AMG_PROFILE=1: device-side stage marks (capturable, one thread): acc[idx] += time since the previous mark
+__global__ void amg_mark_kernel(unsigned long long* acc, int idx, const int* skip) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  if (idx >= 0 && !(skip && *skip)) acc[idx] += t - acc[63];
+  acc[63] = t;
 }
 
 // ---- PCG pieces (Chronopoulos-Gear with a general preconditioner) ----
@@ -853,6 +895,7 @@ static void amg_destroy(pgo::Amg* M, int device) {
   pgo::pool_event_release(device, M->ev[1]);
   for (auto& e : M->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
   if (M->tail_graph) cudaGraphExecDestroy(M->tail_graph);
+  if (M->peer) peer_destroy(M->owner, M->peer);
   delete M;   // device blocks were borrowed through dev_alloc and go back with the graph's
 }
 
@@ -870,7 +913,28 @@ static int amg_exchange(pgo_graph* g, pgo::Amg* M, const pgo::AmgLevelDev& L, do
   (void)M;
   if (g->world <= 1 || L.replicated || L.nbr.empty()) return PGO_OK;
   if (stride != width) return set_error(PGO_ERR_INVALID_ARGUMENT, "amg_exchange: strided vectors are not supported");
+  if (M && M->peer && L.peer_ch >= 0 && width == 6) {
+    if (L.push.n_targets > 0) pgo::peer_push_kernel<<<L.push_ctas, pgo::kPeerThreads, 0, g->stream>>>(L.push, L.send_idx, v, skip);
+    if (L.wait.n_sources > 0) pgo::peer_wait_kernel<<<L.wait_ctas, pgo::kPeerThreads, 0, g->stream>>>(L.wait, v, skip);
+    g->launches += 2;
+    M->peer->pushes++; M->peer->push_bytes += (long long)L.send_ptr.back() * 48;
+    return PGO_OK;
+  }
   return halo_exchange(g, L.nbr, L.send_ptr, L.recv_ptr, L.send_idx, L.n_own, v, width, skip);
+}
+
+// Per-iteration all-gather of the residual of the first replicated level (rows computed rank by rank).
+static int amg_gather(pgo_graph* g, double* v, const std::vector<int>& off, int unit);
+static int amg_gather_residual(pgo_graph* g, pgo::Amg* M, const pgo::AmgLevelDev& C, const int* skip) {
+  if (g->world <= 1 || C.gather_off.empty()) return PGO_OK;
+  if (M->peer && C.gather_ch >= 0) {
+    if (C.gpush.n_targets > 0) pgo::peer_push_kernel<<<C.gpush_ctas, pgo::kPeerThreads, 0, g->stream>>>(C.gpush, nullptr, C.r, skip);
+    if (C.gwait.n_sources > 0) pgo::peer_wait_kernel<<<C.gwait_ctas, pgo::kPeerThreads, 0, g->stream>>>(C.gwait, C.r, skip);
+    g->launches += 2;
+    M->peer->pushes++; M->peer->push_bytes += (long long)(C.gather_off[g->rank + 1] - C.gather_off[g->rank]) * 48 * (g->world - 1);
+    return PGO_OK;
+  }
+  return amg_gather(g, C.r, C.gather_off, 6);
 }
 
 // All-gather of rank-owned ranges of a replicated array (`unit` doubles per item, item ranges off[r]..off[r+1]).
@@ -891,6 +955,91 @@ static int amg_gather(pgo_graph* g, double* v, const std::vector<int>& off, int 
 
 static int amg_allreduce(pgo_graph* g, double* buf, int count) { return allreduce_sum(g, buf, (size_t)count); }
 
+// Peer-memory channels of the per-iteration exchanges: the halo of every distributed level, the residual gather of the
+// first replicated level, the scalar all-reduce.  Collective; leaves M->peer == nullptr when windows cannot be mapped.
+static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
+  using namespace pgo;
+  const int nl = M->num_levels, W = g->world, me = g->rank;
+  std::vector<PeerChannelSpec> spec;
+  for (int l = 0; l < nl; ++l) {
+    AmgLevelDev& D = M->lv[l];
+    if (!D.replicated) {
+      PeerChannelSpec c;
+      c.stage_items = (size_t)D.n_halo;
+      c.recv_item_off.assign(W, -1);
+      for (size_t k = 0; k < D.nbr.size(); ++k)
+        if (D.recv_ptr[k + 1] > D.recv_ptr[k]) c.recv_item_off[D.nbr[k]] = D.recv_ptr[k];
+      // (the argument that two staging buffers are enough needs symmetric partners)
+      for (size_t k = 0; k < D.nbr.size(); ++k)
+        if ((D.recv_ptr[k + 1] > D.recv_ptr[k]) != (D.send_ptr[k + 1] > D.send_ptr[k])) return PGO_OK;
+      D.peer_ch = (int)spec.size();
+      spec.push_back(c);
+    }
+    if (!D.gather_off.empty()) {
+      PeerChannelSpec c;
+      c.stage_items = (size_t)D.n_own;
+      c.recv_item_off.assign(W, -1);
+      for (int r = 0; r < W; ++r) if (r != me && D.gather_off[r + 1] > D.gather_off[r]) c.recv_item_off[r] = D.gather_off[r];
+      D.gather_ch = (int)spec.size();
+      spec.push_back(c);
+    }
+  }
+  PeerChannelSpec red;
+  red.stage_items = (size_t)W;
+  red.recv_item_off.assign(W, -1);
+  for (int r = 0; r < W; ++r) if (r != me) red.recv_item_off[r] = r;
+  const int ch_red = (int)spec.size();
+  spec.push_back(red);
+  PGO_TRY(peer_create(g, spec, &M->peer));
+  if (!M->peer) {
+    for (auto& D : M->lv) { D.peer_ch = -1; D.gather_ch = -1; }
+    return PGO_OK;
+  }
+  const PeerCtx* P = M->peer;
+  auto ctas_for = [](long long doubles) { return (int)std::max<long long>(1, std::min<long long>(64, (doubles + 4 * kPeerThreads - 1) / (4 * kPeerThreads))); };
+  int* timeout = &M->state->pad;
+  for (int l = 0; l < nl; ++l) {
+    AmgLevelDev& D = M->lv[l];
+    if (D.peer_ch >= 0) {
+      D.push = peer_push_args(P, D.peer_ch, D.nbr, std::vector<int>(D.send_ptr.begin(), D.send_ptr.end() - 1),
+                              std::vector<int>(D.send_ptr.begin() + 1, D.send_ptr.end()));
+      std::vector<int> src;
+      for (size_t k = 0; k < D.nbr.size(); ++k) if (D.recv_ptr[k + 1] > D.recv_ptr[k]) src.push_back(D.nbr[k]);
+      D.wait = peer_wait_args(P, D.peer_ch, src);
+      D.wait.timeout_flag = timeout;
+      D.wait.n_copies = 1; D.wait.copy_src[0] = 0; D.wait.copy_dst[0] = 6 * D.n_own; D.wait.copy_n[0] = 6 * D.n_halo;
+      D.push_ctas = ctas_for(6ll * (D.send_ptr.empty() ? 0 : D.send_ptr.back()));
+      D.wait_ctas = ctas_for(6ll * D.n_halo);
+    }
+    if (D.gather_ch >= 0) {
+      std::vector<int> others, src;
+      for (int r = 0; r < W; ++r) {
+        if (r == me) continue;
+        others.push_back(r);
+        if (D.gather_off[r + 1] > D.gather_off[r]) src.push_back(r);
+      }
+      D.gpush = peer_push_args(P, D.gather_ch, others, std::vector<int>(others.size(), D.gather_off[me]),
+                               std::vector<int>(others.size(), D.gather_off[me + 1]));
+      D.gwait = peer_wait_args(P, D.gather_ch, src);
+      D.gwait.timeout_flag = timeout;
+      D.gwait.n_copies = 2;
+      D.gwait.copy_src[0] = 0; D.gwait.copy_dst[0] = 0; D.gwait.copy_n[0] = 6 * D.gather_off[me];
+      D.gwait.copy_src[1] = 6 * D.gather_off[me + 1]; D.gwait.copy_dst[1] = 6 * D.gather_off[me + 1];
+      D.gwait.copy_n[1] = 6 * (D.n_own - D.gather_off[me + 1]);
+      D.gpush_ctas = ctas_for(6ll * (D.gather_off[me + 1] - D.gather_off[me]) * (W - 1));
+      D.gwait_ctas = ctas_for(6ll * D.n_own);
+    }
+  }
+  {
+    std::vector<int> others;
+    for (int r = 0; r < W; ++r) if (r != me) others.push_back(r);
+    M->rpush = peer_push_args(P, ch_red, others, std::vector<int>(others.size(), 0), std::vector<int>(others.size(), 1));
+    M->rwait = peer_wait_args(P, ch_red, others);
+    M->rwait.timeout_flag = timeout;
+  }
+  return PGO_OK;
+}
+
 // Build the hierarchy for this graph (host analysis + uploads).  pos0: [N_global][3] setup-time positions.
 static int amg_create(pgo_graph* g, pgo::Amg** out) {
   using namespace pgo;
@@ -900,6 +1049,12 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   if (const char* e = getenv("PGO_AMG_OMEGA")) M->omega = atof(e);
   if (const char* e = getenv("PGO_AMG_NU")) M->nu = std::max(1, atoi(e));
   if (const char* e = getenv("PGO_AMG_COARSE_SWEEPS")) M->coarse_sweeps = std::max(1, atoi(e));
+  // cycle shape: a second visit of the first two coarse levels pays when level 0 is a long streaming sweep (>= 400 k rows
+  // here: 1M-pose grid 208 -> 120 PCG iterations per LM step, 5.2 -> 4.4 s); on smaller slices the extra coarse visits are
+  // pure launch latency and the V-cycle is faster (100 k torus: 354 ms V, 452 ms W) -- profiles/r2q_w_cycle_ab_1xB200.txt
+  if (g->n_own >= 400000) { M->gamma = 2; M->gamma_depth = 2; }
+  if (const char* e = getenv("PGO_AMG_GAMMA")) { M->gamma = std::max(1, atoi(e)); M->gamma_depth = M->gamma >= 2 ? 99 : 0; }
+  if (const char* e = getenv("PGO_AMG_GAMMA_DEPTH")) M->gamma_depth = std::max(0, atoi(e));
   std::vector<AmgGlobalLevel> G;
   std::vector<AmgLocalLevel> Lh;
   const double t0 = wall_s();
@@ -931,6 +1086,10 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
     }
     PGO_TRY(dev_alloc(g, &D.x, n_loc * 6));
     PGO_TRY(dev_alloc(g, &D.y, n_loc * 6));
+    if (l > 0) {
+      PGO_TRY(dev_alloc(g, &D.z, n_loc * 6));
+      CUDA_TRY(cudaMemsetAsync(D.z, 0, std::max<size_t>(n_loc * 6, 1) * sizeof(double), g->stream));
+    }
     CUDA_TRY(cudaMemsetAsync(D.x, 0, std::max<size_t>(n_loc * 6, 1) * sizeof(double), g->stream));
     CUDA_TRY(cudaMemsetAsync(D.y, 0, std::max<size_t>(n_loc * 6, 1) * sizeof(double), g->stream));
     if (l + 1 < nl) {
@@ -967,6 +1126,12 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   static_assert(2 * sizeof(PcgMultiState) <= kPinnedBytes, "pinned PCG state slots");
   CUDA_TRY(pool_event(g->device, &M->ev[0]));
   CUDA_TRY(pool_event(g->device, &M->ev[1]));
+  M->owner = g;
+  if (getenv("PGO_AMG_PROFILE")) {
+    PGO_TRY(dev_alloc(g, &M->prof, 64));
+    CUDA_TRY(cudaMemsetAsync(M->prof, 0, 64 * sizeof(unsigned long long), g->stream));
+  }
+  if (g->world > 1) PGO_TRY(amg_peer_setup(g, M));
   M->part_cap = 3 * std::max(8 * g->num_sms, 1);
   PGO_TRY(dev_alloc(g, &M->part, (size_t)M->part_cap));
   PGO_TRY(dev_alloc(g, &M->red, 8));
@@ -991,6 +1156,9 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   }
   return PGO_OK;
 }
+
+static long long amg_peer_pushes(const pgo_graph* g) { return g->amg && g->amg->peer ? g->amg->peer->pushes : 0; }
+static long long amg_peer_bytes(const pgo_graph* g) { return g->amg && g->amg->peer ? g->amg->peer->push_bytes : 0; }
 
 static pgo::BsrView amg_view(const pgo::AmgLevelDev& D) {
   pgo::BsrView A;
@@ -1061,6 +1229,10 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
   return PGO_OK;
 }
 
+static inline void amg_mark(pgo_graph* g, pgo::Amg* M, int idx) {
+  if (M->prof) pgo::amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, idx, &M->state->done);
+}
+
 // One smoothing sweep y = x + omega Dinv (r - A x) on level l (halo of x exchanged first).
 static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, const int* skip) {
   using namespace pgo;
@@ -1074,8 +1246,15 @@ static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, con
   return PGO_OK;
 }
 
-// u = M^-1 r: V(nu, nu) cycle.  Level 0: r = the CG residual (g->vr) and lv[0].x already holds omega Minv r.
+// u = M^-1 r: one multigrid cycle.  Level 0: r = the CG residual (g->vr) and lv[0].x already holds omega Minv r.
 // The result is a level-0 vector (owned rows valid); *out points at it.
+//
+// Cycle shape.  gamma == 1: V(nu, nu).  gamma == 2: levels 1 .. gamma_depth are visited TWICE from their parent (a
+// W-cycle truncated at gamma_depth): after the first coarse correction e = M r_c the parent asks for a second one on
+// r_c - A_c e and adds it -- the coarse operator applied is 2M - M A_c M, symmetric like M.  An aggregation cycle with
+// piecewise-rigid (unsmoothed) coarse spaces loses a constant factor per level (the pose-graph Hessian bends like a
+// plate: translations follow the integral of the rotations), and the second visit buys most of it back:
+// tools/amg_prototype.py --gamma 2, 400 x 400 grid 53 -> 34 iterations, and the 1M-pose grid below.
 static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
   using namespace pgo;
   const int nl = M->num_levels;
@@ -1097,6 +1276,7 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     // the next level's first sweep is fused unless its residual still has to be gathered or it is solved densely
     const bool coarsest_next = l + 2 == nl;
     const bool fuse_next = C.gather_off.empty() && !(coarsest_next && M->dense_inv);
+    cur[l + 1] = C.x; oth[l + 1] = C.y;
     if (ncomp > 0) {
       // residual into the spare buffer (small level: a whole warp per row; large level: streaming, six lanes per row),
       // then the restriction (a warp per coarse row)
@@ -1110,7 +1290,7 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
                                                                           M->omega, cur[l + 1], skip);
       g->launches += 2;
     }
-    if (!C.gather_off.empty()) PGO_TRY(amg_gather(g, C.r, C.gather_off, 6));
+    PGO_TRY(amg_gather_residual(g, M, C, skip));
     return PGO_OK;
   };
   auto coarsest = [&]() -> int {
@@ -1139,27 +1319,59 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     for (int s = 0; s < M->nu; ++s) { PGO_TRY(amg_sweep(g, M, l, cur[l], oth[l], skip)); std::swap(cur[l], oth[l]); }
     return PGO_OK;
   };
+  // second visit of level l (its first correction e = cur[l] stays where it is): r_l <- r_l - A_l e, a fresh cycle on
+  // it in the level's two other buffers, e += its result
+  std::function<int(int)> cycle;
+  auto revisit = [&](int l) -> int {
+    const AmgLevelDev& D = M->lv[l];
+    double* e = cur[l];
+    double* b1 = e == D.x ? D.y : D.x;
+    double* b2 = e == D.z ? D.y : D.z;
+    PGO_TRY(amg_exchange(g, M, D, e, 6, 6, skip));
+    if (D.n_own <= kAmgWarpRowMax)
+      amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), nullptr, nullptr, D.r, e, 0.0, b2, skip);
+    else
+      amg_residual_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), nullptr, D.r, e, b2, skip);
+    amg_rhs_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, b2, M->omega, D.r, b1, skip);
+    g->launches += 2;
+    cur[l] = b1; oth[l] = b2;
+    PGO_TRY(cycle(l));
+    amg_add_kernel<<<(6 * D.n_own + 255) / 256, 256, 0, g->stream>>>(6 * D.n_own, e, cur[l], skip);
+    g->launches++;
+    return PGO_OK;
+  };
+  // one cycle from level l down and back: on entry lv[l].r holds the right-hand side and cur[l] = omega Dinv r
+  cycle = [&](int l) -> int {
+    if (l == nl - 1) { PGO_TRY(coarsest()); amg_mark(g, M, nl - 1); return PGO_OK; }
+    PGO_TRY(down(l));
+    amg_mark(g, M, l);
+    PGO_TRY(cycle(l + 1));
+    if (M->gamma >= 2 && l + 1 < nl - 1 && l + 1 <= M->gamma_depth) PGO_TRY(revisit(l + 1));
+    PGO_TRY(up(l));
+    amg_mark(g, M, nl + l);
+    return PGO_OK;
+  };
   // Levels [Lc, nl) are the replicated tail of a multi-GPU hierarchy (one GPU: just the coarsest): no communication in
   // there, the same launches with the same pointers in every cycle -- and each of them a few microseconds long, i.e.
-  // launch bound.  Multi-GPU runs replay that tail as a CUDA graph (NCCL stays outside of captures; on one GPU the whole
-  // PCG iteration is one graph anyway).
+  // launch bound.  Multi-GPU runs whose exchanges go through NCCL replay that tail as a CUDA graph (NCCL stays outside
+  // of captures; with peer-memory exchanges and on one GPU the whole PCG iteration is one graph anyway).
   int Lr = nl;
   for (int l = nl - 1; l >= 0; --l) if (g->world > 1 && M->lv[l].replicated) Lr = l;
   const int Lc = std::min(Lr, nl - 1);
-  auto tail = [&]() -> int {
-    for (int l = Lc; l + 1 < nl; ++l) PGO_TRY(down(l));
-    PGO_TRY(coarsest());
-    for (int l = nl - 2; l >= Lc; --l) PGO_TRY(up(l));
-    return PGO_OK;
-  };
-  for (int l = 0; l < Lc; ++l) PGO_TRY(down(l));
   static const bool tail_graph_off = getenv("PGO_AMG_TAIL_GRAPH") && atoi(getenv("PGO_AMG_TAIL_GRAPH")) == 0;
-  const bool want_tail_graph = g->world > 1 && Lc < nl - 1 && !tail_graph_off;
-  if (want_tail_graph && M->tail_graph) {
+  const bool want_tail_graph = g->world > 1 && Lc < nl - 1 && Lc > 0 && !tail_graph_off && !M->whole_iteration_graph && M->gamma < 2;
+  if (!want_tail_graph) {
+    PGO_TRY(cycle(0));
+    *out = cur[0];
+    return PGO_OK;
+  }
+  for (int l = 0; l < Lc; ++l) { PGO_TRY(down(l)); amg_mark(g, M, l); }
+  auto tail = [&]() -> int { return cycle(Lc); };
+  if (M->tail_graph) {
     CUDA_TRY(cudaGraphLaunch(M->tail_graph, g->stream));
     g->launches += M->tail_graph_kernels;
     for (int l = Lc; l < nl; ++l) cur[l] = M->tail_cur[l];
-  } else if (want_tail_graph && M->tail_calls >= 1 && !M->tail_graph_failed) {
+  } else if (M->tail_calls >= 1 && !M->tail_graph_failed) {
     // (the first cycle ran as plain launches: every lazy initialisation is behind us)
     const std::vector<double*> cur0 = cur, oth0 = oth;
     const long long l0 = g->launches;
@@ -1186,7 +1398,7 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     PGO_TRY(tail());
     M->tail_calls++;
   }
-  for (int l = Lc - 1; l >= 0; --l) PGO_TRY(up(l));
+  for (int l = Lc - 1; l >= 0; --l) { PGO_TRY(up(l)); amg_mark(g, M, nl + l); }
   *out = cur[0];
   return PGO_OK;
 }
@@ -1198,8 +1410,10 @@ static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_opt
   PcgMultiState* st = M->state;
   const int n = L0.n_own;
   double* u = nullptr;
+  const int nl = M->num_levels;
   PGO_TRY(amg_vcycle(g, M, &u));
   PGO_TRY(amg_exchange(g, M, L0, u, 6, 6, &st->done));
+  amg_mark(g, M, 2 * nl);
   if (M->warp_spmv) {
     amg_spmv_dots_warp_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(amg_view(L0), g->dlm, u, g->vr, g->vw, M->part, &st->done);
   } else {
@@ -1207,15 +1421,25 @@ static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_opt
     amg_dot_kernel<<<sp_ctas, kAmgThreads, 0, g->stream>>>(6 * n, g->vr, u, M->part + sp_ctas, &st->done);
     g->launches++;
   }
+  amg_mark(g, M, 2 * nl + 1);
   if (g->world > 1) {
     amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
-    PGO_TRY(amg_allreduce(g, M->red, 2));
+    if (M->peer) {
+      peer_push_kernel<<<1, kPeerThreads, 0, g->stream>>>(M->rpush, nullptr, M->red, &st->done);
+      peer_allreduce_wait_kernel<<<1, 32, 0, g->stream>>>(M->rwait, g->world, g->rank, 2, M->red, M->red, &st->done);
+      g->launches += 2;
+      M->peer->pushes++; M->peer->push_bytes += 48ll * (g->world - 1);
+    } else {
+      PGO_TRY(amg_allreduce(g, M->red, 2));
+    }
     amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
     g->launches++;
   } else {
     amg_pcg_reduce_scalar_kernel<<<1, kAmgThreads, 0, g->stream>>>(st, M->part, sp_ctas, o->pcg_max_iterations, o->pcg_tolerance);
   }
+  amg_mark(g, M, 2 * nl + 2);
   amg_pcg_update_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
+  amg_mark(g, M, 2 * nl + 3);
   g->launches += 3;
   return PGO_OK;
 }
@@ -1240,8 +1464,11 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
   CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
   amg_pcg_init_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, g->Minv, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
   g->launches++;
+  if (M->prof) amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, -1, nullptr);
   static const int graph_env = getenv("PGO_AMG_GRAPH") ? atoi(getenv("PGO_AMG_GRAPH")) : -1;
-  const bool use_graph = graph_env >= 0 ? graph_env != 0 : g->world == 1;
+  // (multi-GPU: only when every per-iteration exchange runs over peer memory -- NCCL calls stay out of captures)
+  const bool use_graph = (graph_env >= 0 ? graph_env != 0 : true) && (g->world == 1 || M->peer != nullptr);
+  M->whole_iteration_graph = use_graph;
   Amg::IterGraph* ig = nullptr;
   if (use_graph) {
     const void* key[4] = {g->Hdiag, g->Hoff, g->poses, g->scale};
@@ -1283,9 +1510,23 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
     if (enqueued >= 2) {
       const int prev = (enqueued - 2) & 1;
       CUDA_TRY(cudaEventSynchronize(M->ev[prev]));
+      if (M->state_h[prev].pad) return set_error(PGO_ERR_NCCL, "multilevel PCG: a peer-memory exchange timed out (a rank of the solve is gone?)");
       if (M->state_h[prev].done) finished = true;
     }
     if (enqueued >= max_batches) finished = true;
+  }
+  if (M->prof && g->rank == 0 && getenv("PGO_AMG_PROFILE") && atoi(getenv("PGO_AMG_PROFILE")) > 1) {
+    // cumulative stage times so far (all solves of this graph): printed after every solve at level 2
+    unsigned long long h[64];
+    CUDA_TRY(cudaMemcpyAsync(h, M->prof, sizeof h, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    const int nl = M->num_levels;
+    fprintf(stderr, "[pgo amg profile] cumulative ms:");
+    for (int l = 0; l + 1 < nl; ++l) fprintf(stderr, " down%d %.2f", l, 1e-6 * (double)h[l]);
+    fprintf(stderr, " coarsest %.2f", 1e-6 * (double)h[nl - 1]);
+    for (int l = nl - 2; l >= 0; --l) fprintf(stderr, " up%d %.2f", l, 1e-6 * (double)h[nl + l]);
+    fprintf(stderr, " | exchange(u) %.2f spmv+dots %.2f reduce+scalar %.2f update %.2f\n", 1e-6 * (double)h[2 * nl], 1e-6 * (double)h[2 * nl + 1],
+            1e-6 * (double)h[2 * nl + 2], 1e-6 * (double)h[2 * nl + 3]);
   }
   // epilogue: w = A x for the model cost change
   PGO_TRY(amg_exchange(g, M, L0, g->vx, 6, 6, nullptr));

@@ -308,9 +308,9 @@ extern "C" void pgo_graph_destroy(pgo_graph* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->own_stream && g->own_stream != g->stream) cudaStreamSynchronize(g->own_stream);
   // a rank that failed inside a collective solve must not leave its peers blocked in NCCL: abort instead of a graceful destroy
+  if (g->amg) amg_destroy(g->amg, g->device);   // (its peer windows close with a last collective: before the communicator goes)
   if (g->comm) { if (g->failed) ncclCommAbort(g->comm); else ncclCommDestroy(g->comm); }
   if (g->chol) level_chol_destroy(g->chol, g->device);
-  if (g->amg) amg_destroy(g->amg, g->device);
   if (g->lm_graph) cudaGraphExecDestroy(g->lm_graph);
   for (auto& blk : g->blocks) pool_free(g->device, blk.first, blk.second);
   pool_pinned_release(g->device, g->scalars_h);
@@ -1176,6 +1176,7 @@ static int graph_amg_hierarchy(pgo_graph* g, const AmgHostParams& prm, std::vect
   amg_localize(*G, g->rank, g->world, l0, L);
   return PGO_OK;
 }
+#include "pgo_peer.cuh"
 #include "pgo_amg.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -1451,6 +1452,7 @@ static int graph_solve_impl(pgo_graph* g, const pgo_solver_options* opt, pgo_sol
   const int R = g->n_own;        // block rows = variables stored here
   const int tpb = 128, nblk = (R + tpb - 1) / tpb;
   const long long comm_calls0 = g->comm_calls, comm_bytes0 = g->comm_bytes;
+  const long long peer_x0 = amg_peer_pushes(g), peer_b0 = amg_peer_bytes(g);
   const int solver = resolve_linear_solver(g, opt);
   if (solver < 0) return solver;
   summary->linear_solver_used = solver;
@@ -1638,6 +1640,12 @@ static int graph_solve_impl(pgo_graph* g, const pgo_solver_options* opt, pgo_sol
   summary->comm_calls = g->comm_calls - comm_calls0;
   summary->comm_bytes = g->comm_bytes - comm_bytes0;
   if (g->amg) { summary->comm_bytes_per_pcg_iteration = g->amg->comm_bytes_per_iteration; summary->comm_calls_per_pcg_iteration = g->amg->comm_calls_per_iteration; }
+  summary->peer_exchanges = amg_peer_pushes(g) - peer_x0;
+  summary->peer_bytes = amg_peer_bytes(g) - peer_b0;
+  if (g->amg && g->amg->peer) {
+    summary->peer_exchanges_per_pcg_iteration = g->amg->comm_calls_per_iteration;
+    summary->comm_calls_per_pcg_iteration = 0;
+  }
   summary->kernel_launches = g->launches - launches0;
   summary->time_total_s = wall_s() - t_begin;
   return PGO_OK;

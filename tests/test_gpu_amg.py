@@ -35,13 +35,20 @@ def _check_against_oracle(pgo, oracle, g, options=None, pos_tol=1e-4, rot_tol=1e
     return s, its, dp
 
 
-@pytest.mark.parametrize("name", ["manhattan", "sphere200", "grid", "torus"])
-def test_amg_linear_solve_matches_oracle_cholesky(pgo, oracle, name):
+@pytest.mark.parametrize("name", ["manhattan", "sphere200", "grid", "torus", "grid40_dense_level", "grid40_w_cycle"])
+def test_amg_linear_solve_matches_oracle_cholesky(pgo, oracle, name, monkeypatch):
     """(J^T J + D) y = J^T r by the multilevel PCG vs the oracle's sparse Cholesky, on graphs of 100 .. 400 poses
-    (two to three levels)."""
+    (two to three levels, coarsest inverted in shared memory) and on a 1 600-pose grid whose last level (> 16 nodes) is
+    inverted by the cooperative-grid block Gauss-Jordan kernel -- with the V-cycle and with the W-cycle."""
     D = pgo.datasets
+    if name == "grid40_w_cycle":
+        monkeypatch.setenv("PGO_AMG_GAMMA", "2")
     g = {"manhattan": D.manhattan_loop(), "sphere200": D.sphere(10, 20, None), "grid": D.manhattan_grid(12, 15, 20),
-         "torus": D.torus(400, winds=10)}[name]
+         "torus": D.torus(400, winds=10), "grid40_dense_level": D.manhattan_grid(40, 40, 80),
+         "grid40_w_cycle": D.manhattan_grid(40, 40, 80)}[name]
+    if name.startswith("grid40"):
+        sizes, _ = pgo.amg_aggregates(g, 1)
+        assert 16 < sizes[-1] <= 100 and len(sizes) >= 3, sizes
     G = pgo.Graph.from_dataset(g)
     G.linearize(loss_type=1, loss_a=1.0)
     _, _, _, grad = G.hessian()

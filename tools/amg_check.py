@@ -25,6 +25,8 @@ ap.add_argument("--cases", default="")
 ap.add_argument("--tol", type=float, default=0.0)
 ap.add_argument("--no-oracle", action="store_true")
 ap.add_argument("--verbose", type=int, default=0)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--no-1gpu", action="store_true", help="multi-GPU: skip the one-GPU comparison solve on rank 0")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -63,7 +65,7 @@ for name in names:
     o.verbose = args.verbose if rank == 0 else 0
     G.snapshot_poses()
     best = None
-    for rep in range(2):
+    for rep in range(args.reps):
         G.restore_poses()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -89,7 +91,7 @@ for name in names:
         line += f" | rank spread {spread:.1e}"
         ok &= spread == 0.0
     if rank == 0:
-        if world > 1:
+        if world > 1 and not args.no_1gpu:
             G1 = P.Graph.from_dataset(g, device=local)
             s1, _ = G1.solve(o)
             p1 = G1.get_poses()

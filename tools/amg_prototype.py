@@ -103,22 +103,73 @@ def block_diag_inv(A, n):
     """inverse of the 6x6 diagonal blocks -> BSR"""
     Ab = A.tobsr(blocksize=(6, 6))
     Dinv = np.zeros((n, 6, 6))
-    for i in range(n):
-        for p in range(Ab.indptr[i], Ab.indptr[i + 1]):
-            if Ab.indices[p] == i:
-                Dinv[i] = np.linalg.inv(Ab.data[p])
+    rows = np.repeat(np.arange(n), np.diff(Ab.indptr))
+    sel = np.nonzero(Ab.indices == rows)[0]
+    Dinv[rows[sel]] = np.linalg.inv(Ab.data[sel])
     return sp.bsr_matrix((Dinv, np.arange(n), np.arange(n + 1)), shape=(6 * n, 6 * n)).tocsr()
+
+
+def pair_block_diag_inv(A, n, pos, theta, levels_left):
+    """Block-Jacobi inverse whose blocks are 12x12 for pairs of nodes joined by a geometrically WEAK (long-range) edge
+    (greedy matching, strongest algebraic coupling first), 6x6 elsewhere."""
+    Ab = A.tobsr(blocksize=(6, 6))
+    rows = np.repeat(np.arange(n), np.diff(Ab.indptr))
+    cols = Ab.indices
+    off = rows != cols
+    d2 = np.sum((pos[rows] - pos[cols]) ** 2, axis=1) + 1e-12
+    wgt = np.where(off, 1.0 / d2, 0.0)
+    W = sp.csr_matrix((wgt, (rows, cols)), shape=(n, n))
+    rmax = W.max(axis=1).toarray().ravel()
+    weak = off & (wgt < theta * np.maximum(rmax[rows], rmax[cols])) & (rows < cols)
+    nrm = np.linalg.norm(Ab.data.reshape(-1, 36), axis=1)
+    cand = np.nonzero(weak)[0]
+    cand = cand[np.argsort(-nrm[cand])]
+    mate = -np.ones(n, int)
+    for k in cand:
+        i, j = rows[k], cols[k]
+        if mate[i] < 0 and mate[j] < 0:
+            mate[i] = j; mate[j] = i
+    # dense lookup of blocks
+    diag_sel = np.nonzero(~off)[0]
+    Dblk = np.zeros((n, 6, 6)); Dblk[rows[diag_sel]] = Ab.data[diag_sel]
+    key = {}
+    for k in np.nonzero(off & (mate[rows] == cols))[0]:
+        key[(rows[k], cols[k])] = Ab.data[k]
+    ri, ci, vals = [], [], []
+    single = np.nonzero(mate < 0)[0]
+    inv_single = np.linalg.inv(Dblk[single])
+    for t, i in enumerate(single):
+        pass
+    data_rows = []; data_cols = []; data_vals = []
+    # singles as BSR
+    S = sp.bsr_matrix((inv_single, single, np.arange(len(single) + 1)), shape=(6 * len(single), 6 * n))
+    R = sp.csr_matrix((np.ones(6 * len(single)), (np.repeat(single, 6) * 6 + np.tile(np.arange(6), len(single)), np.arange(6 * len(single)))), shape=(6 * n, 6 * len(single)))
+    Dinv = (R @ S).tocsr()
+    pairs = [(i, mate[i]) for i in range(n) if mate[i] > i]
+    if pairs:
+        pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
+        B = np.zeros((len(pairs), 12, 12))
+        B[:, :6, :6] = Dblk[pi]; B[:, 6:, 6:] = Dblk[pj]
+        for t, (i, j) in enumerate(pairs):
+            B[t, :6, 6:] = key[(i, j)]; B[t, 6:, :6] = key[(j, i)]
+        Bi = np.linalg.inv(B)
+        idx = np.concatenate([pi[:, None] * 6 + np.arange(6)[None, :], pj[:, None] * 6 + np.arange(6)[None, :]], axis=1)   # (np, 12)
+        rr = np.repeat(idx[:, :, None], 12, axis=2).ravel(); cc = np.repeat(idx[:, None, :], 12, axis=1).ravel()
+        Dinv = Dinv + sp.csr_matrix((Bi.ravel(), (rr, cc)), shape=(6 * n, 6 * n))
+    print(f"    pair smoother: {len(pairs)} pairs of {n} nodes")
+    return Dinv.tocsr()
 
 
 class Level:
     pass
 
 
-def build_hierarchy(A, pos, n, scale_inv, args, active):
+def build_hierarchy(A, pos, n, scale_inv, args, active, A_far=None):
     """A: (6n x 6n) csr incl. LM diagonal, in SCALED coordinates; pos: (n,3) positions; scale_inv (n,6): 1/scale
     (the rigid-body modes of the unscaled problem are B_i = [[I, -2[p_i - c]x],[0, I]]; scaled: S^-1 B)."""
     levels = []
     cur_A, cur_pos, cur_n = A, pos, n
+    cur_far = A_far
     cur_Sinv = scale_inv
     cur_active = active
     while True:
@@ -126,6 +177,9 @@ def build_hierarchy(A, pos, n, scale_inv, args, active):
         L.A = cur_A
         L.n = cur_n
         L.Dinv = block_diag_inv(cur_A, cur_n) if cur_n > 0 else None
+        L.Dsm = L.Dinv
+        if args.pair_levels > len(levels) and cur_n > args.dense_below and cur_n > args.coarsest:
+            L.Dsm = pair_block_diag_inv(cur_A, cur_n, cur_pos, max(args.theta, 0.3), 0)
         levels.append(L)
         if (cur_n <= args.coarsest and not (args.agg == "cxx" and len(levels) - 1 < len(args.cxx_aggs))) or cur_n <= args.dense_below:
             L.dense = np.linalg.pinv(cur_A.toarray())
@@ -195,7 +249,13 @@ def build_hierarchy(A, pos, n, scale_inv, args, active):
         if args.smooth_p > 0:
             P = P - args.smooth_p * (L.Dinv @ (cur_A @ P))
         L.P = P
-        cur_A = (P.T @ cur_A @ P).tocsr()
+        if cur_far is not None and args.local_scale != 1.0:
+            far_c = (P.T @ cur_far @ P).tocsr()
+            near_c = (P.T @ (cur_A - cur_far) @ P).tocsr()
+            cur_A = (near_c / args.local_scale + far_c).tocsr()
+            cur_far = far_c
+        else:
+            cur_A = (P.T @ cur_A @ P).tocsr()
         cur_pos, cur_n = cpos, na
         cur_Sinv = np.ones((na, 6))
         cur_active = np.ones(na)
@@ -207,9 +267,9 @@ def vcycle(levels, k, r, args):
     if k == len(levels) - 1:
         return L.dense @ r
     om = args.omega
-    x = om * (L.Dinv @ r)
+    x = om * (L.Dsm @ r)
     for _ in range(args.nu - 1):
-        x = x + om * (L.Dinv @ (r - L.A @ x))
+        x = x + om * (L.Dsm @ (r - L.A @ x))
     rc = L.P.T @ (r - L.A @ x)
     ec = vcycle(levels, k + 1, rc, args)
     if args.gamma == 2 and k + 1 < len(levels) - 1 and k + 1 <= args.gamma_depth:
@@ -218,7 +278,7 @@ def vcycle(levels, k, r, args):
         ec = ec + vcycle(levels, k + 1, rc2, args)
     x = x + args.over * (L.P @ ec)
     for _ in range(args.nu):
-        x = x + om * (L.Dinv @ (r - L.A @ x))
+        x = x + om * (L.Dsm @ (r - L.A @ x))
     return x
 
 
@@ -266,6 +326,9 @@ def main():
     ap.add_argument("--loops", type=int, default=-1)
     ap.add_argument("--world", type=int, default=1)
     ap.add_argument("--at-truth", action="store_true")
+    ap.add_argument("--no-jacobi", action="store_true")
+    ap.add_argument("--local-scale", type=float, default=1.0, help="coarse operators: local (non-loop) part divided by this per level")
+    ap.add_argument("--pair-levels", type=int, default=0, help="levels 0..k-1 smooth with 12x12 blocks over long-range edge pairs")
     args = ap.parse_args()
     if args.graph == "sphere":
         g = D.sphere()
@@ -300,10 +363,25 @@ def main():
         # constant pose rows: identity-ish (diag = d only) -- fine
         Dinv = block_diag_inv(A, N)
         t0 = time.time()
-        _, it_j = pcg(A, gs, lambda r: Dinv @ r, args.tol, 20000)
+        it_j = -1
+        if not args.no_jacobi:
+            _, it_j = pcg(A, gs, lambda r: Dinv @ r, args.tol, 20000)
         tj = time.time() - t0
         t0 = time.time()
-        levels = build_hierarchy(A, poses[:, :3], N, scale_inv, args, active)
+        A_far = None
+        if args.local_scale != 1.0:
+            far = np.abs(g.edge_ids[:, 0] - g.edge_ids[:, 1]) > 1
+            if args.graph == "grid":
+                s_ = args.n or 100
+                far = np.arange(g.n_edges) >= (s_ * s_ - 1) + (s_ - 1) * s_ - s_   # the random loops come last
+                far &= np.abs(g.edge_ids[:, 0] - g.edge_ids[:, 1]) > 2 * s_
+            class _G: pass
+            gf = _G()
+            gf.edge_ids = g.edge_ids[far]; gf.n_edges = int(far.sum()); gf.n_poses = g.n_poses
+            Hf = assemble(gf, jac[far])
+            A_far = (S @ Hf @ S).tocsr()
+            print(f"    far edges: {int(far.sum())}")
+        levels = build_hierarchy(A, poses[:, :3], N, scale_inv, args, active, A_far)
         tb = time.time() - t0
         sizes = [L.n for L in levels]
         nnz = [L.A.nnz // 36 for L in levels]
