@@ -818,6 +818,26 @@ __device__ __forceinline__ void amg_pcg_scalar_step(PcgMultiState* st, double de
 __global__ void amg_pcg_scalar_kernel(PcgMultiState* st, const double* __restrict__ red, int max_iterations, double tol) {
   if (threadIdx.x == 0) amg_pcg_scalar_step(st, red[0], red[1], max_iterations, tol);
 }
+// multi-GPU over peer memory: wait for every rank's partial sums (pushed into slot [rank] of my window), add them in
+// rank order -- bit-identical on every rank -- and take the scalar step (one warp)
+__global__ void amg_pcg_scalar_peer_kernel(const PeerWaitArgs A, int world, int me, const double* __restrict__ mine, PcgMultiState* st,
+                                           int max_iterations, double tol) {
+  if (st->done) return;
+  const unsigned int s = *A.seq;
+  if (threadIdx.x < A.n_sources) {
+    if (!peer_spin(A.flags + A.src_rank[threadIdx.x], s) && A.timeout_flag) *A.timeout_flag = 1;
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const double* stage = A.stage[s & 1];
+    double d = 0.0, gm = 0.0;
+    for (int r = 0; r < world; ++r) {
+      d += r == me ? mine[0] : __ldcg(stage + 6 * (size_t)r);
+      gm += r == me ? mine[1] : __ldcg(stage + 6 * (size_t)r + 1);
+    }
+    amg_pcg_scalar_step(st, d, gm, max_iterations, tol);
+  }
+}
 // one GPU: sum the per-CTA partials (fixed order) and take the scalar step in the same one-CTA kernel
 __global__ void __launch_bounds__(kAmgThreads) amg_pcg_reduce_scalar_kernel(PcgMultiState* st, const double* __restrict__ part, int nparts,
                                                                             int max_iterations, double tol) {
@@ -914,8 +934,12 @@ static int amg_exchange(pgo_graph* g, pgo::Amg* M, const pgo::AmgLevelDev& L, do
   if (g->world <= 1 || L.replicated || L.nbr.empty()) return PGO_OK;
   if (stride != width) return set_error(PGO_ERR_INVALID_ARGUMENT, "amg_exchange: strided vectors are not supported");
   if (M && M->peer && L.peer_ch >= 0 && width == 6) {
-    if (L.push.n_targets > 0) pgo::peer_push_kernel<<<L.push_ctas, pgo::kPeerThreads, 0, g->stream>>>(L.push, L.send_idx, v, skip);
+    const bool prof = M->prof && skip;   // PGO_AMG_PROFILE: [40] time before the exchange since the last mark, [41] push, [42] wait
+    if (prof) pgo::amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, 40, skip);
+    if (L.push.n_targets > 0) pgo::peer_push_kernel<<<dim3(L.push_ctas, L.push.n_targets), pgo::kPeerThreads, 0, g->stream>>>(L.push, L.send_idx, v, skip);
+    if (prof) pgo::amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, 41, skip);
     if (L.wait.n_sources > 0) pgo::peer_wait_kernel<<<L.wait_ctas, pgo::kPeerThreads, 0, g->stream>>>(L.wait, v, skip);
+    if (prof) pgo::amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, 42, skip);
     g->launches += 2;
     M->peer->pushes++; M->peer->push_bytes += (long long)L.send_ptr.back() * 48;
     return PGO_OK;
@@ -928,7 +952,7 @@ static int amg_gather(pgo_graph* g, double* v, const std::vector<int>& off, int 
 static int amg_gather_residual(pgo_graph* g, pgo::Amg* M, const pgo::AmgLevelDev& C, const int* skip) {
   if (g->world <= 1 || C.gather_off.empty()) return PGO_OK;
   if (M->peer && C.gather_ch >= 0) {
-    if (C.gpush.n_targets > 0) pgo::peer_push_kernel<<<C.gpush_ctas, pgo::kPeerThreads, 0, g->stream>>>(C.gpush, nullptr, C.r, skip);
+    if (C.gpush.n_targets > 0) pgo::peer_push_kernel<<<dim3(C.gpush_ctas, C.gpush.n_targets), pgo::kPeerThreads, 0, g->stream>>>(C.gpush, nullptr, C.r, skip);
     if (C.gwait.n_sources > 0) pgo::peer_wait_kernel<<<C.gwait_ctas, pgo::kPeerThreads, 0, g->stream>>>(C.gwait, C.r, skip);
     g->launches += 2;
     M->peer->pushes++; M->peer->push_bytes += (long long)(C.gather_off[g->rank + 1] - C.gather_off[g->rank]) * 48 * (g->world - 1);
@@ -1008,7 +1032,11 @@ static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
       D.wait = peer_wait_args(P, D.peer_ch, src);
       D.wait.timeout_flag = timeout;
       D.wait.n_copies = 1; D.wait.copy_src[0] = 0; D.wait.copy_dst[0] = 6 * D.n_own; D.wait.copy_n[0] = 6 * D.n_halo;
-      D.push_ctas = ctas_for(6ll * (D.send_ptr.empty() ? 0 : D.send_ptr.back()));
+      {
+        long long most = 0;
+        for (size_t k = 0; k + 1 < D.send_ptr.size(); ++k) most = std::max<long long>(most, D.send_ptr[k + 1] - D.send_ptr[k]);
+        D.push_ctas = (int)std::max<long long>(1, std::min<long long>(16, (6 * most + 8 * kPeerThreads - 1) / (8 * kPeerThreads)));
+      }
       D.wait_ctas = ctas_for(6ll * D.n_halo);
     }
     if (D.gather_ch >= 0) {
@@ -1026,7 +1054,7 @@ static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
       D.gwait.copy_src[0] = 0; D.gwait.copy_dst[0] = 0; D.gwait.copy_n[0] = 6 * D.gather_off[me];
       D.gwait.copy_src[1] = 6 * D.gather_off[me + 1]; D.gwait.copy_dst[1] = 6 * D.gather_off[me + 1];
       D.gwait.copy_n[1] = 6 * (D.n_own - D.gather_off[me + 1]);
-      D.gpush_ctas = ctas_for(6ll * (D.gather_off[me + 1] - D.gather_off[me]) * (W - 1));
+      D.gpush_ctas = (int)std::max<long long>(1, std::min<long long>(16, (6ll * (D.gather_off[me + 1] - D.gather_off[me]) + 8 * kPeerThreads - 1) / (8 * kPeerThreads)));
       D.gwait_ctas = ctas_for(6ll * D.n_own);
     }
   }
@@ -1425,14 +1453,14 @@ static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_opt
   if (g->world > 1) {
     amg_reduce_kernel<<<1, kAmgThreads, 0, g->stream>>>(M->part, sp_ctas, 2, M->red);
     if (M->peer) {
-      peer_push_kernel<<<1, kPeerThreads, 0, g->stream>>>(M->rpush, nullptr, M->red, &st->done);
-      peer_allreduce_wait_kernel<<<1, 32, 0, g->stream>>>(M->rwait, g->world, g->rank, 2, M->red, M->red, &st->done);
-      g->launches += 2;
+      peer_push_kernel<<<dim3(1, M->rpush.n_targets), 32, 0, g->stream>>>(M->rpush, nullptr, M->red, &st->done);
+      amg_pcg_scalar_peer_kernel<<<1, 32, 0, g->stream>>>(M->rwait, g->world, g->rank, M->red, st, o->pcg_max_iterations, o->pcg_tolerance);
+      g->launches += 1;
       M->peer->pushes++; M->peer->push_bytes += 48ll * (g->world - 1);
     } else {
       PGO_TRY(amg_allreduce(g, M->red, 2));
+      amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
     }
-    amg_pcg_scalar_kernel<<<1, 32, 0, g->stream>>>(st, M->red, o->pcg_max_iterations, o->pcg_tolerance);
     g->launches++;
   } else {
     amg_pcg_reduce_scalar_kernel<<<1, kAmgThreads, 0, g->stream>>>(st, M->part, sp_ctas, o->pcg_max_iterations, o->pcg_tolerance);
@@ -1525,8 +1553,9 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
     for (int l = 0; l + 1 < nl; ++l) fprintf(stderr, " down%d %.2f", l, 1e-6 * (double)h[l]);
     fprintf(stderr, " coarsest %.2f", 1e-6 * (double)h[nl - 1]);
     for (int l = nl - 2; l >= 0; --l) fprintf(stderr, " up%d %.2f", l, 1e-6 * (double)h[nl + l]);
-    fprintf(stderr, " | exchange(u) %.2f spmv+dots %.2f reduce+scalar %.2f update %.2f\n", 1e-6 * (double)h[2 * nl], 1e-6 * (double)h[2 * nl + 1],
-            1e-6 * (double)h[2 * nl + 2], 1e-6 * (double)h[2 * nl + 3]);
+    fprintf(stderr, " | exchange(u) %.2f spmv+dots %.2f reduce+scalar %.2f update %.2f | halo exchanges: compute before %.2f push %.2f wait %.2f\n",
+            1e-6 * (double)h[2 * nl], 1e-6 * (double)h[2 * nl + 1], 1e-6 * (double)h[2 * nl + 2], 1e-6 * (double)h[2 * nl + 3],
+            1e-6 * (double)h[40], 1e-6 * (double)h[41], 1e-6 * (double)h[42]);
   }
   // epilogue: w = A x for the model cost change
   PGO_TRY(amg_exchange(g, M, L0, g->vx, 6, 6, nullptr));

@@ -70,8 +70,8 @@ def test_sphere2500_full_size_matches_oracle_and_needs_few_pcg_iterations(pgo, o
     g = pgo.datasets.sphere()
     assert (g.n_poses, g.n_edges) == (2500, 9799)
     s, its, dp = _check_against_oracle(pgo, oracle, g)
-    assert s.linear_solver_used == AMG and s.amg_levels >= 4
-    assert s.total_pcg_iterations / (len(its) - 1) <= 70      # block-Jacobi PCG: ~900 per LM step
+    assert s.linear_solver_used == AMG and s.amg_levels >= 3  # 2500 -> 742 -> 118 (inverted densely)
+    assert s.total_pcg_iterations / (len(its) - 1) <= 40      # measured 28; block-Jacobi PCG: ~900 per LM step
     assert dp <= 1e-6                                         # measured 1e-9 m
 
 
