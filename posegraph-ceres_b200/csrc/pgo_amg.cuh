@@ -27,6 +27,7 @@ constexpr int kAmgDenseMaxNodes = 512;     // ... up to this many: block Gauss-J
 constexpr int kGjThreads = 1024;
 constexpr int kGjMaxOwnRows = 6 * 8;       // block rows of the dense system a CTA may own (x 6 scalar rows)
 
+template <typename T> struct BsrViewT { int n; const T* Hdiag; const T* Hoff; const int* row_ptr; const int* col_idx; };
 struct AmgLevelDev {
   bool replicated = false;
   int n_own = 0, n_halo = 0;
@@ -36,6 +37,7 @@ struct AmgLevelDev {
   int* row_ptr = nullptr;
   int* col_idx = nullptr;
   long long nnz = 0;
+  float *Adiag_f = nullptr, *Aoff_f = nullptr;   // fp32 copy of the operator: what the sweeps INSIDE the preconditioner read
   double* Dinv = nullptr;                  // [n_own][36] row-major inverses of the diagonal blocks (level 0: Minv)
   double *r = nullptr, *x = nullptr, *y = nullptr;   // [n_own + n_halo][6]
   double* z = nullptr;                     // third iterate buffer of the levels a W-cycle visits twice
@@ -65,6 +67,7 @@ struct Amg {
   int nu = 1;
   int coarse_sweeps = 4;
   int gamma = 1, gamma_depth = 0;          // cycle shape, see amg_vcycle
+  bool fp32_ops = true;                    // smoothing / residual sweeps of the cycle read the fp32 operator copies
   pgo_graph* owner = nullptr;
   PcgMultiState* state = nullptr;
   PcgMultiState* state_h = nullptr;        // pinned, two slots
@@ -463,6 +466,11 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth0_kernel(int n, const d
   if (L.on) x[q] = omega * t;
 }
 
+// fp32 copy of an operator array (once per LM step and level)
+__global__ void __launch_bounds__(256) amg_to_float_kernel(size_t n, const double* __restrict__ src, float* __restrict__ dst) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[k] = (float)src[k];
+}
+
 // second visit of a level: r = t (the new right-hand side), x = omega * Dinv t
 __global__ void __launch_bounds__(kAmgThreads) amg_rhs_smooth0_kernel(int n, const double* __restrict__ Dinv, const double* __restrict__ t,
                                                                       double omega, double* __restrict__ r, double* __restrict__ x, const int* skip) {
@@ -481,7 +489,8 @@ __global__ void amg_add_kernel(int n6, const double* __restrict__ x, double* __r
 }
 
 // y = x + omega * Dinv (r - A x)
-__global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ Dinv,
+template <typename T>
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrViewT<T> A, const double* __restrict__ d, const double* __restrict__ Dinv,
                                                                  const double* __restrict__ r, const double* __restrict__ x, double omega,
                                                                  double* __restrict__ y, const int* skip) {
   if (skip && *skip) return;
@@ -494,7 +503,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A
     const bool on = grp < kRowsPerWarp && i < A.n;
     const size_t q = 6 * (size_t)(on ? i : 0) + c;
     double t = 0.0;
-    if (on) t = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
+    if (on) t = r[q] - bsr6_row<false, T>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
     const double z = amg_block_row_dot(on ? Dinv + 36 * (size_t)i : nullptr, c, g0, t);
     if (on) y[q] = x[q] + omega * z;
   }
@@ -503,7 +512,8 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrView A
 // t = r - A x over the stored rows (six lanes per row): the residual half of residual + restriction on LARGE levels.
 // (A fused kernel -- one six-lane group walking its aggregate's member rows -- was measured at 515 us on the 1M-pose level
 // against 360 us for a whole smoothing sweep: a long dependent chain per group; this is a streaming SpMV.)
-__global__ void __launch_bounds__(kAmgThreads) amg_residual_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ r,
+template <typename T>
+__global__ void __launch_bounds__(kAmgThreads) amg_residual_kernel(const BsrViewT<T> A, const double* __restrict__ d, const double* __restrict__ r,
                                                                    const double* __restrict__ x, double* __restrict__ t, const int* skip) {
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6;
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_residual_kernel(const BsrView
     const int i = base + grp;
     if (grp < kRowsPerWarp && i < A.n) {
       const size_t q = 6 * (size_t)i + c;
-      t[q] = r[q] - bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
+      t[q] = r[q] - bsr6_row<false, T>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
     }
   }
 }
@@ -548,15 +558,17 @@ __global__ void __launch_bounds__(kAmgThreads) amg_prolong_kernel(int n, const i
 // sweep is the length of the longest dependent chain, and coarse Galerkin rows hold up to a few hundred blocks.  Five
 // 6-lane groups stride through the row's blocks; a shuffle tree adds the five partial rows.  Result on lanes 0..5.
 constexpr int kAmgWarpRowMax = 32768;
-__device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag, const double* __restrict__ Hoff,
+template <typename T>
+__device__ __forceinline__ double bsr6_row_warp(const T* __restrict__ Hdiag, const T* __restrict__ Hoff,
                                                 const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                                                 const double* __restrict__ x, const double* __restrict__ d, int i, int lane) {
+  typedef typename Pair2<T>::type T2;
   const int grp = lane / 6, r = lane - grp * 6;
   double acc = 0.0;
   if (grp < 5) {
     if (grp == 0) {
-      const double2* hd = reinterpret_cast<const double2*>(Hdiag + 36 * (size_t)i) + r;
-      const double2 h0 = __ldg(hd), h1 = __ldg(hd + 6), h2 = __ldg(hd + 12);
+      const T2* hd = reinterpret_cast<const T2*>(Hdiag + 36 * (size_t)i) + r;
+      const double2 h0 = ldg_pair<T>(hd), h1 = ldg_pair<T>(hd + 6), h2 = ldg_pair<T>(hd + 12);
       const double* xi = x + 6 * (size_t)i;
       const double2 x0 = __ldg(reinterpret_cast<const double2*>(xi)), x1 = __ldg(reinterpret_cast<const double2*>(xi + 2)),
                     x2 = __ldg(reinterpret_cast<const double2*>(xi + 4));
@@ -580,8 +592,8 @@ __device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag
       double2 hb[4][3], xb[4][3];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)(p + 5 * q)) + r;
-        hb[q][0] = __ldg(ha); hb[q][1] = __ldg(ha + 6); hb[q][2] = __ldg(ha + 12);
+        const T2* ha = reinterpret_cast<const T2*>(Hoff + 36 * (size_t)(p + 5 * q)) + r;
+        hb[q][0] = ldg_pair<T>(ha); hb[q][1] = ldg_pair<T>(ha + 6); hb[q][2] = ldg_pair<T>(ha + 12);
         const double2* xa = reinterpret_cast<const double2*>(x + 6 * (size_t)j[q]);
         xb[q][0] = __ldg(xa); xb[q][1] = __ldg(xa + 1); xb[q][2] = __ldg(xa + 2);
       }
@@ -594,8 +606,8 @@ __device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag
     }
     for (; p < p1; p += 5) {
       const int j = __ldg(col_idx + p);
-      const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
-      const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
+      const T2* ha = reinterpret_cast<const T2*>(Hoff + 36 * (size_t)p) + r;
+      const double2 a0 = ldg_pair<T>(ha), a1 = ldg_pair<T>(ha + 6), a2 = ldg_pair<T>(ha + 12);
       const double* xa = x + 6 * (size_t)j;
       const double2 u0 = __ldg(reinterpret_cast<const double2*>(xa)), u1 = __ldg(reinterpret_cast<const double2*>(xa + 2)),
                     u2 = __ldg(reinterpret_cast<const double2*>(xa + 4));
@@ -611,15 +623,15 @@ __device__ __forceinline__ double bsr6_row_warp(const double* __restrict__ Hdiag
 }
 
 // y = x + omega Dinv (r - A x), one warp per row; kResidualOnly: y = r - A x
-template <bool kResidualOnly>
-__global__ void __launch_bounds__(kAmgThreads) amg_smooth_warp_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ Dinv,
+template <bool kResidualOnly, typename T>
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth_warp_kernel(const BsrViewT<T> A, const double* __restrict__ d, const double* __restrict__ Dinv,
                                                                       const double* __restrict__ r, const double* __restrict__ x, double omega,
                                                                       double* __restrict__ y, const int* skip) {
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
   if (i >= A.n) return;                         // warp-uniform
-  const double ax = bsr6_row_warp(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, lane);
+  const double ax = bsr6_row_warp<T>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, lane);
   const bool on = lane < 6;
   const size_t q = 6 * (size_t)i + (on ? lane : 0);
   const double t = on ? r[q] - ax : 0.0;
@@ -741,7 +753,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_warp_kernel(const B
   const int i = blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5);
   double a0 = 0.0, a1 = 0.0;
   if (!idle && i < A.n) {
-    const double v = bsr6_row_warp(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, u, d, i, lane);
+    const double v = bsr6_row_warp<double>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, u, d, i, lane);
     if (lane < 6) {
       const size_t q = 6 * (size_t)i + lane;
       w[q] = v;
@@ -1077,6 +1089,7 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   if (const char* e = getenv("PGO_AMG_OMEGA")) M->omega = atof(e);
   if (const char* e = getenv("PGO_AMG_NU")) M->nu = std::max(1, atoi(e));
   if (const char* e = getenv("PGO_AMG_COARSE_SWEEPS")) M->coarse_sweeps = std::max(1, atoi(e));
+  if (const char* e = getenv("PGO_AMG_FP32")) M->fp32_ops = atoi(e) != 0;
   // cycle shape: a second visit of the first two coarse levels pays when level 0 is a long streaming sweep (>= 400 k rows
   // here: 1M-pose grid 208 -> 120 PCG iterations per LM step, 5.2 -> 4.4 s); on smaller slices the extra coarse visits are
   // pure launch latency and the V-cycle is faster (100 k torus: 354 ms V, 452 ms W) -- profiles/r2q_w_cycle_ab_1xB200.txt
@@ -1111,6 +1124,10 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
       PGO_TRY(dev_alloc(g, &D.r, n_loc * 6));
       PGO_TRY(dev_alloc(g, &D.pos, n_loc * 3));
       D.pos_stride = 3;
+    }
+    if (M->fp32_ops) {
+      PGO_TRY(dev_alloc(g, &D.Adiag_f, (size_t)H.n_own * 36));
+      PGO_TRY(dev_alloc(g, &D.Aoff_f, (size_t)D.nnz * 36));
     }
     PGO_TRY(dev_alloc(g, &D.x, n_loc * 6));
     PGO_TRY(dev_alloc(g, &D.y, n_loc * 6));
@@ -1185,6 +1202,16 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   return PGO_OK;
 }
 
+static pgo::BsrViewT<float> amg_view_f(const pgo::AmgLevelDev& D) {
+  pgo::BsrViewT<float> A;
+  A.n = D.n_own; A.Hdiag = D.Adiag_f; A.Hoff = D.Aoff_f; A.row_ptr = D.row_ptr; A.col_idx = D.col_idx;
+  return A;
+}
+static pgo::BsrViewT<double> amg_view_d(const pgo::AmgLevelDev& D) {
+  pgo::BsrViewT<double> A;
+  A.n = D.n_own; A.Hdiag = D.Adiag; A.Hoff = D.Aoff; A.row_ptr = D.row_ptr; A.col_idx = D.col_idx;
+  return A;
+}
 static long long amg_peer_pushes(const pgo_graph* g) { return g->amg && g->amg->peer ? g->amg->peer->pushes : 0; }
 static long long amg_peer_bytes(const pgo_graph* g) { return g->amg && g->amg->peer ? g->amg->peer->push_bytes : 0; }
 
@@ -1200,6 +1227,15 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
   const int nl = M->num_levels;
   AmgLevelDev& L0 = M->lv[0];
   L0.Adiag = g->Hdiag; L0.Aoff = g->Hoff; L0.Dinv = g->Minv; L0.pos = g->poses; L0.r = g->vr;
+  // fp32 copies of the operators the cycle sweeps over (the CG product and the Galerkin products keep reading fp64)
+  auto to_float = [&](const AmgLevelDev& D) {
+    if (!M->fp32_ops) return;
+    const size_t nd = (size_t)D.n_own * 36, no = (size_t)D.nnz * 36;
+    if (nd) amg_to_float_kernel<<<(int)std::min<size_t>((nd + 255) / 256, (size_t)8 * g->num_sms), 256, 0, g->stream>>>(nd, D.Adiag, D.Adiag_f);
+    if (no) amg_to_float_kernel<<<(int)std::min<size_t>((no + 255) / 256, (size_t)8 * g->num_sms), 256, 0, g->stream>>>(no, D.Aoff, D.Aoff_f);
+    g->launches += 2;
+  };
+  if (nl > 1) to_float(L0);
   for (int l = 0; l + 1 < nl; ++l) {
     AmgLevelDev& F = M->lv[l];
     AmgLevelDev& C = M->lv[l + 1];
@@ -1225,6 +1261,7 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
       PGO_TRY(amg_gather(g, C.Adiag, C.gather_off, 36));
       PGO_TRY(amg_gather(g, C.Aoff, C.gather_slot_off, 36));
     }
+    if (!(l + 2 == nl && M->dense_inv)) to_float(C);
     if (l + 2 == nl && M->dense_inv && C.n_own > kAmgDenseSmemNodes) {
       const size_t m = 6 * (size_t)C.n_own;
       CUDA_TRY(cudaMemsetAsync(M->dense_inv, 0, m * m * sizeof(double), g->stream));
@@ -1261,16 +1298,43 @@ static inline void amg_mark(pgo_graph* g, pgo::Amg* M, int idx) {
   if (M->prof) pgo::amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, idx, &M->state->done);
 }
 
+// y = x + omega Dinv (r - A x) / t = r - A x on level l: streaming six-lanes-per-row form on large levels, a warp per row on
+// small ones; the operator is read from its fp32 copy when the cycle runs in mixed precision (vectors and arithmetic: fp64)
+template <typename T>
+static void amg_launch_smooth_t(pgo_graph* g, pgo::Amg* M, int l, const pgo::BsrViewT<T>& A, const double* x, double* y, const int* skip) {
+  using namespace pgo;
+  const AmgLevelDev& D = M->lv[l];
+  if (D.n_own <= kAmgWarpRowMax)
+    amg_smooth_warp_kernel<false, T><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  else
+    amg_smooth_kernel<T><<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  g->launches++;
+}
+template <typename T>
+static void amg_launch_residual_t(pgo_graph* g, pgo::Amg* M, int l, const pgo::BsrViewT<T>& A, const double* x, double* t, const int* skip) {
+  using namespace pgo;
+  const AmgLevelDev& D = M->lv[l];
+  if (D.n_own <= kAmgWarpRowMax)
+    amg_smooth_warp_kernel<true, T><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, nullptr, D.r, x, 0.0, t, skip);
+  else
+    amg_residual_kernel<T><<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.r, x, t, skip);
+  g->launches++;
+}
+static void amg_launch_smooth(pgo_graph* g, pgo::Amg* M, int l, const double* x, double* y, const int* skip) {
+  if (M->fp32_ops) amg_launch_smooth_t<float>(g, M, l, amg_view_f(M->lv[l]), x, y, skip);
+  else amg_launch_smooth_t<double>(g, M, l, amg_view_d(M->lv[l]), x, y, skip);
+}
+static void amg_launch_residual(pgo_graph* g, pgo::Amg* M, int l, const double* x, double* t, const int* skip) {
+  if (M->fp32_ops) amg_launch_residual_t<float>(g, M, l, amg_view_f(M->lv[l]), x, t, skip);
+  else amg_launch_residual_t<double>(g, M, l, amg_view_d(M->lv[l]), x, t, skip);
+}
+
 // One smoothing sweep y = x + omega Dinv (r - A x) on level l (halo of x exchanged first).
 static int amg_sweep(pgo_graph* g, pgo::Amg* M, int l, double* x, double* y, const int* skip) {
   using namespace pgo;
   const AmgLevelDev& D = M->lv[l];
   PGO_TRY(amg_exchange(g, M, D, x, 6, 6, skip));
-  if (D.n_own <= kAmgWarpRowMax)
-    amg_smooth_warp_kernel<false><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
-  else
-    amg_smooth_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
-  g->launches++;
+  amg_launch_smooth(g, M, l, x, y, skip);
   return PGO_OK;
 }
 
@@ -1308,15 +1372,11 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     if (ncomp > 0) {
       // residual into the spare buffer (small level: a whole warp per row; large level: streaming, six lanes per row),
       // then the restriction (a warp per coarse row)
-      if (D.n_own <= kAmgWarpRowMax)
-        amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, nullptr, D.r, cur[l],
-                                                                                        0.0, oth[l], skip);
-      else
-        amg_residual_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), l == 0 ? g->dlm : nullptr, D.r, cur[l], oth[l], skip);
+      amg_launch_residual(g, M, l, cur[l], oth[l], skip);
       amg_restrict_kernel<<<(ncomp + 7) / 8, kAmgThreads, 0, g->stream>>>(oth[l], ncomp, D.c_row0, D.mem_ptr, D.mem_idx, D.pos, D.pos_stride, C.pos,
                                                                           l == 0 ? g->scale : nullptr, C.r, fuse_next ? C.Dinv : nullptr,
                                                                           M->omega, cur[l + 1], skip);
-      g->launches += 2;
+      g->launches += 1;
     }
     PGO_TRY(amg_gather_residual(g, M, C, skip));
     return PGO_OK;
@@ -1356,12 +1416,9 @@ static int amg_vcycle(pgo_graph* g, pgo::Amg* M, double** out) {
     double* b1 = e == D.x ? D.y : D.x;
     double* b2 = e == D.z ? D.y : D.z;
     PGO_TRY(amg_exchange(g, M, D, e, 6, 6, skip));
-    if (D.n_own <= kAmgWarpRowMax)
-      amg_smooth_warp_kernel<true><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(amg_view(D), nullptr, nullptr, D.r, e, 0.0, b2, skip);
-    else
-      amg_residual_kernel<<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(amg_view(D), nullptr, D.r, e, b2, skip);
+    amg_launch_residual(g, M, l, e, b2, skip);
     amg_rhs_smooth0_kernel<<<amg_rows_grid(D.n_own), kAmgThreads, 0, g->stream>>>(D.n_own, D.Dinv, b2, M->omega, D.r, b1, skip);
-    g->launches += 2;
+    g->launches += 1;
     cur[l] = b1; oth[l] = b2;
     PGO_TRY(cycle(l));
     amg_add_kernel<<<(6 * D.n_own + 255) / 256, 256, 0, g->stream>>>(6 * D.n_own, e, cur[l], skip);

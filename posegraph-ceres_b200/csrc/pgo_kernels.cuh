@@ -414,15 +414,26 @@ __global__ void __launch_bounds__(kLinWarps * 32, kMinBlocks) linearize_kernel(c
 // Panel layout => the 6 lanes of a group read 96 contiguous bytes per 128-bit load.
 // kCoherent: gather x with ld.global.cg (x was written by other CTAs of the same launch).
 // --------------------------------------------------------------------------------------------
-template <bool kCoherent>
-__device__ __forceinline__ double bsr6_row(const double* __restrict__ Hdiag, const double* __restrict__ Hoff,
+// (T = float: the operator copy the multilevel preconditioner sweeps over, pgo_amg.cuh -- half the bytes; the arithmetic
+// stays fp64)
+template <typename T> struct Pair2;
+template <> struct Pair2<double> { typedef double2 type; };
+template <> struct Pair2<float> { typedef float2 type; };
+template <typename T>
+__device__ __forceinline__ double2 ldg_pair(const typename Pair2<T>::type* p) {
+  const typename Pair2<T>::type v = __ldg(p);
+  return make_double2((double)v.x, (double)v.y);
+}
+template <bool kCoherent, typename T = double>
+__device__ __forceinline__ double bsr6_row(const T* __restrict__ Hdiag, const T* __restrict__ Hoff,
                                            const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
                                            const double* x, const double* __restrict__ d, int i, int r, bool with_diag = true) {
+  typedef typename Pair2<T>::type T2;
   auto ldx = [&](const double* q) -> double2 {
     return kCoherent ? __ldcg(reinterpret_cast<const double2*>(q)) : __ldg(reinterpret_cast<const double2*>(q));
   };
-  const double2* hd = reinterpret_cast<const double2*>(Hdiag + 36 * (size_t)i) + r;
-  const double2 h0 = __ldg(hd), h1 = __ldg(hd + 6), h2 = __ldg(hd + 12);
+  const T2* hd = reinterpret_cast<const T2*>(Hdiag + 36 * (size_t)i) + r;
+  const double2 h0 = ldg_pair<T>(hd), h1 = ldg_pair<T>(hd + 6), h2 = ldg_pair<T>(hd + 12);
   const double* xi = x + 6 * (size_t)i;
   const double2 x0 = ldx(xi), x1 = ldx(xi + 2), x2 = ldx(xi + 4);
   double acc = h0.x * x0.x;
@@ -438,10 +449,10 @@ __device__ __forceinline__ double bsr6_row(const double* __restrict__ Hdiag, con
   int p = p0;
   for (; p + 1 < p1; p += 2) {
     const int j0 = __ldg(col_idx + p), j1 = __ldg(col_idx + p + 1);
-    const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
-    const double2* hb = ha + 18;
-    const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
-    const double2 b0 = __ldg(hb), b1 = __ldg(hb + 6), b2 = __ldg(hb + 12);
+    const T2* ha = reinterpret_cast<const T2*>(Hoff + 36 * (size_t)p) + r;
+    const T2* hb = ha + 18;
+    const double2 a0 = ldg_pair<T>(ha), a1 = ldg_pair<T>(ha + 6), a2 = ldg_pair<T>(ha + 12);
+    const double2 b0 = ldg_pair<T>(hb), b1 = ldg_pair<T>(hb + 6), b2 = ldg_pair<T>(hb + 12);
     const double* xa = x + 6 * (size_t)j0;
     const double* xb = x + 6 * (size_t)j1;
     const double2 u0 = ldx(xa), u1 = ldx(xa + 2), u2 = ldx(xa + 4);
@@ -453,8 +464,8 @@ __device__ __forceinline__ double bsr6_row(const double* __restrict__ Hdiag, con
   }
   if (p < p1) {
     const int j0 = __ldg(col_idx + p);
-    const double2* ha = reinterpret_cast<const double2*>(Hoff + 36 * (size_t)p) + r;
-    const double2 a0 = __ldg(ha), a1 = __ldg(ha + 6), a2 = __ldg(ha + 12);
+    const T2* ha = reinterpret_cast<const T2*>(Hoff + 36 * (size_t)p) + r;
+    const double2 a0 = ldg_pair<T>(ha), a1 = ldg_pair<T>(ha + 6), a2 = ldg_pair<T>(ha + 12);
     const double* xa = x + 6 * (size_t)j0;
     const double2 u0 = ldx(xa), u1 = ldx(xa + 2), u2 = ldx(xa + 4);
     acc = fma(a0.x, u0.x, acc); acc = fma(a0.y, u0.y, acc); acc = fma(a1.x, u1.x, acc);

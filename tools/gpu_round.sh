@@ -21,12 +21,12 @@ if [ "$1" == "profile" ]; then
       python tools/kitti_step.py 2 > gpurun_out/prof_chol.log 2>&1
   # the multilevel PCG on the 1M-pose grid: launch list of its iterations and full captures of its two heaviest kernels
   PGO_AMG_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2500 -c 300 --csv --log-file gpurun_out/launches_amg_grid.csv \
-      python tools/amg_check.py --cases grid1000 --no-oracle > gpurun_out/amg_under_ncu.log 2>&1
+      python tools/amg_check.py --cases grid1000 --no-oracle --reps 1 > gpurun_out/amg_under_ncu.log 2>&1
   PGO_AMG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:amg_smooth_kernel -s 20 -c 1 -f -o gpurun_out/prof_amg_smooth \
-      python tools/amg_check.py --cases grid1000 --no-oracle > gpurun_out/prof_amg_smooth.log 2>&1
-  PGO_AMG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:amg_spmv_dots_kernel -s 20 -c 1 -f -o gpurun_out/prof_amg_spmv \
-      python tools/amg_check.py --cases grid1000 --no-oracle > gpurun_out/prof_amg_spmv.log 2>&1
-  for k in linearize spmv chol amg_smooth amg_spmv; do python tools/ncu_summary.py kernel gpurun_out/prof_$k.ncu-rep > gpurun_out/summary_$k.txt 2>&1; done
+      python tools/amg_check.py --cases grid1000 --no-oracle --reps 1 > gpurun_out/prof_amg_smooth.log 2>&1
+  PGO_AMG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:amg_dense_gj_kernel -s 1 -c 1 -f -o gpurun_out/prof_amg_gj \
+      python tools/amg_check.py --cases grid1000 --no-oracle --reps 1 > gpurun_out/prof_amg_gj.log 2>&1
+  for k in linearize spmv chol amg_smooth amg_gj; do python tools/ncu_summary.py kernel gpurun_out/prof_$k.ncu-rep > gpurun_out/summary_$k.txt 2>&1; done
   python tools/ncu_summary.py launches gpurun_out/launches.csv > gpurun_out/summary_launches_kitti.txt 2>&1
   python tools/ncu_summary.py launches gpurun_out/launches_amg_grid.csv > gpurun_out/summary_launches_amg_grid.txt 2>&1
 fi
