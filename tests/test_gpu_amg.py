@@ -134,7 +134,7 @@ def test_torus_100k_converges(pgo):
 def test_grid_1m_converges(pgo):
     """configs[3] at full size: 1 000 000 poses / 2 048 000 edges, solved to Ceres' default tolerances on one GPU."""
     g = pgo.datasets.manhattan_grid(1000, 1000, 50000)
-    s, its, poses = _converged_solve_properties(pgo, g, max_pcg_per_lm=320)
+    s, its, poses = _converged_solve_properties(pgo, g, max_pcg_per_lm=160)      # measured 121 (W-cycle on the first two coarse levels); V-cycle: 208
     _check_chi2_level(g, s)
 
 
@@ -155,19 +155,24 @@ def test_second_device_in_the_same_process(pgo, oracle):
                 assert np.abs(poses[:, :3] - ref[:, :3]).max() <= 1e-4, (g.name, dev, solver)
 
 
-def _torchrun(script_args, nproc, timeout=900):
+def _torchrun(script_args, nproc, timeout=900, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + os.getpid() % 200)] + script_args
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
 
 
-def test_row_partitioned_solve_on_all_visible_gpus(pgo):
-    """The multi-GPU path (owner-computes row partition, halo exchange + scalar all-reduce over NCCL): on every visible
-    GPU (2, 4 or 8) the partitioned solve of four graphs equals the one-GPU solve (1e-6 on the poses; measured 1e-11),
-    every rank ends with bit-identical poses, and the result is within the north-star tolerance of the CPU oracle."""
+@pytest.mark.parametrize("exchange", ["peer_memory", "nccl"])
+def test_row_partitioned_solve_on_all_visible_gpus(pgo, exchange):
+    """The multi-GPU path (owner-computes row partition; per PCG iteration halo exchanges, a residual gather and a scalar
+    all-reduce -- over NVLink peer memory, csrc/pgo_peer.cuh, or, PGO_PEER=0, as NCCL calls): on every visible GPU (2, 4 or
+    8) the partitioned solve of four graphs equals the one-GPU solve (1e-6 on the poses; measured 1e-9), every rank ends
+    with bit-identical poses, and the result is within the north-star tolerance of the CPU oracle."""
     n = pgo.device_count()
     if n < 2:
         pytest.skip("one GPU visible")
     world = 8 if n >= 8 else 4 if n >= 4 else 2
-    r = _torchrun([os.path.join(ROOT, "tools", "amg_check.py"), "--cases", "sphere200,sphere,grid100,torus5k"], world)
+    r = _torchrun([os.path.join(ROOT, "tools", "amg_check.py"), "--cases", "sphere200,sphere,grid100,torus5k"], world,
+                  env={"PGO_PEER": "1" if exchange == "peer_memory" else "0"})
+    if exchange == "nccl":
+        assert "per PCG it 0 calls" not in r.stdout
     assert r.returncode == 0 and "AMG_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
