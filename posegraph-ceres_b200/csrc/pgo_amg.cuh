@@ -24,7 +24,7 @@ namespace pgo {
 constexpr int kAmgThreads = 256;
 constexpr int kAmgDenseSmemNodes = 16;     // coarsest level of at most this many nodes: Gauss-Jordan in the shared memory of one CTA
 constexpr int kAmgDenseMaxNodes = 512;     // ... up to this many: block Gauss-Jordan in global memory by a cooperative grid (3072^2 fp64 = 75 MB)
-constexpr int kGjThreads = 1024;
+constexpr int kGjThreads = 512;
 constexpr int kGjMaxOwnRows = 6 * 8;       // block rows of the dense system a CTA may own (x 6 scalar rows)
 
 template <typename T> struct BsrViewT { int n; const T* Hdiag; const T* Hoff; const int* row_ptr; const int* col_idx; };
@@ -146,48 +146,82 @@ struct GalerkinParams {
   double *Cdiag, *Coff;
 };
 
-// One thread per element (r, c) of a coarse block: Z(r,c) = sum over the fine blocks of the gather list of
-// sum_{k,m} P_i(k,r) A(k,m) P_j(m,c), summed in list order (deterministic).
-__global__ void __launch_bounds__(288) amg_galerkin_kernel(const GalerkinParams P) {
-  const int cb = blockIdx.x * 8 + threadIdx.x / 36;
-  if (cb >= P.n_cblk) return;
-  const int e = threadIdx.x % 36, r = e / 6, c = e - r * 6;
-  double acc = 0.0;
-  const int q0 = P.gal_ptr[cb], q1 = P.gal_ptr[cb + 1];
-  for (int q = q0; q < q1; ++q) {
-    const int i = P.gal_row[q], p = P.gal_slot[q];
-    const int j = p < 0 ? i : P.col_idx[p];
-    const double* A = p < 0 ? P.Adiag + 36 * (size_t)i : P.Aoff + 36 * (size_t)p;
-    double di[3], dj[3];
-    amg_delta(P.pos, P.pos_stride, i, P.cpos, P.agg[i], di);
-    amg_delta(P.pos, P.pos_stride, j, P.cpos, P.agg[j], dj);
-    // rows k of A that reach coarse row r: k = r, and k = 0..2 when r >= 3 (through X_i); likewise columns m for c
-    double t = 0.0;
+// Six lanes per coarse block (lane r owns row r of it), five blocks per warp -- the lane layout of bsr6_row, so every lane
+// loads only ITS row of a fine block (three 128-bit loads, 96 contiguous bytes per load across the group):
+//   Z = sum over the gather list of P_i^T A P_j,   P = S^-1 [[I, X], [0, I]],
+//   y_r = row r of P_i^T A = A(r,:)/s_i[r] + [r >= 3] sum_{k<3} X_i(k, r-3)/s_i[k] A(k,:)     (rows 0..2 come by shuffle)
+//   Z(r,c) = y_r(c)/s_j[c] + [c >= 3] sum_{m<3} y_r(m) X_j(m, c-3)/s_j[m]
+// summed in list order (deterministic).  (Round 2 first had one thread per ELEMENT of the coarse block: 36 threads redid
+// the index chasing and the mode algebra of every contribution -- 19 ms on the 1M-pose level, instruction bound.)
+__global__ void __launch_bounds__(kAmgThreads) amg_galerkin_kernel(const GalerkinParams P) {
+  const int lane = threadIdx.x & 31, grp = lane / 6, r = lane - grp * 6, g0 = grp * 6;
+  const int cb = (blockIdx.x * (kAmgThreads / 32) + (threadIdx.x >> 5)) * kRowsPerWarp + grp;
+  const bool valid = grp < kRowsPerWarp && cb < P.n_cblk;
+  const int q0 = valid ? __ldg(P.gal_ptr + cb) : 0, q1 = valid ? __ldg(P.gal_ptr + cb + 1) : 0;
+  const unsigned full = 0xffffffffu;
+  int maxlen = q1 - q0;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int k = kk == 0 ? r : kk - 1;
-      if (kk > 0 && r < 3) continue;
-      double bi = amg_mode(di, k, r);
-      if (P.scale) { const double s = P.scale[6 * (size_t)i + k]; bi = s > 0.0 ? bi / s : 0.0; }
-      if (bi == 0.0) continue;
-      double u = 0.0;
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(full, maxlen, o));
+  double z[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int t = 0; t < maxlen; ++t) {
+    const bool on = q0 + t < q1;
+    double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double si[3] = {1.0, 1.0, 1.0}, sir = 1.0, sj[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+    double di[3] = {0.0, 0.0, 0.0}, dj[3] = {0.0, 0.0, 0.0};
+    if (on) {
+      const int i = __ldg(P.gal_row + q0 + t), p = __ldg(P.gal_slot + q0 + t);
+      const int j = p < 0 ? i : __ldg(P.col_idx + p);
+      const double2* blk = reinterpret_cast<const double2*>(p < 0 ? P.Adiag + 36 * (size_t)i : P.Aoff + 36 * (size_t)p) + r;
+      const double2 a0 = __ldg(blk), a1 = __ldg(blk + 6), a2 = __ldg(blk + 12);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y;
+      if (p < 0 && P.dlm) {
+        const double dl = __ldg(P.dlm + 6 * (size_t)i + r);
 #pragma unroll
-      for (int mm = 0; mm < 4; ++mm) {
-        const int m = mm == 0 ? c : mm - 1;
-        if (mm > 0 && c < 3) continue;
-        double bj = amg_mode(dj, m, c);
-        if (P.scale) { const double s = P.scale[6 * (size_t)j + m]; bj = s > 0.0 ? bj / s : 0.0; }
-        if (bj == 0.0) continue;
-        double a = A[pidx(k, m)];
-        if (p < 0 && P.dlm && k == m) a += P.dlm[6 * (size_t)i + k];
-        u = fma(a, bj, u);
+        for (int c = 0; c < 6; ++c) if (c == r) a[c] += dl;
       }
-      t = fma(bi, u, t);
+      amg_delta(P.pos, P.pos_stride, i, P.cpos, __ldg(P.agg + i), di);
+      amg_delta(P.pos, P.pos_stride, j, P.cpos, __ldg(P.agg + j), dj);
+      if (P.scale) {
+        const double* sc = P.scale + 6 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double v = __ldg(sc + k); si[k] = v > 0.0 ? 1.0 / v : 0.0; }
+        { const double v = __ldg(sc + r); sir = v > 0.0 ? 1.0 / v : 0.0; }
+        const double* sd = P.scale + 6 * (size_t)j;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) { const double v = __ldg(sd + m); sj[m] = v > 0.0 ? 1.0 / v : 0.0; }
+      }
     }
-    acc += t;
+    // rows 0..2 of A from the lanes that hold them
+    double top[3][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) top[k][c] = __shfl_sync(full, a[c], g0 + k);
+    if (!on) continue;
+    // X(k, c') of a node with offset d: [[0, 2dz, -2dy], [-2dz, 0, 2dx], [2dy, -2dx, 0]]
+    double y[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) y[c] = a[c] * sir;
+    if (r >= 3) {
+      const int cc = r - 3;
+      const double x0 = cc == 0 ? 0.0 : (cc == 1 ? 2.0 * di[2] : -2.0 * di[1]);     // X_i(0, cc)
+      const double x1 = cc == 0 ? -2.0 * di[2] : (cc == 1 ? 0.0 : 2.0 * di[0]);     // X_i(1, cc)
+      const double x2 = cc == 0 ? 2.0 * di[1] : (cc == 1 ? -2.0 * di[0] : 0.0);     // X_i(2, cc)
+      const double w0 = x0 * si[0], w1 = x1 * si[1], w2 = x2 * si[2];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) y[c] = fma(w0, top[0][c], fma(w1, top[1][c], fma(w2, top[2][c], y[c])));
+    }
+    const double u0 = y[0] * sj[0], u1 = y[1] * sj[1], u2 = y[2] * sj[2];
+    z[0] += u0; z[1] += u1; z[2] += u2;
+    // columns 3..5: y(c) / s_j[c] + sum_{m<3} u_m X_j(m, c - 3)
+    z[3] += fma(u1, -2.0 * dj[2], fma(u2, 2.0 * dj[1], y[3] * sj[3]));
+    z[4] += fma(u0, 2.0 * dj[2], fma(u2, -2.0 * dj[0], y[4] * sj[4]));
+    z[5] += fma(u0, -2.0 * dj[1], fma(u1, 2.0 * dj[0], y[5] * sj[5]));
   }
+  if (!valid) return;
   double* out = cb < P.ncomp ? P.Cdiag + 36 * (size_t)(P.c_row0 + cb) : P.Coff + 36 * (size_t)(P.c_slot0 + cb - P.ncomp);
-  out[pidx(r, c)] = acc;
+  double2* o2 = reinterpret_cast<double2*>(out) + r;
+  o2[0] = make_double2(z[0], z[1]); o2[6] = make_double2(z[2], z[3]); o2[12] = make_double2(z[4], z[5]);
 }
 
 // inverse of a symmetric positive definite 6x6 block by Cholesky; false when a pivot is not positive
@@ -378,21 +412,47 @@ __global__ void __launch_bounds__(kGjThreads) amg_dense_gj_kernel(const GjParams
     const double* R = P.R + (size_t)(k & 1) * 6 * m;
     for (int t = threadIdx.x; t < nrows * 6; t += blockDim.x) Cs[t / 6][t % 6] = M[(6 * (size_t)b0 + t / 6) * m + 6 * (size_t)k + t % 6];
     __syncthreads();
-    auto update = [&](int r_lo, int r_hi) {           // local scalar rows [r_lo, r_hi)
-      for (int j = threadIdx.x; j < (int)m; j += blockDim.x) {
-        double Rq[6];
+    // rows come in blocks of six: all twelve loads of a (block row, column) item are issued before its 36 FMAs (the
+    // matrix lives in L2: a row-at-a-time loop exposed one ~0.7 us round trip per row -- 29 us per step at 2 400 unknowns)
+    auto update = [&](int r_lo, int r_hi) {           // local scalar rows [r_lo, r_hi), a multiple of six
+      for (int rb = r_lo; rb < r_hi; rb += 6) {
+        const int gi0 = 6 * b0 + rb;
+        const bool pivot_rows = gi0 == 6 * k;
+        for (int j0 = threadIdx.x; j0 < (int)m; j0 += 2 * blockDim.x) {
+          // two columns per trip: 24 loads in flight per thread
+          double Rq[2][6], a[2][6];
+          int jj[2];
+          bool on[2], in_k[2];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Rq[q] = __ldcg(R + q * m + j);
-        const bool in_k = (j / 6) == k;
-        for (int i = r_lo; i < r_hi; ++i) {
-          const int gi = 6 * b0 + i;
-          double* a = M + (size_t)gi * m + j;
-          const int pr = gi - 6 * k;
-          if (pr >= 0 && pr < 6) { *a = Rq[pr]; continue; }
-          double t = in_k ? 0.0 : *a;
+          for (int u = 0; u < 2; ++u) {
+            jj[u] = j0 + u * blockDim.x;
+            on[u] = jj[u] < (int)m;
+            in_k[u] = (jj[u] / 6) == k;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) t = fma(-Cs[i][q], Rq[q], t);
-          *a = t;
+            for (int q = 0; q < 6; ++q) Rq[u][q] = on[u] ? __ldcg(R + q * m + jj[u]) : 0.0;
+          }
+          if (!pivot_rows) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int i = 0; i < 6; ++i) a[u][i] = (on[u] && !in_k[u]) ? M[(size_t)(gi0 + i) * m + jj[u]] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            double* col = M + (size_t)gi0 * m + jj[u];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              double t;
+              if (pivot_rows) t = Rq[u][i];
+              else {
+                t = a[u][i];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) t = fma(-Cs[rb + i][q], Rq[u][q], t);
+              }
+              col[(size_t)i * m] = t;
+            }
+          }
         }
       }
     };
@@ -1254,7 +1314,7 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
       P.dlm = l == 0 ? g->dlm : nullptr; P.scale = l == 0 ? g->scale : nullptr;
       P.agg = F.agg; P.pos = F.pos; P.pos_stride = F.pos_stride; P.cpos = C.pos;
       P.Cdiag = C.Adiag; P.Coff = C.Aoff;
-      amg_galerkin_kernel<<<(F.n_cblk + 7) / 8, 288, 0, g->stream>>>(P);
+      amg_galerkin_kernel<<<amg_rows_grid(F.n_cblk), kAmgThreads, 0, g->stream>>>(P);
       g->launches++;
     }
     if (!C.gather_off.empty()) {
