@@ -68,6 +68,7 @@ struct Amg {
   int coarse_sweeps = 4;
   int gamma = 1, gamma_depth = 0;          // cycle shape, see amg_vcycle
   bool fp32_ops = true;                    // smoothing / residual sweeps of the cycle read the fp32 operator copies
+  float* Minv_f = nullptr;                 // fp32 copy of level 0's block inverses (large level 0 only), else nullptr
   pgo_graph* owner = nullptr;
   PcgMultiState* state = nullptr;
   PcgMultiState* state_h = nullptr;        // pinned, two slots
@@ -505,13 +506,15 @@ __device__ __forceinline__ RowLane amg_row_lane(int n) {
   return L;
 }
 // row c of a row-major 6x6 block times the 6-vector spread over the lanes of the group
-__device__ __forceinline__ double amg_block_row_dot(const double* blk, int c, int g0, double v) {
+// (TD = float: the fp32 copy of level 0's block inverses on large graphs -- the same copy in the pre- and the post-sweep)
+template <typename TD = double>
+__device__ __forceinline__ double amg_block_row_dot(const TD* blk, int c, int g0, double v) {
   const unsigned m = 0xffffffffu;
   const double v0 = __shfl_sync(m, v, g0), v1 = __shfl_sync(m, v, g0 + 1), v2 = __shfl_sync(m, v, g0 + 2);
   const double v3 = __shfl_sync(m, v, g0 + 3), v4 = __shfl_sync(m, v, g0 + 4), v5 = __shfl_sync(m, v, g0 + 5);
   if (blk == nullptr) return 0.0;
-  const double2* b = reinterpret_cast<const double2*>(blk + 6 * c);
-  const double2 m0 = __ldg(b), m1 = __ldg(b + 1), m2 = __ldg(b + 2);
+  const typename Pair2<TD>::type* b = reinterpret_cast<const typename Pair2<TD>::type*>(blk + 6 * c);
+  const double2 m0 = ldg_pair<TD>(b), m1 = ldg_pair<TD>(b + 1), m2 = ldg_pair<TD>(b + 2);
   return m0.x * v0 + m0.y * v1 + m1.x * v2 + m1.y * v3 + m2.x * v4 + m2.y * v5;
 }
 
@@ -549,8 +552,8 @@ __global__ void amg_add_kernel(int n6, const double* __restrict__ x, double* __r
 }
 
 // y = x + omega * Dinv (r - A x)
-template <typename T>
-__global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrViewT<T> A, const double* __restrict__ d, const double* __restrict__ Dinv,
+template <typename T, typename TD>
+__global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrViewT<T> A, const double* __restrict__ d, const TD* __restrict__ Dinv,
                                                                  const double* __restrict__ r, const double* __restrict__ x, double omega,
                                                                  double* __restrict__ y, const int* skip) {
   if (skip && *skip) return;
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_smooth_kernel(const BsrViewT<
     const size_t q = 6 * (size_t)(on ? i : 0) + c;
     double t = 0.0;
     if (on) t = r[q] - bsr6_row<false, T>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, x, d, i, c);
-    const double z = amg_block_row_dot(on ? Dinv + 36 * (size_t)i : nullptr, c, g0, t);
+    const double z = amg_block_row_dot<TD>(on ? Dinv + 36 * (size_t)i : nullptr, c, g0, t);
     if (on) y[q] = x[q] + omega * z;
   }
 }
@@ -759,12 +762,13 @@ __global__ void amg_mark_kernel(unsigned long long* acc, int idx, const int* ski
 
 // ---- PCG pieces (Chronopoulos-Gear with a general preconditioner) ----
 // init: x = 0, r = b, p = s = 0, x0 = omega Minv r (first pre-smoothing sweep of the first V-cycle)
-__global__ void __launch_bounds__(kAmgThreads) amg_pcg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ Minv,
+template <typename TD>
+__global__ void __launch_bounds__(kAmgThreads) amg_pcg_init_kernel(int n, const double* __restrict__ b, const TD* __restrict__ Minv,
                                                                    double omega, double* x, double* r, double* p, double* s, double* x0) {
   const RowLane L = amg_row_lane(n);
   const size_t q = 6 * (size_t)(L.on ? L.i : 0) + L.c;
   const double rv = L.on ? b[q] : 0.0;
-  const double t = amg_block_row_dot(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
+  const double t = amg_block_row_dot<TD>(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
   if (L.on) { x[q] = 0.0; r[q] = rv; p[q] = 0.0; s[q] = 0.0; x0[q] = omega * t; }
 }
 
@@ -929,7 +933,8 @@ __global__ void __launch_bounds__(kAmgThreads) amg_pcg_reduce_scalar_kernel(PcgM
 }
 
 // p = u + beta p, s = w + beta s, x += alpha p, r -= alpha s, x0 = omega Minv r
-__global__ void __launch_bounds__(kAmgThreads) amg_pcg_update_kernel(int n, const double* __restrict__ Minv, const double* __restrict__ u,
+template <typename TD>
+__global__ void __launch_bounds__(kAmgThreads) amg_pcg_update_kernel(int n, const TD* __restrict__ Minv, const double* __restrict__ u,
                                                                      const double* __restrict__ w, double omega, double* x, double* r,
                                                                      double* p, double* s, double* x0, const PcgMultiState* st) {
   if (st->done) return;
@@ -945,7 +950,7 @@ __global__ void __launch_bounds__(kAmgThreads) amg_pcg_update_kernel(int n, cons
     rv = r[q] - alpha * sv;
     r[q] = rv;
   }
-  const double t = amg_block_row_dot(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
+  const double t = amg_block_row_dot<TD>(L.on ? Minv + 36 * (size_t)L.i : nullptr, L.c, L.g0, rv);
   if (L.on) x0[q] = omega * t;
 }
 
@@ -1232,6 +1237,7 @@ static int amg_create(pgo_graph* g, pgo::Amg** out) {
   CUDA_TRY(pool_event(g->device, &M->ev[0]));
   CUDA_TRY(pool_event(g->device, &M->ev[1]));
   M->owner = g;
+  if (M->fp32_ops && nl > 1 && M->lv[0].n_own > kAmgWarpRowMax) PGO_TRY(dev_alloc(g, &M->Minv_f, (size_t)M->lv[0].n_own * 36));
   if (getenv("PGO_AMG_PROFILE")) {
     PGO_TRY(dev_alloc(g, &M->prof, 64));
     CUDA_TRY(cudaMemsetAsync(M->prof, 0, 64 * sizeof(unsigned long long), g->stream));
@@ -1296,6 +1302,11 @@ static int amg_setup_numeric(pgo_graph* g, pgo::Amg* M) {
     g->launches += 2;
   };
   if (nl > 1) to_float(L0);
+  if (M->Minv_f) {
+    const size_t nd = (size_t)L0.n_own * 36;
+    amg_to_float_kernel<<<(int)std::min<size_t>((nd + 255) / 256, (size_t)8 * g->num_sms), 256, 0, g->stream>>>(nd, g->Minv, M->Minv_f);
+    g->launches++;
+  }
   for (int l = 0; l + 1 < nl; ++l) {
     AmgLevelDev& F = M->lv[l];
     AmgLevelDev& C = M->lv[l + 1];
@@ -1366,8 +1377,10 @@ static void amg_launch_smooth_t(pgo_graph* g, pgo::Amg* M, int l, const pgo::Bsr
   const AmgLevelDev& D = M->lv[l];
   if (D.n_own <= kAmgWarpRowMax)
     amg_smooth_warp_kernel<false, T><<<(D.n_own + 7) / 8, kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+  else if (l == 0 && M->Minv_f)
+    amg_smooth_kernel<T, float><<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(A, g->dlm, M->Minv_f, D.r, x, M->omega, y, skip);
   else
-    amg_smooth_kernel<T><<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
+    amg_smooth_kernel<T, double><<<std::min(amg_rows_grid(D.n_own), 8 * g->num_sms), kAmgThreads, 0, g->stream>>>(A, l == 0 ? g->dlm : nullptr, D.Dinv, D.r, x, M->omega, y, skip);
   g->launches++;
 }
 template <typename T>
@@ -1583,7 +1596,8 @@ static int amg_enqueue_iteration(pgo_graph* g, pgo::Amg* M, const pgo_solver_opt
     amg_pcg_reduce_scalar_kernel<<<1, kAmgThreads, 0, g->stream>>>(st, M->part, sp_ctas, o->pcg_max_iterations, o->pcg_tolerance);
   }
   amg_mark(g, M, 2 * nl + 2);
-  amg_pcg_update_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
+  if (M->Minv_f) amg_pcg_update_kernel<float><<<rows_grid, kAmgThreads, 0, g->stream>>>(n, M->Minv_f, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
+  else amg_pcg_update_kernel<double><<<rows_grid, kAmgThreads, 0, g->stream>>>(n, g->Minv, u, g->vw, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x, st);
   amg_mark(g, M, 2 * nl + 3);
   g->launches += 3;
   return PGO_OK;
@@ -1607,7 +1621,8 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
   const int dot_ctas = std::max(1, std::min((n6 + kAmgThreads - 1) / kAmgThreads, std::min(4 * g->num_sms, M->part_cap / 3)));
   AmgLevelDev& L0 = M->lv[0];
   CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(PcgMultiState), g->stream));
-  amg_pcg_init_kernel<<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, g->Minv, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
+  if (M->Minv_f) amg_pcg_init_kernel<float><<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, M->Minv_f, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
+  else amg_pcg_init_kernel<double><<<rows_grid, kAmgThreads, 0, g->stream>>>(n, b, g->Minv, M->omega, g->vx, g->vr, g->vp, g->vs, L0.x);
   g->launches++;
   if (M->prof) amg_mark_kernel<<<1, 1, 0, g->stream>>>(M->prof, -1, nullptr);
   static const int graph_env = getenv("PGO_AMG_GRAPH") ? atoi(getenv("PGO_AMG_GRAPH")) : -1;
