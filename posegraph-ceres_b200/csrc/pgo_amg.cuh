@@ -1,13 +1,15 @@
-// pgo_amg.cuh -- PCG for the damped normal equations preconditioned by an aggregation multigrid V-cycle whose coarse
+// pgo_amg.cuh -- PCG for the damped normal equations preconditioned by an aggregation multigrid cycle whose coarse
 // spaces are the rigid-body modes of pose patches (hierarchy: pgo_amg_host.hpp).  Solver type PGO_LINEAR_PCG_AMG: the
 // solver of mesh-like graphs (sphere, grids, dense random loops) and of every multi-GPU solve.  Included by pgo_b200.cu.
 //
 // Per LM step (amg_setup_numeric): patch centroids from the current poses, the Galerkin operators A_{l+1} = P^T A_l P
 // gathered block by block in a fixed order (no atomics: every rank computes bit-identical replicated levels), 6x6
-// block-Jacobi inverses, and the dense inverse of the coarsest system.
-// Per PCG iteration (Chronopoulos-Gear form, ONE reduction per iteration): V-cycle u = M^-1 r, halo exchange of u,
-// w = A u with the partial sums of r.u and w.u in its epilogue, all-reduce of the two scalars, vector update fused with
-// the first pre-smoothing sweep of the next V-cycle.
+// block-Jacobi inverses, fp32 copies of the operators for the sweeps inside the cycle, and the dense inverse of the last
+// level (<= 512 nodes: block Gauss-Jordan by a cooperative grid).
+// Per PCG iteration (Chronopoulos-Gear form, ONE reduction per iteration): cycle u = M^-1 r (V, or W on the first coarse
+// levels of large graphs: amg_vcycle), halo exchange of u, w = A u with the partial sum of w.u in its epilogue, r.u,
+// all-reduce of the two scalars, vector update fused with the first pre-smoothing sweep of the next cycle.  The whole
+// iteration is one CUDA graph; on several GPUs its exchanges run over NVLink peer memory (pgo_peer.cuh).
 //
 // Prolongator of fine node i in aggregate I (d = p_i - c_I, c_I the patch centroid, S the Jacobi column scaling):
 //   P_i = S_i^-1 [[I, X], [0, I]],  X = -2 [d]x      (a patch rotation delta moves p_i by 2 delta x d: the local rotation
@@ -772,42 +774,8 @@ __global__ void __launch_bounds__(kAmgThreads) amg_pcg_init_kernel(int n, const 
   if (L.on) { x[q] = 0.0; r[q] = rv; p[q] = 0.0; s[q] = 0.0; x0[q] = omega * t; }
 }
 
-// w = (A + D) u over the owned rows; per-CTA partials of w.u and r.u in a fixed order
-__global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ u,
-                                                                    const double* __restrict__ r, double* __restrict__ w,
-                                                                    double* __restrict__ part /* [2][gridDim.x] */, const int* skip) {
-  __shared__ double red0[kAmgThreads / 32], red1[kAmgThreads / 32];
-  const bool idle = skip && *skip;
-  double a0 = 0.0, a1 = 0.0;
-  if (!idle) {
-    const int lane = threadIdx.x & 31, grp = lane / 6, c = lane - grp * 6;
-    const int wpc = kAmgThreads / 32;
-    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = gridDim.x * wpc;
-    for (int base = gw * kRowsPerWarp; base < A.n; base += nw * kRowsPerWarp) {
-      const int i = base + grp;
-      if (grp < kRowsPerWarp && i < A.n) {
-        const size_t q = 6 * (size_t)i + c;
-        const double v = bsr6_row<false>(A.Hdiag, A.Hoff, A.row_ptr, A.col_idx, u, d, i, c);
-        w[q] = v;
-        const double uv = __ldg(u + q);
-        a0 = fma(v, uv, a0);
-        a1 = fma(__ldg(r + q), uv, a1);
-      }
-    }
-  }
-  a0 = warp_sum(a0); a1 = warp_sum(a1);
-  if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5] = a0; red1[threadIdx.x >> 5] = a1; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < kAmgThreads / 32; ++k) { t0 += red0[k]; t1 += red1[k]; }
-    part[blockIdx.x] = t0;
-    part[gridDim.x + blockIdx.x] = t1;
-  }
-}
-
-// the same with a whole warp per row (small level 0: the sweep is latency bound)
+// w = (A + D) u over the owned rows with per-CTA partials of w.u and r.u in a fixed order: a whole warp per row (small
+// level 0: the sweep is latency bound).  Large level 0: the plain spmv_kernel with w.u in its epilogue + amg_dot_kernel.
 __global__ void __launch_bounds__(kAmgThreads) amg_spmv_dots_warp_kernel(const BsrView A, const double* __restrict__ d, const double* __restrict__ u,
                                                                          const double* __restrict__ r, double* __restrict__ w,
                                                                          double* __restrict__ part /* [2][gridDim.x] */, const int* skip) {

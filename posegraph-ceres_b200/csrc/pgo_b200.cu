@@ -784,6 +784,9 @@ extern "C" int pgo_analyze_partition(int n_poses, int n_edges, const double* pos
       for (int k = L.recv_ptr[q]; k < L.recv_ptr[q + 1]; ++k) hr += mix64(L.nbr[q], rank, (unsigned long long)l << 32 | (unsigned)L.halo_gid[k], k - L.recv_ptr[q]);
     }
     // ---- invariants ----
+    // (peer-memory exchanges, pgo_peer.cuh: two staging buffers per channel are enough only when partners are symmetric)
+    for (size_t q = 0; q < L.nbr.size(); ++q)
+      if ((L.send_ptr[q + 1] > L.send_ptr[q]) != (L.recv_ptr[q + 1] > L.recv_ptr[q])) ok = false;
     const int n_loc = L.n_own + L.n_halo;
     for (size_t p = 0; p < L.col_idx.size(); ++p) if (L.col_idx[p] < 0 || L.col_idx[p] >= n_loc) ok = false;
     if (l + 1 < nl) {

@@ -132,23 +132,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_wait_kernel(const PeerWaitA
     for (int e = gtid; e < A.copy_n[c]; e += gsize) v[A.copy_dst[c] + (size_t)e] = __ldcg(stage + A.copy_src[c] + (size_t)e);
 }
 
-// All-reduce of nq (<= 6) scalars: my partial sums were pushed as ONE item into slot [my rank] of every peer; add the
-// slots in rank order (own value from `mine`) -> out[0..nq).  One warp.
-__global__ void peer_allreduce_wait_kernel(const PeerWaitArgs A, int world, int me, int nq, const double* mine, double* out /* may alias */,
-                                           const int* skip) {
-  if (skip && *skip) return;
-  const unsigned int s = *A.seq;
-  if (threadIdx.x < A.n_sources) {
-    if (!peer_spin(A.flags + A.src_rank[threadIdx.x], s) && A.timeout_flag) *A.timeout_flag = 1;
-  }
-  __syncwarp();
-  const double* stage = A.stage[s & 1];
-  if (threadIdx.x < nq) {
-    double t = 0.0;
-    for (int r = 0; r < world; ++r) t += r == me ? mine[threadIdx.x] : __ldcg(stage + 6 * (size_t)r + threadIdx.x);
-    out[threadIdx.x] = t;
-  }
-}
+// (The scalar all-reduce: every rank pushes its partial sums as ONE item into slot [my rank] of every peer;
+// amg_pcg_scalar_peer_kernel in pgo_amg.cuh waits for all slots, adds them in rank order and takes the CG step.)
 
 }  // namespace pgo
 
