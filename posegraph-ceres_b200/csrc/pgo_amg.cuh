@@ -84,7 +84,7 @@ struct Amg {
   int tail_graph_kernels = 0, tail_calls = 0;
   bool tail_graph_failed = false;
   std::vector<double*> tail_cur;
-  struct IterGraph { const void* key[4]; int max_it; double tol; cudaGraphExec_t exec; int kernels; };
+  struct IterGraph { const void* key[4]; int max_it; double tol; cudaGraphExec_t exec; int kernels; long long pushes, push_bytes; };
   std::vector<IterGraph> graphs;           // captured PCG iteration per (H, poses) buffer pair (the LM loop alternates two)
   // multi-GPU: per-iteration exchanges over peer memory instead of NCCL (nullptr: NCCL)
   PeerCtx* peer = nullptr;
@@ -1030,6 +1030,7 @@ static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
   using namespace pgo;
   const int nl = M->num_levels, W = g->world, me = g->rank;
   std::vector<PeerChannelSpec> spec;
+  bool symmetric = true;
   for (int l = 0; l < nl; ++l) {
     AmgLevelDev& D = M->lv[l];
     if (!D.replicated) {
@@ -1038,9 +1039,10 @@ static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
       c.recv_item_off.assign(W, -1);
       for (size_t k = 0; k < D.nbr.size(); ++k)
         if (D.recv_ptr[k + 1] > D.recv_ptr[k]) c.recv_item_off[D.nbr[k]] = D.recv_ptr[k];
-      // (the argument that two staging buffers are enough needs symmetric partners)
+      // (the argument that two staging buffers are enough needs symmetric partners; a rank that sees otherwise vetoes
+      // inside peer_create -- the decision must be collective, every rank is in its all-gather)
       for (size_t k = 0; k < D.nbr.size(); ++k)
-        if ((D.recv_ptr[k + 1] > D.recv_ptr[k]) != (D.send_ptr[k + 1] > D.send_ptr[k])) return PGO_OK;
+        if ((D.recv_ptr[k + 1] > D.recv_ptr[k]) != (D.send_ptr[k + 1] > D.send_ptr[k])) symmetric = false;
       D.peer_ch = (int)spec.size();
       spec.push_back(c);
     }
@@ -1059,7 +1061,7 @@ static int amg_peer_setup(pgo_graph* g, pgo::Amg* M) {
   for (int r = 0; r < W; ++r) if (r != me) red.recv_item_off[r] = r;
   const int ch_red = (int)spec.size();
   spec.push_back(red);
-  PGO_TRY(peer_create(g, spec, &M->peer));
+  PGO_TRY(peer_create(g, spec, &M->peer, symmetric));
   if (!M->peer) {
     for (auto& D : M->lv) { D.peer_ch = -1; D.gather_ch = -1; }
     return PGO_OK;
@@ -1605,6 +1607,7 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
     if (!ig) {
       if (M->graphs.size() >= 8) { for (auto& e : M->graphs) cudaGraphExecDestroy(e.exec); M->graphs.clear(); }
       const long long l0 = g->launches;
+      const long long px0 = M->peer ? M->peer->pushes : 0, pb0 = M->peer ? M->peer->push_bytes : 0;
       cudaGraph_t graph = nullptr;
       CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
       const int rc = amg_enqueue_iteration(g, M, o, sp_ctas, rows_grid);
@@ -1614,6 +1617,8 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
       Amg::IterGraph e;
       std::memcpy(e.key, key, sizeof key);
       e.max_it = o->pcg_max_iterations; e.tol = o->pcg_tolerance; e.kernels = (int)(g->launches - l0); e.exec = nullptr;
+      e.pushes = M->peer ? M->peer->pushes - px0 : 0; e.push_bytes = M->peer ? M->peer->push_bytes - pb0 : 0;
+      if (M->peer) { M->peer->pushes = px0; M->peer->push_bytes = pb0; }     // counted per replay below
       g->launches = l0;
       const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
       cudaGraphDestroy(graph);
@@ -1628,7 +1633,11 @@ static int amg_pcg_solve(pgo_graph* g, const pgo_solver_options* o, const double
   bool finished = false;
   while (!finished) {
     for (int k = 0; k < batch; ++k) {
-      if (ig) { CUDA_TRY(cudaGraphLaunch(ig->exec, g->stream)); g->launches += ig->kernels; }
+      if (ig) {
+        CUDA_TRY(cudaGraphLaunch(ig->exec, g->stream));
+        g->launches += ig->kernels;
+        if (M->peer) { M->peer->pushes += ig->pushes; M->peer->push_bytes += ig->push_bytes; }
+      }
       else PGO_TRY(amg_enqueue_iteration(g, M, o, sp_ctas, rows_grid));
     }
     const int slot = enqueued & 1;

@@ -167,7 +167,8 @@ static void peer_destroy(pgo_graph* g, PeerCtx* P);
 
 // Collective over the graph's communicator.  *out stays nullptr (and PGO_OK is returned) when peer windows are not
 // available on this box -- every rank takes the same decision -- and the callers keep using NCCL.
-static int peer_create(pgo_graph* g, const std::vector<PeerChannelSpec>& ch, PeerCtx** out) {
+// local_ok == false (this rank's plans do not qualify): the rank still takes part in the collectives and vetoes.
+static int peer_create(pgo_graph* g, const std::vector<PeerChannelSpec>& ch, PeerCtx** out, bool local_ok = true) {
   using namespace pgo;
   *out = nullptr;
   if (g->world <= 1 || g->world > kPeerMaxWorld || (int)ch.size() > kPeerMaxChannels) return PGO_OK;
@@ -196,6 +197,7 @@ static int peer_create(pgo_graph* g, const std::vector<PeerChannelSpec>& ch, Pee
   if (ok) ok = cudaMemsetAsync(P->window, 0, P->bytes, g->stream) == cudaSuccess;
   if (ok) ok = cudaIpcGetMemHandle(&mine.handle, P->window) == cudaSuccess;
   if (!ok) { cudaGetLastError(); mine.ok = 0; }
+  if (!local_ok) mine.ok = 0;
   // all-gather the layouts (device staging through the pool)
   PeerLayout* dev = nullptr;
   PGO_TRY(dev_alloc(g, &dev, (size_t)g->world + 1));
