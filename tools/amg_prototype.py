@@ -1,7 +1,19 @@
 #!/usr/bin/env python3
 """CPU prototype (numpy/scipy + the oracle's Jacobians) of the aggregation-AMG preconditioner for the damped normal
 equations of a pose graph.  Design evidence only: it answers "how many PCG iterations does a rigid-body-mode
-aggregation V-cycle need on sphere / grid / torus" before the CUDA version is written.  Not part of the product."""
+aggregation cycle need on sphere / grid / torus" before the CUDA version is written.  Not part of the product.
+
+Experiments recorded in DESIGN.md section 3.3 (all with --agg cxx --omega 0.85, i.e. the library's own aggregates):
+  --dense-below N          solve the first level of <= N nodes exactly           (built: amg_dense_gj_kernel)
+  --gamma 2 [--gamma-depth d]   visit levels 1..d twice (truncated W-cycle)      (built: amg_vcycle)
+  --at-truth               linearise at the optimum: the long-range loop edges carry full weight there (Huber
+                           down-weights them at the noisy initial poses) and the 1000 x 1000 grid needs 214 iterations
+                           instead of 86; --loops N varies their number
+  --smooth-p 0.66          smoothed aggregation (prolongator smoothing with the full matrix): 15-20 iterations
+                           everywhere, operator complexity 6-16 unfiltered                          (next step)
+  --pair-levels k, --local-scale s, --geo-smooth w     12x12 pair smoother over the loop edges, rescaled local part of
+                           the coarse operators, topology-only prolongator weights: tried, none helps
+"""
 import argparse
 import os
 import sys
@@ -135,12 +147,8 @@ def pair_block_diag_inv(A, n, pos, theta, levels_left):
     key = {}
     for k in np.nonzero(off & (mate[rows] == cols))[0]:
         key[(rows[k], cols[k])] = Ab.data[k]
-    ri, ci, vals = [], [], []
     single = np.nonzero(mate < 0)[0]
     inv_single = np.linalg.inv(Dblk[single])
-    for t, i in enumerate(single):
-        pass
-    data_rows = []; data_cols = []; data_vals = []
     # singles as BSR
     S = sp.bsr_matrix((inv_single, single, np.arange(len(single) + 1)), shape=(6 * len(single), 6 * n))
     R = sp.csr_matrix((np.ones(6 * len(single)), (np.repeat(single, 6) * 6 + np.tile(np.arange(6), len(single)), np.arange(6 * len(single)))), shape=(6 * n, 6 * len(single)))
