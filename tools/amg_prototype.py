@@ -11,6 +11,9 @@ Experiments recorded in DESIGN.md section 3.3 (all with --agg cxx --omega 0.85, 
                            instead of 86; --loops N varies their number
   --smooth-p 0.66          smoothed aggregation (prolongator smoothing with the full matrix): 15-20 iterations
                            everywhere, operator complexity 6-16 unfiltered                          (next step)
+  --smooth-p 0.66 --smooth-filter   the same with a filtered matrix (near blocks, far ones lumped rigidly into the
+                           diagonal): complexity 2.5-4, but 29 instead of 16 iterations on the 100 x 100 grid at the optimum
+                           and PCG breaks down on the 200^2 / 400^2 grids there
   --pair-levels k, --local-scale s, --geo-smooth w     12x12 pair smoother over the loop edges, rescaled local part of
                            the coarse operators, topology-only prolongator weights: tried, none helps
 """
@@ -254,7 +257,39 @@ def build_hierarchy(A, pos, n, scale_inv, args, active, A_far=None):
             P = sp.bsr_matrix((Pb[order], Wt.col[order], indptr), shape=(6 * cur_n, 6 * na)).tocsr()
         else:
             P = sp.bsr_matrix((Pb, agg, np.arange(cur_n + 1)), shape=(6 * cur_n, 6 * na)).tocsr()
-        if args.smooth_p > 0:
+        if args.smooth_p > 0 and args.smooth_filter:
+            # FILTERED prolongator smoothing: only the geometrically strong (local) blocks of A take part; every dropped
+            # block A_ij is lumped into the diagonal through the rigid transfer T(p_j - p_i) (scaled: S_j^-1 T S_i), so
+            # the filtered matrix annihilates exactly what A annihilates and the smoothed P still reproduces rigid motions
+            Ab2 = cur_A.tobsr(blocksize=(6, 6))
+            rows2 = np.repeat(np.arange(cur_n), np.diff(Ab2.indptr)); cols2 = Ab2.indices
+            is_diag = rows2 == cols2
+            # "far" = much farther than the nearest neighbours of both ends (a looser test than the aggregation's theta:
+            # with theta itself most coarse-level neighbours count as weak and the lumped diagonal loses its stiffness)
+            d2f = np.sum((cur_pos[rows2] - cur_pos[cols2]) ** 2, axis=1) + 1e-12
+            wf = np.where(is_diag, 0.0, 1.0 / d2f)
+            rmaxf = sp.csr_matrix((wf, (rows2, cols2)), shape=(cur_n, cur_n)).max(axis=1).toarray().ravel()
+            keep = is_diag | (wf >= args.filter_theta * np.minimum(rmaxf[rows2], rmaxf[cols2]))
+            weak = ~keep
+            Dblk = np.zeros((cur_n, 6, 6)); Dblk[rows2[is_diag]] = Ab2.data[is_diag]
+            if weak.any():
+                dd = cur_pos[cols2[weak]] - cur_pos[rows2[weak]]
+                T = np.zeros((int(weak.sum()), 6, 6)); T[:, np.arange(6), np.arange(6)] = 1.0
+                T[:, 0, 4] = 2 * dd[:, 2]; T[:, 0, 5] = -2 * dd[:, 1]
+                T[:, 1, 3] = -2 * dd[:, 2]; T[:, 1, 5] = 2 * dd[:, 0]
+                T[:, 2, 3] = 2 * dd[:, 1]; T[:, 2, 4] = -2 * dd[:, 0]
+                Si = np.where(cur_Sinv > 0, 1.0 / np.maximum(cur_Sinv, 1e-300), 0.0)
+                Ts = cur_Sinv[cols2[weak]][:, :, None] * T * Si[rows2[weak]][:, None, :]
+                np.add.at(Dblk, rows2[weak], np.einsum("bij,bjk->bik", Ab2.data[weak], Ts))
+            data = Ab2.data[keep].copy()
+            kd = is_diag[keep]
+            data[kd] = Dblk[rows2[keep][kd]]
+            order = np.lexsort((cols2[keep], rows2[keep]))
+            indptr = np.concatenate([[0], np.cumsum(np.bincount(rows2[keep], minlength=cur_n))])
+            AF = sp.bsr_matrix((data[order], cols2[keep][order], indptr), shape=cur_A.shape).tocsr()
+            DFinv = sp.bsr_matrix((np.linalg.inv(Dblk + 1e-300 * np.eye(6)[None]), np.arange(cur_n), np.arange(cur_n + 1)), shape=cur_A.shape).tocsr()
+            P = P - args.smooth_p * (DFinv @ (AF @ P))
+        elif args.smooth_p > 0:
             P = P - args.smooth_p * (L.Dinv @ (cur_A @ P))
         L.P = P
         if cur_far is not None and args.local_scale != 1.0:
@@ -325,6 +360,8 @@ def main():
     ap.add_argument("--gamma", type=int, default=1)
     ap.add_argument("--gamma-depth", type=int, default=99, help="levels 1..depth are visited twice (truncated W-cycle)")
     ap.add_argument("--smooth-p", type=float, default=0.0)
+    ap.add_argument("--smooth-filter", action="store_true", help="--smooth-p with the filtered (near blocks + rigidly lumped diagonal) matrix")
+    ap.add_argument("--filter-theta", type=float, default=0.05, help="a block is far (dropped from the smoothing matrix) when 1/d^2 < this x the smaller row maximum")
     ap.add_argument("--geo-smooth", type=float, default=0.0, help="topology-only prolongator smoothing weight")
     ap.add_argument("--geo-unweighted", action="store_true")
     ap.add_argument("--coarsest", type=int, default=8)
