@@ -13,7 +13,8 @@ Experiments recorded in DESIGN.md section 3.3 (all with --agg cxx --omega 0.85, 
                            everywhere, operator complexity 6-16 unfiltered                          (next step)
   --smooth-p 0.66 --smooth-filter   the same with a filtered matrix (near blocks, far ones lumped rigidly into the
                            diagonal): complexity 2.5-4, but 29 instead of 16 iterations on the 100 x 100 grid at the optimum
-                           and PCG breaks down on the 200^2 / 400^2 grids there
+                           and PCG breaks down on the 200^2 / 400^2 grids there; --filter-nolump (far blocks dropped,
+                           full diagonal kept, i.e. rigid motions no longer reproduced at the loop ends): 86 / 177 / 258
   --pair-levels k, --local-scale s, --geo-smooth w     12x12 pair smoother over the loop edges, rescaled local part of
                            the coarse operators, topology-only prolongator weights: tried, none helps
 """
@@ -272,7 +273,7 @@ def build_hierarchy(A, pos, n, scale_inv, args, active, A_far=None):
             keep = is_diag | (wf >= args.filter_theta * np.minimum(rmaxf[rows2], rmaxf[cols2]))
             weak = ~keep
             Dblk = np.zeros((cur_n, 6, 6)); Dblk[rows2[is_diag]] = Ab2.data[is_diag]
-            if weak.any():
+            if weak.any() and not args.filter_nolump:
                 dd = cur_pos[cols2[weak]] - cur_pos[rows2[weak]]
                 T = np.zeros((int(weak.sum()), 6, 6)); T[:, np.arange(6), np.arange(6)] = 1.0
                 T[:, 0, 4] = 2 * dd[:, 2]; T[:, 0, 5] = -2 * dd[:, 1]
@@ -361,6 +362,7 @@ def main():
     ap.add_argument("--gamma-depth", type=int, default=99, help="levels 1..depth are visited twice (truncated W-cycle)")
     ap.add_argument("--smooth-p", type=float, default=0.0)
     ap.add_argument("--smooth-filter", action="store_true", help="--smooth-p with the filtered (near blocks + rigidly lumped diagonal) matrix")
+    ap.add_argument("--filter-nolump", action="store_true", help="--smooth-filter keeping the FULL diagonal blocks (far blocks dropped, not lumped)")
     ap.add_argument("--filter-theta", type=float, default=0.05, help="a block is far (dropped from the smoothing matrix) when 1/d^2 < this x the smaller row maximum")
     ap.add_argument("--geo-smooth", type=float, default=0.0, help="topology-only prolongator smoothing weight")
     ap.add_argument("--geo-unweighted", action="store_true")
