@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PGO_B200_ABI_VERSION 5
+#define PGO_B200_ABI_VERSION 6
 
 typedef enum {
   PGO_OK = 0,

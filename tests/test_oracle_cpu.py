@@ -289,7 +289,7 @@ def test_cabi_exports_every_declared_symbol(pgo):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     assert set(pgo.EXPORTED_SYMBOLS) == declared
-    assert lib.pgo_abi_version() == 5
+    assert lib.pgo_abi_version() == 6
 
 
 def test_cabi_defaults_mirror_ceres_and_reference(pgo):
